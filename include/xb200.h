@@ -1,0 +1,150 @@
+/*
+ * xb200.h - C-ABI of the B200-native rollout->update hot path for agi-brain/xuance (v1.4.4 @ 4f0b05b).
+ *
+ * The reference has NO native/FFI layer: its hot path is Python classes resolved
+ * through registries.  This header is therefore the boundary a maintainer would bind from those classes
+ * (ctypes stubs in INTEGRATION.md); every entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream, allocates
+ *     nothing, and returns 0 on success, a negative XB_E* code for a rejected argument, or a positive
+ *     cudaError_t if the launch failed
+ *   - row-major layouts; [N,T,...] buffers are the reference's `create_memory` layout
+ *     (xuance/common/memory_tools.py:12-40) so that flat slot = env*T + step = the index handed to sample()
+ *   - scalar fields (actions of a Discrete space, rewards, values, terminals, old_logp, returns, advantages)
+ *     are float32, exactly as the reference stores them (memory_tools.py:15)
+ */
+#ifndef XB200_H_
+#define XB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XB_OK 0
+#define XB_EINVAL (-1)   /* bad size / null pointer */
+#define XB_EALIGN (-2)   /* pointer or row size not aligned as the entry point requires */
+#define XB_ERANGE (-3)   /* argument outside the supported range (documented per call) */
+
+/* observation output formats of xb_gather_obs */
+#define XB_OBS_U8 0        /* byte copy (bit-exact gather)                                          */
+#define XB_OBS_F32_NHWC 1  /* float32 = u8/255.0 (correctly rounded division), same element order   */
+#define XB_OBS_F32_NCHW 2  /* float32 = u8/255.0, channel planes (HWC -> CHW per row)               */
+#define XB_OBS_BF16_NHWC 3 /* bfloat16(round-to-nearest-even of u8/255.0f), same element order      */
+#define XB_OBS_F16_NHWC 4  /* float16 (rn) of u8/255.0f, same element order                         */
+
+int xb_version(void);
+const char *xb_error_string(int code);
+/* sm_count, compute capability of the current device; returns cudaError on failure */
+int xb_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---------------------------------------------------------------- K1: rollout / replay store ---------
+ * Replaces store_element(): `memory[:, ptr] = data`  (memory_tools.py:43-61), as used by
+ * DummyOnPolicyBuffer.store :232-240, DummyOffPolicyBuffer.store :364-372, PerOffPolicyBuffer.store :537-543.
+ * rows:    dst[N, T, row_bytes] (bytes)  <- src[N, row_bytes]   at step t      (row_bytes % 4 == 0)
+ * scalars: dst[F, N, T] (float32)        <- src[F, N]           at step t      (F may be 0)
+ * One launch does both; pass rows_dst = NULL to store scalars only. */
+int xb_rollout_store(void *rows_dst, const void *rows_src, int64_t row_bytes,
+                     float *scal_dst, const float *scal_src, int F,
+                     int N, int T, int t, void *stream);
+
+/* ---------------------------------------------------------------- K2: GAE / returns scan -------------
+ * Replaces DummyOnPolicyBuffer.finish_path (memory_tools.py:242-265) for ALL envs and ALL path segments of a
+ * rollout in one launch.  rew/val/term/adv/ret are [N,T] float32.  seg_end[N,T] (uint8) marks the last step
+ * of each finished path, bootstrap[N,T] holds the `val` passed to finish_path at that step, covered[N] is the
+ * number of leading steps of env i that belong to finished paths (steps >= covered[i] get adv = ret = 0, as in
+ * the reference where they are never written).
+ *   use_gae=1:  delta_t = r_t + (1-d_t)*gamma*V_{t+1} - V_t ;  A_t = delta_t + (1-d_t)*gamma*lam*A_{t+1}
+ *               ret_t = A_t + V_t   (float32; warp-level scan of the affine maps, so +-few ulp of the loop)
+ *   use_gae=0:  ret_t = r_t + gamma*ret_{t+1} (float64 scan, as scipy.lfilter), A_t = r_t + gamma*V_{t+1} - V_t */
+int xb_gae_scan(const float *rew, const float *val, const float *term,
+                const uint8_t *seg_end, const float *bootstrap, const int32_t *covered,
+                float *adv, float *ret, int N, int T, float gamma, float lam, int use_gae, void *stream);
+
+/* ---------------------------------------------------------------- K3: minibatch gather ---------------
+ * Replaces sample_batch(): `memory[(env_idx, step_idx)]` (memory_tools.py:64-84) as used by
+ * DummyOnPolicyBuffer.sample :267-287 and the replay buffers' sample().  idx[B] are flat slots (env*T+step);
+ * idx == NULL means identity (rows 0..B-1), which turns xb_gather_obs into the u8 -> float preprocessing of
+ * AC_CNN_Atari.forward / Basic_CNN.forward (xuance/torch/rl_models/representations/cnn.py:45-50,98-102).
+ * xb_gather_rows: dst[B,row_bytes] <- src[idx[b]]            (row_bytes % 4 == 0; bulk-async path if % 16 == 0)
+ * xb_gather_obs : dst[B, H*W*C] in `format` <- u8 src rows; H*W*C % 16 == 0; NCHW needs C == 4, W % 4 == 0. */
+int xb_gather_rows(const void *src, const int64_t *idx, int64_t B, int64_t row_bytes, void *dst, void *stream);
+int xb_gather_obs(const uint8_t *src, const int64_t *idx, int64_t B, int H, int W, int C,
+                  void *dst, int format, void *stream);
+
+/* Gathers F float32 fields fields[F, slots] at idx[B] into out[F, B]; if adv_field >= 0 that field is
+ * replaced by (x - mean) / (std + 1e-8) with the POPULATION std over the B gathered values
+ * (memory_tools.py:280-282).  stats_out[2] receives (mean, std).  scratch: >= xb_scratch_doubles() doubles
+ * plus one trailing int32 counter, zeroed once by the caller (the kernels re-zero it).
+ * world-size > 1 is handled above the ABI (all-reduce of the partial sums). */
+int64_t xb_scratch_doubles(void);
+int xb_gather_scalars(const float *fields, int64_t slots, const int64_t *idx, int64_t B, int F,
+                      float *out, int adv_field, float *stats_out, double *scratch, void *stream);
+
+/* ---------------------------------------------------------------- K4: fused PPO-Clip loss fwd+bwd ----
+ * Replaces ppo_learner.py:46-60 plus the autograd backward of those lines down to (logits, value):
+ *   logp = log_softmax(logits)[a]; ratio = exp(logp - old_logp)
+ *   a_loss = -mean(min(clamp(ratio,1-eps,1+eps)*adv, adv*ratio)); c_loss = mean((v-ret)^2); e = mean(H)
+ *   loss = a_loss - ent_coef*e + vf_coef*c_loss
+ * Writes dlogits[B,A] = dloss/dlogits, dvalue[B] = dloss/dvalue (means over B_total >= B rows so a
+ * rank-local shard of a global minibatch produces correctly scaled gradients) and
+ * stats[8] = {a_loss, c_loss, entropy, mean(v), clip_fraction, loss, 0, 0} * (B/B_total weighting applied,
+ * i.e. sums over the local rows divided by B_total).  actions are float32 (reference quirk).  A <= 64. */
+int xb_ppo_loss_fwd_bwd(const float *logits, const float *value, const float *actions,
+                        const float *old_logp, const float *adv, const float *ret,
+                        int64_t B, int A, int64_t B_total, float clip_range, float vf_coef, float ent_coef,
+                        float *dlogits, float *dvalue, float *stats, double *scratch, void *stream);
+
+/* ---------------------------------------------------------------- K5: prioritized-replay trees -------
+ * Replaces SumSegmentTree/MinSegmentTree (xuance/common/segtree_tool.py:4-220) and their use in
+ * PerOffPolicyBuffer (memory_tools.py:505-598).  One (sum,min) pair PER ENV, float32 nodes, heap layout
+ * tree[env][2*cap] (node 1 = root, leaves at cap..2cap-1); parents are fl32(l+r) / min(l,r).
+ * insert : leaf[ptr] = max_prio[env]^alpha in both trees for every env           (:545-548)
+ * sample : per env, k stratified draws: p_total = sum(0,size-1) with the reference's association order,
+ *          mass_j = fl(fl(u_j*seg) + fl(j*seg)), find_prefixsum_idx; weights = p_j/p_min computed as the
+ *          reference does (:563-572); u[N,k] float32 uniforms supplied by the caller
+ *          outputs: step_out[N,k] int64, flat_out[N*k] int64 (= env*S + step), w_out[N,k] float64
+ * update : leaf = p^alpha (p==0 -> 1e-8), later duplicates win, parents recomputed, max_prio updated (:588-598) */
+/* out[i] = x[i]^y evaluated exactly as glibc 2.39 powf does (the routine numpy's float32 ** python-float calls, i.e.
+ * what memory_tools.py:547,596 evaluate); exported so the parity tests can check the restatement on its own. */
+int xb_powf_libm(const float *x, float y, float *out, int64_t n, void *stream);
+int xb_per_insert(float *sum_tree, float *min_tree, float *max_prio, int N, int cap, int ptr, float alpha,
+                  void *stream);
+int xb_per_sample(const float *sum_tree, const float *min_tree, const float *u, int N, int cap, int size,
+                  int k, int64_t S, float size_pow_neg_beta,
+                  int64_t *step_out, int64_t *flat_out, double *w_out, void *stream);
+int xb_per_update(float *sum_tree, float *min_tree, float *max_prio, const int64_t *idx, const float *prio,
+                  int N, int cap, int k, float alpha, void *stream);
+
+/* ---------------------------------------------------------------- K6: DQN TD target + loss fwd+bwd ---
+ * Replaces dqn_learner.py:41-46 / perdqn_learner.py:44-50: predictQ = Q[b, a_b]; y = r + gamma*(1-d)*max_a Q'
+ * loss = mean((predictQ - y)^2); dq[B,A] = dloss/dQ; td[B] = y - predictQ; stats[4] = {loss, mean predictQ,0,0}
+ * (sums over local rows / B_total). */
+int xb_dqn_td_fwd_bwd(const float *q_eval, const float *q_next, const float *actions, const float *rew,
+                      const float *term, int64_t B, int A, int64_t B_total, float gamma,
+                      float *dq, float *td, float *stats, double *scratch, void *stream);
+
+/* ---------------------------------------------------------------- K7: flat-bucket optimiser step -----
+ * Replaces clip_grad_norm_ + torch.optim.Adam.step on the learner's parameters (ppo_learner.py:61-65;
+ * Adam eps=1e-5, no weight decay, no amsgrad) over ONE flat float32 bucket (params/grads/exp_avg/exp_avg_sq
+ * are each a single contiguous array - the same bucket the NCCL all-reduce uses).
+ * xb_grad_sumsq  : norm_out[0] = sqrt(sum g^2) * grad_scale   (deterministic two-level reduction)
+ * xb_adam_step   : g' = g * grad_scale * min(1, max_norm/(norm+1e-6)) (max_norm <= 0: no clip);
+ *                  m = m + (g'-m)*(1-b1); v = v*b2 + g'*g'*(1-b2); p -= step_size * m/(sqrt(v)/bc2_sqrt + eps)
+ *                  hyper (device, float32[4]) = {step_size = lr/(1-b1^t), bc2_sqrt = sqrt(1-b2^t), unused, unused}
+ *                  write_back_grad != 0 stores g' into g (what clip_grad_norm_ leaves in .grad)
+ * xb_soft_update : target = target*(1-tau) + tau*source    (SoftActorCritic.soft_update, actor_critic.py:155-158)
+ */
+int xb_grad_sumsq(const float *g, int64_t n, float grad_scale, float *norm_out, double *scratch, void *stream);
+int xb_adam_step(float *p, float *g, float *m, float *v, int64_t n, const float *hyper,
+                 float beta1, float beta2, float eps, float max_norm, const float *norm, float grad_scale,
+                 int write_back_grad, void *stream);
+int xb_soft_update(float *target, const float *source, int64_t n, float tau, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XB200_H_ */

@@ -1,0 +1,187 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (agi-brain/xuance v1.4.4 @ 4f0b05b).
+
+Run in the build container only (needs /root/reference):   python tests/golden/make_golden.py
+The reference is imported read-only with two import stubs (oracle/ref_stubs: gymnasium, pyglet).  Each fixture
+stores the seeded inputs that cannot be re-derived cheaply plus the reference's outputs; the CPU tests re-run
+the oracle on the same inputs and compare.  Environment of record is written into every file."""
+import os
+import random
+import sys
+from argparse import Namespace
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle.ref_loader import import_reference  # noqa: E402
+
+import_reference()
+from gymnasium.spaces import Box, Discrete  # noqa: E402
+from xuance.common import BaseCallback  # noqa: E402
+from xuance.common.common_tools import discount_cumsum  # noqa: E402
+from xuance.common.memory_tools import (DummyOnPolicyBuffer, DummyOnPolicyBuffer_Atari, PerOffPolicyBuffer,  # noqa
+                                        DummyOffPolicyBuffer)
+from xuance.torch.learners import PPO_Learner, DQN_Learner, PerDQN_Learner  # noqa: E402
+from xuance.torch.rl_models.representations import AC_CNN_Atari, Basic_CNN  # noqa: E402
+from xuance.torch.rl_models.heads import CategoricalActorHead, ValueHead  # noqa: E402
+from xuance.torch.rl_models.architectures.single_agent.actor_critic import SharedActorCritic  # noqa: E402
+from xuance.torch.rl_models.architectures.single_agent.deep_q_network import DeepQNetwork  # noqa: E402
+from helpers import synth_rollout, fill_buffers  # noqa: E402
+
+ENV = "torch %s / numpy %s / reference 4f0b05b" % (torch.__version__, np.__version__)
+
+
+def golden_onpolicy():
+    out = {"env": ENV}
+    cases = [("vec_gae", 6, 24, (5,), False, True), ("vec_nstep", 6, 24, (5,), False, False),
+             ("atari_gae", 4, 16, (8, 8, 4), True, True)]
+    for name, N, T, shape, atari, use_gae in cases:
+        rng = np.random.default_rng(hash(name) % 1000 if False else len(name) * 7 + N)
+        ro = synth_rollout(rng, N, T, shape, obs_dtype=np.uint8 if atari else np.float32, p_term=0.08)
+        cls = DummyOnPolicyBuffer_Atari if atari else DummyOnPolicyBuffer
+        space = Box(0, 255, shape, np.uint8) if atari else Box(-10, 10, shape, np.float32)
+        ref = cls(space, Discrete(4), {"old_logp": ()}, N, T, use_gae=use_gae)
+        mids = [(T // 3, 1, np.float32(0.37)), (T // 2, 0, 0.0), (T // 2 + 1, 0, np.float32(-1.5))]
+        fill_buffers([ref], ro, mids)
+        idx = rng.permutation(N * T)[: N * T // 2]
+        s = ref.sample(idx)
+        for k, v in ro.items():
+            out[f"{name}/in/{k}"] = v
+        # 4th column: 1 if the bootstrap was a Python float (np.append then promotes the path to float64, as
+        # happens for the reference's finish_path(0.0, i) calls), 0 if it was an np.float32 (model output)
+        out[f"{name}/in/mids"] = np.array([(t, e, float(v), float(isinstance(v, float))) for t, e, v in mids])
+        out[f"{name}/in/idx"] = idx
+        out[f"{name}/returns"], out[f"{name}/advantages"] = ref.returns, ref.advantages
+        out[f"{name}/start_ids"] = ref.start_ids
+        for k in ("obs", "actions", "returns", "values", "advantages"):
+            out[f"{name}/sample/{k}"] = s[k]
+        out[f"{name}/sample/old_logp"] = s["aux_batch"]["old_logp"]
+    out["kat/discount_cumsum"] = np.asarray(discount_cumsum(np.array([0, 1, 2, 2]), 0.99))
+    np.savez_compressed(os.path.join(HERE, "onpolicy.npz"), **out)
+
+
+def golden_per():
+    """PER under the canonical float32 rule: the reference's float64 ``_max_priority`` array is replaced by a float32
+    one right after construction (state change in the test harness, no reference source change) - see oracle/replay.py."""
+    out = {"env": ENV}
+    N, S, B, alpha = 4, 48, 32, 0.5
+    rng = np.random.default_rng(42)
+    ref = PerOffPolicyBuffer(Box(-1, 1, (3,)), Discrete(4), None, N, N * S, B, alpha=alpha)
+    ref._max_priority = np.ones(N, np.float32)
+    steps, samples = [], []
+    for t in range(70):
+        st = (rng.normal(size=(N, 3)).astype(np.float32), rng.integers(0, 4, N), rng.normal(size=N).astype(np.float32),
+              rng.random(N) < 0.1, rng.normal(size=(N, 3)).astype(np.float32))
+        ref.store(*st)
+        steps.append(st)
+        if t > 5 and t % 6 == 0:
+            random.seed(t)
+            u = np.array([[random.random() for _ in range(B // N)] for _ in range(N)])
+            random.seed(t)
+            s = ref.sample(0.4)
+            td = np.abs(rng.normal(size=B)).astype(np.float32)
+            td[2] = 0.0
+            ref.update_priorities(s["step_choices"], td)
+            samples.append(dict(t=t, u=u, step_choices=s["step_choices"], weights=s["weights"], td=td,
+                                obs=s["obs"], rewards=s["rewards"],
+                                sum_tree=np.array([np.array(tr._value, dtype=np.float64) for tr in ref._it_sum]),
+                                min_tree=np.array([np.array(tr._value, dtype=np.float64) for tr in ref._it_min]),
+                                max_priority=ref._max_priority.astype(np.float64).copy()))
+    for i, name in enumerate(("obs", "acts", "rews", "terms", "next_obs")):
+        out[f"in/{name}"] = np.stack([s[i] for s in steps])
+    out["n_samples"] = len(samples)
+    for j, s in enumerate(samples):
+        for k, v in s.items():
+            out[f"s{j}/{k}"] = v
+    out["cfg"] = np.array([N, S, B, alpha])
+    # the default (mixed float64/float32) behaviour of the reference under NumPy>=2, recorded for DESIGN.md
+    ref2 = PerOffPolicyBuffer(Box(-1, 1, (3,)), Discrete(4), None, 2, 8, 2, alpha=alpha)
+    ref2.store(np.zeros((2, 3)), np.zeros(2), np.zeros(2), np.zeros(2), np.zeros((2, 3)))
+    ref2.store(np.zeros((2, 3)), np.zeros(2), np.zeros(2), np.zeros(2), np.zeros((2, 3)))
+    ref2.update_priorities(np.array([[0], [1]]), np.array([0.3, 0.7], np.float32))
+    out["note/default_leaf_dtypes"] = np.array([type(ref2._it_sum[0]._value[4]).__name__,
+                                                type(ref2._it_sum[0]._value[5]).__name__])
+    np.savez_compressed(os.path.join(HERE, "per.npz"), **out)
+
+
+def _learner_cfg(**kw):
+    cfg = dict(distributed_training=False, episode_length=1000, use_grad_clip=True, grad_clip_norm=0.5, device="cpu",
+               model_dir="/tmp/xb_golden", running_steps=4096 * 10, parallels=32, learning_rate=2.5e-4,
+               use_linear_lr_decay=True, end_factor_lr_decay=0.5, horizon_size=128, n_epochs=4, n_minibatch=4,
+               vf_coef=0.25, ent_coef=0.01, clip_range=0.2, gamma=0.99, sync_frequency=2, start_training=0,
+               training_frequency=1)
+    cfg.update(kw)
+    return Namespace(**cfg)
+
+
+def golden_ppo():
+    """Two PPO updates of the reference learner on the NatureCNN actor-critic at 84x84x4, B=24.  Initial weights are
+    reproduced from torch.manual_seed (construction order is part of the oracle's contract); the fixture keeps
+    inputs, info dicts and per-tensor digests of the parameters after the updates."""
+    out = {"env": ENV}
+    A, B = 6, 24
+    torch.manual_seed(3)
+    rep = AC_CNN_Atari(input_shape=(84, 84, 4), kernels=[8, 4, 3], strides=[4, 2, 1], filters=[32, 64, 64],
+                       activation=torch.nn.ReLU, device="cpu", fc_hidden_sizes=[512])
+    actor = CategoricalActorHead(512, [], A, None, torch.nn.init.orthogonal_, torch.nn.ReLU, "cpu")
+    critic = ValueHead(512, [], None, torch.nn.init.orthogonal_, torch.nn.ReLU, "cpu")
+    model = SharedActorCritic(rep, actor, critic)
+    init = {k: v.clone() for k, v in model.state_dict().items()}
+    learner = PPO_Learner(_learner_cfg(), model, BaseCallback())
+    rng = np.random.default_rng(9)
+    infos = []
+    for it in range(2):
+        s = {"obs": rng.integers(0, 256, size=(B, 84, 84, 4), dtype=np.uint8),
+             "actions": rng.integers(0, A, size=B).astype(np.float32),
+             "returns": rng.normal(size=B).astype(np.float32), "advantages": rng.normal(size=B).astype(np.float32),
+             "aux_batch": {"old_logp": (rng.normal(size=B) * 0.05 - np.log(A)).astype(np.float32)}}
+        info = learner.update(**s)
+        infos.append([info["actor_loss"], info["critic_loss"], info["entropy"], info["learning_rate"],
+                      info["predict_value"], float(info["clip_ratio"])])
+    out["infos"] = np.array(infos, dtype=np.float64)
+    out["total_iters"] = learner.total_iters
+    for k, v in model.state_dict().items():
+        out[f"init_digest/{k}"] = np.array([v_.double().sum().item() for v_ in (init[k], init[k].abs())])
+        flat = v.detach().reshape(-1)
+        out[f"final_head/{k}"] = flat[:64].numpy().copy()
+        out[f"final_digest/{k}"] = np.array([flat.double().sum().item(), flat.double().abs().sum().item()])
+    np.savez_compressed(os.path.join(HERE, "ppo_update.npz"), **out)
+
+
+def golden_dqn():
+    out = {"env": ENV}
+    A, B = 5, 16
+    torch.manual_seed(4)
+    rep = Basic_CNN(input_shape=(84, 84, 4), kernels=[8, 4, 3], strides=[4, 2, 1], filters=[32, 64, 64],
+                    activation=torch.nn.ReLU, device="cpu")
+    model = DeepQNetwork(rep, [512], Discrete(A), None, None, torch.nn.ReLU, "cpu")
+    learner = PerDQN_Learner(_learner_cfg(learning_rate=1e-4, use_grad_clip=False), model, BaseCallback())
+    rng = np.random.default_rng(10)
+    infos, tds = [], []
+    for it in range(3):
+        s = {"obs": rng.integers(0, 256, size=(B, 84, 84, 4), dtype=np.uint8).astype(np.float32),
+             "actions": rng.integers(0, A, size=B).astype(np.float32),
+             "obs_next": rng.integers(0, 256, size=(B, 84, 84, 4), dtype=np.uint8).astype(np.float32),
+             "rewards": rng.normal(size=B).astype(np.float32), "terminals": (rng.random(B) < 0.2).astype(np.float32)}
+        td, info = learner.update(**s)
+        infos.append([info["Qloss"], info["learning_rate"], info["predictQ"]])
+        tds.append(td)
+    out["infos"], out["abs_td"] = np.array(infos, dtype=np.float64), np.stack(tds)
+    for k, v in model.state_dict().items():
+        flat = v.detach().reshape(-1)
+        out[f"final_digest/{k}"] = np.array([flat.double().sum().item(), flat.double().abs().sum().item()])
+    np.savez_compressed(os.path.join(HERE, "dqn_update.npz"), **out)
+
+
+if __name__ == "__main__":
+    golden_onpolicy()
+    golden_per()
+    golden_ppo()
+    golden_dqn()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))

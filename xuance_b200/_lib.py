@@ -1,0 +1,110 @@
+"""ctypes binding of libxb200.so (the C-ABI declared in include/xb200.h).
+
+There is NO CPU or PyTorch fallback: if the library cannot be loaded, or a call returns a non-zero status,
+this module raises.  Tensors are passed as raw device pointers (``tensor.data_ptr()``) plus sizes; the stream
+is torch's current CUDA stream so launches interleave correctly with cuDNN/cuBLAS work issued by torch."""
+import ctypes
+import os
+from ctypes import c_int, c_int64, c_float, c_void_p, c_char_p, POINTER
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libxb200.so")
+
+OBS_U8, OBS_F32_NHWC, OBS_F32_NCHW, OBS_BF16_NHWC, OBS_F16_NHWC = 0, 1, 2, 3, 4
+
+_P = c_void_p
+_SIGNATURES = {
+    "xb_version": (c_int, []),
+    "xb_error_string": (c_char_p, [c_int]),
+    "xb_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "xb_rollout_store": (c_int, [_P, _P, c_int64, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "xb_gae_scan": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_float, c_float, c_int, _P]),
+    "xb_gather_rows": (c_int, [_P, _P, c_int64, c_int64, _P, _P]),
+    "xb_gather_obs": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P, c_int, _P]),
+    "xb_scratch_doubles": (c_int64, []),
+    "xb_gather_scalars": (c_int, [_P, c_int64, _P, c_int64, c_int, _P, c_int, _P, _P, _P]),
+    "xb_ppo_loss_fwd_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int64, c_float, c_float, c_float,
+                                    _P, _P, _P, _P, _P]),
+    "xb_per_insert": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_float, _P]),
+    "xb_per_sample": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int64, c_float, _P, _P, _P, _P]),
+    "xb_per_update": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P]),
+    "xb_dqn_td_fwd_bwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int64, c_float, _P, _P, _P, _P, _P]),
+    "xb_grad_sumsq": (c_int, [_P, c_int64, c_float, _P, _P, _P]),
+    "xb_adam_step": (c_int, [_P, _P, _P, _P, c_int64, _P, c_float, c_float, c_float, c_float, _P, c_float,
+                             c_int, _P]),
+    "xb_soft_update": (c_int, [_P, _P, c_int64, c_float, _P]),
+    "xb_powf_libm": (c_int, [_P, c_float, _P, c_int64, _P]),
+}
+_OPTIONAL = {
+    "xb_qmix_mix_fwd": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "xb_qmix_mix_bwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
+}
+
+_lib = None
+launch_count = 0  # number of xb200 kernel-launching ABI calls issued (bench.py's gpu_launches evidence)
+
+
+def exported_symbols():
+    """Names include/xb200.h declares; tests check that each one resolves in the loaded library."""
+    return [k for k, v in _SIGNATURES.items() if v is not None]
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "xuance_b200: %s is missing - build it with `python -m xuance_b200.build` (nvcc, sm_100a). "
+            "There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, sig in list(_SIGNATURES.items()) + list(_OPTIONAL.items()):
+        if sig is None:
+            continue
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            if name in _OPTIONAL:
+                continue
+            raise RuntimeError("xuance_b200: %s does not export %s" % (LIB_PATH, name))
+        fn.restype, fn.argtypes = sig
+    _lib = lib
+    return lib
+
+
+def error_string(code):
+    return load().xb_error_string(int(code)).decode()
+
+
+def check(code, what=""):
+    if code != 0:
+        raise RuntimeError("xb200 %s failed: %s (code %d)" % (what, error_string(code), code))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL).  Refuses CPU tensors: the ABI takes device memory only."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("xb200: expected a CUDA tensor, got a %s tensor (no CPU fallback)" % t.device)
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    """Invoke an ABI entry point, appending the current stream, and raise on a non-zero status."""
+    global launch_count
+    fn = getattr(load(), name)
+    launch_count += 1
+    check(fn(*args, stream()), name)
+
+
+def scratch(device):
+    """Zeroed reduction scratch (doubles + ticket) for the deterministic grid reductions."""
+    n = load().xb_scratch_doubles()
+    return torch.zeros(n, dtype=torch.float64, device=device)

@@ -1,0 +1,82 @@
+"""PPO-Clip learner - mirror of xuance/torch/learners/policy_gradient/ppo_learner.py:12-95.
+
+``update(**samples)`` keeps the reference's signature, info keys and numerics (fp32 tolerance, tests/), but runs
+as: network forward (cuDNN/cuBLAS via torch) -> K4 fused loss forward+backward (one launch producing dlogits,
+dvalue and the logged statistics) -> torch backward through the network into the flat gradient bucket ->
+[one NCCL all-reduce] -> K7 fused clip-norm + Adam.  No ``.item()`` until the info dict is built (one D2H of
+8 floats; skipped entirely with ``sync=False`` as train_epochs does for all but the last minibatch)."""
+import torch
+
+from ... import _lib
+from ..utils import FusedAdam, allreduce_sum_
+from .learner import Learner
+
+
+class PPO_Learner(Learner):
+    def __init__(self, config, model, callback):
+        super().__init__(config, model, callback)
+        self.optimizer = FusedAdam(self.model.parameters(), self.config.learning_rate, eps=1e-5)
+        self.scheduler = torch.optim.lr_scheduler.LinearLR(self.optimizer, start_factor=1.0,
+                                                           end_factor=self.end_factor_lr_decay,
+                                                           total_iters=self.total_iters)
+        self.vf_coef, self.ent_coef, self.clip_range = config.vf_coef, config.ent_coef, config.clip_range
+        self._stats = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self._scratch = _lib.scratch(self.device)
+
+    def estimate_total_iterations(self):
+        """ppo_learner.py:28-33."""
+        buffer_size = self.config.horizon_size * self.config.parallels
+        update_times = self.config.running_steps // buffer_size
+        return update_times * self.config.n_epochs * self.config.n_minibatch
+
+    def _f32(self, x):
+        return torch.as_tensor(x, device=self.device).to(torch.float32).contiguous()
+
+    def update(self, sync=True, **samples):
+        self.iterations += 1
+        obs = samples['obs']
+        if not hasattr(obs, "fmt"):  # PreparedObs passes through; arrays / tensors go to the device
+            obs = torch.as_tensor(obs, device=self.device)
+        act = self._f32(samples['actions'])
+        ret = self._f32(samples['returns'])
+        adv = self._f32(samples['advantages'])
+        old_logp = self._f32(samples['aux_batch']['old_logp'])
+        info = self.callback.on_update_start(self.iterations, policy=self.model, obs=obs, act=act, returns=ret,
+                                             advantages=adv, old_logp=old_logp) or {}
+        B = act.shape[0]
+        if hasattr(self.model, "forward_raw"):
+            logits, v_pred = self.model.forward_raw(obs)
+        else:
+            out = self.model(obs)
+            logits, v_pred = out.distributions.logits, out.values
+        logits_c, v_c = logits.contiguous(), v_pred.contiguous()
+        A = logits_c.shape[-1]
+        dlogits = torch.empty_like(logits_c)
+        dvalue = torch.empty_like(v_c)
+        B_total = B * self.world_size
+        _lib.call("xb_ppo_loss_fwd_bwd", _lib.ptr(logits_c), _lib.ptr(v_c), _lib.ptr(act), _lib.ptr(old_logp),
+                  _lib.ptr(adv), _lib.ptr(ret), B, A, B_total, float(self.clip_range), float(self.vf_coef),
+                  float(self.ent_coef), _lib.ptr(dlogits), _lib.ptr(dvalue), _lib.ptr(self._stats),
+                  _lib.ptr(self._scratch))
+        self.optimizer.zero_grad()
+        torch.autograd.backward([logits_c, v_c], [dlogits, dvalue])
+        if self.world_size > 1:
+            allreduce_sum_(self.optimizer.bucket.grad)   # the one data-path collective
+            allreduce_sum_(self._stats)
+        self.optimizer.step(max_norm=self.grad_clip_norm if self.use_grad_clip else None)
+        if self.scheduler is not None:
+            self.scheduler.step()
+        if sync:
+            info.update(self.materialize_info())
+            info.update(self.callback.on_update_end(self.iterations, policy=self.model, info=info) or {})
+        return info
+
+    def materialize_info(self):
+        """The single device->host read of an update: 8 floats."""
+        s = self._stats.tolist()
+        lr = self.optimizer.state_dict()['param_groups'][0]['lr'] if False else self.optimizer.param_groups[0]['lr']
+        vals = {"actor_loss": s[0], "critic_loss": s[1], "entropy": s[2], "learning_rate": lr,
+                "predict_value": s[3], "clip_ratio": s[4]}
+        if self.distributed_training:
+            return {f"{k}/rank_{self.rank}": v for k, v in vals.items()}
+        return vals

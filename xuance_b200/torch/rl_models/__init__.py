@@ -1,0 +1,7 @@
+from .layers import mlp_block, cnn_block, ActivationFunctions
+from .outputs import ModelOutput, RepresentationOutput, ActionOutput, StochasticActorOutput, TwinCriticOutput
+from .distributions import CategoricalDistribution, DiagGaussianDistribution, ActivatedDiagGaussianDistribution
+from .representations import Basic_Identical, Basic_MLP, Basic_CNN, AC_CNN_Atari, REGISTRY_Representation
+from .heads import CategoricalActorHead, GaussianActorHead, SAC_GaussianActorHead, ValueHead, QValueHead
+from .architectures import (ActorCritic, SharedActorCritic, DeepQNetwork, GaussianActor, SAC_GaussianActor,
+                            TwinActionValueCritic, SoftActorCritic)

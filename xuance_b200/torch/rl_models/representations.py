@@ -1,0 +1,156 @@
+"""Observation encoders (reference: xuance/torch/rl_models/representations/{mlp,cnn}.py).
+
+``Basic_CNN`` / ``AC_CNN_Atari`` accept exactly what the reference accepts (uint8 / float NHWC arrays or
+tensors -> ``x / 255.0`` -> float32 -> NCHW, cnn.py:45-50, 98-102) AND the two device-side fast inputs of this
+repo: a CUDA uint8 tensor (converted by the K3 kernel, u8/255 correctly rounded, written straight in the layout
+the convolutions run in) or a ``PreparedObs`` produced by the buffer's fused gather.  ``compute`` selects how the
+convolution stack runs: 'fp32' (strict IEEE fp32, TF32 off - the reference's CPU arithmetic), 'tf32' (PyTorch's
+default conv behaviour on GPUs), 'bf16' (autocast, channels-last)."""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ... import _lib
+from ...common.memory_tools import PreparedObs
+from .layers import cnn_block, mlp_block
+from .outputs import RepresentationOutput
+
+
+class Basic_Identical(nn.Module):
+    def __init__(self, input_shape, device=None, **kwargs):
+        super().__init__()
+        assert len(input_shape) == 1
+        self.output_shapes = {'state': (input_shape[0],)}
+        self.device = device
+
+    def forward(self, observations, **kwargs):
+        return RepresentationOutput(embeddings=torch.as_tensor(observations, dtype=torch.float32, device=self.device))
+
+
+class Basic_MLP(nn.Module):
+    def __init__(self, input_shape, hidden_sizes, normalize=None, initialize=None, activation=None, device=None,
+                 **kwargs):
+        super().__init__()
+        self.input_shape, self.hidden_sizes, self.device = input_shape, hidden_sizes, device
+        self.output_shapes = {'state': (hidden_sizes[-1],)}
+        layers, shape = [], input_shape
+        for h in hidden_sizes:
+            mlp, shape = mlp_block(shape[0], h, normalize, activation, initialize, device=device)
+            layers.extend(mlp)
+        self.model = nn.Sequential(*layers)
+
+    def forward(self, observations, **kwargs):
+        x = torch.as_tensor(observations, dtype=torch.float32, device=self.device)
+        return RepresentationOutput(embeddings=self.model(x))
+
+
+class _PixelEncoder(nn.Module):
+    """Shared input handling for the two CNN encoders."""
+
+    compute = "fp32"
+
+    def set_compute(self, mode):
+        assert mode in ("fp32", "tf32", "bf16")
+        self.compute = mode
+        fmt = torch.channels_last if mode != "fp32" else torch.contiguous_format
+        for m in self.model:
+            if isinstance(m, nn.Conv2d):
+                m.to(memory_format=fmt)
+        return self
+
+    def preferred_obs_format(self):
+        """K3 output format this encoder consumes without any further copy."""
+        return {"fp32": _lib.OBS_F32_NCHW, "tf32": _lib.OBS_F32_NHWC, "bf16": _lib.OBS_BF16_NHWC}[self.compute]
+
+    def _as_input(self, observations):
+        fmt = self.preferred_obs_format()
+        if isinstance(observations, PreparedObs):
+            x = observations.tensor
+            return x if observations.fmt == _lib.OBS_F32_NCHW else x.permute(0, 3, 1, 2)
+        if isinstance(observations, torch.Tensor) and observations.is_cuda and observations.dtype == torch.uint8:
+            obs = observations.contiguous()
+            B, H, W, C = obs.shape
+            if (H * W * C) % 16 == 0 and (fmt != _lib.OBS_F32_NCHW or (C == 4 and W % 4 == 0)):
+                dt = torch.bfloat16 if fmt == _lib.OBS_BF16_NHWC else torch.float32
+                shape = (B, C, H, W) if fmt == _lib.OBS_F32_NCHW else (B, H, W, C)
+                out = torch.empty(shape, dtype=dt, device=obs.device)
+                _lib.call("xb_gather_obs", _lib.ptr(obs), None, B, H, W, C, _lib.ptr(out), fmt)
+                return out if fmt == _lib.OBS_F32_NCHW else out.permute(0, 3, 1, 2)
+        # reference path (cnn.py:98-101): true division, float32, NHWC -> NCHW view
+        if isinstance(observations, np.ndarray):
+            observations = torch.from_numpy(observations).to(self.device)
+        observations = observations / 255.0
+        return torch.as_tensor(observations, dtype=torch.float32, device=self.device).permute((0, 3, 1, 2))
+
+    def _run(self, x):
+        if self.compute == "bf16":
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return self.model(x).float()
+        if x.dtype != torch.float32:
+            x = x.float()
+        return self.model(x)
+
+
+class Basic_CNN(_PixelEncoder):
+    """cnn.py:11-50: conv stack (config initialiser) -> AdaptiveMaxPool2d(1,1) -> Flatten -> filters[-1] features."""
+
+    def __init__(self, input_shape, kernels, strides, filters, normalize=None, initialize=None, activation=None,
+                 device=None, **kwargs):
+        super().__init__()
+        self.input_shape = (input_shape[2], input_shape[0], input_shape[1])
+        self.kernels, self.strides, self.filters = kernels, strides, filters
+        self.device = device
+        self.output_shapes = {'state': (filters[-1],)}
+        layers, shape = [], self.input_shape
+        for k, s, f in zip(kernels, strides, filters):
+            cnn, shape = cnn_block(shape, f, k, s, normalize, activation, initialize, device)
+            layers.extend(cnn)
+        layers.append(nn.AdaptiveMaxPool2d((1, 1)))
+        layers.append(nn.Flatten())
+        self.model = nn.Sequential(*layers)
+
+    def forward(self, observations, **kwargs):
+        return RepresentationOutput(embeddings=self._run(self._as_input(observations)))
+
+
+class AC_CNN_Atari(_PixelEncoder):
+    """cnn.py:53-102: conv stack + Flatten + FC hidden layers, orthogonal(gain sqrt 2) weights, zero biases.
+    With the reference's padding rule the 84x84x4 NatureCNN flattens to 6400 features."""
+
+    def __init__(self, input_shape, kernels, strides, filters, normalize=None, initialize=None, activation=None,
+                 device=None, fc_hidden_sizes=(), **kwargs):
+        super().__init__()
+        self.input_shape = (input_shape[2], input_shape[0], input_shape[1])
+        self.kernels, self.strides, self.filters = kernels, strides, filters
+        self.device = device
+        self.fc_hidden_sizes = fc_hidden_sizes
+        self.output_shapes = {'state': (fc_hidden_sizes[-1],)}
+        layers, shape = [], self.input_shape
+        for k, s, f in zip(kernels, strides, filters):
+            cnn, shape = cnn_block(shape, f, k, s, None, activation, None, device)
+            cnn[0] = self._init_layer(cnn[0])
+            layers.extend(cnn)
+        layers.append(nn.Flatten())
+        shape = (int(np.prod(shape, dtype=np.int64)),)
+        for h in fc_hidden_sizes:
+            mlp, shape = mlp_block(shape[0], h, None, activation, None, device)
+            mlp[0] = self._init_layer(mlp[0])
+            layers.extend(mlp)
+        self.model = nn.Sequential(*layers)
+
+    @staticmethod
+    def _init_layer(layer, gain=np.sqrt(2), bias=0.0):
+        nn.init.orthogonal_(layer.weight, gain=gain)
+        nn.init.constant_(layer.bias, bias)
+        return layer
+
+    def forward(self, observations, **kwargs):
+        return RepresentationOutput(embeddings=self._run(self._as_input(observations)))
+
+
+REGISTRY_Representation = {
+    "Basic_Identical": Basic_Identical,
+    "Basic_MLP": Basic_MLP,
+    "Basic_CNN": Basic_CNN,
+    "AC_CNN_Atari": AC_CNN_Atari,
+}

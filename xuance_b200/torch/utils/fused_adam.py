@@ -1,0 +1,84 @@
+"""Flat-bucket Adam with fused global-norm clipping (K7, include/xb200.h).
+
+Replaces ``torch.nn.utils.clip_grad_norm_`` + ``torch.optim.Adam.step`` as the reference learners call them
+(e.g. xuance/torch/learners/policy_gradient/ppo_learner.py:18-22, 61-65): same update rule (Adam, betas
+(0.9, 0.999), ``eps`` as given, no weight decay / amsgrad), same clip rule
+(coef = min(1, max_norm / (total_norm + 1e-6))).  It IS a ``torch.optim.Optimizer`` so the reference's
+``LinearLR`` scheduler, ``optimizer.state_dict()['param_groups'][0]['lr']`` logging and checkpoint format keep
+working.  Two kernel launches per step, no host synchronisation."""
+import math
+
+import torch
+
+from ... import _lib
+from .flat_bucket import FlatBucket
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        params = list(params)
+        if weight_decay != 0.0:
+            raise NotImplementedError("weight_decay is not on the hot path (reference configs use 0)")
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False, maximize=False,
+                        foreach=None, capturable=False, differentiable=False, fused=None)
+        super().__init__(params, defaults)
+        if len(self.param_groups) != 1:
+            raise NotImplementedError("FusedAdam drives exactly one parameter group")
+        self.bucket = FlatBucket(self.param_groups[0]["params"])
+        dev = self.bucket.flat.device
+        self.exp_avg = torch.zeros_like(self.bucket.flat)
+        self.exp_avg_sq = torch.zeros_like(self.bucket.flat)
+        self.step_count = 0
+        self._hyper = torch.zeros(4, dtype=torch.float32, device=dev)
+        self._norm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._scratch = _lib.scratch(dev)
+        self._step_t = torch.zeros((), dtype=torch.float32)
+        for p, m, v in zip(self.bucket.params, self.bucket.views(self.exp_avg), self.bucket.views(self.exp_avg_sq)):
+            self.state[p] = {"step": self._step_t, "exp_avg": m, "exp_avg_sq": v}
+
+    @property
+    def grad_norm(self):
+        """Device scalar: the (pre-clip, post-averaging) global gradient L2 norm of the last clipped step."""
+        return self._norm
+
+    def zero_grad(self, set_to_none=False):
+        self.bucket.zero_grad()
+
+    @torch.no_grad()
+    def step(self, closure=None, max_norm=None, grad_scale=1.0, write_back_grad=False):
+        """One Adam step over the bucket.  ``max_norm`` (float or None) applies clip_grad_norm_ semantics first;
+        ``grad_scale`` multiplies the gradient (1/world_size after a sum all-reduce)."""
+        group = self.param_groups[0]
+        self.step_count += 1
+        self._step_t.fill_(float(self.step_count))
+        b1, b2 = group["betas"]
+        t = self.step_count
+        step_size = group["lr"] / (1.0 - b1 ** t)
+        bc2_sqrt = math.sqrt(1.0 - b2 ** t)
+        self._hyper.copy_(torch.tensor([step_size, bc2_sqrt, group["lr"], 0.0], dtype=torch.float32))
+        n = self.bucket.numel
+        clip = float(max_norm) if max_norm is not None else -1.0
+        if clip > 0:
+            _lib.call("xb_grad_sumsq", _lib.ptr(self.bucket.grad), n, float(grad_scale), _lib.ptr(self._norm),
+                      _lib.ptr(self._scratch))
+        _lib.call("xb_adam_step", _lib.ptr(self.bucket.flat), _lib.ptr(self.bucket.grad), _lib.ptr(self.exp_avg),
+                  _lib.ptr(self.exp_avg_sq), n, _lib.ptr(self._hyper), float(b1), float(b2), float(group["eps"]),
+                  clip, _lib.ptr(self._norm), float(grad_scale), 1 if write_back_grad else 0)
+        return None
+
+    def load_state_dict(self, state_dict):
+        """Accepts a torch.optim.Adam state_dict (reference checkpoints) and copies it into the flat buffers."""
+        groups = state_dict["param_groups"]
+        for k in ("lr", "betas", "eps"):
+            if k in groups[0]:
+                self.param_groups[0][k] = groups[0][k]
+        if "initial_lr" in groups[0]:
+            self.param_groups[0]["initial_lr"] = groups[0]["initial_lr"]
+        st = state_dict.get("state", {})
+        ms, vs = self.bucket.views(self.exp_avg), self.bucket.views(self.exp_avg_sq)
+        for i, pid in enumerate(groups[0]["params"]):
+            if pid in st:
+                ms[i].copy_(st[pid]["exp_avg"])
+                vs[i].copy_(st[pid]["exp_avg_sq"])
+                self.step_count = int(float(st[pid]["step"]))
+        self._step_t.fill_(float(self.step_count))
