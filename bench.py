@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark: learner.update() env-steps/s, PPO-Clip 256 envs x 128 steps, Atari-shaped.
+
+    python bench.py --gpus N --steps K --warmup W             (N > 1 is launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (the reference's torch-CPU path, rank 0 only)
+
+A "step" is one pass of the hot path over one resident synthetic rollout: ``train_epochs(n_epochs=4)`` =
+4 x shuffle + 16 x (memory.sample(8192) + learner.update), exactly the loop of
+xuance/torch/agents/core/on_policy.py:182-205.  env-steps/s = N*T*K / (device time of K steps, max over ranks).
+Strong scaling: the 256 x 128 rollout and the 8192-row global minibatch are fixed, rank g owns 256/G envs and
+contributes 8192/G rows to every update; one NCCL all-reduce of the 13.4 MB flat gradient bucket per update.
+
+Prints ONE JSON line (see DESIGN.md "Measurement" for every field)."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ENVS, HORIZON, N_ACTIONS = 256, 128, 4
+OBS_SHAPE = (84, 84, 4)
+N_EPOCHS, N_MINIBATCH = 4, 4
+METRIC = "learner.update() env-steps/s, PPO 256x128 Atari-shaped"
+UNIT = "env-steps/s"
+WORKLOAD = ("PPO-Clip train_epochs(4) = 16 x (sample 8192 + update) over a resident 256 envs x 128 steps rollout, "
+            "84x84x4 uint8 obs, NatureCNN actor-critic 3.36M params (BASELINE.json configs[1])")
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def ppo_namespace(device, n_envs_local, distributed, compute):
+    from argparse import Namespace
+    return Namespace(agent="PPO", learner="PPO_Learner", representation="AC_CNN_Atari", env_name="Atari",
+                     distributed_training=distributed, device=device, seed=1, parallels=N_ENVS,
+                     running_steps=10_000_000, horizon_size=HORIZON, n_epochs=N_EPOCHS, n_minibatch=N_MINIBATCH,
+                     learning_rate=2.5e-4, vf_coef=0.25, ent_coef=0.01, clip_range=0.2, gamma=0.99, use_gae=True,
+                     gae_lambda=0.95, use_advnorm=True, use_grad_clip=True, grad_clip_norm=0.5,
+                     use_obsnorm=False, use_rewnorm=False, obsnorm_range=5, rewnorm_range=5, activation="relu",
+                     filters=[32, 64, 64], kernels=[8, 4, 3], strides=[4, 2, 1], fc_hidden_sizes=[512],
+                     actor_hidden_size=[], critic_hidden_size=[], model_dir="models/ppo", log_dir="logs/ppo",
+                     logger=None, compute=compute, use_linear_lr_decay=False, end_factor_lr_decay=1.0,
+                     episode_length=None)
+
+
+def synth_scalars(rng, T, N):
+    acts = rng.integers(0, N_ACTIONS, size=(T, N)).astype(np.float32)
+    rews = rng.choice(np.array([-1.0, 0.0, 1.0], np.float32), size=(T, N), p=[0.05, 0.9, 0.05])
+    vals = rng.normal(size=(T, N)).astype(np.float32)
+    terms = (rng.random((T, N)) < 0.01).astype(np.float32)
+    logits = rng.normal(size=(T, N, N_ACTIONS)).astype(np.float32)
+    logp = (np.take_along_axis(logits, acts.astype(np.int64)[..., None], -1)[..., 0]
+            - np.log(np.exp(logits).sum(-1))).astype(np.float32)
+    boot = rng.normal(size=N).astype(np.float32)
+    return acts, rews, vals, terms, logp, boot
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_reference_rate(rows_budget_s, steps, warmup, threads=None, verbose=False):
+    """Times the reference's torch-CPU path (oracle port of DummyOnPolicyBuffer_Atari.sample + PPO_Learner.update on
+    the NatureCNN actor-critic) on a bounded sample of the workload.  Returns (env_steps_per_s per step list, info)."""
+    import torch
+    from oracle.onpolicy import OnPolicyBufferOracle
+    from oracle.nets import SharedActorCriticOracle
+    from oracle.learners import PPOLearnerOracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(threads or cores)
+    torch.manual_seed(1)
+    rng = np.random.default_rng(0)
+    N, T = N_ENVS, HORIZON
+    buf = OnPolicyBufferOracle(OBS_SHAPE, (), {"old_logp": ()}, N, T, obs_dtype=np.uint8)
+    buf.observations = rng.integers(0, 256, size=(N, T) + OBS_SHAPE, dtype=np.uint8)
+    acts, rews, vals, terms, logp, boot = synth_scalars(rng, T, N)
+    buf.actions[...], buf.rewards[...], buf.values[...] = acts.T, rews.T, vals.T
+    buf.terminals[...], buf.aux["old_logp"][...] = terms.T, logp.T
+    buf.ptr, buf.size = 0, T
+    t0 = time.perf_counter()
+    for i in range(N):
+        buf.finish_path(0.0 if terms[T - 1, i] else boot[i], i)
+    t_gae = time.perf_counter() - t0
+    model = SharedActorCriticOracle(N_ACTIONS)
+    lrn = PPOLearnerOracle(model, total_iters=1000)
+    np.random.seed(1)
+    perm = np.arange(N * T)
+    np.random.shuffle(perm)
+    # calibrate: rows/s from a 512-row sample+update
+    t0 = time.perf_counter()
+    lrn.update(**buf.sample(perm[:512]))
+    per_row = (time.perf_counter() - t0) / 512
+    rows = int(min(8192, max(256, rows_budget_s / max(per_row, 1e-9))))
+    rates, pos = [], 512
+    for it in range(warmup + steps):
+        if pos + rows > perm.size:
+            np.random.shuffle(perm)
+            pos = 0
+        t0 = time.perf_counter()
+        lrn.update(**buf.sample(perm[pos:pos + rows]))
+        dt = time.perf_counter() - t0
+        pos += rows
+        if it >= warmup:
+            rates.append((rows / N_EPOCHS) / dt)   # one env-step is visited n_epochs times by train_epochs
+    info = {"cores": threads or cores, "rows_per_step": rows, "finish_path_256_s": t_gae,
+            "sample": "%d timed steps, each = sample(%d rows)+update of the 256x128 workload; env-steps = rows/%d"
+                      % (steps, rows, N_EPOCHS)}
+    return rates, info
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    rates, info = cpu_reference_rate(min(budget, 20.0), args.steps, args.warmup)
+    value = float(np.mean(rates))
+    rows = info["rows_per_step"]
+    ms = 1000.0 * (rows / N_EPOCHS) / value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "arm": "reference torch-CPU path (oracle port: the reference is Python "
+                       "and /root/reference does not travel to the GPU box)", "cpu_threads": info["cores"]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": "port",
+                             "sample": info["sample"]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ own arm
+def run_own_arm(args):
+    import torch
+    import torch.distributed as dist
+    from xuance_b200 import _lib
+    from xuance_b200.common import Box, Discrete
+    from xuance_b200.torch.agents import PPO_Agent
+    from xuance_b200.torch.utils import init_distributed_mode
+
+    rank, world, local_rank = init_distributed_mode()
+    if world > 1:
+        assert world == args.gpus, "torchrun world size must equal --gpus"
+    torch.cuda.set_device(local_rank)
+    device = "cuda:%d" % local_rank
+    torch.backends.cudnn.allow_tf32 = args.compute != "fp32"
+    torch.backends.cuda.matmul.allow_tf32 = args.compute != "fp32"
+    torch.backends.cudnn.benchmark = True
+    assert N_ENVS % world == 0
+    n_local = N_ENVS // world
+    cfg = ppo_namespace(device, n_local, world > 1, args.compute)
+    obs_space, act_space = Box(0, 255, OBS_SHAPE, np.uint8), Discrete(N_ACTIONS)
+    agent = PPO_Agent(cfg, envs=None, observation_space=obs_space, action_space=act_space)  # buffer: n_local envs
+    assert agent.n_envs == n_local
+    torch.manual_seed(1)  # identical initial weights on every rank
+    for p in agent.model.parameters():
+        if world > 1:
+            dist.broadcast(p.data, src=0)
+    mem, T = agent.memory, HORIZON
+
+    # ---- synthetic rollout: scalars from NumPy (global, sliced per rank), frames generated on the device
+    rng = np.random.default_rng(0)
+    acts, rews, vals, terms, logp, boot = synth_scalars(rng, T, N_ENVS)
+    lo, hi = rank * n_local, (rank + 1) * n_local
+    sl = lambda a: a[:, lo:hi]
+    g = torch.Generator(device=device).manual_seed(100 + rank)
+    host_obs = None
+    if args.e2e_steps > 0:
+        host_obs = torch.empty((T, n_local) + OBS_SHAPE, dtype=torch.uint8).pin_memory()
+    for t in range(T):
+        frame = torch.randint(0, 256, (n_local,) + OBS_SHAPE, dtype=torch.uint8, device=device, generator=g)
+        if host_obs is not None:
+            host_obs[t].copy_(frame)
+        mem.store(frame, torch.from_numpy(sl(acts)[t]).to(device), torch.from_numpy(sl(rews)[t]).to(device),
+                  torch.from_numpy(sl(vals)[t]).to(device), torch.from_numpy(sl(terms)[t]).to(device),
+                  {"old_logp": torch.from_numpy(sl(logp)[t]).to(device)})
+    for i in range(n_local):
+        mem.finish_path(0.0 if terms[T - 1, lo + i] else boot[lo + i], i)
+    np.random.seed(1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return agent.train_epochs(N_EPOCHS)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    _lib.profile = {"xb_gather_obs": []}
+    launches0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        info = step()
+    e1.record()
+    barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count - launches0
+    prof = _lib.profile["xb_gather_obs"]
+    _lib.profile = None
+    k3_ms = float(np.mean([a.elapsed_time(b) for a, b in prof])) if prof else None
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = N_ENVS * T * args.steps / (elapsed_ms / 1000.0)
+
+    # ---- e2e: rollout in pinned HOST memory -> 128 x store (H2D) + finish_path + train_epochs + info D2H
+    e2e = None
+    if args.e2e_steps > 0:
+        h_np = host_obs.numpy()
+        scal = [np.ascontiguousarray(sl(a)) for a in (acts, rews, vals, terms, logp)]
+
+        def e2e_step():
+            mem.clear()
+            mem.start_ids[:] = 0
+            for tt in range(T):
+                mem.store(h_np[tt], scal[0][tt], scal[1][tt], scal[2][tt], scal[3][tt], {"old_logp": scal[4][tt]})
+            for i in range(n_local):
+                mem.finish_path(0.0 if terms[T - 1, lo + i] else boot[lo + i], i)
+            out = agent.train_epochs(N_EPOCHS)      # last update materialises the info dict (D2H of 8 floats)
+            return out
+
+        e2e_step()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        a0.record()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        a1.record()
+        barrier()
+        wall = time.perf_counter() - w0
+        tt = torch.tensor([max(a0.elapsed_time(a1) / 1000.0, wall)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        per_step = float(tt.item()) / args.e2e_steps
+        h2d = n_local * T * (int(np.prod(OBS_SHAPE)) + 5 * 4) + N_EPOCHS * n_local * T * 8
+        e2e = {"value": N_ENVS * T / per_step, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
+               "d2h_bytes_per_step": 32 * world, "steps": args.e2e_steps,
+               "what": "128 x memory.store(pinned host arrays) + finish_path + train_epochs(4) + info dict read"}
+
+    # ---- roofline of the dominant kernel written here (K3 fused gather + u8->float)
+    peak, peak_src = measured_peaks()
+    B_local = (N_ENVS * T // N_MINIBATCH) // world
+    obs_bytes = int(np.prod(OBS_SHAPE))
+    out_w = {"fp32": 4, "tf32": 4, "bf16": 2}[args.compute]
+    alg_bytes = B_local * obs_bytes * (1 + out_w) + 8 * B_local
+    roofline = None
+    if k3_ms:
+        ach = alg_bytes / (k3_ms * 1e-3) / 1e9
+        roofline = {"kernel": "gather_obs_kernel (K3: minibatch gather + u8->float)", "bound": "hbm",
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                    "avg_launch_ms": k3_ms, "launches_timed": len(prof),
+                    "share_of_step": (k3_ms * len(prof) / args.steps) / (elapsed_ms / args.steps)}
+
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rates, cinfo = cpu_reference_rate(8.0, 2, 0)
+        cpu = {"value": float(np.mean(rates)), "unit": UNIT, "cores": cinfo["cores"], "kind": "port",
+               "sample": cinfo["sample"]}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32" if args.compute != "bf16" else "bf16",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_minibatch": N_ENVS * T // N_MINIBATCH,
+                       "parallelism": "dp%d (envs sharded, 1 NCCL grad all-reduce/update)" % world,
+                       "compute": {"fp32": "fp32, TF32 disabled (reference arithmetic)", "tf32": "fp32 storage, TF32 convs/matmuls",
+                                   "bf16": "bf16 autocast convs, fp32 master weights"}[args.compute],
+                       "l2": "inputs (925 MB uint8 rollout / G) exceed the 126 MB L2; no explicit flush"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "last_info": {k: (float(v) if not isinstance(v, dict) else v) for k, v in info.items()}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="xuance_b200", choices=["xuance_b200", "reference"])
+    ap.add_argument("--compute", default="fp32", choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl != "reference":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_own_arm(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == "__main__":
+    main()

@@ -96,11 +96,22 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+_KERNELS_PER_CALL = {"xb_gather_scalars": 2}   # calls that launch more than one kernel (second one: normalise)
+profile = None   # optional {abi_name: [(start_event, end_event), ...]} filled when set (bench.py roofline timing)
+
+
 def call(name, *args):
     """Invoke an ABI entry point, appending the current stream, and raise on a non-zero status."""
     global launch_count
     fn = getattr(load(), name)
-    launch_count += 1
+    launch_count += _KERNELS_PER_CALL.get(name, 1)
+    if profile is not None and name in profile:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(fn(*args, stream()), name)
+        e1.record()
+        profile[name].append((e0, e1))
+        return
     check(fn(*args, stream()), name)
 
 

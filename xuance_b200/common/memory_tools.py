@@ -231,8 +231,15 @@ class DummyOnPolicyBuffer(Buffer):
             for f, x in enumerate(scal_in):
                 host[f] = x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else x
             scal = self._stage_scal[i].to(self.device, non_blocking=True)
+        pinned = None
+        if isinstance(obs, np.ndarray) and obs.flags["C_CONTIGUOUS"] and obs.dtype == np.dtype(str(self.obs_dtype).split(".")[-1]):
+            cand = torch.from_numpy(obs)
+            if cand.is_pinned():   # caller's array already lives in pinned memory: DMA straight from it
+                pinned = cand
         if isinstance(obs, torch.Tensor) and obs.is_cuda:
             obs_d = obs.to(self.obs_dtype).reshape(N, -1).contiguous()
+        elif pinned is not None:
+            obs_d = pinned.to(self.device, non_blocking=True).reshape(N, -1)
         else:
             i = self._stage_i
             if self._stage_evt[i] is not None:

@@ -65,7 +65,9 @@ class Agent(ABC):
         if envs is None:
             if observation_space is None or action_space is None:
                 raise ValueError("Please provide the observation_space and action_space when the envs is not provided.")
-            self.n_envs = config.parallels
+            # config.parallels is the GLOBAL env count; under distributed training each rank owns an equal shard
+            assert config.parallels % self.world_size == 0, "parallels must be divisible by the world size"
+            self.n_envs = config.parallels // self.world_size
             self.observation_space, self.action_space = observation_space, action_space
             self.episode_length = config.episode_length = getattr(config, "episode_length", None)
         else:
