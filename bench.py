@@ -125,8 +125,11 @@ def cpu_reference_rate(rows_budget_s, steps, warmup, threads=None, verbose=False
     from oracle.onpolicy import OnPolicyBufferOracle
     from oracle.nets import SharedActorCriticOracle
     from oracle.learners import PPOLearnerOracle
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(threads or cores)
+    # all the host threads torch will use: its default intra-op pool = one thread per physical core, which is what
+    # the reference gets out of the box (it never calls set_num_threads); logical-core oversubscription is slower
+    if threads:
+        torch.set_num_threads(threads)
+    cores = torch.get_num_threads()
     torch.manual_seed(1)
     rng = np.random.default_rng(0)
     N, T = N_ENVS, HORIZON
@@ -145,7 +148,8 @@ def cpu_reference_rate(rows_budget_s, steps, warmup, threads=None, verbose=False
     np.random.seed(1)
     perm = np.arange(N * T)
     np.random.shuffle(perm)
-    # calibrate: rows/s from a 512-row sample+update
+    # calibrate: rows/s from the second of two 512-row sample+update calls (the first pays one-time oneDNN setup)
+    lrn.update(**buf.sample(perm[:512]))
     t0 = time.perf_counter()
     lrn.update(**buf.sample(perm[:512]))
     per_row = (time.perf_counter() - t0) / 512
@@ -161,7 +165,7 @@ def cpu_reference_rate(rows_budget_s, steps, warmup, threads=None, verbose=False
         pos += rows
         if it >= warmup:
             rates.append((rows / N_EPOCHS) / dt)   # one env-step is visited n_epochs times by train_epochs
-    info = {"cores": threads or cores, "rows_per_step": rows, "finish_path_256_s": t_gae,
+    info = {"cores": cores, "logical_cpus": os.cpu_count(), "rows_per_step": rows, "finish_path_256_s": t_gae,
             "sample": "%d timed steps, each = sample(%d rows)+update of the 256x128 workload; env-steps = rows/%d"
                       % (steps, rows, N_EPOCHS)}
     return rates, info

@@ -127,6 +127,21 @@ int xb_dqn_td_fwd_bwd(const float *q_eval, const float *q_next, const float *act
                       const float *term, int64_t B, int A, int64_t B_total, float gamma,
                       float *dq, float *td, float *stats, double *scratch, void *stream);
 
+/* ---------------------------------------------------------------- K8: SAC loss stages ----------------
+ * Replaces the elementwise/reduction parts of SAC_Learner.update (xuance/torch/learners/policy_gradient/
+ * sac_learner.py:52-88).  `alpha` is a DEVICE scalar (exp(log_alpha)).
+ * actor : p_loss = mean(alpha*log_pi - min(q1,q2)); writes dlog_pi, dq1, dq2 (torch.min ties split 1/2),
+ *         stats[4] = {Ploss, mean(min q), mean(log_pi), 0}
+ * critic: backup = r + (1-d)*gamma*(target_q - alpha*log_pi_next); q_loss = mse(q1,backup)+mse(q2,backup);
+ *         writes dq1, dq2, backup; stats[2] = {Qloss, 0} */
+int xb_sac_actor_loss(const float *log_pi, const float *q1, const float *q2, const float *alpha, int64_t B,
+                      int64_t B_total, float *dlog_pi, float *dq1, float *dq2, float *stats, double *scratch,
+                      void *stream);
+int xb_sac_critic_loss(const float *q1, const float *q2, const float *target_q, const float *log_pi_next,
+                       const float *rew, const float *term, const float *alpha, float gamma, int64_t B,
+                       int64_t B_total, float *dq1, float *dq2, float *backup, float *stats, double *scratch,
+                       void *stream);
+
 /* ---------------------------------------------------------------- K7: flat-bucket optimiser step -----
  * Replaces clip_grad_norm_ + torch.optim.Adam.step on the learner's parameters (ppo_learner.py:61-65;
  * Adam eps=1e-5, no weight decay, no amsgrad) over ONE flat float32 bucket (params/grads/exp_avg/exp_avg_sq

@@ -35,6 +35,8 @@ _SIGNATURES = {
     "xb_adam_step": (c_int, [_P, _P, _P, _P, c_int64, _P, c_float, c_float, c_float, c_float, _P, c_float,
                              c_int, _P]),
     "xb_soft_update": (c_int, [_P, _P, c_int64, c_float, _P]),
+    "xb_sac_actor_loss": (c_int, [_P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
+    "xb_sac_critic_loss": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_float, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
     "xb_powf_libm": (c_int, [_P, c_float, _P, c_int64, _P]),
 }
 _OPTIONAL = {

@@ -1,4 +1,16 @@
 from .learner import Learner
 from .ppo_learner import PPO_Learner
+from .dqn_learner import DQN_Learner, PerDQN_Learner
 
-REGISTRY_Learners = {"PPO_Learner": PPO_Learner, "PPOCLIP_Learner": PPO_Learner}
+REGISTRY_Learners = {"PPO_Learner": PPO_Learner, "PPOCLIP_Learner": PPO_Learner, "DQN_Learner": DQN_Learner,
+                     "PerDQN_Learner": PerDQN_Learner}
+try:
+    from .sac_learner import SAC_Learner
+    REGISTRY_Learners["SAC_Learner"] = SAC_Learner
+except ImportError:
+    pass
+try:
+    from .qmix_learner import QMIX_Learner
+    REGISTRY_Learners["QMIX_Learner"] = QMIX_Learner
+except ImportError:
+    pass
