@@ -127,6 +127,30 @@ int xb_dqn_td_fwd_bwd(const float *q_eval, const float *q_next, const float *act
                       const float *term, int64_t B, int A, int64_t B_total, float gamma,
                       float *dq, float *td, float *stats, double *scratch, void *stream);
 
+/* ---------------------------------------------------------------- K9: QMIX selection / mixing / TD ----
+ * Replaces, for one parameter-sharing group with use_rnn=True (episodes padded to T, `filled` mask):
+ * select  : qmix_learner.py:42-66 + iql_learner.py:57-59 - gather Q(o_t, a_t) from the eval net outputs
+ *           q_all[B,n,T+1,A], the double-Q / max next value from the target outputs q_tgt at step t+1, both
+ *           multiplied by agent_mask*filled and written agent-minor [B*T, n] (the layout Q_tot concatenates,
+ *           value_factorization.py:137-142); also filled_sum[0] = sum(filled).  actions/masks are float32.
+ *           select_bwd scatters d(q_eval_taken) back into a zeroed dq_all.
+ * mix     : QMIX_Mixer.forward epilogue (q_mix_head.py:81-94) on precomputed hypernet outputs:
+ *           hidden = elu(q . |w1_raw|[n,H] + b1) ; q_tot = hidden . |w2_raw| + b2   (n <= 16), and its backward
+ *           (abs' = sign, elu' = exp) producing dq, dw1_raw, db1, dw2_raw (db2 = dq_tot).
+ * td      : qmix_learner.py:34-35,76-84 masked TD loss; writes dq_tot and stats[2] = {loss_Q, mean(q_tot)}. */
+int xb_qmix_select_fwd(const float *q_all, const float *q_tgt, const float *actions, const float *agent_mask,
+                       const float *filled, int B, int n, int T, int A, int double_q, float *q_eval_taken,
+                       float *q_next_taken, float *filled_sum, double *scratch, void *stream);
+int xb_qmix_select_bwd(const float *d_taken, const float *actions, const float *agent_mask, const float *filled,
+                       int B, int n, int T, int A, float *dq_all, void *stream);
+int xb_qmix_mix_fwd(const float *q, const float *w1_raw, const float *b1, const float *w2_raw, const float *b2,
+                    int64_t R, int n, int H, float *q_tot, void *stream);
+int xb_qmix_mix_bwd(const float *dq_tot, const float *q, const float *w1_raw, const float *b1, const float *w2_raw,
+                    int64_t R, int n, int H, float *dq, float *dw1_raw, float *db1, float *dw2_raw, void *stream);
+int xb_qmix_td(const float *q_tot, const float *q_tot_next, const float *rewards, const float *terminals,
+               const float *filled, const float *filled_sum, int B, int n, int T, float gamma, float grad_scale,
+               float *dq_tot, float *stats, double *scratch, void *stream);
+
 /* ---------------------------------------------------------------- K8: SAC loss stages ----------------
  * Replaces the elementwise/reduction parts of SAC_Learner.update (xuance/torch/learners/policy_gradient/
  * sac_learner.py:52-88).  `alpha` is a DEVICE scalar (exp(log_alpha)).

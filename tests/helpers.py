@@ -59,3 +59,24 @@ def ppo_config(device, **kw):
                n_epochs=4, n_minibatch=4, vf_coef=0.25, ent_coef=0.01, clip_range=0.2, gamma=0.99)
     cfg.update(kw)
     return Namespace(**cfg)
+
+
+def qmix_episode_stream(rng, keys, n_envs, T, obs_dim, A, S, episodes):
+    """Yields ('store', step_dict) / ('finish', env, terminal_dict) events of a synthetic SMAC-shaped rollout."""
+    for ep in range(episodes):
+        L = rng.integers(max(2, T // 3), T + 1, size=n_envs)
+        for t in range(T):
+            yield ('store', dict(
+                obs={k: rng.normal(size=(n_envs, obs_dim)).astype(np.float32) for k in keys},
+                actions={k: rng.integers(0, A, n_envs) for k in keys},
+                rewards={k: rng.normal(size=n_envs).astype(np.float32) for k in keys},
+                terminals={k: (rng.random(n_envs) < 0.1) for k in keys},
+                agent_mask={k: np.ones(n_envs, bool) for k in keys},
+                state=rng.normal(size=(n_envs, S)).astype(np.float32), episode_steps=np.full(n_envs, t)))
+            for e in range(n_envs):
+                if t + 1 == L[e]:
+                    yield ('finish', e, dict(episode_step=t + 1,
+                                             obs={k: rng.normal(size=obs_dim).astype(np.float32) for k in keys},
+                                             state=rng.normal(size=S).astype(np.float32)))
+
+

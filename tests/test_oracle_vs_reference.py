@@ -8,7 +8,7 @@ import pytest
 import torch
 import torch.nn as nn
 
-from helpers import synth_rollout, fill_buffers
+from helpers import synth_rollout, fill_buffers, qmix_episode_stream
 
 pytestmark = pytest.mark.reference
 
@@ -94,25 +94,6 @@ def _qmix_pair(n, obs_dim, A, S, T, lr_decay=0.5):
     orc = QMIXLearnerOracle(om, keys, learning_rate=7e-4, sync_frequency=2, double_q=True, end_factor_lr_decay=lr_decay,
                             total_iters=lrn.total_iters, detach_q_eval=True)   # the reference as it is (see oracle/qmix.py)
     return keys, model, lrn, om, orc
-
-
-def qmix_episode_stream(rng, keys, n_envs, T, obs_dim, A, S, episodes):
-    """Yields ('store', step_dict) / ('finish', env, terminal_dict) events of a synthetic SMAC-shaped rollout."""
-    for ep in range(episodes):
-        L = rng.integers(max(2, T // 3), T + 1, size=n_envs)
-        for t in range(T):
-            yield ('store', dict(
-                obs={k: rng.normal(size=(n_envs, obs_dim)).astype(np.float32) for k in keys},
-                actions={k: rng.integers(0, A, n_envs) for k in keys},
-                rewards={k: rng.normal(size=n_envs).astype(np.float32) for k in keys},
-                terminals={k: (rng.random(n_envs) < 0.1) for k in keys},
-                agent_mask={k: np.ones(n_envs, bool) for k in keys},
-                state=rng.normal(size=(n_envs, S)).astype(np.float32), episode_steps=np.full(n_envs, t)))
-            for e in range(n_envs):
-                if t + 1 == L[e]:
-                    yield ('finish', e, dict(episode_step=t + 1,
-                                             obs={k: rng.normal(size=obs_dim).astype(np.float32) for k in keys},
-                                             state=rng.normal(size=S).astype(np.float32)))
 
 
 def test_qmix_buffer_and_learner_live(ref):

@@ -37,12 +37,14 @@ _SIGNATURES = {
     "xb_soft_update": (c_int, [_P, _P, c_int64, c_float, _P]),
     "xb_sac_actor_loss": (c_int, [_P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
     "xb_sac_critic_loss": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_float, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
+    "xb_qmix_select_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
+    "xb_qmix_select_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "xb_qmix_mix_fwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, _P, _P]),
+    "xb_qmix_mix_bwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, _P, _P, _P, _P, _P]),
+    "xb_qmix_td": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P]),
     "xb_powf_libm": (c_int, [_P, c_float, _P, c_int64, _P]),
 }
-_OPTIONAL = {
-    "xb_qmix_mix_fwd": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P]),
-    "xb_qmix_mix_bwd": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
-}
+_OPTIONAL = {}
 
 _lib = None
 launch_count = 0  # number of xb200 kernel-launching ABI calls issued (bench.py's gpu_launches evidence)

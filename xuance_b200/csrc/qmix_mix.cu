@@ -1,0 +1,243 @@
+// K6 QMIX: (a) action-value selection over the padded episode batch, (b) the per-row monotonic mixing network
+// (abs / batched [1 x n]x[n x H] and [1 x H]x[H x 1] contractions / ELU) forward and backward, (c) masked TD loss.
+// One warp per (episode, step) row: lane j owns hidden unit j (H <= 32 per pass), the n agent utilities are
+// broadcast, the two contractions are warp-shuffle reductions.  The hypernetwork linear layers that produce
+// w1/b1/w2/b2 from the global state are plain GEMMs and stay in cuBLAS (include/xb200.h, K6).
+#include "xb_common.cuh"
+
+// =====================================================================================================
+// (a) selection:  q_eval_taken[b*T+t, i] = Q[b,i,t,a_{b,i,t}] * mask ;  q_next_taken = Q'[b,i,t+1, argmax/max] * mask
+// =====================================================================================================
+// Layouts: q_all, q_tgt [B, n, T+1, A]; actions, agent_mask [B, n, T] (float32); filled [B, T] (float32).
+// One thread per (b, i, t).  Also accumulates sum(filled) (needed by the masked loss) deterministically.
+__global__ void __launch_bounds__(256) qmix_select_fwd_kernel(const float *__restrict__ q_all,
+                                                              const float *__restrict__ q_tgt,
+                                                              const float *__restrict__ actions,
+                                                              const float *__restrict__ agent_mask,
+                                                              const float *__restrict__ filled, int B, int n, int T,
+                                                              int A, int double_q, float *__restrict__ q_eval_taken,
+                                                              float *__restrict__ q_next_taken,
+                                                              float *__restrict__ filled_sum,
+                                                              double *__restrict__ scratch) {
+    __shared__ double red[32];
+    double acc[1] = {0.0};
+    const int64_t total = (int64_t)B * n * T;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int t = (int)(e % T);
+        const int i = (int)((e / T) % n);
+        const int b = (int)(e / ((int64_t)T * n));
+        const float m = agent_mask[e] * filled[(int64_t)b * T + t];
+        const float *qe = q_all + (((int64_t)b * n + i) * (T + 1) + t) * A;
+        const float *qe1 = qe + A;  // step t+1 of the eval network (double-Q argmax)
+        const float *qt1 = q_tgt + (((int64_t)b * n + i) * (T + 1) + t + 1) * A;
+        const int a = (int)actions[e];
+        float nxt;
+        if (double_q) {
+            int best = 0;
+            float bv = qe1[0];
+            for (int k = 1; k < A; ++k)
+                if (qe1[k] > bv) {  // torch.argmax: first maximal index
+                    bv = qe1[k];
+                    best = k;
+                }
+            nxt = qt1[best];
+        } else {
+            nxt = qt1[0];
+            for (int k = 1; k < A; ++k) nxt = fmaxf(nxt, qt1[k]);
+        }
+        const int64_t row = (int64_t)b * T + t;
+        q_eval_taken[row * n + i] = qe[a] * m;
+        q_next_taken[row * n + i] = nxt * m;
+        if (i == 0) acc[0] += (double)filled[row];
+    }
+    grid_sum_finalize<1>(acc, scratch, red, [&](double(&tot)[1]) { filled_sum[0] = (float)tot[0]; });
+}
+
+// backward of the eval selection: dq_all[b,i,t,a] = d_taken[row,i] * mask  (dq_all pre-zeroed by the caller)
+__global__ void __launch_bounds__(256) qmix_select_bwd_kernel(const float *__restrict__ d_taken,
+                                                              const float *__restrict__ actions,
+                                                              const float *__restrict__ agent_mask,
+                                                              const float *__restrict__ filled, int B, int n, int T,
+                                                              int A, float *__restrict__ dq_all) {
+    const int64_t total = (int64_t)B * n * T;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int t = (int)(e % T);
+        const int i = (int)((e / T) % n);
+        const int b = (int)(e / ((int64_t)T * n));
+        const float m = agent_mask[e] * filled[(int64_t)b * T + t];
+        const int a = (int)actions[e];
+        dq_all[(((int64_t)b * n + i) * (T + 1) + t) * A + a] = d_taken[((int64_t)b * T + t) * n + i] * m;
+    }
+}
+
+extern "C" int xb_qmix_select_fwd(const float *q_all, const float *q_tgt, const float *actions,
+                                  const float *agent_mask, const float *filled, int B, int n, int T, int A,
+                                  int double_q, float *q_eval_taken, float *q_next_taken, float *filled_sum,
+                                  double *scratch, void *stream) {
+    if (!q_all || !q_tgt || !actions || !agent_mask || !filled || !q_eval_taken || !q_next_taken || !filled_sum ||
+        !scratch)
+        return XB_EINVAL;
+    if (B <= 0 || n <= 0 || T <= 0 || A <= 0) return XB_EINVAL;
+    int64_t total = (int64_t)B * n * T, want = (total + 255) / 256;
+    int grid = (int)(want < XB_MAX_PARTIALS ? want : XB_MAX_PARTIALS);
+    qmix_select_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(q_all, q_tgt, actions, agent_mask, filled, B, n, T, A,
+                                                                   double_q, q_eval_taken, q_next_taken, filled_sum,
+                                                                   scratch);
+    return xb_launch_status();
+}
+
+extern "C" int xb_qmix_select_bwd(const float *d_taken, const float *actions, const float *agent_mask,
+                                  const float *filled, int B, int n, int T, int A, float *dq_all, void *stream) {
+    if (!d_taken || !actions || !agent_mask || !filled || !dq_all) return XB_EINVAL;
+    if (B <= 0 || n <= 0 || T <= 0 || A <= 0) return XB_EINVAL;
+    int64_t total = (int64_t)B * n * T, want = (total + 255) / 256;
+    int64_t cap = (int64_t)xb_sm_count() * 8;
+    qmix_select_bwd_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(d_taken, actions, agent_mask,
+                                                                                           filled, B, n, T, A, dq_all);
+    return xb_launch_status();
+}
+
+// =====================================================================================================
+// (b) mixing network epilogue (xuance/torch/rl_models/heads/q_mix_head.py:66-95)
+//     hidden = elu(q . |w1| + b1) ; q_tot = hidden . |w2| + b2          per row
+// =====================================================================================================
+// w1_raw [R, n*H] (row-major [n][H] per row), b1 [R, H], w2_raw [R, H], b2 [R], q [R, n].  Warp per row.
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : (expf(x) - 1.f); }
+
+__global__ void __launch_bounds__(256) qmix_mix_fwd_kernel(const float *__restrict__ q, const float *__restrict__ w1,
+                                                           const float *__restrict__ b1, const float *__restrict__ w2,
+                                                           const float *__restrict__ b2, int64_t R, int n, int H,
+                                                           float *__restrict__ q_tot) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < R; r += nwarps) {
+        const float *w1r = w1 + r * (int64_t)n * H;
+        float part = 0.f;
+        for (int j = lane; j < H; j += 32) {
+            float pre = b1[r * H + j];
+            for (int i = 0; i < n; ++i) pre += q[r * n + i] * fabsf(w1r[i * H + j]);
+            part += elu1(pre) * fabsf(w2[r * H + j]);
+        }
+        part = warp_sum_f(part);
+        if (lane == 0) q_tot[r] = part + b2[r];
+    }
+}
+
+__global__ void __launch_bounds__(256) qmix_mix_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ q,
+                                                           const float *__restrict__ w1, const float *__restrict__ b1,
+                                                           const float *__restrict__ w2, int64_t R, int n, int H,
+                                                           float *__restrict__ dq, float *__restrict__ dw1,
+                                                           float *__restrict__ db1, float *__restrict__ dw2) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < R; r += nwarps) {
+        const float g = dy[r];
+        const float *w1r = w1 + r * (int64_t)n * H;
+        float *dw1r = dw1 + r * (int64_t)n * H;
+        float dq_acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dq_acc[i] = 0.f;
+        for (int j = lane; j < H; j += 32) {
+            float pre = b1[r * H + j];
+            for (int i = 0; i < n; ++i) pre += q[r * n + i] * fabsf(w1r[i * H + j]);
+            const float h = elu1(pre);
+            const float w2v = w2[r * H + j];
+            const float sgn2 = (w2v > 0.f) - (w2v < 0.f);
+            dw2[r * H + j] = g * h * sgn2;
+            const float dpre = g * fabsf(w2v) * (pre > 0.f ? 1.f : (h + 1.f));  // elu' = exp(pre) = h + 1
+            db1[r * H + j] = dpre;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if (i < n) {
+                    const float wv = w1r[i * H + j];
+                    const float sgn = (wv > 0.f) - (wv < 0.f);
+                    dw1r[i * H + j] = dpre * q[r * n + i] * sgn;
+                    dq_acc[i] += dpre * fabsf(wv);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (i < n) {
+                float s = warp_sum_f(dq_acc[i]);
+                if (lane == 0) dq[r * n + i] = s;
+            }
+        }
+    }
+}
+
+extern "C" int xb_qmix_mix_fwd(const float *q, const float *w1_raw, const float *b1, const float *w2_raw,
+                               const float *b2, int64_t R, int n, int H, float *q_tot, void *stream) {
+    if (!q || !w1_raw || !b1 || !w2_raw || !b2 || !q_tot || R <= 0 || n <= 0 || H <= 0) return XB_EINVAL;
+    if (n > 16) return XB_ERANGE;
+    int64_t want = (R * 32 + 255) / 256, cap = (int64_t)xb_sm_count() * 8;
+    qmix_mix_fwd_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(q, w1_raw, b1, w2_raw, b2, R, n,
+                                                                                        H, q_tot);
+    return xb_launch_status();
+}
+
+extern "C" int xb_qmix_mix_bwd(const float *dq_tot, const float *q, const float *w1_raw, const float *b1,
+                               const float *w2_raw, int64_t R, int n, int H, float *dq, float *dw1_raw, float *db1,
+                               float *dw2_raw, void *stream) {
+    if (!dq_tot || !q || !w1_raw || !b1 || !w2_raw || !dq || !dw1_raw || !db1 || !dw2_raw) return XB_EINVAL;
+    if (R <= 0 || n <= 0 || H <= 0) return XB_EINVAL;
+    if (n > 16) return XB_ERANGE;
+    int64_t want = (R * 32 + 255) / 256, cap = (int64_t)xb_sm_count() * 8;
+    qmix_mix_bwd_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(dq_tot, q, w1_raw, b1, w2_raw, R,
+                                                                                        n, H, dq, dw1_raw, db1, dw2_raw);
+    return xb_launch_status();
+}
+
+// =====================================================================================================
+// (c) masked TD loss (qmix_learner.py:34-35, 76-84): team reward = mean over agents, team terminal = all agents,
+//     y = r + (1-d)*gamma*Qtot' ; td = (Qtot - y)*filled ; loss = sum(td^2)/sum(filled) ; dQtot = 2*td*filled/sum(filled)
+// =====================================================================================================
+__global__ void __launch_bounds__(256) qmix_td_kernel(const float *__restrict__ q_tot, const float *__restrict__ q_tot_next,
+                                                      const float *__restrict__ rewards,
+                                                      const float *__restrict__ terminals,
+                                                      const float *__restrict__ filled,
+                                                      const float *__restrict__ filled_sum, int B, int n, int T,
+                                                      float gamma, float inv_world, float *__restrict__ dq_tot,
+                                                      float *__restrict__ stats, double *__restrict__ scratch) {
+    __shared__ double red[2 * 32];
+    double acc[2] = {0, 0};
+    const float fs = filled_sum[0];
+    const int64_t R = (int64_t)B * T;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < R; row += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(row / T), t = (int)(row % T);
+        float rs = 0.f;
+        bool all_term = true;
+        for (int i = 0; i < n; ++i) {
+            const int64_t e = ((int64_t)b * n + i) * T + t;
+            rs += rewards[e];
+            all_term = all_term && (terminals[e] != 0.f);
+        }
+        const float r_tot = rs / (float)n;
+        const float d_tot = all_term ? 1.f : 0.f;
+        const float y = r_tot + (1.f - d_tot) * gamma * q_tot_next[row];
+        const float f = filled[row];
+        const float td = (q_tot[row] - y) * f;
+        dq_tot[row] = 2.f * td * f / fs * inv_world;
+        acc[0] += (double)td * td;
+        acc[1] += (double)q_tot[row];
+    }
+    grid_sum_finalize<2>(acc, scratch, red, [&](double(&tsum)[2]) {
+        stats[0] = (float)(tsum[0] / (double)fs);   // loss_Q
+        stats[1] = (float)(tsum[1] / (double)R);    // predictQ = mean(q_tot_eval)
+    });
+}
+
+extern "C" int xb_qmix_td(const float *q_tot, const float *q_tot_next, const float *rewards, const float *terminals,
+                          const float *filled, const float *filled_sum, int B, int n, int T, float gamma,
+                          float inv_world, float *dq_tot, float *stats, double *scratch, void *stream) {
+    if (!q_tot || !q_tot_next || !rewards || !terminals || !filled || !filled_sum || !dq_tot || !stats || !scratch)
+        return XB_EINVAL;
+    if (B <= 0 || n <= 0 || T <= 0) return XB_EINVAL;
+    int64_t R = (int64_t)B * T, want = (R + 255) / 256;
+    int grid = (int)(want < XB_MAX_PARTIALS ? want : XB_MAX_PARTIALS);
+    qmix_td_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(q_tot, q_tot_next, rewards, terminals, filled, filled_sum, B, n,
+                                                           T, gamma, inv_world, dq_tot, stats, scratch);
+    return xb_launch_status();
+}

@@ -5,3 +5,5 @@ from .representations import Basic_Identical, Basic_MLP, Basic_CNN, AC_CNN_Atari
 from .heads import CategoricalActorHead, GaussianActorHead, SAC_GaussianActorHead, ValueHead, QValueHead
 from .architectures import (ActorCritic, SharedActorCritic, DeepQNetwork, GaussianActor, SAC_GaussianActor,
                             TwinActionValueCritic, SoftActorCritic)
+from .qmix import Basic_RNN, AgentFeatureEncoder, DiscreteActionValueCritic, QMIX_Mixer, MixingQNetwork
+REGISTRY_Representation["Basic_RNN"] = Basic_RNN
