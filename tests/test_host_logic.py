@@ -1,0 +1,130 @@
+"""CPU: host-side logic - configs, vector envs, running statistics, sharding helpers, the multi-rank gradient identity
+(world_size-2 gloo)."""
+import os
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+
+
+def test_config_loader_merges_like_the_reference():
+    from xuance_b200.common.common_tools import get_arguments, recursive_dict_update
+    assert recursive_dict_update({'a': 1, 'b': 2}, {'a': 3, 'c': 4}) == {'a': 3, 'b': 2, 'c': 4}   # common_tools.py docstring
+    c = get_arguments('ppo', 'atari', 'atari', parser_args=Namespace(parallels=64, device="cuda:1"))
+    assert c.agent == "PPO" and c.parallels == 64 and c.device == "cuda:1" and c.horizon_size == 128
+    assert c.kernels == [8, 4, 3] and c.fc_hidden_sizes == [512] and c.dl_toolbox == "torch"
+    for algo, env in (('ppo', 'CartPole-v1'), ('perdqn', 'atari'), ('sac', 'mujoco'), ('qmix', '5m_vs_6m')):
+        get_arguments(algo, env, env)    # the 5 BASELINE configs all resolve
+
+
+@pytest.mark.parametrize("vec", ["DummyVecEnv", "SubprocVecEnv"])
+def test_vector_env_contract(vec):
+    from xuance_b200.environment import make_envs
+    from xuance_b200.environment.vector_envs import AlreadySteppingError, NotSteppingError
+    envs = make_envs(Namespace(env_id="CartPole-v1", vectorize=vec, parallels=4, env_seed=1))
+    obs, infos = envs.reset()
+    assert obs.shape == (4, 4) and obs.dtype == np.float32 and len(infos) == 4 and envs.num_envs == 4
+    with pytest.raises(NotSteppingError):
+        envs.step_wait()
+    envs.step_async(np.zeros(4, np.int64))
+    with pytest.raises(AlreadySteppingError):
+        envs.step_async(np.zeros(4, np.int64))
+    envs.step_wait()
+    ended = 0
+    for t in range(80):        # always pushing left ends every episode quickly
+        obs, rew, term, trunc, infos = envs.step(np.zeros(4, np.int64))
+        for i in range(4):
+            assert infos[i]["episode_step"] >= 1
+            if term[i] or trunc[i]:
+                ended += 1
+                assert "reset_obs" in infos[i] and infos[i]["reset_obs"].shape == (4,)
+                assert infos[i]["episode_score"] == infos[i]["episode_step"]       # reward 1 per step
+    assert ended >= 4 and rew.dtype == np.float32 and term.dtype == np.bool_
+    envs.close()
+
+
+def test_atari_vector_env_is_uint8():
+    from xuance_b200.environment import make_envs
+    envs = make_envs(Namespace(env_id="SyntheticAtari", vectorize="Dummy_Atari", parallels=2, env_seed=3))
+    obs, _ = envs.reset()
+    assert obs.dtype == np.uint8 and obs.shape == (2, 84, 84, 4) and envs.buf_obs.dtype == np.uint8
+    envs.close()
+
+
+def test_running_mean_std_matches_batch_statistics():
+    from xuance_b200.common.statistic_tools import RunningMeanStd
+    rng = np.random.default_rng(0)
+    x = rng.normal(2.0, 3.0, size=(1000, 5)).astype(np.float32)
+    rms = RunningMeanStd((5,))
+    for i in range(0, 1000, 100):
+        rms.update(x[i:i + 100])
+    np.testing.assert_allclose(rms.mean, x.mean(0), rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(rms.std, x.std(0), rtol=1e-3)
+
+
+@pytest.mark.reference
+def test_running_mean_std_matches_reference():
+    from oracle.ref_loader import import_reference
+    import_reference()
+    from xuance.common.statistic_tools import RunningMeanStd as Ref
+    from xuance_b200.common.statistic_tools import RunningMeanStd
+    rng = np.random.default_rng(1)
+    a, b = Ref((3,)), RunningMeanStd((3,))
+    for _ in range(7):
+        x = rng.normal(size=(8, 3)).astype(np.float32)
+        a.update(x), b.update(x)
+    assert np.array_equal(a.mean, b.mean) and np.array_equal(a.var, b.var) and a.count == b.count
+
+
+def test_stratified_minibatches_partition_every_shard():
+    from xuance_b200.torch.utils import stratified_minibatches, shard_bounds
+    rng = np.random.default_rng(0)
+    b = stratified_minibatches(4096, 4, rng)
+    assert len(b) == 4 and all(len(x) == 1024 for x in b)
+    assert np.array_equal(np.sort(np.concatenate(b)), np.arange(4096))
+    assert shard_bounds(256, 3, 8) == (96, 128)
+
+
+def _grad_worker(rank, world, port, out):
+    """Each rank: PPO loss on ITS half of a global minibatch, scaled by 1/B_total, then a sum all-reduce."""
+    import torch.distributed as dist
+    from oracle.learners import ppo_clip_terms
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    B, A = 64, 4
+    lin = torch.nn.Linear(8, A + 1)
+    x, act = torch.randn(B, 8), torch.randint(0, A, (B,)).float()
+    ret, adv, old = torch.randn(B), torch.randn(B), torch.randn(B) * 0.1 - 1.4
+    lo, hi = rank * B // world, (rank + 1) * B // world
+    o = lin(x[lo:hi])
+    a, c, e, _ = ppo_clip_terms(o[:, :A], o[:, A], act[lo:hi], ret[lo:hi], adv[lo:hi], old[lo:hi], 0.2)
+    loss = (a - 0.01 * e + 0.25 * c) * (hi - lo) / B          # mean over the GLOBAL batch
+    loss.backward()
+    flat = torch.cat([p.grad.reshape(-1) for p in lin.parameters()])
+    dist.all_reduce(flat)                                       # the one collective
+    if rank == 0:
+        o = lin(x)
+        a, c, e, _ = ppo_clip_terms(o[:, :A], o[:, A], act, ret, adv, old, 0.2)
+        lin.zero_grad()
+        (a - 0.01 * e + 0.25 * c).backward()
+        full = torch.cat([p.grad.reshape(-1) for p in lin.parameters()])
+        out.put(float((flat - full).abs().max()))
+    dist.destroy_process_group()
+
+
+def test_sharded_gradient_identity_gloo_world2():
+    """sum over ranks of grad(local rows / B_total) == grad of the global minibatch: the identity the single
+    NCCL all-reduce of the flat bucket relies on (K4/K6 take B_total for exactly this)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+    assert err < 1e-6, err
