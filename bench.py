@@ -193,6 +193,15 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------ own arm
+_T0 = time.time()
+
+
+def _log(msg):
+    if os.environ.get("XB_BENCH_VERBOSE", "1") != "0":
+        sys.stderr.write("[bench %6.1fs rank %s] %s\n" % (time.time() - _T0, os.environ.get("RANK", "0"), msg))
+        sys.stderr.flush()
+
+
 def run_own_arm(args):
     import torch
     import torch.distributed as dist
@@ -201,7 +210,9 @@ def run_own_arm(args):
     from xuance_b200.torch.agents import PPO_Agent
     from xuance_b200.torch.utils import init_distributed_mode
 
+    _log("imports done")
     rank, world, local_rank = init_distributed_mode()
+    _log("process group ready (world %d)" % world)
     if world > 1:
         assert world == args.gpus, "torchrun world size must equal --gpus"
     torch.cuda.set_device(local_rank)
@@ -240,6 +251,7 @@ def run_own_arm(args):
     for i in range(n_local):
         mem.finish_path(0.0 if terms[T - 1, lo + i] else boot[lo + i], i)
     np.random.seed(1)
+    _log("synthetic rollout resident")
 
     def barrier():
         if world > 1:
@@ -251,6 +263,7 @@ def run_own_arm(args):
 
     for _ in range(args.warmup):
         step()
+        _log("warm-up step done")
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -265,6 +278,7 @@ def run_own_arm(args):
     e1.record()
     barrier()
     elapsed_ms = e0.elapsed_time(e1)
+    _log("timed region done: %.1f ms/step" % (elapsed_ms / args.steps))
     launches = _lib.launch_count - launches0
     prof = _lib.profile["xb_gather_obs"]
     _lib.profile = None
@@ -306,6 +320,7 @@ def run_own_arm(args):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         per_step = float(tt.item()) / args.e2e_steps
+        _log("e2e done: %.1f ms/step" % (per_step * 1000))
         h2d = n_local * T * (int(np.prod(OBS_SHAPE)) + 5 * 4) + N_EPOCHS * n_local * T * 8
         e2e = {"value": N_ENVS * T / per_step, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
                "d2h_bytes_per_step": 32 * world, "steps": args.e2e_steps,

@@ -28,8 +28,9 @@ def init_distributed_mode(master_port=None, backend=None):
         use_cuda = torch.cuda.is_available()
         if use_cuda:
             torch.cuda.set_device(local_rank)
+        kw = {"device_id": torch.device("cuda", local_rank)} if use_cuda else {}
         dist.init_process_group(backend=backend or ("nccl" if use_cuda else "gloo"), rank=rank,
-                                world_size=world_size)
+                                world_size=world_size, **kw)
     return rank, world_size, local_rank
 
 
