@@ -123,3 +123,25 @@ def test_qmix_learner_matches_oracle(detach, double_q):
     for k in so_:
         np.testing.assert_allclose(sp_[k].cpu().numpy(), so_[k].numpy(), rtol=2e-3, atol=3e-4, err_msg=k)
     agents_moved = any(not torch.equal(sp_[k].cpu(), QMIXModelOracle.__init__ and v) for k, v in []) if False else None
+
+
+@pytest.mark.parametrize("R,n,S", [(1920, 5, 98), (128, 5, 98), (1000, 8, 160), (77, 3, 17), (245760, 5, 98)])
+def test_tensor_core_mixer_forward(R, n, S):
+    """K9-TC (tcgen05.mma, TMEM accumulators, bf16 hi/lo split x 4 products) vs the fp32 torch-CPU mixer."""
+    from xuance_b200.torch.rl_models import QMIX_Mixer
+    torch.manual_seed(R + n)
+    om = MixerOracle(S, 32, 32, n)
+    pm = QMIX_Mixer(S, 32, 32, n, "cuda:0")
+    pm.load_state_dict(om.state_dict())
+    q = torch.randn(R, n) * 2
+    st = torch.randn(R, S)
+    with torch.no_grad():
+        want = om(q, st).reshape(-1).numpy()
+        got = pm(q.cuda(), st.cuda()).reshape(-1).cpu().numpy()         # no-grad forward -> fused tensor-core path
+        pm.use_tensor_core_forward = False
+        plain = pm(q.cuda(), st.cuda()).reshape(-1).cpu().numpy()       # cuBLAS + K9 mix epilogue
+    np.testing.assert_allclose(plain, want, rtol=1e-5, atol=1e-5)
+    scale = np.abs(want).mean()
+    err = np.abs(got - want).max()
+    assert err <= 2e-4 * max(scale, 1.0), (err, scale)
+    np.testing.assert_allclose(got, want, rtol=2e-3, atol=2e-4 * max(scale, 1.0))

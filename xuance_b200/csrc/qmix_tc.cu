@@ -1,0 +1,281 @@
+// K9-TC: the QMIX mixing network forward as ONE tensor-core kernel (tcgen05.mma, accumulators in TMEM).
+//
+//   Z      = X[rows x S] . W1cat^T[S x 128]              (first layers of hyper_w_1 | hyper_b_1 | hyper_w_2 | hyper_b_2)
+//   W1raw  = relu(Z[:,  0: 32] + c) . Wb1^T [32 x n*32]  (second layer of hyper_w_1)
+//   W2raw  = relu(Z[:, 64: 96] + c) . Wb2^T [32 x 32]    (second layer of hyper_w_2)
+//   b2     = relu(Z[:, 96:128] + c) . wb2^T [32 x 1]     (second layer of hyper_b_2)
+//   q_tot  = elu(q . |W1raw + c| + (Z[:,32:64] + c)) . |W2raw + c| + b2 + c         per row
+// (xuance/torch/rl_models/heads/q_mix_head.py:52-95).  One CTA (128 threads) owns a tile of 128 rows: M = 128,
+// thread i <-> TMEM lane i <-> row i.  All GEMM operands sit in shared memory in the K-major no-swizzle canonical
+// layout (8-row x 16-byte core matrices), written by the threads themselves; the weights are staged once per CTA,
+// the CTA then loops over its tiles (persistent grid = SM count).
+//
+// Numerics: the reference computes these layers in fp32.  The tensor pipe takes bf16 here, so every fp32 operand is
+// split x = hi + lo (two bf16 values, |x - hi - lo| <= 2^-17 |x|) and each product is the sum of the four MMAs
+// hi.hi + hi.lo + lo.hi + lo.lo accumulated in fp32 in TMEM: relative error ~1e-5 per layer (a plain bf16 or TF32
+// pass would be ~4e-3 / ~5e-4).  tests/test_gpu_qmix.py pins it against the fp32 oracle.
+#include "xb_common.cuh"
+
+namespace {
+
+constexpr int TC_ROWS = 128;   // M
+constexpr int TC_HH = 32;      // hypernet hidden = mixing hidden = 32 (the shipped QMIX configs)
+constexpr int TC_N1 = 128;     // 4 x 32 first-layer outputs
+constexpr int TC_TMEM_COLS = 512;
+constexpr int COL_Z = 0, COL_W1 = 128, COL_W2 = 384, COL_B2 = 416;   // W1raw may take up to 256 columns (n <= 8)
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// byte offset of element (r, k) of a [rows x KP] bf16 operand in the K-major no-swizzle canonical layout:
+// core matrix = 8 rows x 8 elements (16 B per row, 128 B per core), K-adjacent cores contiguous (LBO = 128 B),
+// 8-row groups SBO = KP/8 * 128 B apart.
+__device__ __forceinline__ uint32_t canon_off(int r, int k, int KP) {
+    return (uint32_t)((r >> 3) * (KP >> 3) * 128 + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2);
+}
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, int KP) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);               // start address
+    d |= (uint64_t)((128 >> 4) & 0x3fff) << 16;               // LBO: next core matrix along K
+    d |= (uint64_t)((((KP >> 3) * 128) >> 4) & 0x3fff) << 32; // SBO: next 8-row group
+    d |= (uint64_t)1 << 46;                                   // descriptor version (sm_100)
+    return d;                                                 // layout_type = 0 (no swizzle), base_offset = 0
+}
+
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// stage a [rows x K] fp32 row-major matrix (leading dimension ld) as hi/lo bf16 canonical operands, zero padded
+__device__ __forceinline__ void stage_operand(const float *__restrict__ g, int rows_valid, int rows_total, int K, int ld,
+                                              int KP, uint8_t *hi, uint8_t *lo) {
+    const int total = rows_total * KP;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        const int r = e / KP, k = e - r * KP;
+        float x = (r < rows_valid && k < K) ? g[(int64_t)r * ld + k] : 0.f;
+        __nv_bfloat16 h, l;
+        split_bf16(x, h, l);
+        const uint32_t off = canon_off(r, k, KP);
+        *reinterpret_cast<__nv_bfloat16 *>(hi + off) = h;
+        *reinterpret_cast<__nv_bfloat16 *>(lo + off) = l;
+    }
+}
+
+// issue the four split products of one GEMM: D[128 x N] (+)= A[128 x KP] . B[N x KP]^T
+__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, const uint8_t *a_hi, const uint8_t *a_lo,
+                                           const uint8_t *b_hi, const uint8_t *b_lo, int KP, int N) {
+    const uint32_t idesc = make_idesc(TC_ROWS, N);
+    const uint8_t *as[2] = {a_hi, a_lo};
+    const uint8_t *bs[2] = {b_hi, b_lo};
+    uint32_t acc = 0;
+    for (int pa = 0; pa < 2; ++pa)
+        for (int pb = 0; pb < 2; ++pb)
+            for (int ks = 0; ks < KP / 16; ++ks) {  // one MMA = K 16 = two core matrices = 256 B along K
+                const uint64_t da = make_desc(smem_u32(as[pa]) + ks * 256, KP);
+                const uint64_t db = make_desc(smem_u32(bs[pb]) + ks * 256, KP);
+                mma_bf16(d_tmem, da, db, idesc, acc);
+                acc = 1;
+            }
+}
+
+struct TcParams {
+    const float *states, *q;                 // [R,S], [R,n]
+    const float *w1cat, *bias1;              // [128,S], [128]
+    const float *wb1, *bias_wb1;             // [n*32,32], [n*32]
+    const float *wb2, *bias_wb2;             // [32,32], [32]
+    const float *wb2c, *bias_wb2c;           // [1,32], [1]
+    float *q_tot;                            // [R]
+    int64_t R;
+    int S, n;
+};
+
+__global__ void __launch_bounds__(128, 1) qmix_mix_tc_kernel(TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ float s_bias1[TC_N1], s_bias_wb1[256], s_bias_wb2[TC_HH], s_bias_b2;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int S = p.S, n = p.n, KP1 = (S + 15) & ~15, N2A = n * TC_HH;
+    // ---- shared memory carve-up (every operand base 128-B aligned)
+    const int szA1 = TC_ROWS * KP1 * 2, szB1 = TC_N1 * KP1 * 2, szA2 = TC_ROWS * TC_HH * 2;
+    const int szB2a = N2A * TC_HH * 2, szB2b = TC_HH * TC_HH * 2, szB2c = 16 * TC_HH * 2;
+    uint8_t *A1h = smem, *A1l = A1h + szA1, *B1h = A1l + szA1, *B1l = B1h + szB1;
+    uint8_t *A2h[3], *A2l[3];
+    uint8_t *cur = B1l + szB1;
+    for (int i = 0; i < 3; ++i) {
+        A2h[i] = cur;
+        A2l[i] = cur + szA2;
+        cur += 2 * szA2;
+    }
+    uint8_t *B2ah = cur, *B2al = B2ah + szB2a, *B2bh = B2al + szB2a, *B2bl = B2bh + szB2b;
+    uint8_t *B2ch = B2bl + szB2b, *B2cl = B2ch + szB2c;
+
+    // ---- one-time setup: mbarrier, TMEM, weights
+    if (tid == 0) {
+        mbar_init(&mma_bar, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(TC_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    stage_operand(p.w1cat, TC_N1, TC_N1, S, S, KP1, B1h, B1l);
+    stage_operand(p.wb1, N2A, N2A, TC_HH, TC_HH, TC_HH, B2ah, B2al);
+    stage_operand(p.wb2, TC_HH, TC_HH, TC_HH, TC_HH, TC_HH, B2bh, B2bl);
+    stage_operand(p.wb2c, 1, 16, TC_HH, TC_HH, TC_HH, B2ch, B2cl);
+    for (int i = tid; i < TC_N1; i += blockDim.x) s_bias1[i] = p.bias1[i];
+    for (int i = tid; i < N2A; i += blockDim.x) s_bias_wb1[i] = p.bias_wb1[i];
+    if (tid < TC_HH) s_bias_wb2[tid] = p.bias_wb2[tid];
+    if (tid == 0) s_bias_b2 = p.bias_wb2c[0];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_slot;
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes
+    uint32_t phase = 0;
+
+    const int64_t n_tiles = (p.R + TC_ROWS - 1) / TC_ROWS;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * TC_ROWS;
+        const int rows_valid = (int)((p.R - row0) < TC_ROWS ? (p.R - row0) : TC_ROWS);
+        // ---- stage X tile (split to bf16 hi/lo)
+        stage_operand(p.states + row0 * S, rows_valid, TC_ROWS, S, S, KP1, A1h, A1l);
+        fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        tc_fence_before();
+        __syncthreads();       // also orders the previous tile's TMEM reads before this tile's MMAs
+        tc_fence_after();
+        if (tid == 0) {
+            issue_gemm(tmem + COL_Z, A1h, A1l, B1h, B1l, KP1, TC_N1);
+            mma_commit(&mma_bar);
+        }
+        mbar_wait(&mma_bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        // ---- layer-1 epilogue: thread = row.  relu(Z + bias) of the three hidden blocks -> GEMM2 A operands
+        float b1v[TC_HH];
+        {
+            float z[32];
+            const int blocks[3] = {0, 64, 96};
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                tmem_ld32(lane_addr + COL_Z + blocks[g], z);
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    float v = fmaxf(z[k] + s_bias1[blocks[g] + k], 0.f);
+                    __nv_bfloat16 h, l;
+                    split_bf16(v, h, l);
+                    const uint32_t off = canon_off(tid, k, TC_HH);
+                    *reinterpret_cast<__nv_bfloat16 *>(A2h[g] + off) = h;
+                    *reinterpret_cast<__nv_bfloat16 *>(A2l[g] + off) = l;
+                }
+            }
+            tmem_ld32(lane_addr + COL_Z + 32, z);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) b1v[k] = z[k] + s_bias1[32 + k];
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (tid == 0) {
+            issue_gemm(tmem + COL_W1, A2h[0], A2l[0], B2ah, B2al, TC_HH, N2A);
+            issue_gemm(tmem + COL_W2, A2h[1], A2l[1], B2bh, B2bl, TC_HH, TC_HH);
+            issue_gemm(tmem + COL_B2, A2h[2], A2l[2], B2ch, B2cl, TC_HH, 16);
+            mma_commit(&mma_bar);
+        }
+        mbar_wait(&mma_bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        // ---- mixing epilogue (q_mix_head.py:81-94), thread = row
+        const bool live = tid < rows_valid;
+        float pre[TC_HH];
+#pragma unroll
+        for (int j = 0; j < TC_HH; ++j) pre[j] = b1v[j];
+        float w[32];
+        for (int i = 0; i < n; ++i) {
+            tmem_ld32(lane_addr + COL_W1 + i * TC_HH, w);
+            const float qi = live ? p.q[(row0 + tid) * n + i] : 0.f;
+#pragma unroll
+            for (int j = 0; j < TC_HH; ++j) pre[j] += qi * fabsf(w[j] + s_bias_wb1[i * TC_HH + j]);
+        }
+        tmem_ld32(lane_addr + COL_W2, w);
+        float y = 0.f;
+#pragma unroll
+        for (int j = 0; j < TC_HH; ++j) {
+            const float h = pre[j] > 0.f ? pre[j] : (expf(pre[j]) - 1.f);
+            y += h * fabsf(w[j] + s_bias_wb2[j]);
+        }
+        tmem_ld32(lane_addr + COL_B2, w);
+        if (live) p.q_tot[row0 + tid] = y + w[0] + s_bias_b2;
+    }
+    // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS));
+    }
+}
+
+}  // namespace
+
+extern "C" int xb_qmix_mix_fused_fwd(const float *states, const float *q, const float *w1cat, const float *bias1,
+                                     const float *wb1, const float *bias_wb1, const float *wb2, const float *bias_wb2,
+                                     const float *wb2c, const float *bias_wb2c, int64_t R, int S, int n, int H, int HH,
+                                     float *q_tot, void *stream) {
+    if (!states || !q || !w1cat || !bias1 || !wb1 || !bias_wb1 || !wb2 || !bias_wb2 || !wb2c || !bias_wb2c || !q_tot)
+        return XB_EINVAL;
+    if (R <= 0 || S <= 0 || n <= 0) return XB_EINVAL;
+    if (H != TC_HH || HH != TC_HH || n > 8 || S > 160) return XB_ERANGE;   // shapes of the shipped QMIX configs
+    const int KP1 = (S + 15) & ~15;
+    const size_t smem = (size_t)2 * TC_ROWS * KP1 * 2 + (size_t)2 * TC_N1 * KP1 * 2 + 6 * TC_ROWS * TC_HH * 2 +
+                        2 * (size_t)n * TC_HH * TC_HH * 2 + 2 * TC_HH * TC_HH * 2 + 2 * 16 * TC_HH * 2;
+    if (smem > 220 * 1024) return XB_ERANGE;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(qmix_mix_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        attr = true;
+    }
+    TcParams p{states, q, w1cat, bias1, wb1, bias_wb1, wb2, bias_wb2, wb2c, bias_wb2c, q_tot, R, S, n};
+    int64_t tiles = (R + TC_ROWS - 1) / TC_ROWS;
+    int grid = (int)(tiles < xb_sm_count() ? tiles : xb_sm_count());
+    qmix_mix_tc_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(p);
+    return xb_launch_status();
+}

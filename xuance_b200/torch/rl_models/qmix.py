@@ -123,7 +123,33 @@ class QMIX_Mixer(nn.Module):
         self.hyper_b_2 = nn.Sequential(nn.Linear(dim_state, dim_hypernet_hidden), nn.ReLU(),
                                        nn.Linear(dim_hypernet_hidden, 1)).to(device)
 
+    use_tensor_core_forward = True   # no-grad forwards (target mixer, inference) take the fused tcgen05 kernel
+
+    def _fusable(self):
+        return (self.use_tensor_core_forward and self.dim_hidden == 32 and self.dim_hypernet_hidden == 32
+                and self.n_agents <= 8 and self.dim_state <= 160)
+
+    def forward_fused(self, values_n, states):
+        """Whole mixer in ONE tensor-core kernel (K9-TC, xb_qmix_mix_fused_fwd).  Forward only."""
+        states = torch.as_tensor(states, dtype=torch.float32, device=self.device).reshape(-1, self.dim_state).contiguous()
+        q = values_n.reshape(-1, self.n_agents).to(torch.float32).contiguous()
+        w1cat = torch.cat([self.hyper_w_1[0].weight, self.hyper_b_1.weight, self.hyper_w_2[0].weight,
+                           self.hyper_b_2[0].weight], dim=0).contiguous()
+        bias1 = torch.cat([self.hyper_w_1[0].bias, self.hyper_b_1.bias, self.hyper_w_2[0].bias,
+                           self.hyper_b_2[0].bias], dim=0).contiguous()
+        R = q.shape[0]
+        out = torch.empty(R, dtype=torch.float32, device=q.device)
+        keep = [self.hyper_w_1[2].weight.contiguous(), self.hyper_w_1[2].bias.contiguous(),
+                self.hyper_w_2[2].weight.contiguous(), self.hyper_w_2[2].bias.contiguous(),
+                self.hyper_b_2[2].weight.contiguous(), self.hyper_b_2[2].bias.contiguous()]
+        _lib.call("xb_qmix_mix_fused_fwd", _lib.ptr(states), _lib.ptr(q), _lib.ptr(w1cat), _lib.ptr(bias1),
+                  *[_lib.ptr(t) for t in keep], R, self.dim_state, self.n_agents, self.dim_hidden,
+                  self.dim_hypernet_hidden, _lib.ptr(out))
+        return out.view(-1, 1)
+
     def forward(self, values_n, states):
+        if not torch.is_grad_enabled() and self._fusable():
+            return self.forward_fused(values_n, states)
         states = torch.as_tensor(states, dtype=torch.float32, device=self.device).reshape(-1, self.dim_state)
         q = values_n.reshape(-1, self.n_agents)
         w1 = self.hyper_w_1(states)          # abs() is applied inside the fused kernel
