@@ -125,7 +125,7 @@ def test_qmix_learner_matches_oracle(detach, double_q):
     agents_moved = any(not torch.equal(sp_[k].cpu(), QMIXModelOracle.__init__ and v) for k, v in []) if False else None
 
 
-@pytest.mark.parametrize("R,n,S", [(1920, 5, 98), (128, 5, 98), (1000, 8, 160), (77, 3, 17), (245760, 5, 98)])
+@pytest.mark.parametrize("R,n,S", [(1920, 5, 98), (128, 5, 98), (1000, 8, 64), (77, 3, 17), (245760, 5, 98), (300, 2, 160)])
 def test_tensor_core_mixer_forward(R, n, S):
     """K9-TC (tcgen05.mma, TMEM accumulators, bf16 hi/lo split x 4 products) vs the fp32 torch-CPU mixer."""
     from xuance_b200.torch.rl_models import QMIX_Mixer
@@ -137,6 +137,7 @@ def test_tensor_core_mixer_forward(R, n, S):
     st = torch.randn(R, S)
     with torch.no_grad():
         want = om(q, st).reshape(-1).numpy()
+        assert pm._fusable() == (S <= 128)
         got = pm(q.cuda(), st.cuda()).reshape(-1).cpu().numpy()         # no-grad forward -> fused tensor-core path
         pm.use_tensor_core_forward = False
         plain = pm(q.cuda(), st.cuda()).reshape(-1).cpu().numpy()       # cuBLAS + K9 mix epilogue

@@ -1,0 +1,220 @@
+#!/usr/bin/env python
+"""Per-kernel roofline numbers for every entry point of include/xb200.h, at the BASELINE shapes and at HBM-sized
+shapes (SURVEY.md section 7 "hard parts": at the named PPO shape K2/K4/K5 move < 1 MB and are launch-bound, so the
+bandwidth fraction is also reported at a scaled shape).  CUDA events on the launching stream, >= 3 warm-ups, L2
+flushed between timed launches (256 MB memset).  Prints one JSON object; profiles/rNN_kernels.json keeps a copy.
+
+    python tools/kernel_bench.py [--only k2,k4] [--reps 20]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from xuance_b200 import _lib  # noqa: E402
+
+DEV = torch.device("cuda:0")
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops", 1590.0)), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+_flush = None
+
+
+def timeit(fn, reps, flush=True):
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        if flush:
+            _flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    return float(np.median(ts))
+
+
+def entry(name, shape, us, alg_bytes, hbm, flops=None, tpeak=None):
+    d = {"kernel": name, "shape": shape, "us": round(us, 2), "algorithmic_bytes": int(alg_bytes),
+         "GBps": round(alg_bytes / us / 1e3, 1), "frac_hbm": round(alg_bytes / us / 1e3 / hbm, 3)}
+    if flops:
+        d["TFLOPs"] = round(flops / us / 1e6, 2)
+        d["frac_bf16_peak"] = round(flops / us / 1e6 / tpeak, 4)
+    return d
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--reps", type=int, default=20)
+    args = ap.parse_args()
+    only = set(x for x in args.only.split(",") if x)
+    want = lambda k: not only or k in only
+    hbm, tpk, src = peak()
+    out = {"hbm_peak_GBps": hbm, "bf16_peak_TFLOPs": tpk, "peak_source": src, "kernels": []}
+    add = out["kernels"].append
+    g = torch.Generator(device=DEV).manual_seed(0)
+    R = args.reps
+
+    if want("k1"):
+        N, T, rb = 256, 128, 28224
+        buf = torch.zeros((N, T, rb), dtype=torch.uint8, device=DEV)
+        src_rows = torch.randint(0, 256, (N, rb), dtype=torch.uint8, device=DEV, generator=g)
+        fields = torch.zeros((5, N, T), device=DEV)
+        scal = torch.randn((5, N), device=DEV)
+        us = timeit(lambda: _lib.call("xb_rollout_store", _lib.ptr(buf), _lib.ptr(src_rows), rb, _lib.ptr(fields),
+                                      _lib.ptr(scal), 5, N, T, 7), R)
+        add(entry("K1 xb_rollout_store", "256 envs x 28224 B + 5 fields", us, 2 * N * (rb + 20), hbm))
+        del buf
+
+    if want("k2"):
+        for N, T in ((256, 128), (4096, 1024)):
+            rew, val = torch.randn((N, T), device=DEV), torch.randn((N, T), device=DEV)
+            term = (torch.rand((N, T), device=DEV) < 0.01).float()
+            seg = torch.zeros((N, T), dtype=torch.uint8, device=DEV)
+            seg[:, -1] = 1
+            boot = torch.randn((N, T), device=DEV)
+            cov = torch.full((N,), T, dtype=torch.int32, device=DEV)
+            adv, ret = torch.empty((N, T), device=DEV), torch.empty((N, T), device=DEV)
+            us = timeit(lambda: _lib.call("xb_gae_scan", _lib.ptr(rew), _lib.ptr(val), _lib.ptr(term), _lib.ptr(seg),
+                                          _lib.ptr(boot), _lib.ptr(cov), _lib.ptr(adv), _lib.ptr(ret), N, T, 0.99, 0.95, 1), R)
+            add(entry("K2 xb_gae_scan", f"{N} envs x {T} steps", us, 21 * N * T + 8 * N, hbm))
+
+    if want("k3"):
+        S, B, H, W, C = 256 * 128, 8192, 84, 84, 4
+        rb = H * W * C
+        src_obs = torch.randint(0, 256, (S, rb), dtype=torch.uint8, device=DEV, generator=g)
+        idx = torch.randperm(S, device=DEV, generator=g)[:B].contiguous()
+        dst = torch.empty((B, rb), dtype=torch.uint8, device=DEV)
+        us = timeit(lambda: _lib.call("xb_gather_rows", _lib.ptr(src_obs), _lib.ptr(idx), B, rb, _lib.ptr(dst)), R)
+        add(entry("K3 xb_gather_rows (u8, bulk-async)", "8192 rows x 28224 B", us, 2 * B * rb + 8 * B, hbm))
+        for fmt, name, w, dt in ((_lib.OBS_F32_NCHW, "f32 NCHW", 4, torch.float32), (_lib.OBS_F32_NHWC, "f32 NHWC", 4, torch.float32),
+                                 (_lib.OBS_BF16_NHWC, "bf16 NHWC", 2, torch.bfloat16)):
+            o = torch.empty((B, rb), dtype=dt, device=DEV)
+            us = timeit(lambda: _lib.call("xb_gather_obs", _lib.ptr(src_obs), _lib.ptr(idx), B, H, W, C, _lib.ptr(o), fmt), R)
+            add(entry(f"K3 xb_gather_obs ({name})", "8192 rows x 28224 px", us, B * rb * (1 + w) + 8 * B, hbm))
+            del o
+        del src_obs, dst
+        for slots, Bs in ((256 * 128, 8192), (1 << 24, 1 << 22)):
+            F = 5
+            fields = torch.randn((F, slots), device=DEV)
+            idx = torch.randint(0, slots, (Bs,), device=DEV, generator=g)
+            o = torch.empty((F, Bs), device=DEV)
+            stats, scratch = torch.zeros(2, device=DEV), _lib.scratch(DEV)
+            us = timeit(lambda: _lib.call("xb_gather_scalars", _lib.ptr(fields), slots, _lib.ptr(idx), Bs, F, _lib.ptr(o),
+                                          4, _lib.ptr(stats), _lib.ptr(scratch)), R)
+            add(entry("K3 xb_gather_scalars (+adv norm, 2 launches)", f"{Bs} of {slots} slots x 5 fields", us,
+                      Bs * (8 + 4 * F * 2 + 8), hbm))
+
+    if want("k4"):
+        for B in (8192, 1 << 22):
+            A = 4
+            lg, v = torch.randn((B, A), device=DEV), torch.randn(B, device=DEV)
+            act = torch.randint(0, A, (B,), device=DEV).float()
+            old, adv, ret = torch.randn(B, device=DEV) * 0.1 - 1.4, torch.randn(B, device=DEV), torch.randn(B, device=DEV)
+            dl, dv = torch.empty((B, A), device=DEV), torch.empty(B, device=DEV)
+            stats, scratch = torch.zeros(8, device=DEV), _lib.scratch(DEV)
+            us = timeit(lambda: _lib.call("xb_ppo_loss_fwd_bwd", _lib.ptr(lg), _lib.ptr(v), _lib.ptr(act), _lib.ptr(old),
+                                          _lib.ptr(adv), _lib.ptr(ret), B, A, B, 0.2, 0.25, 0.01, _lib.ptr(dl), _lib.ptr(dv),
+                                          _lib.ptr(stats), _lib.ptr(scratch)), R)
+            add(entry("K4 xb_ppo_loss_fwd_bwd", f"B={B}, A=4", us, B * 56, hbm))
+
+    if want("k5"):
+        N, cap, B = 16, 65536, 512
+        k = B // N
+        st = torch.rand((N, 2 * cap), device=DEV)
+        mt = torch.rand((N, 2 * cap), device=DEV)
+        mp = torch.ones(N, device=DEV)
+        u = torch.rand((N, k), device=DEV)
+        so, fo = torch.empty((N, k), dtype=torch.int64, device=DEV), torch.empty(N * k, dtype=torch.int64, device=DEV)
+        wo = torch.empty((N, k), dtype=torch.float64, device=DEV)
+        lvl = cap // 2
+        while lvl >= 1:
+            st[:, lvl:2 * lvl] = st[:, 2 * lvl:4 * lvl:2] + st[:, 2 * lvl + 1:4 * lvl:2]
+            lvl //= 2
+        us = timeit(lambda: _lib.call("xb_per_sample", _lib.ptr(st), _lib.ptr(mt), _lib.ptr(u), N, cap, cap, k, cap, 0.01,
+                                      _lib.ptr(so), _lib.ptr(fo), _lib.ptr(wo)), R, flush=False)
+        add(entry("K5 xb_per_sample (L2-resident trees)", "16 envs x 65536 leaves, B=512", us, B * (17 * 4 + 24), hbm))
+        pr = torch.rand(B, device=DEV)
+        us = timeit(lambda: _lib.call("xb_per_update", _lib.ptr(st), _lib.ptr(mt), _lib.ptr(mp), _lib.ptr(so), _lib.ptr(pr),
+                                      N, cap, k, 0.5), R, flush=False)
+        add(entry("K5 xb_per_update", "16 envs x 65536 leaves, B=512", us, B * 2 * 16 * 12, hbm))
+        us = timeit(lambda: _lib.call("xb_per_insert", _lib.ptr(st), _lib.ptr(mt), _lib.ptr(mp), N, cap, 123, 0.5), R, flush=False)
+        add(entry("K5 xb_per_insert", "16 envs", us, N * 2 * 16 * 12, hbm))
+
+    if want("k6"):
+        for B in (512, 1 << 22):
+            A = 6
+            qe, qn = torch.randn((B, A), device=DEV), torch.randn((B, A), device=DEV)
+            act = torch.randint(0, A, (B,), device=DEV).float()
+            rew, ter = torch.randn(B, device=DEV), (torch.rand(B, device=DEV) < 0.1).float()
+            dq, td = torch.empty((B, A), device=DEV), torch.empty(B, device=DEV)
+            stats, scratch = torch.zeros(4, device=DEV), _lib.scratch(DEV)
+            us = timeit(lambda: _lib.call("xb_dqn_td_fwd_bwd", _lib.ptr(qe), _lib.ptr(qn), _lib.ptr(act), _lib.ptr(rew),
+                                          _lib.ptr(ter), B, A, B, 0.99, _lib.ptr(dq), _lib.ptr(td), _lib.ptr(stats),
+                                          _lib.ptr(scratch)), R)
+            add(entry("K6 xb_dqn_td_fwd_bwd", f"B={B}, A=6", us, B * ((2 * A + 3) * 4 + (A + 1) * 4), hbm))
+
+    if want("k7"):
+        for n in (3358887, 100_000_000):
+            n = (n + 31) // 32 * 32
+            p, gr = torch.randn(n, device=DEV), torch.randn(n, device=DEV)
+            m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+            hyper, norm, scratch = torch.tensor([1e-4, 0.03, 0, 0], device=DEV), torch.zeros(1, device=DEV), _lib.scratch(DEV)
+            us = timeit(lambda: _lib.call("xb_grad_sumsq", _lib.ptr(gr), n, 1.0, _lib.ptr(norm), _lib.ptr(scratch)), R)
+            add(entry("K7 xb_grad_sumsq", f"n={n}", us, 4 * n, hbm))
+            us = timeit(lambda: _lib.call("xb_adam_step", _lib.ptr(p), _lib.ptr(gr), _lib.ptr(m), _lib.ptr(v), n, _lib.ptr(hyper),
+                                          0.9, 0.999, 1e-5, 0.5, _lib.ptr(norm), 1.0, 0), R)
+            add(entry("K7 xb_adam_step", f"n={n}", us, 28 * n, hbm))
+            del p, gr, m, v
+
+    if want("k9"):
+        from xuance_b200.torch.rl_models import QMIX_Mixer
+        n, S, H = 5, 98, 32
+        mixer = QMIX_Mixer(S, 32, 32, n, "cuda:0")
+        for Rr in (1920, 245760):
+            q, w1 = torch.randn((Rr, n), device=DEV), torch.randn((Rr, n * H), device=DEV)
+            b1, w2, b2 = torch.randn((Rr, H), device=DEV), torch.randn((Rr, H), device=DEV), torch.randn(Rr, device=DEV)
+            y = torch.empty(Rr, device=DEV)
+            us = timeit(lambda: _lib.call("xb_qmix_mix_fwd", _lib.ptr(q), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2),
+                                          Rr, n, H, _lib.ptr(y)), R)
+            add(entry("K9 xb_qmix_mix_fwd (epilogue only)", f"{Rr} rows", us, Rr * (n * H + 2 * H + n + 2) * 4, hbm))
+            dy = torch.randn(Rr, device=DEV)
+            dq, dw1, db1, dw2 = torch.empty_like(q), torch.empty_like(w1), torch.empty_like(b1), torch.empty_like(w2)
+            us = timeit(lambda: _lib.call("xb_qmix_mix_bwd", _lib.ptr(dy), _lib.ptr(q), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2),
+                                          Rr, n, H, _lib.ptr(dq), _lib.ptr(dw1), _lib.ptr(db1), _lib.ptr(dw2)), R)
+            add(entry("K9 xb_qmix_mix_bwd", f"{Rr} rows", us, Rr * ((n * H + 2 * H + n + 1) * 4 + (n * H + 2 * H + n) * 4), hbm))
+            st = torch.randn((Rr, S), device=DEV)
+            flops = Rr * 2.0 * (S * 128 + 32 * (n * H + H + 1))
+            with torch.no_grad():
+                mixer.use_tensor_core_forward = True
+                us_tc = timeit(lambda: mixer(q, st), R)
+                mixer.use_tensor_core_forward = False
+                us_lib = timeit(lambda: mixer(q, st), R)
+            e = entry("K9-TC xb_qmix_mix_fused_fwd (tcgen05, incl. torch.cat of weights)", f"{Rr} rows, S=98, n=5", us_tc,
+                      Rr * (S + n + 1) * 4, hbm, flops, tpk)
+            e["vs_cublas_plus_epilogue_us"] = round(us_lib, 2)
+            add(e)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -26,11 +26,17 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const float *__restrict__
         float z[A_MAX];
         const float *zr = logits + b * A;
         float m = -INFINITY;
+        if (A_MAX == 4 && A == 4) {  // the BASELINE action count: one 16-byte load per row
+            const float4 z4 = *reinterpret_cast<const float4 *>(zr);
+            z[0] = z4.x, z[1] = z4.y, z[2] = z4.z, z[3] = z4.w;
+            m = fmaxf(fmaxf(z4.x, z4.y), fmaxf(z4.z, z4.w));
+        } else {
 #pragma unroll
-        for (int i = 0; i < A_MAX; ++i) {
-            if (i < A) {
-                z[i] = zr[i];
-                m = fmaxf(m, z[i]);
+            for (int i = 0; i < A_MAX; ++i) {
+                if (i < A) {
+                    z[i] = zr[i];
+                    m = fmaxf(m, z[i]);
+                }
             }
         }
         float se = 0.f;
@@ -63,13 +69,21 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const float *__restrict__
         const float d_logp = d_ratio * ratio;  // d ratio / d logp = ratio
         const float dent = -ent_coef * inv_bt;  // d loss / d entropy_b
         float *dz = dlogits + b * A;
+        float gz[A_MAX];
 #pragma unroll
         for (int i = 0; i < A_MAX; ++i) {
             if (i < A) {
                 float g = d_logp * ((i == a ? 1.f : 0.f) - p[i]);  // d logp_a / d z_i
                 g += dent * (-p[i] * (lp[i] + ent));               // d H / d z_i
-                dz[i] = g;
+                gz[i] = g;
             }
+        }
+        if (A_MAX == 4 && A == 4) {
+            *reinterpret_cast<float4 *>(dz) = make_float4(gz[0], gz[1], gz[2], gz[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < A_MAX; ++i)
+                if (i < A) dz[i] = gz[i];
         }
         const float v = value[b], r = ret[b];
         const float dv = v - r;
@@ -106,6 +120,7 @@ extern "C" int xb_ppo_loss_fwd_bwd(const float *logits, const float *value, cons
     int64_t want = (B + 255) / 256;
     int grid = (int)(want < XB_MAX_PARTIALS ? want : XB_MAX_PARTIALS);
     const float inv_bt = 1.0f / (float)B_total;
+    if (A == 4 && (!xb_aligned(logits, 16) || !xb_aligned(dlogits, 16))) return XB_EALIGN;
 #define XB_PPO(AM)                                                                                                   \
     ppo_loss_kernel<AM><<<grid, 256, 0, s>>>(logits, value, actions, old_logp, adv, ret, B, A, inv_bt, clip_range,   \
                                               vf_coef, ent_coef, dlogits, dvalue, stats, scratch)

@@ -168,11 +168,115 @@ __global__ void __launch_bounds__(256) qmix_mix_bwd_kernel(const float *__restri
     }
 }
 
+// ---- H == 32 fast path: 8 lanes per row (4 rows per warp), each lane owns 4 hidden units through 16-byte loads
+__device__ __forceinline__ float4 abs4(float4 v) { return make_float4(fabsf(v.x), fabsf(v.y), fabsf(v.z), fabsf(v.w)); }
+__device__ __forceinline__ float sum8(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+__device__ __forceinline__ float sgnf(float v) { return (float)((v > 0.f) - (v < 0.f)); }
+
+template <int N_MAX>
+__global__ void __launch_bounds__(256) qmix_mix_fwd_h32_kernel(const float *__restrict__ q, const float *__restrict__ w1,
+                                                               const float *__restrict__ b1, const float *__restrict__ w2,
+                                                               const float *__restrict__ b2, int64_t R, int n,
+                                                               float *__restrict__ q_tot) {
+    const int sub = threadIdx.x & 7;
+    const int64_t grp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int64_t ngrp = ((int64_t)gridDim.x * blockDim.x) >> 3;
+    const int64_t Rp = (R + 3) & ~(int64_t)3;  // whole warps stay converged (4 rows per warp)
+    for (int64_t r = grp0; r < Rp; r += ngrp) {
+        const bool live = r < R;
+        const int64_t rr = live ? r : R - 1;
+        float4 pre = *reinterpret_cast<const float4 *>(b1 + rr * 32 + sub * 4);
+#pragma unroll
+        for (int i = 0; i < N_MAX; ++i) {
+            if (i < n) {
+                const float qi = q[rr * n + i];
+                const float4 w = abs4(*reinterpret_cast<const float4 *>(w1 + (rr * n + i) * 32 + sub * 4));
+                pre.x += qi * w.x, pre.y += qi * w.y, pre.z += qi * w.z, pre.w += qi * w.w;
+            }
+        }
+        const float4 w2v = abs4(*reinterpret_cast<const float4 *>(w2 + rr * 32 + sub * 4));
+        float part = elu1(pre.x) * w2v.x + elu1(pre.y) * w2v.y + elu1(pre.z) * w2v.z + elu1(pre.w) * w2v.w;
+        part = sum8(part);
+        if (live && sub == 0) q_tot[r] = part + b2[r];
+    }
+}
+
+template <int N_MAX>
+__global__ void __launch_bounds__(256) qmix_mix_bwd_h32_kernel(const float *__restrict__ dy, const float *__restrict__ q,
+                                                               const float *__restrict__ w1, const float *__restrict__ b1,
+                                                               const float *__restrict__ w2, int64_t R, int n,
+                                                               float *__restrict__ dq, float *__restrict__ dw1,
+                                                               float *__restrict__ db1, float *__restrict__ dw2) {
+    const int sub = threadIdx.x & 7;
+    const int64_t grp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int64_t ngrp = ((int64_t)gridDim.x * blockDim.x) >> 3;
+    const int64_t Rp = (R + 3) & ~(int64_t)3;
+    for (int64_t r = grp0; r < Rp; r += ngrp) {
+        const bool live = r < R;
+        const int64_t rr = live ? r : R - 1;
+        const float g = dy[rr];
+        float qv[N_MAX];
+        float4 wv[N_MAX];
+        float4 pre = *reinterpret_cast<const float4 *>(b1 + rr * 32 + sub * 4);
+#pragma unroll
+        for (int i = 0; i < N_MAX; ++i) {
+            if (i < n) {
+                qv[i] = q[rr * n + i];
+                wv[i] = *reinterpret_cast<const float4 *>(w1 + (rr * n + i) * 32 + sub * 4);
+                pre.x += qv[i] * fabsf(wv[i].x), pre.y += qv[i] * fabsf(wv[i].y);
+                pre.z += qv[i] * fabsf(wv[i].z), pre.w += qv[i] * fabsf(wv[i].w);
+            }
+        }
+        const float4 w2v = *reinterpret_cast<const float4 *>(w2 + rr * 32 + sub * 4);
+        const float4 h = make_float4(elu1(pre.x), elu1(pre.y), elu1(pre.z), elu1(pre.w));
+        const float4 dpre = make_float4(g * fabsf(w2v.x) * (pre.x > 0.f ? 1.f : h.x + 1.f),
+                                        g * fabsf(w2v.y) * (pre.y > 0.f ? 1.f : h.y + 1.f),
+                                        g * fabsf(w2v.z) * (pre.z > 0.f ? 1.f : h.z + 1.f),
+                                        g * fabsf(w2v.w) * (pre.w > 0.f ? 1.f : h.w + 1.f));
+        if (live) {
+            *reinterpret_cast<float4 *>(dw2 + r * 32 + sub * 4) =
+                make_float4(g * h.x * sgnf(w2v.x), g * h.y * sgnf(w2v.y), g * h.z * sgnf(w2v.z), g * h.w * sgnf(w2v.w));
+            *reinterpret_cast<float4 *>(db1 + r * 32 + sub * 4) = dpre;
+        }
+#pragma unroll
+        for (int i = 0; i < N_MAX; ++i) {
+            if (i < n) {
+                if (live)
+                    *reinterpret_cast<float4 *>(dw1 + (r * n + i) * 32 + sub * 4) =
+                        make_float4(dpre.x * qv[i] * sgnf(wv[i].x), dpre.y * qv[i] * sgnf(wv[i].y),
+                                    dpre.z * qv[i] * sgnf(wv[i].z), dpre.w * qv[i] * sgnf(wv[i].w));
+                float s = dpre.x * fabsf(wv[i].x) + dpre.y * fabsf(wv[i].y) + dpre.z * fabsf(wv[i].z) +
+                          dpre.w * fabsf(wv[i].w);
+                s = sum8(s);
+                if (live && sub == 0) dq[r * n + i] = s;
+            }
+        }
+    }
+}
+
+static inline bool mix_fast_ok(int H, int n, const void *a, const void *b, const void *c, const void *d = nullptr,
+                               const void *e = nullptr, const void *f = nullptr) {
+    return H == 32 && n <= 8 && xb_aligned(a, 16) && xb_aligned(b, 16) && xb_aligned(c, 16) &&
+           (!d || xb_aligned(d, 16)) && (!e || xb_aligned(e, 16)) && (!f || xb_aligned(f, 16));
+}
+
 extern "C" int xb_qmix_mix_fwd(const float *q, const float *w1_raw, const float *b1, const float *w2_raw,
                                const float *b2, int64_t R, int n, int H, float *q_tot, void *stream) {
     if (!q || !w1_raw || !b1 || !w2_raw || !b2 || !q_tot || R <= 0 || n <= 0 || H <= 0) return XB_EINVAL;
     if (n > 16) return XB_ERANGE;
-    int64_t want = (R * 32 + 255) / 256, cap = (int64_t)xb_sm_count() * 8;
+    int64_t cap = (int64_t)xb_sm_count() * 8;
+    if (mix_fast_ok(H, n, w1_raw, b1, w2_raw)) {
+        int64_t want = (R * 8 + 255) / 256;
+        qmix_mix_fwd_h32_kernel<8><<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(q, w1_raw, b1, w2_raw,
+                                                                                                  b2, R, n, q_tot);
+        return xb_launch_status();
+    }
+    int64_t want = (R * 32 + 255) / 256;
     qmix_mix_fwd_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(q, w1_raw, b1, w2_raw, b2, R, n,
                                                                                         H, q_tot);
     return xb_launch_status();
@@ -184,7 +288,14 @@ extern "C" int xb_qmix_mix_bwd(const float *dq_tot, const float *q, const float 
     if (!dq_tot || !q || !w1_raw || !b1 || !w2_raw || !dq || !dw1_raw || !db1 || !dw2_raw) return XB_EINVAL;
     if (R <= 0 || n <= 0 || H <= 0) return XB_EINVAL;
     if (n > 16) return XB_ERANGE;
-    int64_t want = (R * 32 + 255) / 256, cap = (int64_t)xb_sm_count() * 8;
+    int64_t cap = (int64_t)xb_sm_count() * 8;
+    if (mix_fast_ok(H, n, w1_raw, b1, w2_raw, dw1_raw, db1, dw2_raw)) {
+        int64_t want = (R * 8 + 255) / 256;
+        qmix_mix_bwd_h32_kernel<8><<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+            dq_tot, q, w1_raw, b1, w2_raw, R, n, dq, dw1_raw, db1, dw2_raw);
+        return xb_launch_status();
+    }
+    int64_t want = (R * 32 + 255) / 256;
     qmix_mix_bwd_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(dq_tot, q, w1_raw, b1, w2_raw, R,
                                                                                         n, H, dq, dw1_raw, db1, dw2_raw);
     return xb_launch_status();

@@ -11,8 +11,8 @@
 // the CTA then loops over its tiles (persistent grid = SM count).
 //
 // Numerics: the reference computes these layers in fp32.  The tensor pipe takes bf16 here, so every fp32 operand is
-// split x = hi + lo (two bf16 values, |x - hi - lo| <= 2^-17 |x|) and each product is the sum of the four MMAs
-// hi.hi + hi.lo + lo.hi + lo.lo accumulated in fp32 in TMEM: relative error ~1e-5 per layer (a plain bf16 or TF32
+// split x = hi + lo (two bf16 values, |x - hi - lo| <= 2^-17 |x|) and each product is the sum of the three MMAs
+// hi.hi + hi.lo + lo.hi (lo.lo ~ 2^-18 is below the split residual) accumulated in fp32 in TMEM: relative error ~1e-5 per layer (a plain bf16 or TF32
 // pass would be ~4e-3 / ~5e-4).  tests/test_gpu_qmix.py pins it against the fp32 oracle.
 #include "xb_common.cuh"
 
@@ -81,22 +81,36 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// stage a [rows x K] fp32 row-major matrix (leading dimension ld) as hi/lo bf16 canonical operands, zero padded
+__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+// split 8 consecutive-k floats of one row and store them as ONE 16-byte core-matrix row each (hi, lo)
+__device__ __forceinline__ void store_unit(const float (&x)[8], int r, int k0, int KP, uint8_t *hi, uint8_t *lo) {
+    __nv_bfloat16 h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split_bf16(x[i], h[i], l[i]);
+    const uint32_t off = canon_off(r, k0, KP);
+    *reinterpret_cast<uint4 *>(hi + off) = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
+    *reinterpret_cast<uint4 *>(lo + off) = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+}
+
+// stage a [rows x K] fp32 row-major matrix (leading dimension ld) as hi/lo bf16 canonical operands, zero padded;
+// one thread-iteration = 8 consecutive k of one row (two 16-byte shared-memory stores)
 __device__ __forceinline__ void stage_operand(const float *__restrict__ g, int rows_valid, int rows_total, int K, int ld,
                                               int KP, uint8_t *hi, uint8_t *lo) {
-    const int total = rows_total * KP;
+    const int upr = KP >> 3;  // units per row
+    const int total = rows_total * upr;
     for (int e = threadIdx.x; e < total; e += blockDim.x) {
-        const int r = e / KP, k = e - r * KP;
-        float x = (r < rows_valid && k < K) ? g[(int64_t)r * ld + k] : 0.f;
-        __nv_bfloat16 h, l;
-        split_bf16(x, h, l);
-        const uint32_t off = canon_off(r, k, KP);
-        *reinterpret_cast<__nv_bfloat16 *>(hi + off) = h;
-        *reinterpret_cast<__nv_bfloat16 *>(lo + off) = l;
+        const int r = e / upr, k0 = (e - r * upr) << 3;
+        float x[8];
+        const float *src = g + (int64_t)r * ld + k0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = (r < rows_valid && k0 + i < K) ? src[i] : 0.f;
+        store_unit(x, r, k0, KP, hi, lo);
     }
 }
 
-// issue the four split products of one GEMM: D[128 x N] (+)= A[128 x KP] . B[N x KP]^T
+// issue the three split products of one GEMM: D[128 x N] (+)= A[128 x KP] . B[N x KP]^T
 __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, const uint8_t *a_hi, const uint8_t *a_lo,
                                            const uint8_t *b_hi, const uint8_t *b_lo, int KP, int N) {
     const uint32_t idesc = make_idesc(TC_ROWS, N);
@@ -104,7 +118,7 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, const uint8_t *a_hi,
     const uint8_t *bs[2] = {b_hi, b_lo};
     uint32_t acc = 0;
     for (int pa = 0; pa < 2; ++pa)
-        for (int pb = 0; pb < 2; ++pb)
+        for (int pb = 0; pb < 2 - pa; ++pb)   // (hi,hi) (hi,lo) (lo,hi); lo.lo ~ 2^-18 relative is dropped
             for (int ks = 0; ks < KP / 16; ++ks) {  // one MMA = K 16 = two core matrices = 256 B along K
                 const uint64_t da = make_desc(smem_u32(as[pa]) + ks * 256, KP);
                 const uint64_t db = make_desc(smem_u32(bs[pb]) + ks * 256, KP);
@@ -198,13 +212,11 @@ __global__ void __launch_bounds__(128, 1) qmix_mix_tc_kernel(TcParams p) {
             for (int g = 0; g < 3; ++g) {
                 tmem_ld32(lane_addr + COL_Z + blocks[g], z);
 #pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    float v = fmaxf(z[k] + s_bias1[blocks[g] + k], 0.f);
-                    __nv_bfloat16 h, l;
-                    split_bf16(v, h, l);
-                    const uint32_t off = canon_off(tid, k, TC_HH);
-                    *reinterpret_cast<__nv_bfloat16 *>(A2h[g] + off) = h;
-                    *reinterpret_cast<__nv_bfloat16 *>(A2l[g] + off) = l;
+                for (int k0 = 0; k0 < 32; k0 += 8) {
+                    float x[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) x[i] = fmaxf(z[k0 + i] + s_bias1[blocks[g] + k0 + i], 0.f);
+                    store_unit(x, tid, k0, TC_HH, A2h[g], A2l[g]);
                 }
             }
             tmem_ld32(lane_addr + COL_Z + 32, z);

@@ -78,7 +78,7 @@ __device__ __forceinline__ float shfl_down_t<float>(float v, int d) { return __s
 template <>
 __device__ __forceinline__ double shfl_down_t<double>(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
 
-template <typename R, bool GAE, int V>
+template <typename R, bool GAE, int V, bool VEC>
 __global__ void __launch_bounds__(128) gae_scan_kernel(const float *__restrict__ rew, const float *__restrict__ val,
                                                        const float *__restrict__ term,
                                                        const uint8_t *__restrict__ seg_end,
@@ -97,19 +97,39 @@ __global__ void __launch_bounds__(128) gae_scan_kernel(const float *__restrict__
         const int t0 = hi - TILE + lane * V;  // this lane's first step
         float r[V], v[V + 1], d[V], bs[V];
         uint8_t se[V];
+        if (V == 4 && VEC && t0 + V <= T) {  // 16-byte loads: T % 4 == 0 and 16-B aligned rows (checked on the host)
+            const float4 r4 = *reinterpret_cast<const float4 *>(rew + base + t0);
+            const float4 v4 = *reinterpret_cast<const float4 *>(val + base + t0);
+            const float4 d4 = *reinterpret_cast<const float4 *>(term + base + t0);
+            const uchar4 s4 = *reinterpret_cast<const uchar4 *>(seg_end + base + t0);
+            r[0] = r4.x, r[1] = r4.y, r[2] = r4.z, r[3] = r4.w;
+            v[0] = v4.x, v[1] = v4.y, v[2] = v4.z, v[3] = v4.w;
+            d[0] = d4.x, d[1] = d4.y, d[2] = d4.z, d[3] = d4.w;
+            se[0] = s4.x, se[1] = s4.y, se[2] = s4.z, se[3] = s4.w;
+            if (s4.x | s4.y | s4.z | s4.w) {
+                const float4 b4 = *reinterpret_cast<const float4 *>(boot + base + t0);
+                bs[0] = b4.x, bs[1] = b4.y, bs[2] = b4.z, bs[3] = b4.w;
+            } else {
+                bs[0] = bs[1] = bs[2] = bs[3] = 0.f;
+            }
+        } else {
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            int t = t0 + j;
-            bool in = t < T;
-            r[j] = in ? rew[base + t] : 0.f;
-            v[j] = in ? val[base + t] : 0.f;
-            d[j] = in ? term[base + t] : 0.f;
-            se[j] = in ? seg_end[base + t] : (uint8_t)1;
-            bs[j] = (in && se[j]) ? boot[base + t] : 0.f;
+            for (int j = 0; j < V; ++j) {
+                int t = t0 + j;
+                bool in = t < T;
+                r[j] = in ? rew[base + t] : 0.f;
+                v[j] = in ? val[base + t] : 0.f;
+                d[j] = in ? term[base + t] : 0.f;
+                se[j] = in ? seg_end[base + t] : (uint8_t)1;
+                bs[j] = (in && se[j]) ? boot[base + t] : 0.f;
+            }
         }
         {
-            int t = t0 + V;  // V_{t+1} of the lane's last step
-            v[V] = (t < T) ? val[base + t] : 0.f;
+            // V_{t+1} of the lane's last step = the next lane's first value; lane 31 reads it from memory
+            float nxt = __shfl_down_sync(0xffffffffu, v[0], 1);
+            int t = t0 + V;
+            if (lane == 31) nxt = (t < T) ? val[base + t] : 0.f;
+            v[V] = nxt;
         }
         // local suffix maps, serial from the lane's last step to its first
         Affine<R> loc[V];
@@ -143,23 +163,33 @@ __global__ void __launch_bounds__(128) gae_scan_kernel(const float *__restrict__
         Affine<R> excl = {shfl_down_t<R>(inc.a, 1), shfl_down_t<R>(inc.b, 1)};
         if (lane == 31) excl = {(R)1, (R)0};
         const R x_in = excl.a * carry + excl.b;  // value entering this lane from the right
+        float a_o[V], r_o[V];
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-            int t = t0 + j;
-            if (t < T) {
-                R y = loc[j].a * x_in + loc[j].b;
-                float a_out, r_out;
-                if (GAE) {
-                    a_out = (float)y;
-                    r_out = a_out + v[j];
-                } else {
-                    r_out = (float)y;
-                    a_out = tdres[j];
-                }
-                bool ok = t < cov;
-                adv[base + t] = ok ? a_out : 0.f;
-                ret[base + t] = ok ? r_out : 0.f;
+            const int t = t0 + j;
+            R y = loc[j].a * x_in + loc[j].b;
+            float a_out, r_out;
+            if (GAE) {
+                a_out = (float)y;
+                r_out = a_out + v[j];
+            } else {
+                r_out = (float)y;
+                a_out = tdres[j];
             }
+            const bool ok = t < cov;
+            a_o[j] = ok ? a_out : 0.f;
+            r_o[j] = ok ? r_out : 0.f;
+        }
+        if (V == 4 && VEC && t0 + V <= T) {
+            *reinterpret_cast<float4 *>(adv + base + t0) = make_float4(a_o[0], a_o[1], a_o[2], a_o[3]);
+            *reinterpret_cast<float4 *>(ret + base + t0) = make_float4(r_o[0], r_o[1], r_o[2], r_o[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+                if (t0 + j < T) {
+                    adv[base + t0 + j] = a_o[j];
+                    ret[base + t0 + j] = r_o[j];
+                }
         }
         // carry for the next (earlier) tile = value at this tile's first step = lane 0's y at j=0
         R first = loc[0].a * x_in + loc[0].b;
@@ -175,12 +205,16 @@ extern "C" int xb_gae_scan(const float *rew, const float *val, const float *term
     const int warps_per_block = 4;
     dim3 grid((N + warps_per_block - 1) / warps_per_block), block(32 * warps_per_block);
     cudaStream_t s = (cudaStream_t)stream;
-    if (use_gae)
-        gae_scan_kernel<float, true, 4><<<grid, block, 0, s>>>(rew, val, term, seg_end, bootstrap, covered, adv, ret,
-                                                               N, T, gamma, lam);
-    else
-        gae_scan_kernel<double, false, 4><<<grid, block, 0, s>>>(rew, val, term, seg_end, bootstrap, covered, adv,
-                                                                 ret, N, T, gamma, lam);
+    const bool vec = (T % 4 == 0) && xb_aligned(rew, 16) && xb_aligned(val, 16) && xb_aligned(term, 16) &&
+                     xb_aligned(bootstrap, 16) && xb_aligned(adv, 16) && xb_aligned(ret, 16) && xb_aligned(seg_end, 4);
+#define XB_GAE(RT, G, VECF) \
+    gae_scan_kernel<RT, G, 4, VECF><<<grid, block, 0, s>>>(rew, val, term, seg_end, bootstrap, covered, adv, ret, N, T, gamma, lam)
+    if (use_gae) {
+        if (vec) XB_GAE(float, true, true); else XB_GAE(float, true, false);
+    } else {
+        if (vec) XB_GAE(double, false, true); else XB_GAE(double, false, false);
+    }
+#undef XB_GAE
     return xb_launch_status();
 }
 
