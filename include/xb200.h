@@ -152,15 +152,16 @@ int xb_qmix_td(const float *q_tot, const float *q_tot_next, const float *rewards
                float *dq_tot, float *stats, double *scratch, void *stream);
 
 /* Tensor-core forward of the whole mixer (hypernet GEMMs + epilogue in ONE kernel; tcgen05.mma with TMEM
- * accumulators, bf16 hi/lo split operands, 4 MMAs per product, fp32 accumulate): q_tot[R] from states[R,S], q[R,n]
- * and the raw Linear parameters of QMIX_Mixer (q_mix_head.py:52-64): w1cat[128,S] = rows of hyper_w_1[0] | hyper_b_1 |
- * hyper_w_2[0] | hyper_b_2[0] (bias1[128] likewise), wb1[n*32,32] = hyper_w_1[2], wb2[32,32] = hyper_w_2[2],
- * wb2c[1,32] = hyper_b_2[2].  Requires dim_hidden = dim_hypernet_hidden = 32, n <= 8, S <= 160 (else XB_ERANGE and the
+ * accumulators, bf16 hi/lo split operands, 3 MMAs per product, fp32 accumulate): q_tot[R] from states[R,S], q[R,n]
+ * and the raw Linear parameters of QMIX_Mixer (q_mix_head.py:52-64): w_l1[4] / b_l1[4] are HOST arrays of 4 device
+ * pointers to the first-layer weights [32,S] / biases [32] of hyper_w_1, hyper_b_1, hyper_w_2, hyper_b_2 (in that
+ * order), wb1[n*32,32] = hyper_w_1[2], wb2[32,32] = hyper_w_2[2], wb2c[1,32] = hyper_b_2[2].  Requires dim_hidden =
+ * dim_hypernet_hidden = 32, n <= 8 and the staged operands to fit 220 KB of shared memory (else XB_ERANGE and the
  * caller uses cuBLAS + xb_qmix_mix_fwd).  Forward only: used for the target mixer / inference. */
-int xb_qmix_mix_fused_fwd(const float *states, const float *q, const float *w1cat, const float *bias1,
-                          const float *wb1, const float *bias_wb1, const float *wb2, const float *bias_wb2,
-                          const float *wb2c, const float *bias_wb2c, int64_t R, int S, int n, int H, int HH,
-                          float *q_tot, void *stream);
+int xb_qmix_mix_fused_fwd(const float *states, const float *q, const float *const *w_l1_host,
+                          const float *const *b_l1_host, const float *wb1, const float *bias_wb1, const float *wb2,
+                          const float *bias_wb2, const float *wb2c, const float *bias_wb2c, int64_t R, int S, int n,
+                          int H, int HH, float *q_tot, void *stream);
 
 /* ---------------------------------------------------------------- K8: SAC loss stages ----------------
  * Replaces the elementwise/reduction parts of SAC_Learner.update (xuance/torch/learners/policy_gradient/

@@ -129,7 +129,7 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, const uint8_t *a_hi,
 
 struct TcParams {
     const float *states, *q;                 // [R,S], [R,n]
-    const float *w1cat, *bias1;              // [128,S], [128]
+    const float *w_l1[4], *b_l1[4];          // first layers of hyper_w_1 | hyper_b_1 | hyper_w_2 | hyper_b_2: [32,S], [32]
     const float *wb1, *bias_wb1;             // [n*32,32], [n*32]
     const float *wb2, *bias_wb2;             // [32,32], [32]
     const float *wb2c, *bias_wb2c;           // [1,32], [1]
@@ -171,11 +171,13 @@ __global__ void __launch_bounds__(128, 1) qmix_mix_tc_kernel(TcParams p) {
                      "r"(TC_TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    stage_operand(p.w1cat, TC_N1, TC_N1, S, S, KP1, B1h, B1l);
+    for (int blk = 0; blk < 4; ++blk)   // rows 32*blk .. 32*blk+31 of the concatenated first-layer weight
+        stage_operand(p.w_l1[blk], TC_HH, TC_HH, S, S, KP1, B1h + (size_t)blk * (TC_HH / 8) * (KP1 / 8) * 128,
+                      B1l + (size_t)blk * (TC_HH / 8) * (KP1 / 8) * 128);
     stage_operand(p.wb1, N2A, N2A, TC_HH, TC_HH, TC_HH, B2ah, B2al);
     stage_operand(p.wb2, TC_HH, TC_HH, TC_HH, TC_HH, TC_HH, B2bh, B2bl);
     stage_operand(p.wb2c, 1, 16, TC_HH, TC_HH, TC_HH, B2ch, B2cl);
-    for (int i = tid; i < TC_N1; i += blockDim.x) s_bias1[i] = p.bias1[i];
+    for (int i = tid; i < TC_N1; i += blockDim.x) s_bias1[i] = p.b_l1[i >> 5][i & 31];
     for (int i = tid; i < N2A; i += blockDim.x) s_bias_wb1[i] = p.bias_wb1[i];
     if (tid < TC_HH) s_bias_wb2[tid] = p.bias_wb2[tid];
     if (tid == 0) s_bias_b2 = p.bias_wb2c[0];
@@ -268,12 +270,15 @@ __global__ void __launch_bounds__(128, 1) qmix_mix_tc_kernel(TcParams p) {
 
 }  // namespace
 
-extern "C" int xb_qmix_mix_fused_fwd(const float *states, const float *q, const float *w1cat, const float *bias1,
-                                     const float *wb1, const float *bias_wb1, const float *wb2, const float *bias_wb2,
-                                     const float *wb2c, const float *bias_wb2c, int64_t R, int S, int n, int H, int HH,
-                                     float *q_tot, void *stream) {
-    if (!states || !q || !w1cat || !bias1 || !wb1 || !bias_wb1 || !wb2 || !bias_wb2 || !wb2c || !bias_wb2c || !q_tot)
+extern "C" int xb_qmix_mix_fused_fwd(const float *states, const float *q, const float *const *w_l1,
+                                     const float *const *b_l1, const float *wb1, const float *bias_wb1,
+                                     const float *wb2, const float *bias_wb2, const float *wb2c,
+                                     const float *bias_wb2c, int64_t R, int S, int n, int H, int HH, float *q_tot,
+                                     void *stream) {
+    if (!states || !q || !w_l1 || !b_l1 || !wb1 || !bias_wb1 || !wb2 || !bias_wb2 || !wb2c || !bias_wb2c || !q_tot)
         return XB_EINVAL;
+    for (int i = 0; i < 4; ++i)
+        if (!w_l1[i] || !b_l1[i]) return XB_EINVAL;
     if (R <= 0 || S <= 0 || n <= 0) return XB_EINVAL;
     if (H != TC_HH || HH != TC_HH || n > 8 || S > 160) return XB_ERANGE;   // shapes of the shipped QMIX configs
     const int KP1 = (S + 15) & ~15;
@@ -285,7 +290,8 @@ extern "C" int xb_qmix_mix_fused_fwd(const float *states, const float *q, const 
         cudaFuncSetAttribute(qmix_mix_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         attr = true;
     }
-    TcParams p{states, q, w1cat, bias1, wb1, bias_wb1, wb2, bias_wb2, wb2c, bias_wb2c, q_tot, R, S, n};
+    TcParams p{states, q, {w_l1[0], w_l1[1], w_l1[2], w_l1[3]}, {b_l1[0], b_l1[1], b_l1[2], b_l1[3]},
+               wb1, bias_wb1, wb2, bias_wb2, wb2c, bias_wb2c, q_tot, R, S, n};
     int64_t tiles = (R + TC_ROWS - 1) / TC_ROWS;
     int grid = (int)(tiles < xb_sm_count() ? tiles : xb_sm_count());
     qmix_mix_tc_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(p);

@@ -126,28 +126,25 @@ class QMIX_Mixer(nn.Module):
     use_tensor_core_forward = True   # no-grad forwards (target mixer, inference) take the fused tcgen05 kernel
 
     def _fusable(self):
+        kp1 = (self.dim_state + 15) // 16 * 16
+        smem = 1024 * kp1 + 49152 + 4096 * self.n_agents + 6144          # operands staged by K9-TC (bytes)
         return (self.use_tensor_core_forward and self.dim_hidden == 32 and self.dim_hypernet_hidden == 32
-                and self.n_agents <= 8 and self.dim_state <= 160)
+                and self.n_agents <= 8 and smem <= 220 * 1024)
 
     def forward_fused(self, values_n, states):
         """Whole mixer in ONE tensor-core kernel (K9-TC, xb_qmix_mix_fused_fwd).  Forward only."""
         states = torch.as_tensor(states, dtype=torch.float32, device=self.device).reshape(-1, self.dim_state).contiguous()
         q = values_n.reshape(-1, self.n_agents).to(torch.float32).contiguous()
-        plist = [self.hyper_w_1[0].weight, self.hyper_b_1.weight, self.hyper_w_2[0].weight, self.hyper_b_2[0].weight,
-                 self.hyper_w_1[0].bias, self.hyper_b_1.bias, self.hyper_w_2[0].bias, self.hyper_b_2[0].bias]
-        key = tuple((t.data_ptr(), t._version) for t in plist)
-        if getattr(self, "_cat_key", None) != key:     # re-concatenate only when a parameter was written
-            self._w1cat = torch.cat([t.detach() for t in plist[:4]], dim=0).contiguous()
-            self._bias1 = torch.cat([t.detach() for t in plist[4:]], dim=0).contiguous()
-            self._cat_key = key
-        w1cat, bias1 = self._w1cat, self._bias1
+        import ctypes
+        l1 = [self.hyper_w_1[0], self.hyper_b_1, self.hyper_w_2[0], self.hyper_b_2[0]]
+        w_ptrs = (ctypes.c_void_p * 4)(*[_lib.ptr(m.weight.contiguous()) for m in l1])
+        b_ptrs = (ctypes.c_void_p * 4)(*[_lib.ptr(m.bias.contiguous()) for m in l1])
         R = q.shape[0]
         out = torch.empty(R, dtype=torch.float32, device=q.device)
-        keep = [self.hyper_w_1[2].weight.contiguous(), self.hyper_w_1[2].bias.contiguous(),
-                self.hyper_w_2[2].weight.contiguous(), self.hyper_w_2[2].bias.contiguous(),
-                self.hyper_b_2[2].weight.contiguous(), self.hyper_b_2[2].bias.contiguous()]
-        _lib.call("xb_qmix_mix_fused_fwd", _lib.ptr(states), _lib.ptr(q), _lib.ptr(w1cat), _lib.ptr(bias1),
-                  *[_lib.ptr(t) for t in keep], R, self.dim_state, self.n_agents, self.dim_hidden,
+        l2 = [self.hyper_w_1[2].weight, self.hyper_w_1[2].bias, self.hyper_w_2[2].weight, self.hyper_w_2[2].bias,
+              self.hyper_b_2[2].weight, self.hyper_b_2[2].bias]
+        _lib.call("xb_qmix_mix_fused_fwd", _lib.ptr(states), _lib.ptr(q), w_ptrs, b_ptrs,
+                  *[_lib.ptr(t.contiguous()) for t in l2], R, self.dim_state, self.n_agents, self.dim_hidden,
                   self.dim_hypernet_hidden, _lib.ptr(out))
         return out.view(-1, 1)
 
