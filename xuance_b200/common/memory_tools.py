@@ -302,8 +302,19 @@ class DummyOnPolicyBuffer(Buffer):
         F = len(self._names) - g0
         out = torch.empty((F, B), dtype=torch.float32, device=self.device)
         adv_field = (self._fid["advantages"] - g0) if self.use_advnorm else -1
+        import torch.distributed as dist
+        sharded = adv_field >= 0 and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         _lib.call("xb_gather_scalars", _lib.ptr(self._fields[g0]), self.n_envs * self.n_size, _lib.ptr(idx_t), B, F,
-                  _lib.ptr(out), adv_field, _lib.ptr(self._stats), _lib.ptr(self._scratch))
+                  _lib.ptr(out), -1 if sharded else adv_field, _lib.ptr(self._stats), _lib.ptr(self._scratch))
+        if sharded:
+            # this rank holds B of the B*world rows of the global minibatch: normalise with the GLOBAL mean / population
+            # std (memory_tools.py:281-282 applied to the whole minibatch) - one 3-double all-reduce
+            a = out[adv_field].double()
+            mom = torch.stack([a.sum(), (a * a).sum(), torch.tensor(float(B), dtype=torch.float64, device=self.device)])
+            dist.all_reduce(mom)
+            mean = mom[0] / mom[2]
+            std = (mom[1] / mom[2] - mean * mean).clamp_min(0).sqrt()
+            out[adv_field] = ((a - mean) / (std + 1e-8)).float()
         return out
 
     def _assemble(self, obs, idx_t, fields):

@@ -100,13 +100,25 @@ __device__ __forceinline__ void stage_operand(const float *__restrict__ g, int r
                                               int KP, uint8_t *hi, uint8_t *lo) {
     const int upr = KP >> 3;  // units per row
     const int total = rows_total * upr;
-    for (int e = threadIdx.x; e < total; e += blockDim.x) {
-        const int r = e / upr, k0 = (e - r * upr) << 3;
-        float x[8];
-        const float *src = g + (int64_t)r * ld + k0;
+    constexpr int U = 4;  // units in flight per thread: 32 independent 4-byte loads before the first use
+    for (int e0 = threadIdx.x; e0 < total; e0 += blockDim.x * U) {
+        float x[U][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = (r < rows_valid && k0 + i < K) ? src[i] : 0.f;
-        store_unit(x, r, k0, KP, hi, lo);
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * blockDim.x;
+            const int r = e / upr, k0 = (e - r * upr) << 3;
+            const float *src = g + (int64_t)r * ld + k0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[u][i] = (e < total && r < rows_valid && k0 + i < K) ? src[i] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * blockDim.x;
+            if (e < total) {
+                const int r = e / upr, k0 = (e - r * upr) << 3;
+                store_unit(x[u], r, k0, KP, hi, lo);
+            }
+        }
     }
 }
 
@@ -192,6 +204,10 @@ __global__ void __launch_bounds__(128, 1) qmix_mix_tc_kernel(TcParams p) {
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row0 = tile * TC_ROWS;
         const int rows_valid = (int)((p.R - row0) < TC_ROWS ? (p.R - row0) : TC_ROWS);
+        // ---- this row's agent utilities (latency hidden behind the staging + first GEMM)
+        float qv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) qv[i] = (i < n && tid < rows_valid) ? p.q[(row0 + tid) * n + i] : 0.f;
         // ---- stage X tile (split to bf16 hi/lo)
         stage_operand(p.states + row0 * S, rows_valid, TC_ROWS, S, S, KP1, A1h, A1l);
         fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -244,11 +260,14 @@ __global__ void __launch_bounds__(128, 1) qmix_mix_tc_kernel(TcParams p) {
 #pragma unroll
         for (int j = 0; j < TC_HH; ++j) pre[j] = b1v[j];
         float w[32];
-        for (int i = 0; i < n; ++i) {
-            tmem_ld32(lane_addr + COL_W1 + i * TC_HH, w);
-            const float qi = live ? p.q[(row0 + tid) * n + i] : 0.f;
 #pragma unroll
-            for (int j = 0; j < TC_HH; ++j) pre[j] += qi * fabsf(w[j] + s_bias_wb1[i * TC_HH + j]);
+        for (int i = 0; i < 8; ++i) {
+            if (i < n) {
+                tmem_ld32(lane_addr + COL_W1 + i * TC_HH, w);
+                const float qi = qv[i];
+#pragma unroll
+                for (int j = 0; j < TC_HH; ++j) pre[j] += qi * fabsf(w[j] + s_bias_wb1[i * TC_HH + j]);
+            }
         }
         tmem_ld32(lane_addr + COL_W2, w);
         float y = 0.f;
