@@ -125,8 +125,8 @@ def test_qmix_learner_matches_oracle(detach, double_q):
     agents_moved = any(not torch.equal(sp_[k].cpu(), QMIXModelOracle.__init__ and v) for k, v in []) if False else None
 
 
-@pytest.mark.parametrize("R,n,S", [(1920, 5, 98), (128, 5, 98), (1000, 8, 64), (77, 3, 17), (245760, 5, 98), (300, 2, 160)])
-def test_tensor_core_mixer_forward(R, n, S):
+@pytest.mark.parametrize("R,n,S,fusable", [(1920, 5, 98, True), (128, 5, 98, True), (1000, 8, 112, True), (77, 3, 17, False), (245760, 5, 98, True), (300, 2, 160, False), (999, 5, 98, True), (129, 4, 104, True)])
+def test_tensor_core_mixer_forward(R, n, S, fusable):
     """K9-TC (tcgen05.mma, TMEM accumulators, bf16 hi/lo split x 4 products) vs the fp32 torch-CPU mixer."""
     from xuance_b200.torch.rl_models import QMIX_Mixer
     torch.manual_seed(R + n)
@@ -137,7 +137,7 @@ def test_tensor_core_mixer_forward(R, n, S):
     st = torch.randn(R, S)
     with torch.no_grad():
         want = om(q, st).reshape(-1).numpy()
-        assert pm._fusable() == (S <= 128)
+        assert pm._fusable() == fusable
         got = pm(q.cuda(), st.cuda()).reshape(-1).cpu().numpy()         # no-grad forward -> fused tensor-core path
         pm.use_tensor_core_forward = False
         plain = pm(q.cuda(), st.cuda()).reshape(-1).cpu().numpy()       # cuBLAS + K9 mix epilogue

@@ -94,31 +94,32 @@ __device__ __forceinline__ void store_unit(const float (&x)[8], int r, int k0, i
     *reinterpret_cast<uint4 *>(lo + off) = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
 }
 
-// stage a [rows x K] fp32 row-major matrix (leading dimension ld) as hi/lo bf16 canonical operands, zero padded;
-// one thread-iteration = 8 consecutive k of one row (two 16-byte shared-memory stores)
+// stage a [rows x K] fp32 row-major matrix (leading dimension ld; global OR shared memory) as hi/lo bf16 canonical
+// operands, zero padded; one thread-iteration = 8 consecutive k of one row (two 16-byte shared-memory stores);
+// U units are loaded before the first is used; (r, k0) advance incrementally (no division in the loop)
 __device__ __forceinline__ void stage_operand(const float *__restrict__ g, int rows_valid, int rows_total, int K, int ld,
                                               int KP, uint8_t *hi, uint8_t *lo) {
     const int upr = KP >> 3;  // units per row
     const int total = rows_total * upr;
-    constexpr int U = 4;  // units in flight per thread: 32 independent 4-byte loads before the first use
+    constexpr int U = 4;
+    const int dr = blockDim.x / upr, dk = blockDim.x - dr * upr;   // unit index += blockDim.x  <=>  (r += dr, ku += dk)
+    int r = threadIdx.x / upr, ku = threadIdx.x - r * upr;
     for (int e0 = threadIdx.x; e0 < total; e0 += blockDim.x * U) {
         float x[U][8];
+        int rr[U], kk[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int e = e0 + u * blockDim.x;
-            const int r = e / upr, k0 = (e - r * upr) << 3;
-            const float *src = g + (int64_t)r * ld + k0;
+            rr[u] = r, kk[u] = ku << 3;
+            const float *src = g + (int64_t)r * ld + kk[u];
+            const bool in = (e0 + u * (int)blockDim.x) < total && r < rows_valid;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) x[u][i] = (e < total && r < rows_valid && k0 + i < K) ? src[i] : 0.f;
+            for (int i = 0; i < 8; ++i) x[u][i] = (in && kk[u] + i < K) ? src[i] : 0.f;
+            r += dr, ku += dk;
+            if (ku >= upr) ku -= upr, ++r;
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int e = e0 + u * blockDim.x;
-            if (e < total) {
-                const int r = e / upr, k0 = (e - r * upr) << 3;
-                store_unit(x[u], r, k0, KP, hi, lo);
-            }
-        }
+        for (int u = 0; u < U; ++u)
+            if (e0 + u * (int)blockDim.x < total) store_unit(x[u], rr[u], kk[u], KP, hi, lo);
     }
 }
 
@@ -152,7 +153,7 @@ struct TcParams {
 
 __global__ void __launch_bounds__(128, 1) qmix_mix_tc_kernel(TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ __align__(8) uint64_t mma_bar, x_bar;
     __shared__ uint32_t tmem_base_slot;
     __shared__ float s_bias1[TC_N1], s_bias_wb1[256], s_bias_wb2[TC_HH], s_bias_b2;
 
@@ -162,20 +163,30 @@ __global__ void __launch_bounds__(128, 1) qmix_mix_tc_kernel(TcParams p) {
     const int szA1 = TC_ROWS * KP1 * 2, szB1 = TC_N1 * KP1 * 2, szA2 = TC_ROWS * TC_HH * 2;
     const int szB2a = N2A * TC_HH * 2, szB2b = TC_HH * TC_HH * 2, szB2c = 16 * TC_HH * 2;
     uint8_t *A1h = smem, *A1l = A1h + szA1, *B1h = A1l + szA1, *B1l = B1h + szB1;
+    // the three GEMM2 A operands (relu of the hidden blocks) reuse the X operand region: it is dead once GEMM1 completed
     uint8_t *A2h[3], *A2l[3];
-    uint8_t *cur = B1l + szB1;
     for (int i = 0; i < 3; ++i) {
-        A2h[i] = cur;
-        A2l[i] = cur + szA2;
-        cur += 2 * szA2;
+        A2h[i] = A1h + (size_t)i * 2 * szA2;
+        A2l[i] = A2h[i] + szA2;
     }
-    uint8_t *B2ah = cur, *B2al = B2ah + szB2a, *B2bh = B2al + szB2a, *B2bl = B2bh + szB2b;
+    uint8_t *B2ah = B1l + szB1, *B2al = B2ah + szB2a, *B2bh = B2al + szB2a, *B2bl = B2bh + szB2b;
     uint8_t *B2ch = B2bl + szB2b, *B2cl = B2ch + szB2c;
-
+    float *Xraw = reinterpret_cast<float *>(B2cl + szB2c);   // [128 x S] fp32: the NEXT tile, fetched by the TMA unit
     // ---- one-time setup: mbarrier, TMEM, weights
+    const int64_t n_tiles = (p.R + TC_ROWS - 1) / TC_ROWS;
+    // a tile is one contiguous run of rows_valid*S*4 bytes; the bulk copy needs a multiple of 16 bytes
+    auto tile_copy_bytes = [&](int64_t t) -> uint32_t {
+        const int64_t rows = (p.R - t * TC_ROWS) < TC_ROWS ? (p.R - t * TC_ROWS) : TC_ROWS;
+        return (uint32_t)(rows * S * 4);
+    };
     if (tid == 0) {
         mbar_init(&mma_bar, 1);
+        mbar_init(&x_bar, 1);
         mbar_fence_init();
+        if ((int64_t)blockIdx.x < n_tiles && (tile_copy_bytes(blockIdx.x) & 15) == 0) {   // prefetch the first tile
+            mbar_expect_tx(&x_bar, tile_copy_bytes(blockIdx.x));
+            bulk_g2s(Xraw, p.states + (int64_t)blockIdx.x * TC_ROWS * S, tile_copy_bytes(blockIdx.x), &x_bar);
+        }
     }
     __syncwarp();
     if (warp == 0) {
@@ -198,9 +209,8 @@ __global__ void __launch_bounds__(128, 1) qmix_mix_tc_kernel(TcParams p) {
     tc_fence_after();
     const uint32_t tmem = tmem_base_slot;
     const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes
-    uint32_t phase = 0;
+    uint32_t phase = 0, xphase = 0;
 
-    const int64_t n_tiles = (p.R + TC_ROWS - 1) / TC_ROWS;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row0 = tile * TC_ROWS;
         const int rows_valid = (int)((p.R - row0) < TC_ROWS ? (p.R - row0) : TC_ROWS);
@@ -208,8 +218,14 @@ __global__ void __launch_bounds__(128, 1) qmix_mix_tc_kernel(TcParams p) {
         float qv[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) qv[i] = (i < n && tid < rows_valid) ? p.q[(row0 + tid) * n + i] : 0.f;
-        // ---- stage X tile (split to bf16 hi/lo)
-        stage_operand(p.states + row0 * S, rows_valid, TC_ROWS, S, S, KP1, A1h, A1l);
+        // ---- stage X tile (split to bf16 hi/lo) from the prefetched raw copy (or from global for an unaligned tail)
+        if ((tile_copy_bytes(tile) & 15) == 0) {
+            mbar_wait(&x_bar, xphase);
+            xphase ^= 1;
+            stage_operand(Xraw, rows_valid, TC_ROWS, S, S, KP1, A1h, A1l);
+        } else {
+            stage_operand(p.states + row0 * S, rows_valid, TC_ROWS, S, S, KP1, A1h, A1l);
+        }
         fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
         tc_fence_before();
         __syncthreads();       // also orders the previous tile's TMEM reads before this tile's MMAs
@@ -217,6 +233,12 @@ __global__ void __launch_bounds__(128, 1) qmix_mix_tc_kernel(TcParams p) {
         if (tid == 0) {
             issue_gemm(tmem + COL_Z, A1h, A1l, B1h, B1l, KP1, TC_N1);
             mma_commit(&mma_bar);
+            // Xraw was consumed by every thread (barrier above): fetch the next tile while this one computes
+            const int64_t nt = tile + gridDim.x;
+            if (nt < n_tiles && (tile_copy_bytes(nt) & 15) == 0) {
+                mbar_expect_tx(&x_bar, tile_copy_bytes(nt));
+                bulk_g2s(Xraw, p.states + nt * TC_ROWS * S, tile_copy_bytes(nt), &x_bar);
+            }
         }
         mbar_wait(&mma_bar, phase);
         phase ^= 1;
@@ -301,8 +323,9 @@ extern "C" int xb_qmix_mix_fused_fwd(const float *states, const float *q, const 
     if (R <= 0 || S <= 0 || n <= 0) return XB_EINVAL;
     if (H != TC_HH || HH != TC_HH || n > 8 || S > 160) return XB_ERANGE;   // shapes of the shipped QMIX configs
     const int KP1 = (S + 15) & ~15;
-    const size_t smem = (size_t)2 * TC_ROWS * KP1 * 2 + (size_t)2 * TC_N1 * KP1 * 2 + 6 * TC_ROWS * TC_HH * 2 +
-                        2 * (size_t)n * TC_HH * TC_HH * 2 + 2 * TC_HH * TC_HH * 2 + 2 * 16 * TC_HH * 2;
+    const size_t smem = (size_t)2 * TC_ROWS * KP1 * 2 + (size_t)2 * TC_N1 * KP1 * 2 + 2 * (size_t)n * TC_HH * TC_HH * 2 +
+                        2 * TC_HH * TC_HH * 2 + 2 * 16 * TC_HH * 2 + (size_t)TC_ROWS * S * 4;
+    if ((size_t)6 * TC_ROWS * TC_HH * 2 > (size_t)2 * TC_ROWS * KP1 * 2) return XB_ERANGE;   // A2 operands alias A1
     if (smem > 220 * 1024) return XB_ERANGE;
     static bool attr = false;
     if (!attr) {

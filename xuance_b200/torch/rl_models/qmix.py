@@ -127,9 +127,9 @@ class QMIX_Mixer(nn.Module):
 
     def _fusable(self):
         kp1 = (self.dim_state + 15) // 16 * 16
-        smem = 1024 * kp1 + 49152 + 4096 * self.n_agents + 6144          # operands staged by K9-TC (bytes)
+        smem = 1024 * kp1 + 4096 * self.n_agents + 6144 + 512 * self.dim_state   # operands + raw X tile of K9-TC (bytes)
         return (self.use_tensor_core_forward and self.dim_hidden == 32 and self.dim_hypernet_hidden == 32
-                and self.n_agents <= 8 and smem <= 220 * 1024)
+                and self.n_agents <= 8 and smem <= 220 * 1024 and kp1 >= 96)
 
     def forward_fused(self, values_n, states):
         """Whole mixer in ONE tensor-core kernel (K9-TC, xb_qmix_mix_fused_fwd).  Forward only."""
