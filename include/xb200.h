@@ -92,11 +92,13 @@ int xb_gather_scalars(const float *fields, int64_t slots, const int64_t *idx, in
  * Writes dlogits[B,A] = dloss/dlogits, dvalue[B] = dloss/dvalue (means over B_total >= B rows so a
  * rank-local shard of a global minibatch produces correctly scaled gradients) and
  * stats[8] = {a_loss, c_loss, entropy, mean(v), clip_fraction, loss, 0, 0} * (B/B_total weighting applied,
- * i.e. sums over the local rows divided by B_total).  actions are float32 (reference quirk).  A <= 64. */
+ * i.e. sums over the local rows divided by B_total).  actions are float32 (reference quirk).  A <= 64.
+ * loss_kind 0 = PPO-Clip (above); 1 = plain policy gradient a_loss = -mean(adv*logp) (old_logp unused): A2C
+ * (a2c_learner.py:46-52) with adv = advantages, PG (pg_learner.py:44-47) with adv = returns and vf_coef = 0. */
 int xb_ppo_loss_fwd_bwd(const float *logits, const float *value, const float *actions,
                         const float *old_logp, const float *adv, const float *ret,
                         int64_t B, int A, int64_t B_total, float clip_range, float vf_coef, float ent_coef,
-                        float *dlogits, float *dvalue, float *stats, double *scratch, void *stream);
+                        int loss_kind, float *dlogits, float *dvalue, float *stats, double *scratch, void *stream);
 
 /* ---------------------------------------------------------------- K5: prioritized-replay trees -------
  * Replaces SumSegmentTree/MinSegmentTree (xuance/common/segtree_tool.py:4-220) and their use in
@@ -122,8 +124,9 @@ int xb_per_update(float *sum_tree, float *min_tree, float *max_prio, const int64
 /* ---------------------------------------------------------------- K6: DQN TD target + loss fwd+bwd ---
  * Replaces dqn_learner.py:41-46 / perdqn_learner.py:44-50: predictQ = Q[b, a_b]; y = r + gamma*(1-d)*max_a Q'
  * loss = mean((predictQ - y)^2); dq[B,A] = dloss/dQ; td[B] = y - predictQ; stats[4] = {loss, mean predictQ,0,0}
- * (sums over local rows / B_total). */
-int xb_dqn_td_fwd_bwd(const float *q_eval, const float *q_next, const float *actions, const float *rew,
+ * (sums over local rows / B_total).  q_sel != NULL selects double-Q (ddqn_learner.py:39-44): q_sel[B,A] are the EVAL
+ * network's values at the next observation, y uses q_next[b, argmax_a q_sel[b,a]] instead of the max. */
+int xb_dqn_td_fwd_bwd(const float *q_eval, const float *q_next, const float *q_sel, const float *actions, const float *rew,
                       const float *term, int64_t B, int A, int64_t B_total, float gamma,
                       float *dq, float *td, float *stats, double *scratch, void *stream);
 

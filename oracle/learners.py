@@ -27,8 +27,11 @@ def ppo_clip_terms(logits, v_pred, act, ret, adv, old_logp, clip_range):
 
 
 class PPOLearnerOracle:
+    kind = "ppo"   # "a2c": a2c_learner.py:46-52 ; "pg": pg_learner.py:44-47
+
     def __init__(self, model, learning_rate=2.5e-4, vf_coef=0.25, ent_coef=0.01, clip_range=0.2,
-                 use_grad_clip=True, grad_clip_norm=0.5, end_factor_lr_decay=1.0, total_iters=1):
+                 use_grad_clip=True, grad_clip_norm=0.5, end_factor_lr_decay=1.0, total_iters=1, kind="ppo"):
+        self.kind = kind
         self.model = model
         self.optimizer = torch.optim.Adam(model.parameters(), learning_rate, eps=1e-5)
         self.scheduler = torch.optim.lr_scheduler.LinearLR(self.optimizer, start_factor=1.0,
@@ -43,10 +46,24 @@ class PPOLearnerOracle:
         act = torch.as_tensor(samples['actions'])
         ret = torch.as_tensor(samples['returns'])
         adv = torch.as_tensor(samples['advantages'])
-        old_logp = torch.as_tensor(samples['aux_batch']['old_logp'])
+        old_logp = torch.as_tensor(samples['aux_batch']['old_logp']) if self.kind == "ppo" else None
         logits, v_pred = self.model(obs)
-        a_loss, c_loss, e_loss, ratio = ppo_clip_terms(logits, v_pred, act, ret, adv, old_logp, self.clip_range)
-        loss = a_loss - self.ent_coef * e_loss + self.vf_coef * c_loss
+        if self.kind == "ppo":
+            a_loss, c_loss, e_loss, ratio = ppo_clip_terms(logits, v_pred, act, ret, adv, old_logp, self.clip_range)
+            loss = a_loss - self.ent_coef * e_loss + self.vf_coef * c_loss
+        else:
+            dist = Categorical(logits=logits)
+            log_prob = dist.log_prob(act)
+            e_loss = dist.entropy().mean()
+            if self.kind == "a2c":
+                a_loss = -(adv * log_prob).mean()
+                c_loss = nn.functional.mse_loss(v_pred, ret)
+                loss = a_loss - self.ent_coef * e_loss + self.vf_coef * c_loss
+            else:
+                a_loss = -(ret * log_prob).mean()
+                c_loss = torch.zeros(())
+                loss = a_loss - self.ent_coef * e_loss
+            ratio = torch.ones_like(log_prob)
         self.optimizer.zero_grad()
         loss.backward()
         if self.use_grad_clip:
@@ -63,7 +80,8 @@ class DQNLearnerOracle:
     """DQN_Learner / PerDQN_Learner (``per=True`` also returns |td| as float32 ndarray, perdqn_learner.py:80)."""
 
     def __init__(self, model, learning_rate=1e-4, gamma=0.99, sync_frequency=500, use_grad_clip=False,
-                 grad_clip_norm=0.5, end_factor_lr_decay=1.0, total_iters=1, per=False):
+                 grad_clip_norm=0.5, end_factor_lr_decay=1.0, total_iters=1, per=False, double_q=False):
+        self.double_q = double_q   # ddqn_learner.py:39-44
         self.model = model
         self.optimizer = torch.optim.Adam(model.parameters(), learning_rate, eps=1e-5)
         self.scheduler = torch.optim.lr_scheduler.LinearLR(self.optimizer, start_factor=1.0,
@@ -83,7 +101,11 @@ class DQNLearnerOracle:
         evalQ = self.model(obs)
         targetQ = self.model.target(nxt)
         predictQ = evalQ.gather(-1, act.unsqueeze(-1)).squeeze(-1)
-        targetQ = targetQ.max(dim=-1).values
+        if self.double_q:
+            targetA = self.model(nxt).argmax(dim=-1)
+            targetQ = targetQ.gather(-1, targetA.unsqueeze(-1)).squeeze(-1)
+        else:
+            targetQ = targetQ.max(dim=-1).values
         targetQ = rew + self.gamma * (1 - ter) * targetQ
         td_error = targetQ - predictQ
         loss = nn.functional.mse_loss(predictQ, targetQ.detach())

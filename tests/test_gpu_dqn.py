@@ -38,7 +38,7 @@ def test_dqn_td_kernel(B, A):
     t_in = [torch.tensor(x, device=dev) for x in (qe, qn, act, rew, ter)]
     dq, td, stats = torch.empty((B, A), device=dev), torch.empty(B, device=dev), torch.zeros(4, device=dev)
     scratch = _lib.scratch(dev)
-    _lib.call("xb_dqn_td_fwd_bwd", *[_lib.ptr(t) for t in t_in], B, A, B, 0.99, _lib.ptr(dq), _lib.ptr(td),
+    _lib.call("xb_dqn_td_fwd_bwd", _lib.ptr(t_in[0]), _lib.ptr(t_in[1]), None, *[_lib.ptr(t) for t in t_in[2:]], B, A, B, 0.99, _lib.ptr(dq), _lib.ptr(td),
               _lib.ptr(stats), _lib.ptr(scratch))
     assert np.array_equal(td.cpu().numpy(), (y - pred).detach().numpy())          # same op order: bit-exact
     np.testing.assert_allclose(dq.cpu().numpy(), qt.grad.numpy(), rtol=1e-6, atol=1e-10)
@@ -46,11 +46,11 @@ def test_dqn_td_kernel(B, A):
     np.testing.assert_allclose(stats[1].item(), pred.mean().item(), rtol=1e-5, atol=1e-7)
 
 
-@pytest.mark.parametrize("per", [False, True])
-def test_dqn_learner_matches_oracle(per):
+@pytest.mark.parametrize("per,double_q", [(False, False), (True, False), (False, True)])
+def test_dqn_learner_matches_oracle(per, double_q):
     from xuance_b200.common import Discrete, BaseCallback
     from xuance_b200.torch.rl_models import Basic_CNN, DeepQNetwork
-    from xuance_b200.torch.learners import DQN_Learner, PerDQN_Learner
+    from xuance_b200.torch.learners import DQN_Learner, PerDQN_Learner, DDQN_Learner
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(2)
@@ -60,9 +60,9 @@ def test_dqn_learner_matches_oracle(per):
                     activation=nn.ReLU, device="cuda:0")
     model = DeepQNetwork(rep, [512], Discrete(A), None, None, nn.ReLU, "cuda:0").to("cuda:0")
     model.load_state_dict(om.state_dict())
-    lrn = (PerDQN_Learner if per else DQN_Learner)(_cfg(), model, BaseCallback())
+    lrn = (DDQN_Learner if double_q else PerDQN_Learner if per else DQN_Learner)(_cfg(), model, BaseCallback())
     orc = DQNLearnerOracle(om, learning_rate=1e-4, sync_frequency=2, end_factor_lr_decay=0.5,
-                           total_iters=lrn.total_iters, per=per)
+                           total_iters=lrn.total_iters, per=per, double_q=double_q)
     rng = np.random.default_rng(3)
     for it in range(4):     # crosses two target syncs
         s = {"obs": rng.integers(0, 256, size=(B, 84, 84, 4), dtype=np.uint8),

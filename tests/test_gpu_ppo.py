@@ -42,7 +42,7 @@ def test_ppo_loss_kernel_matches_torch_autograd(B, A):
     stats = torch.zeros(8, device=dev)
     scratch = _lib.scratch(torch.device(dev))
     for _ in range(2):   # twice: the ticket counter must re-arm
-        _lib.call("xb_ppo_loss_fwd_bwd", *[_lib.ptr(t) for t in t_in], B, A, B, clip, vf, ent, _lib.ptr(dl),
+        _lib.call("xb_ppo_loss_fwd_bwd", *[_lib.ptr(t) for t in t_in], B, A, B, clip, vf, ent, 0, _lib.ptr(dl),
                   _lib.ptr(dv), _lib.ptr(stats), _lib.ptr(scratch))
     s = stats.cpu().numpy()
     np.testing.assert_allclose(s[0], a_loss.item(), rtol=1e-4, atol=1e-6)
@@ -120,3 +120,37 @@ def test_ppo_learner_update_matches_oracle(compute, tol):
     so, sp = oracle_model.state_dict(), model.state_dict()
     for k in so:
         np.testing.assert_allclose(sp[k].cpu().numpy(), so[k].numpy(), rtol=1e-3, atol=1e-4, err_msg=k)  # Adam: |step| ~ lr
+
+
+@pytest.mark.parametrize("kind", ["a2c", "pg"])
+def test_a2c_pg_learners_match_oracle(kind):
+    """Sibling learners on the same K4 kernel (loss_kind = 1): A2C and PG."""
+    from xuance_b200.torch.learners import A2C_Learner, PG_Learner
+    from xuance_b200.common import BaseCallback
+    torch.manual_seed(2)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    A, B = 5, 128
+    oracle_model = SharedActorCriticOracle(A)
+    model = build_product_ppo_model(A, "cuda:0")
+    model.load_state_dict(oracle_model.state_dict())
+    cfg = ppo_config("cuda:0", running_steps=256 * 128 * 10)
+    learner = (A2C_Learner if kind == "a2c" else PG_Learner)(cfg, model, BaseCallback())
+    orc = PPOLearnerOracle(oracle_model, end_factor_lr_decay=0.5, kind=kind,
+                           total_iters=cfg.running_steps if kind == "a2c" else learner.total_iters)
+    rng = np.random.default_rng(6)
+    for it in range(3):
+        samples = {"obs": rng.integers(0, 256, size=(B, 84, 84, 4), dtype=np.uint8),
+                   "actions": rng.integers(0, A, size=B).astype(np.float32),
+                   "returns": rng.normal(size=B).astype(np.float32), "advantages": rng.normal(size=B).astype(np.float32),
+                   "aux_batch": {"old_logp": np.zeros(B, np.float32)}, "batch_size": B}
+        io = orc.update(**samples)
+        ip = learner.update(**dict(samples, obs=torch.from_numpy(samples["obs"]).cuda()))
+        np.testing.assert_allclose(ip["actor-loss"], io["actor_loss"], rtol=2e-4, atol=1e-5)
+        np.testing.assert_allclose(ip["entropy"], io["entropy"], rtol=2e-4)
+        if kind == "a2c":
+            np.testing.assert_allclose(ip["critic-loss"], io["critic_loss"], rtol=2e-4, atol=1e-5)
+        assert ip["learning_rate"] == io["learning_rate"]
+    so, sp = oracle_model.state_dict(), model.state_dict()
+    for k in so:
+        np.testing.assert_allclose(sp[k].cpu().numpy(), so[k].numpy(), rtol=1e-3, atol=1e-4, err_msg=k)

@@ -18,7 +18,7 @@ def test_config_loader_merges_like_the_reference():
         get_arguments(algo, env, env)    # the 5 BASELINE configs all resolve
 
 
-@pytest.mark.parametrize("vec", ["DummyVecEnv", "SubprocVecEnv"])
+@pytest.mark.parametrize("vec", ["DummyVecEnv", "SubprocVecEnv", "ShmSubprocVecEnv"])
 def test_vector_env_contract(vec):
     from xuance_b200.environment import make_envs
     from xuance_b200.environment.vector_envs import AlreadySteppingError, NotSteppingError
@@ -128,3 +128,34 @@ def test_sharded_gradient_identity_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert err < 1e-6, err
+
+
+def test_vector_envs_agree_step_for_step():
+    """Dummy / Subproc / shared-memory Subproc produce identical trajectories for identical seeds and actions."""
+    from xuance_b200.environment import make_envs
+    rng = np.random.default_rng(0)
+    acts = rng.integers(0, 2, size=(60, 6))
+    traj = {}
+    for vec in ("DummyVecEnv", "SubprocVecEnv", "ShmSubprocVecEnv"):
+        envs = make_envs(Namespace(env_id="CartPole-v1", vectorize=vec, parallels=6, env_seed=5))
+        obs, _ = envs.reset()
+        out = [obs]
+        for a in acts:
+            obs, rew, term, trunc, infos = envs.step(a)
+            out += [obs, rew, term.astype(np.float32), trunc.astype(np.float32),
+                    np.array([i["episode_step"] for i in infos], np.float32)]
+        traj[vec] = out
+        envs.close()
+    for vec in ("SubprocVecEnv", "ShmSubprocVecEnv"):
+        for a, b in zip(traj["DummyVecEnv"], traj[vec]):
+            assert np.array_equal(a, b), vec
+
+
+def test_shm_vec_env_exposes_shared_block_without_copy():
+    from xuance_b200.environment import make_envs
+    envs = make_envs(Namespace(env_id="SyntheticAtari", vectorize="ShmSubproc_Atari", parallels=4, env_seed=3))
+    envs.reset()
+    envs.step_async(np.zeros(4, np.int64))
+    obs, *_ = envs.step_wait(copy=False)
+    assert obs is envs.buf_obs and obs.dtype == np.uint8 and obs.shape == (4, 84, 84, 4) and obs.any()
+    envs.close()

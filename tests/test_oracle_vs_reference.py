@@ -180,3 +180,60 @@ def test_sac_learner_live(ref):
     sd1, sd2 = model.state_dict(), om.state_dict()
     for k in sd1:
         np.testing.assert_allclose(sd2[k].numpy(), sd1[k].numpy(), rtol=1e-5, atol=1e-6, err_msg=k)
+
+
+@pytest.mark.parametrize("kind", ["a2c", "pg", "ddqn"])
+def test_sibling_learners_live(ref, kind):
+    """A2C / PG / DDQN: oracle variants next to the reference learners."""
+    from gymnasium.spaces import Discrete
+    from xuance.common import BaseCallback
+    from xuance.torch.learners import A2C_Learner, PG_Learner, DDQN_Learner
+    from xuance.torch.rl_models.representations import AC_CNN_Atari, Basic_CNN
+    from xuance.torch.rl_models.heads import CategoricalActorHead, ValueHead
+    from xuance.torch.rl_models.architectures.single_agent.actor_critic import SharedActorCritic
+    from xuance.torch.rl_models.architectures.single_agent.deep_q_network import DeepQNetwork
+    from oracle.nets import SharedActorCriticOracle, DeepQNetworkOracle
+    from oracle.learners import PPOLearnerOracle, DQNLearnerOracle
+    torch.manual_seed(5)
+    A, B = 5, 12
+    cfg = Namespace(distributed_training=False, episode_length=1000, use_grad_clip=True, grad_clip_norm=0.5, device="cpu",
+                    model_dir="/tmp/x", running_steps=4096 * 10, parallels=32, learning_rate=2.5e-4, end_factor_lr_decay=0.5,
+                    horizon_size=128, n_epochs=4, n_minibatch=4, vf_coef=0.25, ent_coef=0.01, gamma=0.99, sync_frequency=2,
+                    start_training=0, training_frequency=1)
+    rng = np.random.default_rng(3)
+    if kind == "ddqn":
+        rep = Basic_CNN(input_shape=(84, 84, 4), kernels=[8, 4, 3], strides=[4, 2, 1], filters=[32, 64, 64],
+                        activation=nn.ReLU, device="cpu")
+        model = DeepQNetwork(rep, [512], Discrete(A), None, None, nn.ReLU, "cpu")
+        lrn = DDQN_Learner(cfg, model, BaseCallback())
+        om = DeepQNetworkOracle(A)
+        om.load_state_dict(model.state_dict())
+        orc = DQNLearnerOracle(om, learning_rate=2.5e-4, sync_frequency=2, use_grad_clip=True, end_factor_lr_decay=0.5,
+                               total_iters=lrn.total_iters, double_q=True)
+    else:
+        rep = AC_CNN_Atari(input_shape=(84, 84, 4), kernels=[8, 4, 3], strides=[4, 2, 1], filters=[32, 64, 64],
+                           activation=nn.ReLU, device="cpu", fc_hidden_sizes=[512])
+        model = SharedActorCritic(rep, CategoricalActorHead(512, [], A, None, nn.init.orthogonal_, nn.ReLU, "cpu"),
+                                  ValueHead(512, [], None, nn.init.orthogonal_, nn.ReLU, "cpu"))
+        lrn = (A2C_Learner if kind == "a2c" else PG_Learner)(cfg, model, BaseCallback())
+        om = SharedActorCriticOracle(A)
+        om.load_state_dict(model.state_dict())
+        # a2c_learner.py:21: LinearLR(total_iters=config.running_steps); pg_learner.py:22: total_iters=self.total_iters
+        orc = PPOLearnerOracle(om, end_factor_lr_decay=0.5, kind=kind,
+                               total_iters=cfg.running_steps if kind == "a2c" else lrn.total_iters)
+    for it in range(3):
+        s = {"obs": rng.integers(0, 256, size=(B, 84, 84, 4), dtype=np.uint8).astype(np.float32),
+             "actions": rng.integers(0, A, size=B).astype(np.float32),
+             "returns": rng.normal(size=B).astype(np.float32), "advantages": rng.normal(size=B).astype(np.float32),
+             "aux_batch": {"old_logp": np.zeros(B, np.float32)},
+             "obs_next": rng.integers(0, 256, size=(B, 84, 84, 4), dtype=np.uint8).astype(np.float32),
+             "rewards": rng.normal(size=B).astype(np.float32), "terminals": (rng.random(B) < 0.2).astype(np.float32)}
+        i1, i2 = lrn.update(**s), orc.update(**s)
+        if kind == "ddqn":
+            np.testing.assert_allclose(i2["Qloss"], i1["Qloss"], rtol=1e-5)
+        else:
+            np.testing.assert_allclose(i2["actor_loss"], i1["actor-loss"], rtol=1e-5, atol=1e-7)
+            np.testing.assert_allclose(i2["entropy"], i1["entropy"], rtol=1e-5)
+    sd1, sd2 = model.state_dict(), om.state_dict()
+    for k in sd1:
+        np.testing.assert_allclose(sd2[k].numpy(), sd1[k].numpy(), rtol=1e-5, atol=1e-6, err_msg=k)

@@ -134,7 +134,7 @@ def main():
             dl, dv = torch.empty((B, A), device=DEV), torch.empty(B, device=DEV)
             stats, scratch = torch.zeros(8, device=DEV), _lib.scratch(DEV)
             us = timeit(lambda: _lib.call("xb_ppo_loss_fwd_bwd", _lib.ptr(lg), _lib.ptr(v), _lib.ptr(act), _lib.ptr(old),
-                                          _lib.ptr(adv), _lib.ptr(ret), B, A, B, 0.2, 0.25, 0.01, _lib.ptr(dl), _lib.ptr(dv),
+                                          _lib.ptr(adv), _lib.ptr(ret), B, A, B, 0.2, 0.25, 0.01, 0, _lib.ptr(dl), _lib.ptr(dv),
                                           _lib.ptr(stats), _lib.ptr(scratch)), R)
             add(entry("K4 xb_ppo_loss_fwd_bwd", f"B={B}, A=4", us, B * 56, hbm))
 
@@ -169,7 +169,7 @@ def main():
             rew, ter = torch.randn(B, device=DEV), (torch.rand(B, device=DEV) < 0.1).float()
             dq, td = torch.empty((B, A), device=DEV), torch.empty(B, device=DEV)
             stats, scratch = torch.zeros(4, device=DEV), _lib.scratch(DEV)
-            us = timeit(lambda: _lib.call("xb_dqn_td_fwd_bwd", _lib.ptr(qe), _lib.ptr(qn), _lib.ptr(act), _lib.ptr(rew),
+            us = timeit(lambda: _lib.call("xb_dqn_td_fwd_bwd", _lib.ptr(qe), _lib.ptr(qn), None, _lib.ptr(act), _lib.ptr(rew),
                                           _lib.ptr(ter), B, A, B, 0.99, _lib.ptr(dq), _lib.ptr(td), _lib.ptr(stats),
                                           _lib.ptr(scratch)), R)
             add(entry("K6 xb_dqn_td_fwd_bwd", f"B={B}, A=6", us, B * ((2 * A + 3) * 4 + (A + 1) * 4), hbm))

@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const float *__restrict__
                                                        const float *__restrict__ old_logp,
                                                        const float *__restrict__ adv, const float *__restrict__ ret,
                                                        int64_t B, int A, float inv_bt, float clip, float vf_coef,
-                                                       float ent_coef, float *__restrict__ dlogits,
+                                                       float ent_coef, int loss_kind, float *__restrict__ dlogits,
                                                        float *__restrict__ dvalue, float *__restrict__ stats,
                                                        double *__restrict__ scratch) {
     __shared__ double red[6 * 32];
@@ -57,16 +57,22 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const float *__restrict__
             }
         }
         const float ad = adv[b];
-        const float ratio = expf(logp_a - old_logp[b]);
-        const float rc = fminf(fmaxf(ratio, lo), hi);
-        const float s1 = rc * ad, s2 = ad * ratio;
-        const float smin = fminf(s1, s2);
-        // d(-mean(min(s1,s2)))/d ratio
-        float g1 = s1 < s2 ? 1.f : (s1 == s2 ? 0.5f : 0.f);
-        float g2 = s2 < s1 ? 1.f : (s1 == s2 ? 0.5f : 0.f);
-        const bool inside = ratio >= lo && ratio <= hi;
-        const float d_ratio = -inv_bt * ad * ((inside ? g1 : 0.f) + g2);
-        const float d_logp = d_ratio * ratio;  // d ratio / d logp = ratio
+        float ratio = 1.f, smin, d_logp;
+        if (loss_kind == 0) {  // PPO-Clip surrogate
+            ratio = expf(logp_a - old_logp[b]);
+            const float rc = fminf(fmaxf(ratio, lo), hi);
+            const float s1 = rc * ad, s2 = ad * ratio;
+            smin = fminf(s1, s2);
+            // d(-mean(min(s1,s2)))/d ratio
+            float g1 = s1 < s2 ? 1.f : (s1 == s2 ? 0.5f : 0.f);
+            float g2 = s2 < s1 ? 1.f : (s1 == s2 ? 0.5f : 0.f);
+            const bool inside = ratio >= lo && ratio <= hi;
+            const float d_ratio = -inv_bt * ad * ((inside ? g1 : 0.f) + g2);
+            d_logp = d_ratio * ratio;  // d ratio / d logp = ratio
+        } else {               // plain policy gradient: a_loss = -mean(w * logp)   (A2C: w = advantage, PG: w = return)
+            smin = ad * logp_a;
+            d_logp = -inv_bt * ad;
+        }
         const float dent = -ent_coef * inv_bt;  // d loss / d entropy_b
         float *dz = dlogits + b * A;
         float gz[A_MAX];
@@ -110,10 +116,11 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const float *__restrict__
 
 extern "C" int xb_ppo_loss_fwd_bwd(const float *logits, const float *value, const float *actions,
                                    const float *old_logp, const float *adv, const float *ret, int64_t B, int A,
-                                   int64_t B_total, float clip_range, float vf_coef, float ent_coef, float *dlogits,
-                                   float *dvalue, float *stats, double *scratch, void *stream) {
-    if (!logits || !value || !actions || !old_logp || !adv || !ret || !dlogits || !dvalue || !stats || !scratch)
-        return XB_EINVAL;
+                                   int64_t B_total, float clip_range, float vf_coef, float ent_coef, int loss_kind,
+                                   float *dlogits, float *dvalue, float *stats, double *scratch, void *stream) {
+    if (!logits || !value || !actions || !adv || !ret || !dlogits || !dvalue || !stats || !scratch) return XB_EINVAL;
+    if (loss_kind != 0 && loss_kind != 1) return XB_EINVAL;
+    if (loss_kind == 0 && !old_logp) return XB_EINVAL;
     if (B <= 0 || B_total < B || A <= 0) return XB_EINVAL;
     if (A > 64) return XB_ERANGE;
     cudaStream_t s = (cudaStream_t)stream;
@@ -123,7 +130,7 @@ extern "C" int xb_ppo_loss_fwd_bwd(const float *logits, const float *value, cons
     if (A == 4 && (!xb_aligned(logits, 16) || !xb_aligned(dlogits, 16))) return XB_EALIGN;
 #define XB_PPO(AM)                                                                                                   \
     ppo_loss_kernel<AM><<<grid, 256, 0, s>>>(logits, value, actions, old_logp, adv, ret, B, A, inv_bt, clip_range,   \
-                                              vf_coef, ent_coef, dlogits, dvalue, stats, scratch)
+                                              vf_coef, ent_coef, loss_kind, dlogits, dvalue, stats, scratch)
     if (A <= 4) XB_PPO(4);
     else if (A <= 8) XB_PPO(8);
     else if (A <= 18) XB_PPO(18);
@@ -137,6 +144,7 @@ extern "C" int xb_ppo_loss_fwd_bwd(const float *logits, const float *value, cons
 // K6  xb_dqn_td_fwd_bwd
 // =====================================================================================================
 __global__ void __launch_bounds__(256) dqn_td_kernel(const float *__restrict__ q_eval, const float *__restrict__ q_next,
+                                                     const float *__restrict__ q_sel,
                                                      const float *__restrict__ actions, const float *__restrict__ rew,
                                                      const float *__restrict__ term, int64_t B, int A, float inv_bt,
                                                      float gamma, float *__restrict__ dq, float *__restrict__ td,
@@ -147,7 +155,19 @@ __global__ void __launch_bounds__(256) dqn_td_kernel(const float *__restrict__ q
         const int a = (int)actions[b];
         const float *qe = q_eval + b * A, *qn = q_next + b * A;
         float mx = -INFINITY;
-        for (int i = 0; i < A; ++i) mx = fmaxf(mx, qn[i]);
+        if (q_sel) {  // double-Q: evaluate the target net at the eval net's greedy action (ddqn_learner.py:39-44)
+            const float *qs = q_sel + b * A;
+            int best = 0;
+            float bv = qs[0];
+            for (int i = 1; i < A; ++i)
+                if (qs[i] > bv) {  // first maximal index, as torch.argmax
+                    bv = qs[i];
+                    best = i;
+                }
+            mx = qn[best];
+        } else {
+            for (int i = 0; i < A; ++i) mx = fmaxf(mx, qn[i]);
+        }
         const float pred = qe[a];
         // targetQ = rew + gamma*(1-ter)*max  evaluated left to right as torch does: (gamma*(1-ter))*max
         const float y = __fadd_rn(rew[b], __fmul_rn(__fmul_rn(gamma, __fsub_rn(1.f, term[b])), mx));
@@ -167,14 +187,15 @@ __global__ void __launch_bounds__(256) dqn_td_kernel(const float *__restrict__ q
     });
 }
 
-extern "C" int xb_dqn_td_fwd_bwd(const float *q_eval, const float *q_next, const float *actions, const float *rew,
+extern "C" int xb_dqn_td_fwd_bwd(const float *q_eval, const float *q_next, const float *q_sel, const float *actions,
+                                 const float *rew,
                                  const float *term, int64_t B, int A, int64_t B_total, float gamma, float *dq,
                                  float *td, float *stats, double *scratch, void *stream) {
     if (!q_eval || !q_next || !actions || !rew || !term || !dq || !td || !stats || !scratch) return XB_EINVAL;
     if (B <= 0 || B_total < B || A <= 0) return XB_EINVAL;
     int64_t want = (B + 255) / 256;
     int grid = (int)(want < XB_MAX_PARTIALS ? want : XB_MAX_PARTIALS);
-    dqn_td_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(q_eval, q_next, actions, rew, term, B, A,
+    dqn_td_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(q_eval, q_next, q_sel, actions, rew, term, B, A,
                                                           1.0f / (float)B_total, gamma, dq, td, stats, scratch);
     return xb_launch_status();
 }

@@ -14,6 +14,7 @@ from .learner import Learner
 
 class DQN_Learner(Learner):
     returns_td = False
+    double_q = False     # DDQN_Learner: target value taken at the eval network's greedy next action
 
     def __init__(self, config, model, callback):
         super().__init__(config, model, callback)
@@ -41,10 +42,11 @@ class DQN_Learner(Learner):
         evalQ = self.model(obs).values.contiguous()
         with torch.no_grad():
             targetQ = self.model.target(nxt).values.contiguous()
+            selQ = self.model(nxt).values.contiguous() if self.double_q else None
         B, A = evalQ.shape
         dq = torch.empty_like(evalQ)
         td = torch.empty(B, dtype=torch.float32, device=self.device)
-        _lib.call("xb_dqn_td_fwd_bwd", _lib.ptr(evalQ), _lib.ptr(targetQ), _lib.ptr(act), _lib.ptr(rew), _lib.ptr(ter),
+        _lib.call("xb_dqn_td_fwd_bwd", _lib.ptr(evalQ), _lib.ptr(targetQ), _lib.ptr(selQ), _lib.ptr(act), _lib.ptr(rew), _lib.ptr(ter),
                   B, A, B * self.world_size, float(self.gamma), _lib.ptr(dq), _lib.ptr(td), _lib.ptr(self._stats),
                   _lib.ptr(self._scratch))
         self.optimizer.zero_grad()
@@ -72,3 +74,8 @@ class DQN_Learner(Learner):
 class PerDQN_Learner(DQN_Learner):
     """perdqn_learner.py:80 returns (|td| [B], info)."""
     returns_td = True
+
+
+class DDQN_Learner(DQN_Learner):
+    """Double DQN - mirror of xuance/torch/learners/qlearning_family/ddqn_learner.py:13-80."""
+    double_q = True

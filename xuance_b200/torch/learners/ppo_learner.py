@@ -13,15 +13,23 @@ from .learner import Learner
 
 
 class PPO_Learner(Learner):
+    loss_kind = 0            # K4: 0 = PPO-Clip surrogate, 1 = plain policy gradient (A2C / PG subclasses)
+    adv_key = "advantages"   # which sample field weights the log-probabilities
+    info_names = ("actor_loss", "critic_loss", "entropy", "learning_rate", "predict_value", "clip_ratio")
+
     def __init__(self, config, model, callback):
         super().__init__(config, model, callback)
         self.optimizer = FusedAdam(self.model.parameters(), self.config.learning_rate, eps=1e-5)
         self.scheduler = torch.optim.lr_scheduler.LinearLR(self.optimizer, start_factor=1.0,
                                                            end_factor=self.end_factor_lr_decay,
-                                                           total_iters=self.total_iters)
-        self.vf_coef, self.ent_coef, self.clip_range = config.vf_coef, config.ent_coef, config.clip_range
+                                                           total_iters=self._lr_total_iters())
+        self.vf_coef, self.ent_coef = getattr(config, "vf_coef", 0.0), config.ent_coef
+        self.clip_range = getattr(config, "clip_range", 0.0)
         self._stats = torch.zeros(8, dtype=torch.float32, device=self.device)
         self._scratch = _lib.scratch(self.device)
+
+    def _lr_total_iters(self):
+        return self.total_iters
 
     def estimate_total_iterations(self):
         """ppo_learner.py:28-33."""
@@ -39,8 +47,8 @@ class PPO_Learner(Learner):
             obs = torch.as_tensor(obs, device=self.device)
         act = self._f32(samples['actions'])
         ret = self._f32(samples['returns'])
-        adv = self._f32(samples['advantages'])
-        old_logp = self._f32(samples['aux_batch']['old_logp'])
+        adv = self._f32(samples[self.adv_key])
+        old_logp = self._f32(samples['aux_batch']['old_logp']) if self.loss_kind == 0 else None
         info = self.callback.on_update_start(self.iterations, policy=self.model, obs=obs, act=act, returns=ret,
                                              advantages=adv, old_logp=old_logp) or {}
         B = act.shape[0]
@@ -56,7 +64,7 @@ class PPO_Learner(Learner):
         B_total = B * self.world_size
         _lib.call("xb_ppo_loss_fwd_bwd", _lib.ptr(logits_c), _lib.ptr(v_c), _lib.ptr(act), _lib.ptr(old_logp),
                   _lib.ptr(adv), _lib.ptr(ret), B, A, B_total, float(self.clip_range), float(self.vf_coef),
-                  float(self.ent_coef), _lib.ptr(dlogits), _lib.ptr(dvalue), _lib.ptr(self._stats),
+                  float(self.ent_coef), self.loss_kind, _lib.ptr(dlogits), _lib.ptr(dvalue), _lib.ptr(self._stats),
                   _lib.ptr(self._scratch))
         self.optimizer.zero_grad()
         torch.autograd.backward([logits_c, v_c], [dlogits, dvalue])
@@ -74,9 +82,32 @@ class PPO_Learner(Learner):
     def materialize_info(self):
         """The single device->host read of an update: 8 floats."""
         s = self._stats.tolist()
-        lr = self.optimizer.state_dict()['param_groups'][0]['lr'] if False else self.optimizer.param_groups[0]['lr']
-        vals = {"actor_loss": s[0], "critic_loss": s[1], "entropy": s[2], "learning_rate": lr,
-                "predict_value": s[3], "clip_ratio": s[4]}
+        lr = self.optimizer.param_groups[0]['lr']
+        full = dict(zip(("actor_loss", "critic_loss", "entropy", "learning_rate", "predict_value", "clip_ratio"),
+                        (s[0], s[1], s[2], lr, s[3], s[4])))
+        vals = {name: full[name.replace("-", "_")] for name in self.info_names}
         if self.distributed_training:
             return {f"{k}/rank_{self.rank}": v for k, v in vals.items()}
         return vals
+
+
+class A2C_Learner(PPO_Learner):
+    """Advantage actor-critic - mirror of xuance/torch/learners/policy_gradient/a2c_learner.py:13-85:
+    a_loss = -mean(adv * logp); same value / entropy terms, optimiser recipe and info keys (hyphenated, as the reference)."""
+    loss_kind = 1
+    info_names = ("actor-loss", "critic-loss", "entropy", "learning_rate", "predict_value")
+
+    def _lr_total_iters(self):
+        return self.config.running_steps   # a2c_learner.py:21 decays over running_steps, not over the update count
+
+
+class PG_Learner(PPO_Learner):
+    """Vanilla policy gradient - mirror of xuance/torch/learners/policy_gradient/pg_learner.py:12-75:
+    loss = -mean(returns * logp) - ent_coef * entropy (no value term)."""
+    loss_kind = 1
+    adv_key = "returns"
+    info_names = ("actor-loss", "entropy", "learning_rate")
+
+    def __init__(self, config, model, callback):
+        super().__init__(config, model, callback)
+        self.vf_coef = 0.0
