@@ -46,8 +46,9 @@ def test_dqn_td_kernel(B, A):
     np.testing.assert_allclose(stats[1].item(), pred.mean().item(), rtol=1e-5, atol=1e-7)
 
 
-@pytest.mark.parametrize("per,double_q", [(False, False), (True, False), (False, True)])
-def test_dqn_learner_matches_oracle(per, double_q):
+@pytest.mark.parametrize("per,double_q,graph", [(False, False, False), (True, False, False), (False, True, False),
+                                                 (True, False, True)])
+def test_dqn_learner_matches_oracle(per, double_q, graph):
     from xuance_b200.common import Discrete, BaseCallback
     from xuance_b200.torch.rl_models import Basic_CNN, DeepQNetwork
     from xuance_b200.torch.learners import DQN_Learner, PerDQN_Learner, DDQN_Learner
@@ -60,7 +61,8 @@ def test_dqn_learner_matches_oracle(per, double_q):
                     activation=nn.ReLU, device="cuda:0")
     model = DeepQNetwork(rep, [512], Discrete(A), None, None, nn.ReLU, "cuda:0").to("cuda:0")
     model.load_state_dict(om.state_dict())
-    lrn = (DDQN_Learner if double_q else PerDQN_Learner if per else DQN_Learner)(_cfg(), model, BaseCallback())
+    lrn = (DDQN_Learner if double_q else PerDQN_Learner if per else DQN_Learner)(_cfg(use_cuda_graph=graph), model,
+                                                                                  BaseCallback())
     orc = DQNLearnerOracle(om, learning_rate=1e-4, sync_frequency=2, end_factor_lr_decay=0.5,
                            total_iters=lrn.total_iters, per=per, double_q=double_q)
     rng = np.random.default_rng(3)

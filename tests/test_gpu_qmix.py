@@ -84,8 +84,9 @@ def test_mixer_forward_backward_matches_torch(R, n, S, H):
         np.testing.assert_allclose(pp.grad.cpu().numpy(), po.grad.numpy(), rtol=2e-4, atol=2e-5, err_msg=k)
 
 
-@pytest.mark.parametrize("detach,double_q", [(True, True), (False, True), (False, False)])
-def test_qmix_learner_matches_oracle(detach, double_q):
+@pytest.mark.parametrize("detach,double_q,graph", [(True, True, False), (False, True, False), (False, False, False),
+                                                   (False, True, True)])
+def test_qmix_learner_matches_oracle(detach, double_q, graph):
     from xuance_b200.common import BaseCallback
     from xuance_b200.torch.learners.qmix_learner import QMIX_Learner
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -98,7 +99,8 @@ def test_qmix_learner_matches_oracle(detach, double_q):
     cfg = Namespace(distributed_training=False, episode_length=T, use_grad_clip=True, grad_clip_norm=10.0,
                     device="cuda:0", model_dir="/tmp/x", running_steps=100000, parallels=4, use_parameter_sharing=True,
                     use_rnn=True, use_actions_mask=False, learning_rate=7e-4, sync_frequency=2, double_q=double_q,
-                    n_epochs=1, start_training=0, gamma=0.99, end_factor_lr_decay=0.5, qmix_rnn_detach_q_eval=detach)
+                    n_epochs=1, start_training=0, gamma=0.99, end_factor_lr_decay=0.5, qmix_rnn_detach_q_eval=detach,
+                    use_cuda_graph=graph)
     lrn = QMIX_Learner(cfg, grouping, model, BaseCallback())
     orc = QMIXLearnerOracle(om, keys, learning_rate=7e-4, sync_frequency=2, double_q=double_q, use_grad_clip=True,
                             grad_clip_norm=10.0, end_factor_lr_decay=0.5, total_iters=lrn.total_iters,

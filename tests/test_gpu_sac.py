@@ -22,8 +22,8 @@ def _build(obs_dim, act_dim, device):
     return SoftActorCritic(actor, critic).to(device)
 
 
-@pytest.mark.parametrize("auto_alpha", [True, False])
-def test_sac_learner_matches_oracle(auto_alpha):
+@pytest.mark.parametrize("auto_alpha,graph", [(True, False), (False, False), (True, True)])
+def test_sac_learner_matches_oracle(auto_alpha, graph):
     from xuance_b200.common import BaseCallback
     from xuance_b200.torch.learners.sac_learner import SAC_Learner
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -35,7 +35,7 @@ def test_sac_learner_matches_oracle(auto_alpha):
     cfg = Namespace(distributed_training=False, episode_length=1000, use_grad_clip=False, grad_clip_norm=0.5,
                     device="cuda:0", model_dir="/tmp/xb", running_steps=100000, parallels=4, start_training=0,
                     training_frequency=1, learning_rate_actor=1e-3, learning_rate_critic=1e-3, tau=0.005, gamma=0.99,
-                    alpha=0.2, use_automatic_entropy_tuning=auto_alpha, end_factor_lr_decay=0.7)
+                    alpha=0.2, use_automatic_entropy_tuning=auto_alpha, end_factor_lr_decay=0.7, use_cuda_graph=graph)
     lrn = SAC_Learner(cfg, model, BaseCallback())
     orc = SACLearnerOracle(om, auto_alpha=auto_alpha, end_factor_lr_decay=0.7, total_iters=lrn.total_iters)
     rng = np.random.default_rng(1)

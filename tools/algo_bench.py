@@ -65,6 +65,7 @@ def bench_perdqn(args):
     cfg = Namespace(distributed_training=False, episode_length=1000, use_grad_clip=False, grad_clip_norm=0.5, device=DEV,
                     model_dir="/tmp/x", running_steps=10**7, parallels=N, learning_rate=1e-4, gamma=0.99, sync_frequency=500,
                     start_training=0, training_frequency=1)
+    cfg.use_cuda_graph = args.graph
     lrn = PerDQN_Learner(cfg, model, BaseCallback())
 
     def step():
@@ -115,6 +116,7 @@ def bench_sac(args):
                     model_dir="/tmp/x", running_steps=10**6, parallels=N, start_training=0, training_frequency=1,
                     learning_rate_actor=1e-3, learning_rate_critic=1e-3, tau=0.005, gamma=0.99, alpha=0.2,
                     use_automatic_entropy_tuning=True)
+    cfg.use_cuda_graph = args.graph
     lrn = REGISTRY_Learners["SAC_Learner"](cfg, model, BaseCallback())
     dt = timed(lambda: lrn.update(sync=False, **buf.sample()), args.iters)
     out = {"config": "SAC, 17-d obs / 6-d act, 1M replay, B=1024, MLP 256-256", "gpu_updates_per_s": 1 / dt,
@@ -149,6 +151,7 @@ def bench_qmix(args, Be=32):
                     model_dir="/tmp/x", running_steps=10**7, parallels=n_envs, use_parameter_sharing=True, use_rnn=True,
                     use_actions_mask=False, learning_rate=7e-4, sync_frequency=200, double_q=True, n_epochs=1,
                     start_training=0, gamma=0.99)
+    cfg.use_cuda_graph = args.graph
     lrn = REGISTRY_Learners["QMIX_Learner"](cfg, grouping, model, BaseCallback())
     dt = timed(lambda: lrn.update(prod.sample(), sync=False), args.iters)
     out = {"config": f"QMIX, 5 agents x 72-d, S=98, A=12, T=60, {Be} episodes/update, GRU 64 + mixer 32/32",
@@ -167,6 +170,7 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--only", default="")
+    ap.add_argument("--graph", action="store_true", help="capture the learners' device update in a CUDA graph")
     args = ap.parse_args()
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -180,6 +184,7 @@ def main():
     if not only or "qmix" in only:
         res["qmix"] = bench_qmix(args)
         res["qmix_4096"] = bench_qmix(Namespace(**{**vars(args), "iters": 20, "no_cpu": True}), Be=1024)
+    res["cuda_graph"] = bool(args.graph)
     print(json.dumps(res))
 
 

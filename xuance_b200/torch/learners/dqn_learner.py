@@ -8,7 +8,7 @@ the PER sample are ignored, as in the reference (appendix B #8)."""
 import torch
 
 from ... import _lib
-from ..utils import FusedAdam, allreduce_sum_
+from ..utils import FusedAdam, allreduce_sum_, CapturedStep
 from .learner import Learner
 
 
@@ -28,9 +28,39 @@ class DQN_Learner(Learner):
         self.n_actions = self.model.n_actions
         self._stats = torch.zeros(4, dtype=torch.float32, device=self.device)
         self._scratch = _lib.scratch(self.device)
+        self.use_cuda_graph = getattr(config, "use_cuda_graph", False)
+        self._graphs = {}
 
     def _f32(self, x):
         return torch.as_tensor(x, device=self.device).to(torch.float32).contiguous()
+
+    def _snapshot(self):
+        return (self.optimizer.snapshot(), [p.detach().clone() for p in self.model.target_parameters()])
+
+    def _restore(self, st):
+        self.optimizer.restore(st[0])
+        for p, q in zip(self.model.target_parameters(), st[1]):
+            p.data.copy_(q)
+
+    def _device_update(self, obs, nxt, act, rew, ter):
+        """dqn_learner.py:38-52 on the device: no host synchronisation, static shapes (CUDA-graph capturable)."""
+        evalQ = self.model(obs).values.contiguous()
+        with torch.no_grad():
+            targetQ = self.model.target(nxt).values.contiguous()
+            selQ = self.model(nxt).values.contiguous() if self.double_q else None
+        B, A = evalQ.shape
+        dq = torch.empty_like(evalQ)
+        td = torch.empty(B, dtype=torch.float32, device=self.device)
+        _lib.call("xb_dqn_td_fwd_bwd", _lib.ptr(evalQ), _lib.ptr(targetQ), _lib.ptr(selQ), _lib.ptr(act), _lib.ptr(rew),
+                  _lib.ptr(ter), B, A, B * self.world_size, float(self.gamma), _lib.ptr(dq), _lib.ptr(td),
+                  _lib.ptr(self._stats), _lib.ptr(self._scratch))
+        self.optimizer.zero_grad()
+        torch.autograd.backward([evalQ], [dq])
+        if self.world_size > 1:
+            allreduce_sum_(self.optimizer.bucket.grad)
+            allreduce_sum_(self._stats)
+        self.optimizer.launch(max_norm=self.grad_clip_norm if self.use_grad_clip else None)
+        return td.abs()
 
     def update(self, sync=True, **samples):
         self.iterations += 1
@@ -39,22 +69,15 @@ class DQN_Learner(Learner):
         act, rew, ter = self._f32(samples['actions']), self._f32(samples['rewards']), self._f32(samples['terminals'])
         info = self.callback.on_update_start(self.iterations, model=self.model, obs=obs, act=act, next_obs=nxt,
                                              rew=rew, termination=ter) or {}
-        evalQ = self.model(obs).values.contiguous()
-        with torch.no_grad():
-            targetQ = self.model.target(nxt).values.contiguous()
-            selQ = self.model(nxt).values.contiguous() if self.double_q else None
-        B, A = evalQ.shape
-        dq = torch.empty_like(evalQ)
-        td = torch.empty(B, dtype=torch.float32, device=self.device)
-        _lib.call("xb_dqn_td_fwd_bwd", _lib.ptr(evalQ), _lib.ptr(targetQ), _lib.ptr(selQ), _lib.ptr(act), _lib.ptr(rew), _lib.ptr(ter),
-                  B, A, B * self.world_size, float(self.gamma), _lib.ptr(dq), _lib.ptr(td), _lib.ptr(self._stats),
-                  _lib.ptr(self._scratch))
-        self.optimizer.zero_grad()
-        torch.autograd.backward([evalQ], [dq])
-        if self.world_size > 1:
-            allreduce_sum_(self.optimizer.bucket.grad)
-            allreduce_sum_(self._stats)
-        self.optimizer.step(max_norm=self.grad_clip_norm if self.use_grad_clip else None)
+        self.optimizer.prepare()
+        if self.use_cuda_graph and self.world_size == 1:
+            key = (tuple(obs.shape), obs.dtype)
+            if key not in self._graphs:
+                self._graphs[key] = CapturedStep(self._device_update, [obs, nxt, act, rew, ter], self._snapshot,
+                                                 self._restore)
+            abs_td = self._graphs[key](obs, nxt, act, rew, ter)
+        else:
+            abs_td = self._device_update(obs, nxt, act, rew, ter)
         if self.scheduler is not None:
             self.scheduler.step()
         if self.iterations % self.sync_frequency == 0:
@@ -67,7 +90,7 @@ class DQN_Learner(Learner):
             info.update(vals)
             info.update(self.callback.on_update_end(self.iterations, model=self.model, info=info) or {})
         if self.returns_td:
-            return td.abs(), info   # |td| stays on the device; PerOffPolicyBuffer.update_priorities takes it as is
+            return abs_td, info   # |td| stays on the device; PerOffPolicyBuffer.update_priorities takes it as is
         return info
 
 

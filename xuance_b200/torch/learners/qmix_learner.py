@@ -13,7 +13,7 @@ evidently intended computation.  DESIGN.md "Reference quirks"."""
 import torch
 
 from ... import _lib
-from ..utils import FusedAdam, allreduce_sum_
+from ..utils import FusedAdam, allreduce_sum_, CapturedStep
 from .learner import Learner
 
 
@@ -62,6 +62,8 @@ class QMIX_Learner(Learner):
         self._filled_sum = torch.zeros(1, dtype=torch.float32, device=dev)
         self._stats = torch.zeros(2, dtype=torch.float32, device=dev)
         self._scratch = _lib.scratch(dev)
+        self.use_cuda_graph = getattr(config, "use_cuda_graph", False)
+        self._graphs = {}
 
     def estimate_total_iterations(self):
         """marl_learner.py:37-47."""
@@ -85,33 +87,53 @@ class QMIX_Learner(Learner):
         out['filled'], out['state'] = f32(sample['filled']), f32(sample['state'])
         return out
 
-    def update(self, sample, sync=True):
-        self.iterations += 1
-        d = self._stacked(sample)
-        B, T, n = sample['batch_size'], sample['sequence_length'], self.n_agents
-        info = self.callback.on_update_start(self.iterations, model=self.model, batch=d) or {}
-        packed = d['obs'].flatten(0, 1)                                     # [B*n, T+1, obs]
+    def _snapshot(self):
+        return (self.optimizer.snapshot(), self._filled_sum.clone())
+
+    def _restore(self, st):
+        self.optimizer.restore(st[0])
+        self._filled_sum.copy_(st[1])
+
+    def _device_update(self, obs, actions, rewards, terminals, agent_mask, filled, state):
+        """qmix_learner.py:24-95 on the device (no host synchronisation, static shapes: CUDA-graph capturable)."""
+        B, n, T1 = obs.shape[0], obs.shape[1], obs.shape[2]
+        T = T1 - 1
+        packed = obs.flatten(0, 1)                                          # [B*n, T+1, obs]
         q_all = self.model.q_values(packed).reshape(B, n, T + 1, -1).contiguous()
         with torch.no_grad():
             q_tgt = self.model.q_values(packed, target=True).reshape(B, n, T + 1, -1).contiguous()
         q_in = q_all.detach() if self.detach_q_eval else q_all
-        q_eval_taken, q_next_taken = _SelectFunction.apply(q_in, q_tgt, d['actions'], d['agent_mask'], d['filled'],
-                                                           self.double_q, self._filled_sum, self._scratch)
+        q_eval_taken, q_next_taken = _SelectFunction.apply(q_in, q_tgt, actions, agent_mask, filled, self.double_q,
+                                                           self._filled_sum, self._scratch)
         if self.world_size > 1:
             allreduce_sum_(self._filled_sum)                                # global sum(filled) for the loss
-        state = d['state']
         q_tot_eval = self.model.Q_tot(q_eval_taken, state[:, :-1]).reshape(-1).contiguous()
         with torch.no_grad():
             q_tot_next = self.model.Qtarget_tot(q_next_taken, state[:, 1:]).reshape(-1).contiguous()
         dq_tot = torch.empty_like(q_tot_eval)
-        _lib.call("xb_qmix_td", _lib.ptr(q_tot_eval), _lib.ptr(q_tot_next), _lib.ptr(d['rewards']),
-                  _lib.ptr(d['terminals']), _lib.ptr(d['filled']), _lib.ptr(self._filled_sum), B, n, T,
-                  float(self.gamma), 1.0, _lib.ptr(dq_tot), _lib.ptr(self._stats), _lib.ptr(self._scratch))
+        _lib.call("xb_qmix_td", _lib.ptr(q_tot_eval), _lib.ptr(q_tot_next), _lib.ptr(rewards), _lib.ptr(terminals),
+                  _lib.ptr(filled), _lib.ptr(self._filled_sum), B, n, T, float(self.gamma), 1.0, _lib.ptr(dq_tot),
+                  _lib.ptr(self._stats), _lib.ptr(self._scratch))
         self.optimizer.zero_grad()
         torch.autograd.backward([q_tot_eval], [dq_tot])
         if self.world_size > 1:
             allreduce_sum_(self.optimizer.bucket.grad)
-        self.optimizer.step(max_norm=self.grad_clip_norm if self.use_grad_clip else None)
+        self.optimizer.launch(max_norm=self.grad_clip_norm if self.use_grad_clip else None)
+        return None
+
+    def update(self, sample, sync=True):
+        self.iterations += 1
+        d = self._stacked(sample)
+        info = self.callback.on_update_start(self.iterations, model=self.model, batch=d) or {}
+        args = [d[k] for k in ('obs', 'actions', 'rewards', 'terminals', 'agent_mask', 'filled', 'state')]
+        self.optimizer.prepare()
+        if self.use_cuda_graph and self.world_size == 1:
+            key = tuple(d['obs'].shape)
+            if key not in self._graphs:
+                self._graphs[key] = CapturedStep(self._device_update, args, self._snapshot, self._restore)
+            self._graphs[key](*args)
+        else:
+            self._device_update(*args)
         if self.scheduler is not None:
             self.scheduler.step()
         if sync:

@@ -9,7 +9,7 @@ import torch
 import torch.nn as nn
 
 from ... import _lib
-from ..utils import FusedAdam, FlatBucket, allreduce_sum_
+from ..utils import FusedAdam, FlatBucket, allreduce_sum_, CapturedStep
 from .learner import Learner
 
 
@@ -34,9 +34,12 @@ class SAC_Learner(Learner):
             self.target_entropy = -np.prod(model.actor.action_space.shape).item()
             self.log_alpha = nn.Parameter(torch.zeros(1, requires_grad=True, device=self.device))
             self.alpha_optimizer = FusedAdam([self.log_alpha], lr=config.learning_rate_actor)
-            self.alpha = self.log_alpha.detach().exp()
+            self._alpha_buf = self.log_alpha.detach().exp()
         else:
-            self.alpha = torch.full((1,), float(config.alpha), device=self.device)
+            self._alpha_buf = torch.full((1,), float(config.alpha), device=self.device)
+        self.alpha = self._alpha_buf
+        self.use_cuda_graph = getattr(config, "use_cuda_graph", False)
+        self._graphs = {}
         dev = self.device
         self._stats_a = torch.zeros(4, dtype=torch.float32, device=dev)
         self._stats_c = torch.zeros(2, dtype=torch.float32, device=dev)
@@ -46,18 +49,28 @@ class SAC_Learner(Learner):
     def _f32(self, x):
         return torch.as_tensor(x, device=self.device).to(torch.float32).contiguous()
 
-    def update(self, sync=True, noise_pi=None, noise_next=None, **samples):
-        """``noise_pi`` / ``noise_next`` (standard normal [B, act_dim]) may be supplied for reproducible tests; by
-        default the model draws them as the reference does (Normal.rsample)."""
-        self.iterations += 1
-        obs, act = self._f32(samples['obs']), self._f32(samples['actions'])
-        nxt, rew, ter = self._f32(samples['obs_next']), self._f32(samples['rewards']), self._f32(samples['terminals'])
-        info = self.callback.on_update_start(self.iterations, model=self.model, obs=obs, act=act, next_obs=nxt,
-                                             rew=rew, termination=ter) or {}
+    def _snapshot(self):
+        st = {k: v.snapshot() for k, v in self.optimizer.items()}
+        st["target"] = self._target_bucket.flat.clone()
+        if self.use_automatic_entropy_tuning:
+            st["alpha_opt"] = self.alpha_optimizer.snapshot()
+        st["alpha"] = self._alpha_buf.clone()
+        return st
+
+    def _restore(self, st):
+        for k, v in self.optimizer.items():
+            v.restore(st[k])
+        self._target_bucket.flat.copy_(st["target"])
+        if self.use_automatic_entropy_tuning:
+            self.alpha_optimizer.restore(st["alpha_opt"])
+        self._alpha_buf.copy_(st["alpha"])
+
+    def _device_update(self, obs, act, nxt, rew, ter, noise_pi=None, noise_next=None):
+        """Everything of sac_learner.py:52-96 that runs on the device; no host synchronisation, static shapes."""
         B = obs.shape[0]
         Bt = B * self.world_size
         clip = self.grad_clip_norm if self.use_grad_clip else None
-        alpha = self.alpha.detach().contiguous()
+        alpha = self._alpha_buf
 
         # ---- actor step (sac_learner.py:53-60)
         log_pi, q1, q2 = self.model.Qpolicy(obs, noise_pi)
@@ -69,7 +82,7 @@ class SAC_Learner(Learner):
         torch.autograd.backward([log_pi, q1, q2], [dlp, dq1, dq2], inputs=self.optimizer['actor'].bucket.params)
         if self.world_size > 1:
             allreduce_sum_(self.optimizer['actor'].bucket.grad)
-        self.optimizer['actor'].step(max_norm=clip)
+        self.optimizer['actor'].launch(max_norm=clip)
 
         # ---- critic step (:62-72)
         aq1, aq2 = self.model.Qaction(obs, act)
@@ -85,7 +98,7 @@ class SAC_Learner(Learner):
         torch.autograd.backward([aq1, aq2], [dq1, dq2])
         if self.world_size > 1:
             allreduce_sum_(self.optimizer['critic'].bucket.grad)
-        self.optimizer['critic'].step(max_norm=clip)
+        self.optimizer['critic'].launch(max_norm=clip)
 
         # ---- temperature step (:74-82): d/dlog_alpha of -mean(log_alpha*(log_pi+H_target)) = -(mean(log_pi)+H_target)
         if self.use_automatic_entropy_tuning:
@@ -93,27 +106,48 @@ class SAC_Learner(Learner):
             if self.world_size > 1:
                 mean_lp = allreduce_sum_(mean_lp.clone())
             g = -(mean_lp + self.target_entropy)
-            self._alpha_loss = self.log_alpha.detach() * g
+            self._alpha_loss.copy_(self.log_alpha.detach() * g)
             self.alpha_optimizer.zero_grad()
             self.alpha_optimizer.bucket.grad[:1].copy_(g)
-            self.alpha_optimizer.step()
-            self.alpha = self.log_alpha.detach().exp()
+            self.alpha_optimizer.launch()
+            torch.exp(self.log_alpha.detach(), out=self._alpha_buf)
 
-        for s in self.scheduler.values():
-            s.step()
         # ---- Polyak update of the target critic (actor_critic.py:155-158) over the two flat buckets
         cb = self.optimizer['critic'].bucket
         _lib.call("xb_soft_update", _lib.ptr(self._target_bucket.flat), _lib.ptr(cb.flat), cb.numel, float(self.tau))
+        return None
 
+    def update(self, sync=True, noise_pi=None, noise_next=None, **samples):
+        """``noise_pi`` / ``noise_next`` (standard normal [B, act_dim]) may be supplied for reproducible tests; by
+        default the model draws them as the reference does (Normal.rsample)."""
+        self.iterations += 1
+        obs, act = self._f32(samples['obs']), self._f32(samples['actions'])
+        nxt, rew, ter = self._f32(samples['obs_next']), self._f32(samples['rewards']), self._f32(samples['terminals'])
+        info = self.callback.on_update_start(self.iterations, model=self.model, obs=obs, act=act, next_obs=nxt,
+                                             rew=rew, termination=ter) or {}
+        for o in self.optimizer.values():
+            o.prepare()
+        if self.use_automatic_entropy_tuning:
+            self.alpha_optimizer.prepare()
+        graphed = self.use_cuda_graph and self.world_size == 1 and (noise_pi is None) == (noise_next is None)
+        if graphed:
+            args = [obs, act, nxt, rew, ter] + ([] if noise_pi is None else [noise_pi, noise_next])
+            key = (tuple(obs.shape), len(args))
+            if key not in self._graphs:
+                self._graphs[key] = CapturedStep(self._device_update, args, self._snapshot, self._restore)
+            self._graphs[key](*args)
+        else:
+            self._device_update(obs, act, nxt, rew, ter, noise_pi, noise_next)
+        self.alpha = self._alpha_buf
+        for sch in self.scheduler.values():
+            sch.step()
         if sync:
             sa, sc = self._stats_a.tolist(), self._stats_c.tolist()
-            if self.world_size > 1:
-                pass  # per-rank statistics, as the reference logs them
             vals = {"Qloss": sc[0], "Ploss": sa[0], "Qvalue": sa[1],
                     "actor_lr": self.optimizer['actor'].param_groups[0]['lr'],
                     "critic_lr": self.optimizer['critic'].param_groups[0]['lr']}
             if self.use_automatic_entropy_tuning:
-                vals.update(alpha_loss=float(self._alpha_loss), alpha=float(self.alpha))
+                vals.update(alpha_loss=float(self._alpha_loss), alpha=float(self._alpha_buf))
             if self.distributed_training:
                 vals = {f"{k}/rank_{self.rank}": v for k, v in vals.items()}
             info.update(vals)

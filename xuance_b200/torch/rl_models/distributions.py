@@ -1,5 +1,7 @@
 """Policy distributions (reference: xuance/torch/rl_models/modules/distributions.py:96-218).  Same method
 surface; the arithmetic is torch.distributions, as in the reference."""
+import math
+
 import torch
 from torch.distributions import Categorical, Normal
 from torch.nn.functional import softplus
@@ -84,6 +86,7 @@ class ActivatedDiagGaussianDistribution(DiagGaussianDistribution):
             pre = self.mu + self.std * noise
         act = self.activation_fn(pre)
         log_prob = self.distribution.log_prob(pre)
-        correction = -2. * (torch.log(torch.tensor([2.0], device=pre.device)) - pre - softplus(-2. * pre))
+        # log(2) as a constant (the reference builds Tensor([2.0]).log() on the host every call - not graph-capturable)
+        correction = -2. * (math.log(2.0) - pre - softplus(-2. * pre))
         log_prob = log_prob + correction
         return act, log_prob.sum(-1)

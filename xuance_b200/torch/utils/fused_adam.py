@@ -30,6 +30,7 @@ class FusedAdam(torch.optim.Optimizer):
         self.exp_avg_sq = torch.zeros_like(self.bucket.flat)
         self.step_count = 0
         self._hyper = torch.zeros(4, dtype=torch.float32, device=dev)
+        self._hyper_host = torch.zeros(4, dtype=torch.float32)
         self._norm = torch.zeros(1, dtype=torch.float32, device=dev)
         self._scratch = _lib.scratch(dev)
         self._step_t = torch.zeros((), dtype=torch.float32)
@@ -44,18 +45,24 @@ class FusedAdam(torch.optim.Optimizer):
     def zero_grad(self, set_to_none=False):
         self.bucket.zero_grad()
 
-    @torch.no_grad()
-    def step(self, closure=None, max_norm=None, grad_scale=1.0, write_back_grad=False):
-        """One Adam step over the bucket.  ``max_norm`` (float or None) applies clip_grad_norm_ semantics first;
-        ``grad_scale`` multiplies the gradient (1/world_size after a sum all-reduce)."""
+    def prepare(self):
+        """Host half of a step: advance the step count and upload (step_size, bc2_sqrt, lr) for the kernels.  Kept apart
+        from ``launch`` so that a CUDA graph can capture the device half only."""
         group = self.param_groups[0]
         self.step_count += 1
         self._step_t.fill_(float(self.step_count))
         b1, b2 = group["betas"]
         t = self.step_count
-        step_size = group["lr"] / (1.0 - b1 ** t)
-        bc2_sqrt = math.sqrt(1.0 - b2 ** t)
-        self._hyper.copy_(torch.tensor([step_size, bc2_sqrt, group["lr"], 0.0], dtype=torch.float32))
+        self._hyper_host[0] = group["lr"] / (1.0 - b1 ** t)
+        self._hyper_host[1] = math.sqrt(1.0 - b2 ** t)
+        self._hyper_host[2] = group["lr"]
+        self._hyper.copy_(self._hyper_host)     # 16-byte pageable H2D: the driver stages it before returning
+
+    @torch.no_grad()
+    def launch(self, max_norm=None, grad_scale=1.0, write_back_grad=False):
+        """Device half: [global-norm reduction] + clip + Adam over the flat bucket (graph-capturable)."""
+        group = self.param_groups[0]
+        b1, b2 = group["betas"]
         n = self.bucket.numel
         clip = float(max_norm) if max_norm is not None else -1.0
         if clip > 0:
@@ -64,7 +71,24 @@ class FusedAdam(torch.optim.Optimizer):
         _lib.call("xb_adam_step", _lib.ptr(self.bucket.flat), _lib.ptr(self.bucket.grad), _lib.ptr(self.exp_avg),
                   _lib.ptr(self.exp_avg_sq), n, _lib.ptr(self._hyper), float(b1), float(b2), float(group["eps"]),
                   clip, _lib.ptr(self._norm), float(grad_scale), 1 if write_back_grad else 0)
+
+    @torch.no_grad()
+    def step(self, closure=None, max_norm=None, grad_scale=1.0, write_back_grad=False):
+        """One Adam step over the bucket.  ``max_norm`` (float or None) applies clip_grad_norm_ semantics first;
+        ``grad_scale`` multiplies the gradient (1/world_size after a sum all-reduce)."""
+        self.prepare()
+        self.launch(max_norm, grad_scale, write_back_grad)
         return None
+
+    def snapshot(self):
+        return (self.bucket.flat.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.step_count)
+
+    def restore(self, snap):
+        self.bucket.flat.copy_(snap[0])
+        self.exp_avg.copy_(snap[1])
+        self.exp_avg_sq.copy_(snap[2])
+        self.step_count = snap[3]
+        self._step_t.fill_(float(self.step_count))
 
     def load_state_dict(self, state_dict):
         """Accepts a torch.optim.Adam state_dict (reference checkpoints) and copies it into the flat buffers."""
