@@ -16,7 +16,7 @@ class CategoricalDistribution:
     def set_param(self, probs=None, logits=None):
         if probs is None and logits is None:
             raise RuntimeError("Failed to setup distributions without given probs or logits.")
-        self.distribution = Categorical(probs=probs, logits=logits)
+        self.distribution = Categorical(probs=probs, logits=logits, validate_args=False)
         self.probs, self.logits = self.distribution.probs, self.distribution.logits
 
     def get_param(self):
@@ -42,7 +42,9 @@ class DiagGaussianDistribution:
 
     def set_param(self, mu, std):
         self.mu, self.std = mu, std
-        self.distribution = Normal(mu, std)
+        # validate_args=False: torch's argument validation does a host-synchronising `.all()` per construction and per
+        # log_prob (not CUDA-graph capturable); the arithmetic is unchanged
+        self.distribution = Normal(mu, std, validate_args=False)
 
     def get_param(self):
         return self.mu, self.std
