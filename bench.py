@@ -217,12 +217,13 @@ def run_own_arm(args):
         assert world == args.gpus, "torchrun world size must equal --gpus"
     torch.cuda.set_device(local_rank)
     device = "cuda:%d" % local_rank
-    torch.backends.cudnn.allow_tf32 = args.compute != "fp32"
-    torch.backends.cuda.matmul.allow_tf32 = args.compute != "fp32"
+    torch.backends.cudnn.allow_tf32 = args.compute not in ("fp32", "fp32_cl")
+    torch.backends.cuda.matmul.allow_tf32 = args.compute not in ("fp32", "fp32_cl")
     torch.backends.cudnn.benchmark = True
     assert N_ENVS % world == 0
     n_local = N_ENVS // world
     cfg = ppo_namespace(device, n_local, world > 1, args.compute)
+    cfg.use_cuda_graph = bool(args.graph) if args.graph >= 0 else world > 1
     obs_space, act_space = Box(0, 255, OBS_SHAPE, np.uint8), Discrete(N_ACTIONS)
     agent = PPO_Agent(cfg, envs=None, observation_space=obs_space, action_space=act_space)  # buffer: n_local envs
     assert agent.n_envs == n_local
@@ -282,6 +283,24 @@ def run_own_arm(args):
     launches = _lib.launch_count - launches0
     prof = _lib.profile["xb_gather_obs"]
     _lib.profile = None
+    k3_how = "CUDA events around every K3 launch inside the timed region"
+    if cfg.use_cuda_graph or not prof:
+        # graph replays hide per-kernel events: time the same 16 minibatch gathers of one epoch right after the region
+        prof = []
+        perm_d = torch.from_numpy(np.random.permutation(agent.buffer_size)).to(device)
+        fmt = agent._obs_format()
+        for start in range(0, agent.buffer_size, agent.batch_size):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            idx = perm_d[start:start + agent.batch_size]
+            out = torch.empty((agent.batch_size, int(np.prod(OBS_SHAPE))), dtype=torch.float32 if fmt != _lib.OBS_BF16_NHWC
+                              else torch.bfloat16, device=device)
+            a.record()
+            _lib.call("xb_gather_obs", _lib.ptr(mem._obs), _lib.ptr(idx), agent.batch_size, *OBS_SHAPE, _lib.ptr(out), fmt)
+            b.record()
+            prof.append((a, b))
+            del out
+        torch.cuda.synchronize()
+        k3_how = "CUDA events around 4 x n_minibatch K3 launches issued right after the timed region (graph replay hides per-kernel events)"
     k3_ms = float(np.mean([a.elapsed_time(b) for a, b in prof])) if prof else None
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
@@ -330,7 +349,7 @@ def run_own_arm(args):
     peak, peak_src = measured_peaks()
     B_local = (N_ENVS * T // N_MINIBATCH) // world
     obs_bytes = int(np.prod(OBS_SHAPE))
-    out_w = {"fp32": 4, "tf32": 4, "bf16": 2}[args.compute]
+    out_w = {"fp32": 4, "fp32_cl": 4, "tf32": 4, "bf16": 2}[args.compute]
     alg_bytes = B_local * obs_bytes * (1 + out_w) + 8 * B_local
     roofline = None
     if k3_ms:
@@ -338,8 +357,8 @@ def run_own_arm(args):
         roofline = {"kernel": "gather_obs_kernel (K3: minibatch gather + u8->float)", "bound": "hbm",
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                    "avg_launch_ms": k3_ms, "launches_timed": len(prof),
-                    "share_of_step": (k3_ms * len(prof) / args.steps) / (elapsed_ms / args.steps)}
+                    "avg_launch_ms": k3_ms, "launches_timed": len(prof), "timed": k3_how,
+                    "share_of_step": (k3_ms * N_EPOCHS * N_MINIBATCH) / (elapsed_ms / args.steps)}
 
     if rank != 0:
         return
@@ -354,9 +373,10 @@ def run_own_arm(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_minibatch": N_ENVS * T // N_MINIBATCH,
                        "parallelism": "dp%d (envs sharded, 1 NCCL grad all-reduce/update)" % world,
-                       "compute": {"fp32": "fp32, TF32 disabled (reference arithmetic)", "tf32": "fp32 storage, TF32 convs/matmuls",
+                       "compute": {"fp32": "fp32, TF32 disabled (reference arithmetic)", "fp32_cl": "fp32, TF32 disabled, channels-last convolutions", "tf32": "fp32 storage, TF32 convs/matmuls",
                                    "bf16": "bf16 autocast convs, fp32 master weights"}[args.compute],
-                       "l2": "inputs (925 MB uint8 rollout / G) exceed the 126 MB L2; no explicit flush"},
+                       "l2": "inputs (925 MB uint8 rollout / G) exceed the 126 MB L2; no explicit flush",
+                       "cuda_graph": bool(cfg.use_cuda_graph)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "last_info": {k: (float(v) if not isinstance(v, dict) else v) for k, v in info.items()}}
     print(json.dumps(line))
@@ -368,9 +388,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="xuance_b200", choices=["xuance_b200", "reference"])
-    ap.add_argument("--compute", default="fp32", choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--compute", default="fp32", choices=["fp32", "fp32_cl", "tf32", "bf16"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", type=int, default=-1, help="CUDA-graph the minibatch update: 1/0; default: on when --gpus > 1")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":
         args.warmup = 3

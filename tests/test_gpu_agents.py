@@ -95,3 +95,36 @@ def test_checkpoint_roundtrip_reference_format(tmp_path):
     assert torch.equal(lrn.optimizer.exp_avg, lrn2.optimizer.exp_avg) and lrn2.optimizer.step_count == 1
     i1, i2 = lrn.update(**s), lrn2.update(**s)
     assert abs(i1["actor_loss"] - i2["actor_loss"]) < 1e-6
+
+
+def test_ppo_train_epochs_cuda_graph_matches_eager():
+    """train_epochs with the minibatch update captured in a CUDA graph == the eager path (same kernels, same order)."""
+    from xuance_b200.common import Box, Discrete
+    from xuance_b200.torch.agents import PPO_Agent
+    from helpers import synth_rollout, fill_buffers
+    import copy
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = False
+    base = dict(agent="PPO", learner="PPO_Learner", representation="AC_CNN_Atari", env_name="Atari",
+                distributed_training=False, device="cuda:0", seed=3, parallels=8, running_steps=100000, horizon_size=16,
+                n_epochs=2, n_minibatch=2, learning_rate=2.5e-4, vf_coef=0.25, ent_coef=0.01, clip_range=0.2, gamma=0.99,
+                use_gae=True, gae_lambda=0.95, use_advnorm=True, use_grad_clip=True, grad_clip_norm=0.5, use_obsnorm=False,
+                use_rewnorm=False, activation="relu", filters=[32, 64, 64], kernels=[8, 4, 3], strides=[4, 2, 1],
+                fc_hidden_sizes=[512], actor_hidden_size=[], critic_hidden_size=[], model_dir="/tmp/xb_models/g",
+                logger=None, compute="fp32", episode_length=None)
+    ro = synth_rollout(np.random.default_rng(0), 8, 16, (84, 84, 4))
+    results = []
+    for graph in (False, True):
+        cfg = Namespace(**dict(base, use_cuda_graph=graph))
+        agent = PPO_Agent(cfg, None, Box(0, 255, (84, 84, 4), np.uint8), Discrete(4))
+        fill_buffers([agent.memory], ro)
+        np.random.seed(11)
+        info = agent.train_epochs(2)
+        info2 = agent.train_epochs(2)          # second call replays the captured graph
+        results.append((info2, {k: v.clone() for k, v in agent.model.state_dict().items()}))
+    (i0, p0), (i1, p1) = results
+    for k in ("actor_loss", "critic_loss", "entropy", "predict_value", "clip_ratio"):
+        np.testing.assert_allclose(i1[k], i0[k], rtol=1e-4, atol=1e-6, err_msg=k)
+    for k in p0:
+        np.testing.assert_allclose(p1[k].cpu().numpy(), p0[k].cpu().numpy(), rtol=1e-4, atol=1e-6, err_msg=k)

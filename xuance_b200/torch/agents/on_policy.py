@@ -63,11 +63,32 @@ class OnPolicyAgent(Agent):
             return rep.preferred_obs_format()
         return _lib.OBS_U8
 
+    def _sample_and_update(self, idx):
+        """Device half of one minibatch: K3 gathers (+ adv-norm) -> network -> K4 -> backward -> [all-reduce] -> K7."""
+        s = self.memory.sample_prepared(idx, self._obs_format()) if getattr(self.config, "fused_sample", True) \
+            else self.memory.sample(idx)
+        lrn = self.learner
+        old_logp = s['aux_batch'].get('old_logp') if lrn.loss_kind == 0 else None
+        lrn._device_update(s['obs'], s['actions'], s['returns'], s[lrn.adv_key], old_logp)
+
+    def _graphed_minibatch(self, idx):
+        """One CUDA-graph replay per minibatch (config.use_cuda_graph): the host only uploads 16 bytes of Adam
+        hyper-parameters and the minibatch's slot indices.  Matters once the per-GPU minibatch is small (8 GPUs: 1024
+        rows per rank) and Python launch overhead would otherwise bound the step."""
+        from ..utils import CapturedStep
+        key = int(idx.numel())
+        if key not in self._graphs:
+            self.memory._ensure_gae()
+            self._graphs[key] = CapturedStep(self._sample_and_update, [idx], self.learner.optimizer.snapshot,
+                                             self.learner.optimizer.restore)
+        self._graphs[key](idx)
+
     def train_epochs(self, n_epochs=1):
         """on_policy.py:182-205."""
         train_info = {}
-        fmt = self._obs_format()
-        fused = getattr(self.config, "fused_sample", True)
+        use_graph = getattr(self.config, "use_cuda_graph", False) and hasattr(self.learner, "_device_update")
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
         total = n_epochs * (self.buffer_size // self.batch_size)
         done = 0
         for _ in range(n_epochs):
@@ -80,9 +101,17 @@ class OnPolicyAgent(Agent):
             perm_d = torch.from_numpy(perm).to(self.device, non_blocking=True)   # one H2D per epoch
             for start in range(0, self.buffer_size, self.batch_size):
                 idx = perm_d[start:start + self.batch_size]
-                samples = self.memory.sample_prepared(idx, fmt) if fused else self.memory.sample(idx)
                 done += 1
-                train_info = self.learner.update(sync=(done == total), **samples)
+                if use_graph:
+                    self.learner.host_pre_step()
+                    self._graphed_minibatch(idx)
+                    self.learner.host_post_step()
+                    if done == total:
+                        train_info = self.learner.materialize_info()
+                else:
+                    samples = self.memory.sample_prepared(idx, self._obs_format()) \
+                        if getattr(self.config, "fused_sample", True) else self.memory.sample(idx)
+                    train_info = self.learner.update(sync=(done == total), **samples)
         return train_info
 
     def test(self, test_episodes=1, test_envs=None, close_envs=True):

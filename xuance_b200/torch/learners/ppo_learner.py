@@ -40,17 +40,8 @@ class PPO_Learner(Learner):
     def _f32(self, x):
         return torch.as_tensor(x, device=self.device).to(torch.float32).contiguous()
 
-    def update(self, sync=True, **samples):
-        self.iterations += 1
-        obs = samples['obs']
-        if not hasattr(obs, "fmt"):  # PreparedObs passes through; arrays / tensors go to the device
-            obs = torch.as_tensor(obs, device=self.device)
-        act = self._f32(samples['actions'])
-        ret = self._f32(samples['returns'])
-        adv = self._f32(samples[self.adv_key])
-        old_logp = self._f32(samples['aux_batch']['old_logp']) if self.loss_kind == 0 else None
-        info = self.callback.on_update_start(self.iterations, policy=self.model, obs=obs, act=act, returns=ret,
-                                             advantages=adv, old_logp=old_logp) or {}
+    def _device_update(self, obs, act, ret, adv, old_logp):
+        """ppo_learner.py:43-65 on the device (no host synchronisation, static shapes: CUDA-graph capturable)."""
         B = act.shape[0]
         if hasattr(self.model, "forward_raw"):
             logits, v_pred = self.model.forward_raw(obs)
@@ -71,9 +62,30 @@ class PPO_Learner(Learner):
         if self.world_size > 1:
             allreduce_sum_(self.optimizer.bucket.grad)   # the one data-path collective
             allreduce_sum_(self._stats)
-        self.optimizer.step(max_norm=self.grad_clip_norm if self.use_grad_clip else None)
+        self.optimizer.launch(max_norm=self.grad_clip_norm if self.use_grad_clip else None)
+
+    def host_pre_step(self):
+        """Host half before the device update (step counter + 16-byte hyper-parameter upload)."""
+        self.iterations += 1
+        self.optimizer.prepare()
+
+    def host_post_step(self):
         if self.scheduler is not None:
             self.scheduler.step()
+
+    def update(self, sync=True, **samples):
+        obs = samples['obs']
+        if not hasattr(obs, "fmt"):  # PreparedObs passes through; arrays / tensors go to the device
+            obs = torch.as_tensor(obs, device=self.device)
+        act = self._f32(samples['actions'])
+        ret = self._f32(samples['returns'])
+        adv = self._f32(samples[self.adv_key])
+        old_logp = self._f32(samples['aux_batch']['old_logp']) if self.loss_kind == 0 else None
+        self.host_pre_step()
+        info = self.callback.on_update_start(self.iterations, policy=self.model, obs=obs, act=act, returns=ret,
+                                             advantages=adv, old_logp=old_logp) or {}
+        self._device_update(obs, act, ret, adv, old_logp)
+        self.host_post_step()
         if sync:
             info.update(self.materialize_info())
             info.update(self.callback.on_update_end(self.iterations, policy=self.model, info=info) or {})

@@ -50,7 +50,7 @@ class _PixelEncoder(nn.Module):
     compute = "fp32"
 
     def set_compute(self, mode):
-        assert mode in ("fp32", "tf32", "bf16")
+        assert mode in ("fp32", "fp32_cl", "tf32", "bf16")
         self.compute = mode
         fmt = torch.channels_last if mode != "fp32" else torch.contiguous_format
         for m in self.model:
@@ -60,7 +60,8 @@ class _PixelEncoder(nn.Module):
 
     def preferred_obs_format(self):
         """K3 output format this encoder consumes without any further copy."""
-        return {"fp32": _lib.OBS_F32_NCHW, "tf32": _lib.OBS_F32_NHWC, "bf16": _lib.OBS_BF16_NHWC}[self.compute]
+        return {"fp32": _lib.OBS_F32_NCHW, "fp32_cl": _lib.OBS_F32_NHWC, "tf32": _lib.OBS_F32_NHWC,
+                "bf16": _lib.OBS_BF16_NHWC}[self.compute]
 
     def _as_input(self, observations):
         fmt = self.preferred_obs_format()

@@ -23,13 +23,19 @@ class CapturedStep:
         torch.cuda.current_stream().wait_stream(side)
         restore(snap)
         torch.cuda.synchronize()
+        from ... import _lib
+        self._lib = _lib
+        before = _lib.launch_count
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.static_out = fn(*self.static_in)
+        self.xb_launches = _lib.launch_count - before     # xb200 kernels inside one replay
+        _lib.launch_count = before
 
     def __call__(self, *inputs):
         for s, x in zip(self.static_in, inputs):
             if isinstance(s, torch.Tensor) and s.data_ptr() != x.data_ptr():
                 s.copy_(x, non_blocking=True)
         self.graph.replay()
+        self._lib.launch_count += self.xb_launches
         return self.static_out
