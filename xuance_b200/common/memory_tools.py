@@ -310,7 +310,7 @@ class DummyOnPolicyBuffer(Buffer):
             # this rank holds B of the B*world rows of the global minibatch: normalise with the GLOBAL mean / population
             # std (memory_tools.py:281-282 applied to the whole minibatch) - one 3-double all-reduce
             a = out[adv_field].double()
-            mom = torch.stack([a.sum(), (a * a).sum(), torch.tensor(float(B), dtype=torch.float64, device=self.device)])
+            mom = torch.stack([a.sum(), (a * a).sum(), torch.full((), float(B), dtype=torch.float64, device=self.device)])
             dist.all_reduce(mom)
             mean = mom[0] / mom[2]
             std = (mom[1] / mom[2] - mean * mean).clamp_min(0).sqrt()
