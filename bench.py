@@ -125,10 +125,15 @@ def cpu_reference_rate(rows_budget_s, steps, warmup, threads=None, verbose=False
     from oracle.onpolicy import OnPolicyBufferOracle
     from oracle.nets import SharedActorCriticOracle
     from oracle.learners import PPOLearnerOracle
-    # all the host threads torch will use: its default intra-op pool = one thread per physical core, which is what
-    # the reference gets out of the box (it never calls set_num_threads); logical-core oversubscription is slower
-    if threads:
-        torch.set_num_threads(threads)
+    # all the host cores: one intra-op thread per PHYSICAL core (torch's own default when OMP_NUM_THREADS is unset -
+    # torchrun sets it to 1, so it is set explicitly here); SMT oversubscription (one thread per logical CPU) is slower
+    if not threads:
+        try:
+            import psutil
+            threads = psutil.cpu_count(logical=False) or os.cpu_count() or 1
+        except Exception:
+            threads = os.cpu_count() or 1
+    torch.set_num_threads(int(threads))
     cores = torch.get_num_threads()
     torch.manual_seed(1)
     rng = np.random.default_rng(0)
