@@ -400,6 +400,21 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":
         args.warmup = 3
+    # exactly ONE line on stdout: libraries (NCCL prints its version banner on fd 1) are diverted to stderr, the JSON
+    # line goes to the real stdout at the end
+    real_stdout = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    import builtins
+    _print = builtins.print
+
+    def emit(*a, **k):
+        k.setdefault("file", real_stdout)
+        _print(*a, **k)
+        real_stdout.flush()
+
+    g = globals()
+    g["print"] = emit
     if args.impl == "reference":
         run_reference_arm(args)
     else:
