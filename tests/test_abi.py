@@ -53,3 +53,48 @@ def test_product_does_not_import_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M):
                     bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_every_entry_point_validates_before_touching_the_device():
+    """Error behaviour of the C-ABI (include/xb200.h): bad sizes / NULL pointers / unsupported ranges are rejected with a
+    negative XB_E* code before any CUDA call, so this runs without a GPU."""
+    import ctypes
+    from xuance_b200 import _lib
+    lib = _lib.load()
+    P = ctypes.c_void_p
+    junk = P(0x1000)          # never dereferenced: validation fails first
+    odd = P(0x1001)           # misaligned pointer
+    EINVAL, EALIGN, ERANGE = -1, -2, -3
+    assert lib.xb_rollout_store(junk, junk, 6, None, None, 0, 4, 8, 0, None) == EALIGN        # row_bytes % 4 != 0
+    assert lib.xb_rollout_store(junk, junk, 16, None, None, 0, 4, 8, 8, None) == EINVAL       # t >= T
+    assert lib.xb_rollout_store(junk, None, 16, None, None, 0, 4, 8, 0, None) == EINVAL       # dst without src
+    assert lib.xb_gae_scan(junk, junk, junk, junk, junk, None, junk, junk, 0, 8, 0.99, 0.95, 1, None) == EINVAL
+    assert lib.xb_gather_rows(junk, None, -1, 16, junk, None) == EINVAL
+    assert lib.xb_gather_rows(junk, None, 4, 6, junk, None) == EALIGN
+    assert lib.xb_gather_rows(junk, None, 0, 16, junk, None) == 0                              # empty batch is a no-op
+    assert lib.xb_gather_obs(junk, None, 4, 84, 84, 3, junk, 2, None) == ERANGE                # NCHW needs C == 4
+    assert lib.xb_gather_obs(junk, None, 4, 5, 5, 1, junk, 1, None) == EALIGN                  # H*W*C % 16 != 0
+    assert lib.xb_gather_obs(junk, None, 4, 84, 84, 4, junk, 9, None) == EINVAL                # unknown format
+    assert lib.xb_gather_scalars(junk, 10, None, 4, 2, junk, 5, junk, junk, None) == EINVAL    # adv_field >= F
+    assert lib.xb_ppo_loss_fwd_bwd(junk, junk, junk, junk, junk, junk, 8, 65, 8, 0.2, 0.25, 0.01, 0, junk, junk, junk, junk, None) == ERANGE
+    assert lib.xb_ppo_loss_fwd_bwd(junk, junk, junk, junk, junk, junk, 8, 4, 4, 0.2, 0.25, 0.01, 0, junk, junk, junk, junk, None) == EINVAL  # B_total < B
+    assert lib.xb_ppo_loss_fwd_bwd(junk, junk, junk, None, junk, junk, 8, 4, 8, 0.2, 0.25, 0.01, 0, junk, junk, junk, junk, None) == EINVAL  # clip needs old_logp
+    assert lib.xb_ppo_loss_fwd_bwd(junk, junk, junk, junk, junk, junk, 8, 4, 8, 0.2, 0.25, 0.01, 7, junk, junk, junk, junk, None) == EINVAL  # loss_kind
+    assert lib.xb_ppo_loss_fwd_bwd(odd, junk, junk, junk, junk, junk, 8, 4, 8, 0.2, 0.25, 0.01, 0, junk, junk, junk, junk, None) == EALIGN
+    assert lib.xb_per_insert(junk, junk, junk, 2, 16, 16, 0.5, None) == EINVAL                 # ptr >= cap
+    assert lib.xb_per_sample(junk, junk, junk, 2, 12, 4, 2, 12, 1.0, junk, junk, junk, None) == EINVAL   # cap not 2^k
+    assert lib.xb_per_sample(junk, junk, junk, 2, 16, 17, 2, 16, 1.0, junk, junk, junk, None) == EINVAL  # size > cap
+    assert lib.xb_per_update(junk, junk, junk, junk, junk, 2, 16, 0, 0.5, None) == EINVAL
+    assert lib.xb_dqn_td_fwd_bwd(junk, junk, None, junk, junk, junk, 0, 4, 0, 0.99, junk, junk, junk, junk, None) == EINVAL
+    assert lib.xb_grad_sumsq(odd, 16, 1.0, junk, junk, None) == EALIGN
+    assert lib.xb_adam_step(junk, junk, junk, junk, 16, junk, 0.9, 0.999, 1e-5, 0.5, None, 1.0, 0, None) == EINVAL  # clip without norm
+    assert lib.xb_soft_update(junk, None, 16, 0.005, None) == EINVAL
+    assert lib.xb_sac_actor_loss(junk, junk, junk, None, 8, 8, junk, junk, junk, junk, junk, None) == EINVAL
+    assert lib.xb_qmix_mix_fwd(junk, junk, junk, junk, junk, 8, 17, 32, junk, None) == ERANGE   # n > 16
+    assert lib.xb_qmix_select_fwd(junk, junk, junk, junk, junk, 0, 5, 60, 12, 1, junk, junk, junk, junk, None) == EINVAL
+    four = (P * 4)(junk, junk, junk, junk)
+    assert lib.xb_qmix_mix_fused_fwd(junk, junk, four, four, junk, junk, junk, junk, junk, junk, 128, 98, 5, 64, 32, junk, None) == ERANGE
+    assert lib.xb_qmix_mix_fused_fwd(junk, junk, four, four, junk, junk, junk, junk, junk, junk, 128, 160, 5, 32, 32, junk, None) == ERANGE  # smem
+    assert lib.xb_powf_libm(None, 0.5, junk, 4, None) == EINVAL
+    for code in (EINVAL, EALIGN, ERANGE):
+        assert lib.xb_error_string(code).startswith(b"xb200:")
