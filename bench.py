@@ -360,7 +360,10 @@ def run_own_arm(args):
     if k3_ms:
         ach = alg_bytes / (k3_ms * 1e-3) / 1e9
         roofline = {"kernel": "gather_obs_kernel (K3: minibatch gather + u8->float)", "bound": "hbm",
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of
+                    # this kernel at this shape (profiles/r01_k3_gather_obs_f32nchw_raw.csv: 231.8 MB + 867.4 MB)
+                    "traffic": 1.0992e9 if (args.compute == "fp32" and B_local == 8192) else None,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                     "avg_launch_ms": k3_ms, "launches_timed": len(prof), "timed": k3_how,
                     "share_of_step": (k3_ms * N_EPOCHS * N_MINIBATCH) / (elapsed_ms / args.steps)}

@@ -128,3 +128,25 @@ def test_ppo_train_epochs_cuda_graph_matches_eager():
         np.testing.assert_allclose(i1[k], i0[k], rtol=1e-4, atol=1e-6, err_msg=k)
     for k in p0:
         np.testing.assert_allclose(p1[k].cpu().numpy(), p0[k].cpu().numpy(), rtol=1e-3, atol=5e-5, err_msg=k)  # cuDNN wgrad atomics
+
+
+def test_tensor_env_wrapper_feeds_the_hbm_buffer():
+    """E4 (tensor_env.py:38-51): device-facing env wrapper -> buffer.store with CUDA tensors, uint8 frames stay uint8."""
+    from xuance_b200.environment import make_envs, TensorEnvWrapper
+    from xuance_b200.common import DummyOnPolicyBuffer_Atari
+    envs = TensorEnvWrapper(make_envs(Namespace(env_id="SyntheticAtari", vectorize="Dummy_Atari", parallels=4, env_seed=2)),
+                            "cuda:0")
+    obs, _ = envs.reset()
+    assert obs.is_cuda and obs.dtype == torch.uint8 and tuple(obs.shape) == (4, 84, 84, 4)
+    buf = DummyOnPolicyBuffer_Atari(envs.observation_space, envs.action_space, {"old_logp": ()}, 4, 8, device="cuda:0")
+    seen = []
+    for t in range(8):
+        acts = torch.randint(0, 4, (4,), device="cuda:0")
+        nxt, rew, term, trunc, infos = envs.step(acts)
+        buf.store(obs, acts, rew, torch.zeros(4, device="cuda:0"), term, {"old_logp": torch.zeros(4, device="cuda:0")})
+        seen.append(obs.cpu())
+        obs = nxt
+    assert buf.full
+    for t in range(8):
+        assert torch.equal(buf.observations[:, t].cpu(), seen[t])
+    envs.close()

@@ -1,6 +1,8 @@
 """Environment construction (reference: xuance/environment/__init__.py:12-76 ``make_envs``)."""
 from .envs import REGISTRY_ENV, XuanCeEnvWrapper, CartPoleEnv, SyntheticAtariEnv
-from .vector_envs import REGISTRY_VEC_ENV, VecEnv, DummyVecEnv, DummyVecEnv_Atari, SubprocVecEnv, SubprocVecEnv_Atari
+from .vector_envs import (REGISTRY_VEC_ENV, VecEnv, DummyVecEnv, DummyVecEnv_Atari, SubprocVecEnv, SubprocVecEnv_Atari,
+                          ShmSubprocVecEnv, ShmSubprocVecEnv_Atari)
+from .tensor_env import TensorEnvWrapper
 
 
 def make_envs(config):
