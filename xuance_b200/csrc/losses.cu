@@ -10,7 +10,7 @@
 //   Categorical(logits): logp_i = z_i - logsumexp(z);  entropy = -sum p_i*logp_i
 //   torch.minimum backward: ties split the gradient in half; clamp backward passes inside [lo,hi] inclusive.
 template <int A_MAX>
-__global__ void __launch_bounds__(256) ppo_loss_kernel(const float *__restrict__ logits,
+__global__ void __launch_bounds__(256, (A_MAX <= 4 ? 3 : 1)) ppo_loss_kernel(const float *__restrict__ logits,
                                                        const float *__restrict__ value,
                                                        const float *__restrict__ actions,
                                                        const float *__restrict__ old_logp,
@@ -22,44 +22,49 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const float *__restrict__
     __shared__ double red[6 * 32];
     double acc[6] = {0, 0, 0, 0, 0, 0};  // a_loss, c_loss, entropy, v, clipped count, (unused)
     const float lo = 1.0f - clip, hi = 1.0f + clip;
-    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x) {
+    struct Row {
         float z[A_MAX];
+        float v, act, ol, ad, r;
+    };
+    auto load_row = [&](int64_t b, Row &in) {
         const float *zr = logits + b * A;
-        float m = -INFINITY;
         if (A_MAX == 4 && A == 4) {  // the BASELINE action count: one 16-byte load per row
             const float4 z4 = *reinterpret_cast<const float4 *>(zr);
-            z[0] = z4.x, z[1] = z4.y, z[2] = z4.z, z[3] = z4.w;
-            m = fmaxf(fmaxf(z4.x, z4.y), fmaxf(z4.z, z4.w));
+            in.z[0] = z4.x, in.z[1] = z4.y, in.z[2] = z4.z, in.z[3] = z4.w;
         } else {
 #pragma unroll
-            for (int i = 0; i < A_MAX; ++i) {
-                if (i < A) {
-                    z[i] = zr[i];
-                    m = fmaxf(m, z[i]);
-                }
-            }
+            for (int i = 0; i < A_MAX; ++i)
+                if (i < A) in.z[i] = zr[i];
         }
+        in.v = value[b], in.act = actions[b], in.ad = adv[b], in.r = ret[b];
+        in.ol = (loss_kind == 0) ? old_logp[b] : 0.f;
+    };
+    auto compute_row = [&](int64_t b, const Row &in) {
+        float m = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < A_MAX; ++i)
+            if (i < A) m = fmaxf(m, in.z[i]);
         float se = 0.f;
 #pragma unroll
         for (int i = 0; i < A_MAX; ++i)
-            if (i < A) se += expf(z[i] - m);
+            if (i < A) se += expf(in.z[i] - m);
         const float lse = m + logf(se);
-        const int a = (int)actions[b];
+        const int a = (int)in.act;
         float ent = 0.f, logp_a = 0.f;
         float p[A_MAX], lp[A_MAX];
 #pragma unroll
         for (int i = 0; i < A_MAX; ++i) {
             if (i < A) {
-                lp[i] = z[i] - lse;
+                lp[i] = in.z[i] - lse;
                 p[i] = expf(lp[i]);
                 ent -= p[i] * lp[i];
                 if (i == a) logp_a = lp[i];
             }
         }
-        const float ad = adv[b];
+        const float ad = in.ad;
         float ratio = 1.f, smin, d_logp;
         if (loss_kind == 0) {  // PPO-Clip surrogate
-            ratio = expf(logp_a - old_logp[b]);
+            ratio = expf(logp_a - in.ol);
             const float rc = fminf(fmaxf(ratio, lo), hi);
             const float s1 = rc * ad, s2 = ad * ratio;
             smin = fminf(s1, s2);
@@ -91,14 +96,32 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const float *__restrict__
             for (int i = 0; i < A_MAX; ++i)
                 if (i < A) dz[i] = gz[i];
         }
-        const float v = value[b], r = ret[b];
-        const float dv = v - r;
+        const float dv = in.v - in.r;
         dvalue[b] = vf_coef * 2.f * dv * inv_bt;
         acc[0] += (double)(-smin);
         acc[1] += (double)dv * (double)dv;
         acc[2] += (double)ent;
-        acc[3] += (double)v;
+        acc[3] += (double)in.v;
         acc[4] += (ratio < lo || ratio > hi) ? 1.0 : 0.0;
+    };
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    if (A_MAX <= 4) {
+        // two rows in flight per thread: the loads of the second row are issued before the (transcendental-heavy)
+        // arithmetic of the first - the kernel is latency-bound on its global loads otherwise (ncu: long_scoreboard)
+        for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += 2 * stride) {
+            Row r0, r1;
+            const bool two = b + stride < B;
+            load_row(b, r0);
+            if (two) load_row(b + stride, r1);
+            compute_row(b, r0);
+            if (two) compute_row(b + stride, r1);
+        }
+    } else {
+        for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += stride) {
+            Row r0;
+            load_row(b, r0);
+            compute_row(b, r0);
+        }
     }
     grid_sum_finalize<6>(acc, scratch, red, [&](double(&t)[6]) {
         const double ib = (double)inv_bt;
