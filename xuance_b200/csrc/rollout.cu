@@ -93,34 +93,15 @@ __global__ void __launch_bounds__(128) gae_scan_kernel(const float *__restrict__
     const float gl = gamma * lam;
     const int TILE = 32 * V;
     R carry = (R)0;  // A_{t+1} (GAE) or ret_{t+1} (n-step) entering the tile from the right
-    // software prefetch: the (always full) next-lower tile is loaded while the current one is scanned - the tiles are
-    // chained only through `carry`, so its loads are independent and hide the HBM latency of a one-warp-per-env kernel
-    float4 pr = make_float4(0, 0, 0, 0), pv = pr, pd = pr;
-    uchar4 ps = make_uchar4(0, 0, 0, 0);
-    bool pref = false;
     for (int hi = ((T + TILE - 1) / TILE) * TILE; hi > 0; hi -= TILE) {
         const int t0 = hi - TILE + lane * V;  // this lane's first step
         float r[V], v[V + 1], d[V], bs[V];
         uint8_t se[V];
         if (V == 4 && VEC && t0 + V <= T) {  // 16-byte loads: T % 4 == 0 and 16-B aligned rows (checked on the host)
-            float4 r4, v4, d4;
-            uchar4 s4;
-            if (pref) {
-                r4 = pr, v4 = pv, d4 = pd, s4 = ps;
-            } else {
-                r4 = *reinterpret_cast<const float4 *>(rew + base + t0);
-                v4 = *reinterpret_cast<const float4 *>(val + base + t0);
-                d4 = *reinterpret_cast<const float4 *>(term + base + t0);
-                s4 = *reinterpret_cast<const uchar4 *>(seg_end + base + t0);
-            }
-            pref = hi - TILE > 0;
-            if (pref) {
-                const int tn = t0 - TILE;  // >= 0 and fully in range: only the topmost tile can be partial
-                pr = *reinterpret_cast<const float4 *>(rew + base + tn);
-                pv = *reinterpret_cast<const float4 *>(val + base + tn);
-                pd = *reinterpret_cast<const float4 *>(term + base + tn);
-                ps = *reinterpret_cast<const uchar4 *>(seg_end + base + tn);
-            }
+            const float4 r4 = *reinterpret_cast<const float4 *>(rew + base + t0);
+            const float4 v4 = *reinterpret_cast<const float4 *>(val + base + t0);
+            const float4 d4 = *reinterpret_cast<const float4 *>(term + base + t0);
+            const uchar4 s4 = *reinterpret_cast<const uchar4 *>(seg_end + base + t0);
             r[0] = r4.x, r[1] = r4.y, r[2] = r4.z, r[3] = r4.w;
             v[0] = v4.x, v[1] = v4.y, v[2] = v4.z, v[3] = v4.w;
             d[0] = d4.x, d[1] = d4.y, d[2] = d4.z, d[3] = d4.w;
