@@ -177,11 +177,122 @@ def golden_dqn():
     np.savez_compressed(os.path.join(HERE, "dqn_update.npz"), **out)
 
 
+def golden_sac():
+    """Three SAC updates of the reference learner (17-d obs / 6-d action, MLP 64-64, automatic entropy tuning).  The
+    reference draws its reparameterisation noise from torch's global RNG; the fixture stores the noise it drew (the stream
+    is replayed: randn(B, act) for the actor step, then randn(B, act) for the target step)."""
+    from copy import deepcopy
+    from xuance.torch.rl_models.representations.mlp import Basic_Identical
+    from xuance.torch.rl_models.actors.gaussian_actors import SAC_GaussianActor
+    from xuance.torch.rl_models.critics.twin_critics import TwinActionValueCritic
+    from xuance.torch.rl_models.architectures.single_agent.actor_critic import SoftActorCritic
+    from xuance.torch.learners import SAC_Learner
+    out = {"env": ENV}
+    torch.manual_seed(7)
+    obs_dim, act_dim, B = 17, 6, 32
+    aspace = Box(-1, 1, (act_dim,), np.float32)
+    rep = Basic_Identical((obs_dim,), device='cpu')
+    actor = SAC_GaussianActor(rep, [64, 64], aspace, None, None, torch.nn.LeakyReLU, torch.nn.Tanh, 'cpu')
+    critic = TwinActionValueCritic(deepcopy(rep), aspace, [64, 64], None, None, torch.nn.LeakyReLU, 'cpu')
+    model = SoftActorCritic(actor, critic)
+    for k, v in model.state_dict().items():
+        out[f"init/{k}"] = v.numpy().copy()
+    cfg = _learner_cfg(learning_rate_actor=1e-3, learning_rate_critic=1e-3, tau=0.005, alpha=0.2, use_grad_clip=False,
+                       use_automatic_entropy_tuning=True, end_factor_lr_decay=0.7, parallels=4, running_steps=100000)
+    lrn = SAC_Learner(cfg, model, BaseCallback())
+    out["total_iters"] = lrn.total_iters
+    rng = np.random.default_rng(12)
+    infos = []
+    for it in range(3):
+        s = {"obs": rng.normal(size=(B, obs_dim)).astype(np.float32),
+             "actions": rng.uniform(-1, 1, size=(B, act_dim)).astype(np.float32),
+             "obs_next": rng.normal(size=(B, obs_dim)).astype(np.float32),
+             "rewards": rng.normal(size=B).astype(np.float32), "terminals": (rng.random(B) < 0.1).astype(np.float32)}
+        torch.manual_seed(500 + it)
+        out[f"noise_pi/{it}"] = torch.randn(B, act_dim).numpy()
+        out[f"noise_next/{it}"] = torch.randn(B, act_dim).numpy()
+        torch.manual_seed(500 + it)
+        info = lrn.update(**s)
+        for k, v in s.items():
+            out[f"in{it}/{k}"] = v
+        infos.append([info["Qloss"], info["Ploss"], info["Qvalue"], info["alpha_loss"], info["alpha"], info["actor_lr"]])
+    out["infos"] = np.array(infos, dtype=np.float64)
+    for k, v in model.state_dict().items():
+        flat = v.detach().reshape(-1)
+        out[f"final_head/{k}"] = flat[:32].numpy().copy()
+        out[f"final_digest/{k}"] = np.array([flat.double().sum().item(), flat.double().abs().sum().item()])
+    np.savez_compressed(os.path.join(HERE, "sac_update.npz"), **out)
+
+
+def golden_qmix():
+    """Episode replay + three QMIX updates of the reference (5 agents x 24-d obs, 7 actions, 30-d state, T=10, GRU 64,
+    mixer 32/32, double-Q, use_actions_mask=False).  Pins BOTH reference behaviours recorded in DESIGN.md: the values and
+    the fact that the agent networks do not move (q_eval is sliced under no_grad)."""
+    from xuance.common import AgentGrouping
+    from xuance.common.memory_tools_marl import MARL_OffPolicyBuffer_RNN
+    from xuance.torch.rl_models.representations.rnn import Basic_RNN
+    from xuance.torch.rl_models.representations.agent_feature import AgentFeatureEncoder
+    from xuance.torch.rl_models.modules.identity_encoder import build_identity_encoder, IdentityFeatureFusion
+    from xuance.torch.rl_models.critics.base_critics import DiscreteActionValueCritic
+    from xuance.torch.rl_models.heads.q_mix_head import QMIX_Mixer
+    from xuance.torch.rl_models.architectures.multi_agent.value_factorization import MixingQNetwork
+    from xuance.torch.learners.multi_agent_rl.qmix_learner import QMIX_Learner
+    from helpers import qmix_episode_stream
+    out = {"env": ENV}
+    torch.manual_seed(8)
+    n, obs_dim, A, S, T = 5, 24, 7, 30, 10
+    keys = [f"agent_{i}" for i in range(n)]
+    rep = Basic_RNN(input_shape=(obs_dim,), hidden_sizes=None, initialize=torch.nn.init.orthogonal_,
+                    activation=torch.nn.ReLU, device='cpu', fc_hidden_sizes=[64], recurrent_hidden_size=64,
+                    N_recurrent_layers=1, dropout=0, rnn='GRU')
+    enc = AgentFeatureEncoder(rep, build_identity_encoder(n, 'none', None, 'cpu'), IdentityFeatureFusion(64, 0, 'concat'))
+    q = torch.nn.ModuleDict({'shared': DiscreteActionValueCritic(enc, Discrete(A), [64], None, torch.nn.init.orthogonal_,
+                                                                   torch.nn.ReLU, 'cpu')})
+    grouping = AgentGrouping.shared(keys)
+    model = MixingQNetwork(grouping, q, QMIX_Mixer(S, 32, 32, n, 'cpu'), use_rnn=True, device='cpu')
+    for k, v in model.state_dict().items():
+        out[f"init/{k}"] = v.numpy().copy()
+    cfg = _learner_cfg(episode_length=T, use_grad_clip=False, parallels=4, running_steps=100000,
+                       use_parameter_sharing=True, use_rnn=True, use_actions_mask=False, learning_rate=7e-4,
+                       sync_frequency=2, double_q=True, n_epochs=1, end_factor_lr_decay=0.5)
+    lrn = QMIX_Learner(cfg, grouping, model, BaseCallback())
+    out["total_iters"] = lrn.total_iters
+    n_envs, C, Be = 3, 12, 6
+    rb = MARL_OffPolicyBuffer_RNN(agent_keys=keys, state_space=Box(-1, 1, (S,)),
+                                  obs_space={k: Box(-1, 1, (obs_dim,)) for k in keys},
+                                  act_space={k: Discrete(A) for k in keys}, n_envs=n_envs, buffer_size=C, batch_size=Be,
+                                  max_episode_steps=T, use_actions_mask=False)
+    for ev in qmix_episode_stream(np.random.default_rng(21), keys, n_envs, T, obs_dim, A, S, 5):
+        if ev[0] == 'store':
+            rb.store(**ev[1])
+        else:
+            rb.finish_path(ev[1], **ev[2])
+    out["cfg"] = np.array([n, obs_dim, A, S, T, n_envs, C, Be])
+    out["buffer/ptr_size"] = np.array([rb.ptr, int(rb.size)])
+    out["buffer/filled"], out["buffer/state"] = rb.data['filled'], rb.data['state']
+    for kname in ('obs', 'actions', 'rewards', 'terminals', 'agent_mask'):
+        out[f"buffer/{kname}"] = np.stack([rb.data[kname][a] for a in keys], axis=1)
+    infos = []
+    for it in range(3):
+        np.random.seed(it)
+        s = rb.sample()
+        info = lrn.update(s)
+        infos.append([info["loss_Q"], info["predictQ"], info["learning_rate"]])
+    out["infos"] = np.array(infos, dtype=np.float64)
+    for k, v in model.state_dict().items():
+        flat = v.detach().reshape(-1)
+        out[f"final_head/{k}"] = flat[:32].numpy().copy()
+        out[f"final_digest/{k}"] = np.array([flat.double().sum().item(), flat.double().abs().sum().item()])
+    np.savez_compressed(os.path.join(HERE, "qmix_update.npz"), **out)
+
+
 if __name__ == "__main__":
     golden_onpolicy()
     golden_per()
     golden_ppo()
     golden_dqn()
+    golden_sac()
+    golden_qmix()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
