@@ -198,6 +198,30 @@ int xb_adam_step(float *p, float *g, float *m, float *v, int64_t n, const float 
                  int write_back_grad, void *stream);
 int xb_soft_update(float *target, const float *source, int64_t n, float tau, void *stream);
 
+/* ---------------------------------------------------------------- K10/K11: device-side rollout glue ---
+ * what OnPolicyAgent.get_actions does after the network (core/on_policy.py:128-169) and what
+ * Agent._process_observation / RunningMeanStd.update do before it (agents/base/agent.py:262-279,
+ * common/statistic_tools.py:117-185), each as ONE launch writing straight into device buffers (e.g. the K1 staging
+ * rows of the rollout buffer), so that a vector-env step costs one H2D of observations and one D2H of N int32 actions.
+ *
+ * xb_categorical_act: CategoricalDistribution over logits[N,A] (modules/distributions.py:128-162), A <= 64.
+ *   forced_actions != NULL : a_n = (int)forced_actions[n]          (log_prob / entropy of given actions)
+ *   else uniforms != NULL  : a_n = min{i : u_n < p_0+..+p_i}, u in [0,1) (stochastic_sample; inverse CDF in index order,
+ *                            last index if rounding leaves the total mass below u_n)
+ *   else                   : a_n = first argmax_i p_i               (deterministic_sample)
+ *   outputs (each nullable, at least one): actions_f32[N] (the float32 the buffers store), actions_i32[N] (for the
+ *   host-side env step), logp[N] = log_softmax(logits)[a], entropy[N] = -sum p log p.
+ * xb_rms_update_normalize: x[N,D] float32.
+ *   update != 0: (mean, var)[D] <- parallel-variance merge with the batch moments, float32 in the reference's operation
+ *                order; `count` is the running count BEFORE the merge (host state, Python float in the reference).
+ *   out != NULL: out = clip((x - mean) / (sqrt(var) + eps), -clip_range, clip_range) with the UPDATED statistics
+ *                (PPO_Agent.train calls obs_rms.update(obs) and then _process_observation(obs), ppo_agent.py:115-116).
+ */
+int xb_categorical_act(const float *logits, const float *uniforms, const float *forced_actions, int N, int A,
+                       float *actions_f32, int32_t *actions_i32, float *logp, float *entropy, void *stream);
+int xb_rms_update_normalize(const float *x, int N, int64_t D, float *mean, float *var, double count, int update,
+                            float *out, float clip_range, float eps, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -286,6 +286,36 @@ def golden_qmix():
     np.savez_compressed(os.path.join(HERE, "qmix_update.npz"), **out)
 
 
+def golden_rollout_glue():
+    """RunningMeanStd + Agent._process_observation arithmetic (statistic_tools.py:117-185, agent.py:273-276) and
+    CategoricalDistribution log_prob / entropy / deterministic_sample (distributions.py:128-162) of the reference."""
+    from xuance.common.statistic_tools import RunningMeanStd
+    from xuance.common.common_tools import EPS
+    from xuance.torch.rl_models.modules.distributions import CategoricalDistribution
+    out = {"env": ENV}
+    rng = np.random.default_rng(33)
+    for name, N, D in (("cartpole", 8, 4), ("wide", 256, 17)):
+        rms = RunningMeanStd(shape=(D,))
+        for it in range(6):
+            x = (rng.normal(size=(N, D)) * (1.0 + 3.0 * it) + 0.5 * it).astype(np.float32)
+            rms.update(x)
+            y = np.clip((x - rms.mean) / (rms.std + EPS), -5, 5)
+            out[f"rms/{name}/x{it}"], out[f"rms/{name}/y{it}"] = x, y
+            out[f"rms/{name}/mean{it}"], out[f"rms/{name}/var{it}"] = rms.mean.copy(), rms.var.copy()
+            out[f"rms/{name}/count{it}"] = np.float64(rms.count)
+    for A in (2, 4, 18):
+        logits = (rng.normal(size=(64, A)) * 2.0).astype(np.float32)
+        acts = rng.integers(0, A, size=64)
+        d = CategoricalDistribution(A)
+        d.set_param(logits=torch.from_numpy(logits))
+        out[f"cat/{A}/logits"], out[f"cat/{A}/actions"] = logits, acts
+        out[f"cat/{A}/log_prob"] = d.log_prob(torch.from_numpy(acts)).numpy()
+        out[f"cat/{A}/entropy"] = d.entropy().numpy()
+        out[f"cat/{A}/argmax"] = d.deterministic_sample().numpy()
+        out[f"cat/{A}/probs"] = d.probs.numpy()
+    np.savez_compressed(os.path.join(HERE, "rollout_glue.npz"), **out)
+
+
 if __name__ == "__main__":
     golden_onpolicy()
     golden_per()
@@ -293,6 +323,7 @@ if __name__ == "__main__":
     golden_dqn()
     golden_sac()
     golden_qmix()
+    golden_rollout_glue()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -5,7 +5,7 @@ this module raises.  Tensors are passed as raw device pointers (``tensor.data_pt
 is torch's current CUDA stream so launches interleave correctly with cuDNN/cuBLAS work issued by torch."""
 import ctypes
 import os
-from ctypes import c_int, c_int64, c_float, c_void_p, c_char_p, POINTER
+from ctypes import c_int, c_int64, c_float, c_double, c_void_p, c_char_p, POINTER
 
 import torch
 
@@ -35,6 +35,8 @@ _SIGNATURES = {
     "xb_adam_step": (c_int, [_P, _P, _P, _P, c_int64, _P, c_float, c_float, c_float, c_float, _P, c_float,
                              c_int, _P]),
     "xb_soft_update": (c_int, [_P, _P, c_int64, c_float, _P]),
+    "xb_categorical_act": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P]),
+    "xb_rms_update_normalize": (c_int, [_P, c_int, c_int64, _P, _P, c_double, c_int, _P, c_float, c_float, _P]),
     "xb_sac_actor_loss": (c_int, [_P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
     "xb_sac_critic_loss": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_float, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
     "xb_qmix_select_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]),

@@ -79,6 +79,51 @@ class Buffer(ABC):
     def finish_path(self, *args):
         pass
 
+    # ------------------------------------------------------------------ checkpoint
+    # The reference never saves its buffers (learners/base/drl_learner.py:64-93 holds the policy and optimiser only), so a
+    # resumed off-policy run starts from an empty replay.  ``state_dict`` / ``load_state_dict`` move the HBM arrays, the
+    # ring cursors and (PER) the trees through host memory; ``Agent.save_model(..., save_buffer=True)`` writes them next
+    # to the ``.pth``.
+    _ckpt_tensors = ()      # attribute names of device tensors (None entries are skipped)
+    _ckpt_host = ()         # attribute names of host tensors / NumPy arrays
+
+    def state_dict(self):
+        sd = {"class": type(self).__name__, "n_envs": self.n_envs, "n_size": self.n_size, "ptr": int(self.ptr),
+              "size": int(self.size)}
+        for name in self._ckpt_tensors:
+            t = getattr(self, name, None)
+            if t is not None:
+                sd[name] = t.detach().cpu()
+        for name in self._ckpt_host:
+            v = getattr(self, name)
+            sd[name] = v.clone() if isinstance(v, torch.Tensor) else np.array(v, copy=True)
+        return sd
+
+    def load_state_dict(self, sd):
+        if sd.get("class") != type(self).__name__ or sd["n_envs"] != self.n_envs or sd["n_size"] != self.n_size:
+            raise ValueError("buffer checkpoint is for %s[%s x %s], this buffer is %s[%d x %d]" % (
+                sd.get("class"), sd.get("n_envs"), sd.get("n_size"), type(self).__name__, self.n_envs, self.n_size))
+        for name in self._ckpt_tensors:
+            t = getattr(self, name, None)
+            if t is None:
+                continue
+            src = sd[name]
+            if tuple(src.shape) != tuple(t.shape) or src.dtype != t.dtype:
+                raise ValueError("buffer checkpoint field %s: %s %s, expected %s %s" % (
+                    name, tuple(src.shape), src.dtype, tuple(t.shape), t.dtype))
+            t.copy_(src)
+        for name in self._ckpt_host:
+            v = getattr(self, name)
+            if isinstance(v, torch.Tensor):
+                v.copy_(sd[name])
+            else:
+                v[...] = sd[name]
+        self.ptr, self.size = int(sd["ptr"]), int(sd["size"])
+        self._after_load()
+
+    def _after_load(self):
+        pass
+
     # ------------------------------------------------------------------ shared helpers
     def _alloc_rows(self, shape, dtype):
         return torch.zeros((self.n_envs, self.n_size) + tuple(shape), dtype=dtype, device=self.device)
@@ -120,6 +165,11 @@ class DummyOnPolicyBuffer(Buffer):
     K2 launch the first time they are needed."""
 
     obs_dtype = torch.float32
+    _ckpt_tensors = ("_obs", "_act_rows", "_fields")
+    _ckpt_host = ("_seg_end_h", "_boot_h", "_covered_h", "start_ids")
+
+    def _after_load(self):
+        self._gae_dirty = True      # returns / advantages are recomputed from the restored segment bookkeeping
 
     def __init__(self, observation_space, action_space, auxiliary_shape, n_envs, horizon_size,
                  use_gae=True, use_advnorm=True, gamma=0.99, gae_lam=0.95, device="cuda:0"):
@@ -259,6 +309,44 @@ class DummyOnPolicyBuffer(Buffer):
         self.ptr = (self.ptr + 1) % self.n_size
         self.size = min(self.size + 1, self.n_size)
 
+    # -------- device-side rollout: the policy kernel writes its outputs for the step being
+    # collected straight into the K1 staging block; after the env step only rewards / terminals cross PCIe.
+    def policy_slots(self):
+        """float32 [N] device views {'actions', 'values', 'aux:<key>'...} of the persistent staging block that
+        ``store_staged`` hands to K1.  Fill them (e.g. K10 ``xb_categorical_act``) before calling ``store_staged``."""
+        if not self._scalar_action:
+            raise NotImplementedError("policy_slots: scalar (Discrete) action spaces only")
+        if getattr(self, "_dev_scal", None) is None:
+            N = self.n_envs
+            self._dev_scal = torch.zeros((self._n_store, N), dtype=torch.float32, device=self.device)
+            self._stage_rt = [torch.zeros((2, N), dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._stage_rt_evt = [None, None]
+            self._stage_rt_i = 0
+        return {n: self._dev_scal[self._fid[n]] for n in self._names[2:self._n_store]}
+
+    def store_staged(self, obs, rews, terminals):
+        """``store`` for a step whose actions / values / aux already sit in ``policy_slots()``: ``obs`` is the CUDA
+        tensor the policy just consumed (no second upload), ``rews`` / ``terminals`` are the env's host arrays."""
+        self.policy_slots()
+        N, T, t = self.n_envs, self.n_size, self.ptr
+        if not (isinstance(obs, torch.Tensor) and obs.is_cuda):
+            raise ValueError("store_staged: obs must be the CUDA tensor fed to the policy")
+        i = self._stage_rt_i
+        if self._stage_rt_evt[i] is not None:
+            self._stage_rt_evt[i].synchronize()
+        host = self._stage_rt[i].numpy()
+        host[0], host[1] = rews, terminals
+        self._dev_scal[0:2].copy_(self._stage_rt[i], non_blocking=True)
+        evt = torch.cuda.Event()
+        evt.record()
+        self._stage_rt_evt[i] = evt
+        self._stage_rt_i ^= 1
+        obs_d = obs.to(self.obs_dtype).reshape(N, -1).contiguous()
+        _lib.call("xb_rollout_store", _lib.ptr(self._obs), _lib.ptr(obs_d), obs_d.shape[1] * obs_d.element_size(),
+                  _lib.ptr(self._fields), _lib.ptr(self._dev_scal), self._n_store, N, T, t)
+        self.ptr = (self.ptr + 1) % self.n_size
+        self.size = min(self.size + 1, self.n_size)
+
     # -------- K2
     def finish_path(self, val, i):
         """reference :242-265 - records that env ``i``'s current path ends at the last stored step with bootstrap
@@ -369,6 +457,7 @@ class DummyOffPolicyBuffer(Buffer):
     """Device-resident mirror of DummyOffPolicyBuffer (reference memory_tools.py:331-387)."""
 
     obs_dtype = torch.float32
+    _ckpt_tensors = ("_obs", "_next_obs", "_act_rows", "_fields")
 
     def __init__(self, observation_space, action_space, auxiliary_shape, n_envs, buffer_size, batch_size,
                  device="cuda:0"):
@@ -485,6 +574,8 @@ class PerOffPolicyBuffer(DummyOffPolicyBuffer):
     xuance/common/segtree_tool.py held in HBM: ``_it_sum`` / ``_it_min`` are ``[n_envs, 2*capacity]`` float32
     heaps (one pair per env, as the reference), driven by the K5 kernels.  Image observations are stored as
     uint8 when the observation space's dtype is uint8 (reference stores float32: appendix B #9)."""
+
+    _ckpt_tensors = DummyOffPolicyBuffer._ckpt_tensors + ("_it_sum", "_it_min", "_max_priority")
 
     def __init__(self, observation_space, action_space, auxiliary_shape, n_envs, buffer_size, batch_size,
                  alpha=0.6, device="cuda:0"):

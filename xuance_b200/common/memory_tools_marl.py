@@ -74,6 +74,25 @@ class MARL_OffPolicyBuffer_RNN:
                              for k, (s, dt) in self._fields().items()}
         self._ep_np = {k: v.numpy() for k, v in self.episode_data.items()}
 
+    # ---- checkpoint (the reference does not save its replay)
+    def state_dict(self):
+        return {"class": type(self).__name__, "buffer_size": self.buffer_size, "n_envs": self.n_envs,
+                "max_eps_len": self.max_eps_len, "ptr": int(self.ptr), "size": int(self.size),
+                "data": {k: v.cpu() for k, v in self._dev.items()},
+                "episode_data": {k: v.clone() for k, v in self.episode_data.items()}}
+
+    def load_state_dict(self, sd):
+        if (sd.get("class"), sd.get("buffer_size"), sd.get("n_envs"), sd.get("max_eps_len")) != \
+                (type(self).__name__, self.buffer_size, self.n_envs, self.max_eps_len):
+            raise ValueError("episode-replay checkpoint does not match this buffer's capacity / envs / episode length")
+        for k, v in self._dev.items():
+            if tuple(sd["data"][k].shape) != tuple(v.shape) or sd["data"][k].dtype != v.dtype:
+                raise ValueError("episode-replay checkpoint field %s has shape %s" % (k, tuple(sd["data"][k].shape)))
+            v.copy_(sd["data"][k])
+        for k, v in self.episode_data.items():
+            v.copy_(sd["episode_data"][k])
+        self.ptr, self.size = int(sd["ptr"]), int(sd["size"])
+
     @property
     def full(self):
         return self.size >= self.buffer_size

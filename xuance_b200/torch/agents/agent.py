@@ -122,7 +122,13 @@ class Agent(ABC):
                     pass
 
     # ---------------------------------------------------------------- checkpoints (agent.py:199-229)
-    def save_model(self, model_name):
+    def save_model(self, model_name, save_buffer=False):
+        """agent.py:199-213.  ``save_buffer=True`` (extension) also writes this rank's replay /
+        rollout buffer - HBM arrays, ring cursors, PER trees - to ``<model_name>.buffer.rank<r>``."""
+        if save_buffer and self.memory is not None and hasattr(self.memory, "state_dict"):
+            os.makedirs(self.model_dir_save, exist_ok=True)
+            torch.save(self.memory.state_dict(),
+                       os.path.join(self.model_dir_save, "%s.buffer.rank%d" % (model_name, self.rank)))
         if self.distributed_training and self.rank > 0:
             return
         os.makedirs(self.model_dir_save, exist_ok=True)
@@ -131,13 +137,20 @@ class Agent(ABC):
             np.save(os.path.join(self.model_dir_save, "obs_rms.npy"),
                     {'count': self.obs_rms.count, 'mean': self.obs_rms.mean, 'var': self.obs_rms.var})
 
-    def load_model(self, path, model=None):
+    def load_model(self, path, model=None, load_buffer=False):
+        """agent.py:215-229.  ``load_buffer=True`` restores the buffer written by ``save_model(save_buffer=True)`` when
+        the file for this rank sits next to the loaded ``.pth``."""
         path_loaded = self.learner.load_model(path, model)
         if self.use_obsnorm:
             p = os.path.join(os.path.dirname(str(path_loaded)), "obs_rms.npy")
             if os.path.exists(p):
                 d = np.load(p, allow_pickle=True).item()
                 self.obs_rms.count, self.obs_rms.mean, self.obs_rms.var = d['count'], d['mean'], d['var']
+        if load_buffer:
+            p = "%s.buffer.rank%d" % (str(path_loaded), self.rank)
+            if not os.path.exists(p):
+                raise FileNotFoundError("no buffer checkpoint %s" % p)
+            self.memory.load_state_dict(torch.load(p, map_location="cpu", weights_only=False))
 
     # ---------------------------------------------------------------- normalisation (agent.py:262-294)
     def _process_observation(self, observations):

@@ -14,6 +14,7 @@ import torch
 
 from ... import _lib
 from ..utils import FusedAdam, allreduce_sum_, CapturedStep
+from ..utils.flat_bucket import cudnn_rnn_front
 from .learner import Learner
 
 
@@ -54,7 +55,8 @@ class QMIX_Learner(Learner):
         self.detach_q_eval = getattr(config, "qmix_rnn_detach_q_eval", False)
         # LearnerMAS.build_optimizer (marl_learner.py:64-76): one Adam(eps=1e-5) + LinearLR over the trainable set
         self.optimizer = FusedAdam(self.model.parameters_model, lr=self.learning_rate, eps=1e-5,
-                                   weight_decay=getattr(config, "weight_decay", 0.0))
+                                   weight_decay=getattr(config, "weight_decay", 0.0),
+                                   front=cudnn_rnn_front(self.model.individual_q_networks))
         self.scheduler = torch.optim.lr_scheduler.LinearLR(self.optimizer, start_factor=1.0,
                                                            end_factor=self.end_factor_lr_decay,
                                                            total_iters=self.total_iters)

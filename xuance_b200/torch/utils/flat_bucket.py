@@ -10,8 +10,20 @@ import torch
 _ALIGN = 32  # elements (128 B): keeps every parameter view 128-byte aligned for cuDNN / cuBLAS vector loads
 
 
+def cudnn_rnn_front(module):
+    """The flat weights of the first ``nn.RNNBase`` inside ``module`` (or []).  cuDNN's RNN path uses the weights in place
+    only when they sit, in ``_flat_weights`` order and back to back, at the START of their storage (ATen
+    cudnn/RNN.cpp ``try_get_weight_buf``); anywhere else it re-packs them on every forward.  Passing this list as
+    ``FlatBucket(..., front=)`` puts that one group at offset 0 of the bucket."""
+    for m in module.modules():
+        if isinstance(m, torch.nn.RNNBase):
+            return [w for w in m._flat_weights if w is not None and w.requires_grad]
+    return []
+
+
 class FlatBucket:
-    def __init__(self, params):
+    def __init__(self, params, front=()):
+        """``front``: parameters to lay out first (see ``cudnn_rnn_front``); ``self.params`` keeps the caller's order."""
         seen, plist = set(), []
         for p in params:
             if p.requires_grad and id(p) not in seen:
@@ -23,11 +35,15 @@ class FlatBucket:
         if dev.type != "cuda":
             raise RuntimeError("FlatBucket: parameters must live on a CUDA device (no CPU fallback)")
         self.params = plist
-        self.offsets, off = [], 0
-        for p in plist:
+        first = [id(p) for p in front if id(p) in seen]
+        layout = sorted(range(len(plist)), key=lambda i: (first.index(id(plist[i])) if id(plist[i]) in first
+                                                          else len(first) + i))
+        self.offsets, off = [0] * len(plist), 0
+        for i in layout:
+            p = plist[i]
             if p.dtype != torch.float32 or p.device != dev:
                 raise ValueError("FlatBucket: all parameters must be float32 on one device")
-            self.offsets.append(off)
+            self.offsets[i] = off
             off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
         self.numel = off
         self.flat = torch.zeros(off, dtype=torch.float32, device=dev)

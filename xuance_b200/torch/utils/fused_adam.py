@@ -15,7 +15,7 @@ from .flat_bucket import FlatBucket
 
 
 class FusedAdam(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, front=()):
         params = list(params)
         if weight_decay != 0.0:
             raise NotImplementedError("weight_decay is not on the hot path (reference configs use 0)")
@@ -24,7 +24,7 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, defaults)
         if len(self.param_groups) != 1:
             raise NotImplementedError("FusedAdam drives exactly one parameter group")
-        self.bucket = FlatBucket(self.param_groups[0]["params"])
+        self.bucket = FlatBucket(self.param_groups[0]["params"], front=front)
         dev = self.bucket.flat.device
         self.exp_avg = torch.zeros_like(self.bucket.flat)
         self.exp_avg_sq = torch.zeros_like(self.bucket.flat)
@@ -49,6 +49,7 @@ class FusedAdam(torch.optim.Optimizer):
         """Host half of a step: advance the step count and upload (step_size, bc2_sqrt, lr) for the kernels.  Kept apart
         from ``launch`` so that a CUDA graph can capture the device half only."""
         group = self.param_groups[0]
+        self._opt_called = True     # what LRScheduler.step() looks at to tell "optimizer stepped first"
         self.step_count += 1
         self._step_t.fill_(float(self.step_count))
         b1, b2 = group["betas"]
