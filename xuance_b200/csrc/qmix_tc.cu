@@ -14,85 +14,16 @@
 // split x = hi + lo (two bf16 values, |x - hi - lo| <= 2^-17 |x|) and each product is the sum of the three MMAs
 // hi.hi + hi.lo + lo.hi (lo.lo ~ 2^-18 is below the split residual) accumulated in fp32 in TMEM: relative error ~1e-5 per layer (a plain bf16 or TF32
 // pass would be ~4e-3 / ~5e-4).  tests/test_gpu_qmix.py pins it against the fp32 oracle.
-#include "xb_common.cuh"
+#include "tc_common.cuh"
 
 namespace {
+using namespace xbtc;
 
 constexpr int TC_ROWS = 128;   // M
 constexpr int TC_HH = 32;      // hypernet hidden = mixing hidden = 32 (the shipped QMIX configs)
 constexpr int TC_N1 = 128;     // 4 x 32 first-layer outputs
 constexpr int TC_TMEM_COLS = 512;
 constexpr int COL_Z = 0, COL_W1 = 128, COL_W2 = 384, COL_B2 = 416;   // W1raw may take up to 256 columns (n <= 8)
-
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {
-    hi = __float2bfloat16_rn(x);
-    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-}
-
-// byte offset of element (r, k) of a [rows x KP] bf16 operand in the K-major no-swizzle canonical layout:
-// core matrix = 8 rows x 8 elements (16 B per row, 128 B per core), K-adjacent cores contiguous (LBO = 128 B),
-// 8-row groups SBO = KP/8 * 128 B apart.
-__device__ __forceinline__ uint32_t canon_off(int r, int k, int KP) {
-    return (uint32_t)((r >> 3) * (KP >> 3) * 128 + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2);
-}
-
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, int KP) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);               // start address
-    d |= (uint64_t)((128 >> 4) & 0x3fff) << 16;               // LBO: next core matrix along K
-    d |= (uint64_t)((((KP >> 3) * 128) >> 4) & 0x3fff) << 32; // SBO: next 8-row group
-    d |= (uint64_t)1 << 46;                                   // descriptor version (sm_100)
-    return d;                                                 // layout_type = 0 (no swizzle), base_offset = 0
-}
-
-__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                         uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
-        : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
-    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
-}
-// split 8 consecutive-k floats of one row and store them as ONE 16-byte core-matrix row each (hi, lo)
-__device__ __forceinline__ void store_unit(const float (&x)[8], int r, int k0, int KP, uint8_t *hi, uint8_t *lo) {
-    __nv_bfloat16 h[8], l[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) split_bf16(x[i], h[i], l[i]);
-    const uint32_t off = canon_off(r, k0, KP);
-    *reinterpret_cast<uint4 *>(hi + off) = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
-    *reinterpret_cast<uint4 *>(lo + off) = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
-}
 
 // stage a [rows x K] fp32 row-major matrix (leading dimension ld; global OR shared memory) as hi/lo bf16 canonical
 // operands, zero padded; one thread-iteration = 8 consecutive k of one row (two 16-byte shared-memory stores);
