@@ -222,6 +222,27 @@ int xb_categorical_act(const float *logits, const float *uniforms, const float *
 int xb_rms_update_normalize(const float *x, int N, int64_t D, float *mean, float *var, double count, int update,
                             float *out, float clip_range, float eps, void *stream);
 
+/* ---------------------------------------------------------------- K12 (EXPERIMENTAL): tensor-core layers ------
+ * Not on any default path; compiled and host-verified (tests/test_conv_index.py), hardware bring-up is round-2 work
+ * (DESIGN.md section 9).  Target: the NatureCNN layers of AC_CNN_Atari / Basic_CNN (rl_models/representations/cnn.py:
+ * 45-50, 84-101; layers.py:16-65) that cuDNN runs as CUDA-core fp32 convolutions.
+ * xb_split_bf16       : x (float32[n]) -> hi = bf16(x), lo = bf16(x - hi)            (n*4 B read, n*4 B written)
+ * xb_pack_conv_weight : torch [N, C, KH, KW] float32 -> [N, (kh, kw, c)] hi / lo bf16 (also Linear over a [C,H,W] flatten)
+ * xb_gemm_gather_tc   : D[m,n] = sum_{t,c} in[b, y*sy+dy[t], x*sx+dx[t], c] * W[n, t*C+c] (+bias, ReLU), m = (b,y,x) over
+ *                       [B,OY,OX]; in / W as hi / lo bf16 pairs (NHWC, [N,K]); three tcgen05.mma per product (hi.hi +
+ *                       hi.lo + lo.hi, fp32 accumulation in TMEM); result as float32 and / or a hi / lo pair written to
+ *                       columns [out_c0, out_c0+N) of row (b*out_H + y*oys+oy0)*out_W + x*oxs+ox0 of a matrix with
+ *                       out_ld elements per row (out_ld % 8 == out_c0 % 8 == 0).  C % 8 == 0, (T*C) % 64 == 0,
+ *                       N % 32 == 0, N <= 256, T <= 64; dy / dx are HOST arrays (copied into the launch parameters).
+ *                       Forward conv: dy = kh - pad, (sy,sx) = stride; Linear: one tap;
+ *                       data gradients: flipped taps over the output gradient, one call per stride phase. */
+int xb_split_bf16(const float *x, int64_t n, void *hi, void *lo, void *stream);
+int xb_pack_conv_weight(const float *w, int N, int C, int KH, int KW, void *hi, void *lo, void *stream);
+int xb_gemm_gather_tc(const void *in_hi, const void *in_lo, const void *w_hi, const void *w_lo, const float *bias,
+                      int B, int IH, int IW, int C, int OY, int OX, int sy, int sx, int T, const int8_t *dy,
+                      const int8_t *dx, int N, int relu, void *out_hi, void *out_lo, float *out_f32, int out_H,
+                      int out_W, int oys, int oxs, int oy0, int ox0, int64_t out_ld, int out_c0, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,99 @@
+// Host emulation of conv_tc.cu's data movement, built by tests/test_conv_index.py with g++ (no CUDA needed).
+// Staging uses the kernel's own index functions (xuance_b200/csrc/conv_index.h); the "tensor core" side re-derives the
+// operand addresses from the shared-memory descriptor semantics that K9-TC validated on hardware (start address + ks*256,
+// LBO = 128 B between K-adjacent core matrices, SBO = KC/8*128 B between 8-row groups, 16 B per core-matrix row), so a
+// wrong placement by the producer shows up as a numeric mismatch (or a NaN from the poisoned stage).
+#include <cmath>
+#include <cstdint>
+#include <limits>
+#include <vector>
+
+#include "../../xuance_b200/csrc/conv_index.h"
+
+namespace {
+inline float &at(std::vector<float> &smem, uint32_t byte_off) { return smem[byte_off / 2]; }   // one slot per bf16
+}
+
+extern "C" int emul_gemm_gather(const float *in_hi, const float *in_lo, const float *w_hi, const float *w_lo, int B,
+                                int IH, int IW, int C, int OY, int OX, int sy, int sx, int T, const int8_t *dy,
+                                const int8_t *dx, int N, int out_H, int out_W, int oys, int oxs, int oy0, int ox0,
+                                int64_t out_ld, int out_c0, int stages, double *out) {
+    XbConvGeom g;
+    g.B = B, g.IH = IH, g.IW = IW, g.C = C, g.OY = OY, g.OX = OX, g.sy = sy, g.sx = sx, g.T = T, g.N = N;
+    for (int t = 0; t < XB_CONV_MAX_TAPS; ++t) g.dy[t] = t < T ? dy[t] : 0, g.dx[t] = t < T ? dx[t] : 0;
+    const int KC = XB_CONV_KC, TM = XB_CONV_TILE_M, K = T * C;
+    if (K % KC || C % 8 || N % 8) return -1;
+    const int n_chunks = K / KC;
+    const uint32_t stage_bytes = xb_conv_stage_bytes(N), a_plane = xb_conv_a_plane_bytes(), w_plane = xb_conv_w_plane_bytes(N);
+    std::vector<float> smem((size_t)stages * stage_bytes / 2);
+    const int64_t M = (int64_t)B * OY * OX, n_tiles = (M + TM - 1) / TM;
+    const float nan = std::numeric_limits<float>::quiet_NaN();
+    uint32_t it = 0;
+    std::vector<double> acc((size_t)TM * N);
+    for (int64_t tile = 0; tile < n_tiles; ++tile) {
+        std::fill(acc.begin(), acc.end(), 0.0);
+        for (int kc = 0; kc < n_chunks; ++kc, ++it) {
+            const uint32_t base = (it % stages) * stage_bytes;
+            for (uint32_t i = 0; i < stage_bytes / 2; ++i) smem[base / 2 + i] = nan;     // poison the stage
+            // ---- producer (conv_tc.cu, warps 5-8): thread = row
+            for (int row = 0; row < TM; ++row) {
+                const int64_t m = tile * TM + row;
+                const bool live = m < M;
+                int b = 0, y = 0, x = 0;
+                if (live) xb_conv_site(g, m, b, y, x);
+                for (int u = 0; u < KC / 8; ++u) {
+                    const int64_t off = live ? xb_conv_unit_src(g, b, y, x, kc * KC + u * 8) : -1;
+                    const uint32_t dst = base + xb_canon_off(row, u * 8, KC);
+                    for (int j = 0; j < 8; ++j) {
+                        at(smem, dst + 2 * j) = off >= 0 ? in_hi[off + j] : 0.f;
+                        at(smem, dst + a_plane + 2 * j) = off >= 0 ? in_lo[off + j] : 0.f;
+                    }
+                }
+                for (int idx = row; idx < N * (KC / 8); idx += TM) {
+                    const int n = idx >> 3, u = idx & 7;
+                    const int64_t src = (int64_t)n * K + kc * KC + u * 8;
+                    const uint32_t dst = base + 2 * a_plane + xb_canon_off(n, u * 8, KC);
+                    for (int j = 0; j < 8; ++j) {
+                        at(smem, dst + 2 * j) = w_hi[src + j];
+                        at(smem, dst + w_plane + 2 * j) = w_lo[src + j];
+                    }
+                }
+            }
+            // ---- tensor core: three products, K 16 per instruction, operands located through the descriptor fields
+            const uint32_t LBO = 128, SBO = (KC / 8) * 128;
+            const uint32_t a_addr[2] = {base, base + a_plane};
+            const uint32_t w_addr[2] = {base + 2 * a_plane, base + 2 * a_plane + w_plane};
+            for (int pa = 0; pa < 2; ++pa)
+                for (int pb = 0; pb < 2 - pa; ++pb)
+                    for (int ks = 0; ks < KC / 16; ++ks) {
+                        const uint32_t sa = a_addr[pa] + ks * 256, sb = w_addr[pb] + ks * 256;
+                        for (int r = 0; r < TM; ++r)
+                            for (int n = 0; n < N; ++n) {
+                                double s = 0.0;
+                                for (int kk = 0; kk < 16; ++kk) {
+                                    const uint32_t inner = (kk >> 3) * LBO + (kk & 7) * 2;
+                                    const float av = at(smem, sa + (r >> 3) * SBO + (r & 7) * 16 + inner);
+                                    const float bv = at(smem, sb + (n >> 3) * SBO + (n & 7) * 16 + inner);
+                                    s += (double)av * (double)bv;
+                                }
+                                acc[(size_t)r * N + n] += s;
+                            }
+                    }
+        }
+        // ---- epilogue: thread = row
+        for (int r = 0; r < TM; ++r) {
+            const int64_t m = tile * TM + r;
+            if (m >= M) continue;
+            int b, y, x;
+            xb_conv_site(g, m, b, y, x);
+            const int64_t orow = (((int64_t)b * out_H + (y * oys + oy0)) * out_W + (x * oxs + ox0)) * out_ld + out_c0;
+            for (int n = 0; n < N; ++n) out[orow + n] = acc[(size_t)r * N + n];
+        }
+    }
+    return 0;
+}
+
+extern "C" void emul_pack_weight(const float *w, int N, int C, int KH, int KW, float *packed) {
+    const int64_t total = (int64_t)N * C * KH * KW;
+    for (int64_t i = 0; i < total; ++i) packed[i] = w[xb_pack_weight_src(i, C, KH, KW)];
+}

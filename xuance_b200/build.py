@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libxb200.so")
 STAMP = os.path.join(HERE, ".libxb200.stamp")
-SOURCES = ["api.cu", "rollout.cu", "losses.cu", "per_tree.cu", "optim.cu", "sac.cu", "qmix_mix.cu", "qmix_tc.cu", "act.cu"]
+SOURCES = ["api.cu", "rollout.cu", "losses.cu", "per_tree.cu", "optim.cu", "sac.cu", "qmix_mix.cu", "qmix_tc.cu", "act.cu", "conv_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--use_fast_math=false", "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v",
               "--expt-relaxed-constexpr", "--expt-extended-lambda"]
@@ -42,7 +42,7 @@ def sources():
 def build(force=False, verbose=False):
     srcs = sources()
     deps = srcs + [os.path.join(CSRC, "xb_common.cuh"), os.path.join(HERE, "..", "include", "xb200.h")]
-    deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh") and f != "xb_common.cuh"]
+    deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")) and f != "xb_common.cuh"]
     dig = _digest(sorted(set(deps)))
     if not force and os.path.exists(OUT) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
         return OUT

@@ -1,0 +1,334 @@
+// K12 (EXPERIMENTAL - compiled and host-verified, not yet run on hardware; nothing on the default path calls it):
+// gathered-operand GEMM on the 5th-generation tensor cores for the NatureCNN layers (cnn.py:45-50, 84-101) - the 85 %
+// of the fp32 PPO step that cuDNN's CUDA-core fp32 convolutions take.
+//
+//   D[m, n] = sum_{t, c} in[b, y*sy + dy[t], x*sx + dx[t], c] * W[n, t*C + c]  (+ bias[n], ReLU)      conv_index.h
+//
+// Numerics as K9-TC: every fp32 operand travels as x = hi + lo (two bf16 tensors) and each product is the three MMAs
+// hi.hi + hi.lo + lo.hi accumulated in fp32 in TMEM (~1e-5 relative, i.e. inside the fp32 parity tolerance).
+//
+// Structure (one CTA per SM, persistent over 128-row tiles, 9 warps):
+//   warps 5-8  producers : thread = tile row.  Per K chunk of 64 the row's 8 units (16 B = 8 channels of one tap) and
+//                          this thread's share of the weight rows are fetched with 16-byte cp.async straight into the
+//                          K-major no-swizzle canonical layout (zero-fill for padding taps / tail rows); a chunk is
+//                          published (wait_group -> fence.proxy.async -> mbarrier arrive) one chunk behind the issue
+//                          point so that a group is always in flight.
+//   warp 4     MMA       : lane 0 waits full[stage], issues 3 x 4 tcgen05.mma (M 128, N, K 16) and commits onto
+//                          empty[stage]; after the last chunk commits onto acc_full[a].  Two accumulators in TMEM.
+//   warps 0-3  epilogue  : thread = row = TMEM lane.  tcgen05.ld 32 columns at a time, bias + ReLU, then the row is
+//                          written as fp32 and / or as the hi / lo bf16 pair the next layer consumes.
+#include "tc_common.cuh"
+#include "conv_index.h"
+
+namespace {
+using namespace xbtc;
+
+constexpr int KC = XB_CONV_KC, TILE_M = XB_CONV_TILE_M;
+constexpr int EPI_WARPS = 4, PROD_WARPS = 4;
+constexpr int MMA_WARP = EPI_WARPS;
+constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;
+constexpr int MAX_STAGES = 6;
+
+struct ConvParams {
+    XbConvGeom g;
+    const __nv_bfloat16 *in_hi, *in_lo;    // [B, IH, IW, C]
+    const __nv_bfloat16 *w_hi, *w_lo;      // [N, K]
+    const float *bias;                     // [N] or null
+    __nv_bfloat16 *out_hi, *out_lo;        // nullable pair
+    float *out_f32;                        // nullable
+    int64_t M;                             // B * OY * OX
+    int relu, stages;
+    // placement of site (b, y, x): row ((b*out_H + y*oys + oy0)*out_W + x*oxs + ox0) of an output matrix whose rows are
+    // out_ld elements apart; this call fills columns [out_c0, out_c0 + N)
+    int out_H, out_W, oys, oxs, oy0, ox0;
+    int64_t out_ld;
+    int out_c0;
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_bias[256];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const XbConvGeom &g = p.g;
+    const int N = g.N, K = g.T * g.C, n_chunks = K / KC, S = p.stages;
+    const uint32_t stage_bytes = xb_conv_stage_bytes(N);
+    const uint32_t a_plane = xb_conv_a_plane_bytes(), w_plane = xb_conv_w_plane_bytes(N);
+    const int64_t n_tiles = (p.M + TILE_M - 1) / TILE_M;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < 2 * N) tmem_cols <<= 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full_bar[s], PROD_WARPS);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], EPI_WARPS);
+        }
+        mbar_fence_init();
+    }
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                     "r"(tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    for (int i = tid; i < N; i += THREADS) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t smem_base = smem_u32(smem);
+
+    if (warp > MMA_WARP) {
+        // ------------------------------------------------------------------ producers
+        const int row = tid - (MMA_WARP + 1) * 32;    // 0..127
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t m = tile * TILE_M + row;
+            const bool live = m < p.M;
+            int b = 0, y = 0, x = 0;
+            if (live) xb_conv_site(g, m, b, y, x);
+            for (int kc = 0; kc < n_chunks; ++kc) {
+                const int stage = (int)(it % (uint32_t)S);
+                mbar_wait(&empty_bar[stage], ((it / (uint32_t)S) & 1u) ^ 1u);
+                const uint32_t base = smem_base + (uint32_t)stage * stage_bytes;
+#pragma unroll
+                for (int u = 0; u < KC / 8; ++u) {
+                    const int64_t off = live ? xb_conv_unit_src(g, b, y, x, kc * KC + u * 8) : -1;
+                    const uint32_t dst = base + xb_canon_off(row, u * 8, KC);
+                    const uint32_t nbytes = off >= 0 ? 16u : 0u;      // 0: the 16 destination bytes are zero-filled
+                    const int64_t o = off >= 0 ? off : 0;
+                    cp_async16(dst, p.in_hi + o, nbytes);
+                    cp_async16(dst + a_plane, p.in_lo + o, nbytes);
+                }
+                const uint32_t wbase = base + 2 * a_plane;
+                for (int idx = row; idx < N * (KC / 8); idx += PROD_WARPS * 32) {
+                    const int n = idx >> 3, u = idx & 7;
+                    const int64_t src = (int64_t)n * K + kc * KC + u * 8;
+                    const uint32_t dst = wbase + xb_canon_off(n, u * 8, KC);
+                    cp_async16(dst, p.w_hi + src, 16u);
+                    cp_async16(dst + w_plane, p.w_lo + src, 16u);
+                }
+                cp_async_commit();
+                if (it > 0) {            // publish the previous chunk; this one stays in flight
+                    cp_async_wait<1>();
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_bar[(it - 1) % (uint32_t)S]);
+                }
+                ++it;
+            }
+        }
+        if (it > 0) {
+            cp_async_wait<0>();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[(it - 1) % (uint32_t)S]);
+        }
+    } else if (warp == MMA_WARP) {
+        // ------------------------------------------------------------------ MMA issue (one thread)
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(TILE_M, N);
+            uint32_t it = 0, tcount = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const uint32_t a = tcount & 1u;
+                mbar_wait(&acc_empty[a], ((tcount >> 1) & 1u) ^ 1u);     // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem + a * (uint32_t)N;
+                uint32_t acc = 0;
+                for (int kc = 0; kc < n_chunks; ++kc) {
+                    const int stage = (int)(it % (uint32_t)S);
+                    mbar_wait(&full_bar[stage], (it / (uint32_t)S) & 1u);
+                    tc_fence_after();
+                    const uint32_t base = smem_base + (uint32_t)stage * stage_bytes;
+                    const uint32_t a_addr[2] = {base, base + a_plane};
+                    const uint32_t w_addr[2] = {base + 2 * a_plane, base + 2 * a_plane + w_plane};
+                    for (int pa = 0; pa < 2; ++pa)
+                        for (int pb = 0; pb < 2 - pa; ++pb)            // (hi,hi) (hi,lo) (lo,hi)
+#pragma unroll
+                            for (int ks = 0; ks < KC / 16; ++ks) {
+                                mma_bf16(d_tmem, make_desc(a_addr[pa] + ks * 256, KC), make_desc(w_addr[pb] + ks * 256, KC),
+                                         idesc, acc);
+                                acc = 1;
+                            }
+                    mma_commit(&empty_bar[stage]);     // the stage is free once these MMAs have read it
+                    ++it;
+                }
+                mma_commit(&acc_full[a]);
+                ++tcount;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ epilogue: thread = row = TMEM lane
+        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        uint32_t tcount = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const uint32_t a = tcount & 1u;
+            mbar_wait(&acc_full[a], (tcount >> 1) & 1u);
+            tc_fence_after();
+            const int64_t m = tile * TILE_M + tid;
+            const bool live = m < p.M;
+            int64_t orow = 0;
+            if (live) {
+                int b, y, x;
+                xb_conv_site(g, m, b, y, x);
+                orow = (((int64_t)b * p.out_H + (y * p.oys + p.oy0)) * p.out_W + (x * p.oxs + p.ox0)) * p.out_ld + p.out_c0;
+            }
+            for (int c0 = 0; c0 < N; c0 += 32) {
+                float v[32];
+                tmem_ld32(lane_addr + a * (uint32_t)N + c0, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    v[j] += s_bias[c0 + j];
+                    if (p.relu) v[j] = fmaxf(v[j], 0.f);
+                }
+                if (live) {
+                    if (p.out_f32) {
+                        float4 *o = reinterpret_cast<float4 *>(p.out_f32 + orow + c0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                    if (p.out_hi) {
+                        uint4 *oh = reinterpret_cast<uint4 *>(p.out_hi + orow + c0);
+                        uint4 *ol = reinterpret_cast<uint4 *>(p.out_lo + orow + c0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            __nv_bfloat16 h[8], l[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) split_bf16(v[8 * j + i], h[i], l[i]);
+                            oh[j] = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
+                            ol[j] = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[a]);
+            ++tcount;
+        }
+    }
+    // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols));
+    }
+}
+
+// ---------------------------------------------------------------- operand preparation (HBM-bound, elementwise)
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float *__restrict__ x, int64_t n8, int64_t n,
+                                                         __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        float v[8];
+        const int64_t e = i * 8;
+        if (e + 8 <= n) {
+            const float4 a = reinterpret_cast<const float4 *>(x + e)[0], b = reinterpret_cast<const float4 *>(x + e)[1];
+            v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = e + j < n ? x[e + j] : 0.f;
+        }
+        __nv_bfloat16 h[8], l[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) split_bf16(v[j], h[j], l[j]);
+        if (e + 8 <= n) {
+            *reinterpret_cast<uint4 *>(hi + e) = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
+            *reinterpret_cast<uint4 *>(lo + e) = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+        } else {
+            for (int j = 0; j < 8 && e + j < n; ++j) hi[e + j] = h[j], lo[e + j] = l[j];
+        }
+    }
+}
+
+// torch weight [N, C, KH, KW] (also a Linear over a flattened [C, H, W] feature map) -> [N, (kh, kw, c)] hi / lo
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float *__restrict__ w, int N, int C, int KH, int KW,
+                                                          __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo) {
+    const int64_t total = (int64_t)N * C * KH * KW;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = w[xb_pack_weight_src(i, C, KH, KW)];
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        hi[i] = h, lo[i] = l;
+    }
+}
+
+}  // namespace
+
+extern "C" int xb_split_bf16(const float *x, int64_t n, void *hi, void *lo, void *stream) {
+    if (!x || !hi || !lo || n <= 0) return XB_EINVAL;
+    if (!xb_aligned(x, 16) || !xb_aligned(hi, 16) || !xb_aligned(lo, 16)) return XB_EALIGN;
+    const int64_t n8 = (n + 7) / 8;
+    int64_t want = (n8 + 255) / 256;
+    const int grid = (int)(want < (int64_t)xb_sm_count() * 8 ? want : (int64_t)xb_sm_count() * 8);
+    split_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n8, n, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo);
+    return xb_launch_status();
+}
+
+extern "C" int xb_pack_conv_weight(const float *w, int N, int C, int KH, int KW, void *hi, void *lo, void *stream) {
+    if (!w || !hi || !lo || N <= 0 || C <= 0 || KH <= 0 || KW <= 0) return XB_EINVAL;
+    const int64_t total = (int64_t)N * C * KH * KW;
+    int64_t want = (total + 255) / 256;
+    const int grid = (int)(want < (int64_t)xb_sm_count() * 8 ? want : (int64_t)xb_sm_count() * 8);
+    pack_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, N, C, KH, KW, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo);
+    return xb_launch_status();
+}
+
+extern "C" int xb_gemm_gather_tc(const void *in_hi, const void *in_lo, const void *w_hi, const void *w_lo,
+                                 const float *bias, int B, int IH, int IW, int C, int OY, int OX, int sy, int sx, int T,
+                                 const int8_t *dy, const int8_t *dx, int N, int relu, void *out_hi, void *out_lo,
+                                 float *out_f32, int out_H, int out_W, int oys, int oxs, int oy0, int ox0,
+                                 int64_t out_ld, int out_c0, void *stream) {
+    if (!in_hi || !in_lo || !w_hi || !w_lo || !dy || !dx) return XB_EINVAL;
+    if ((out_hi == nullptr) != (out_lo == nullptr) || (!out_hi && !out_f32)) return XB_EINVAL;
+    if (B <= 0 || IH <= 0 || IW <= 0 || OY <= 0 || OX <= 0 || sy <= 0 || sx <= 0 || T <= 0) return XB_EINVAL;
+    if (T > XB_CONV_MAX_TAPS || N > 256 || N % 32 != 0 || C % 8 != 0 || ((int64_t)T * C) % XB_CONV_KC != 0)
+        return XB_ERANGE;
+    if (out_H <= 0 || out_W <= 0 || oys <= 0 || oxs <= 0 || oy0 < 0 || ox0 < 0 || (OY - 1) * oys + oy0 >= out_H ||
+        (OX - 1) * oxs + ox0 >= out_W || out_c0 < 0 || out_ld < (int64_t)out_c0 + N)
+        return XB_EINVAL;
+    if (out_ld % 8 != 0 || out_c0 % 8 != 0) return XB_EALIGN;   // 16-byte row segments in both output formats
+    if (!xb_aligned(in_hi, 16) || !xb_aligned(in_lo, 16) || !xb_aligned(w_hi, 16) || !xb_aligned(w_lo, 16) ||
+        (out_hi && (!xb_aligned(out_hi, 16) || !xb_aligned(out_lo, 16))) || (out_f32 && !xb_aligned(out_f32, 16)))
+        return XB_EALIGN;
+    ConvParams p;
+    p.g.B = B, p.g.IH = IH, p.g.IW = IW, p.g.C = C, p.g.OY = OY, p.g.OX = OX, p.g.sy = sy, p.g.sx = sx, p.g.T = T, p.g.N = N;
+    for (int t = 0; t < XB_CONV_MAX_TAPS; ++t) p.g.dy[t] = t < T ? dy[t] : 0, p.g.dx[t] = t < T ? dx[t] : 0;
+    p.in_hi = (const __nv_bfloat16 *)in_hi, p.in_lo = (const __nv_bfloat16 *)in_lo;
+    p.w_hi = (const __nv_bfloat16 *)w_hi, p.w_lo = (const __nv_bfloat16 *)w_lo;
+    p.bias = bias;
+    p.out_hi = (__nv_bfloat16 *)out_hi, p.out_lo = (__nv_bfloat16 *)out_lo, p.out_f32 = out_f32;
+    p.M = (int64_t)B * OY * OX;
+    p.relu = relu;
+    p.out_H = out_H, p.out_W = out_W, p.oys = oys, p.oxs = oxs, p.oy0 = oy0, p.ox0 = ox0;
+    p.out_ld = out_ld, p.out_c0 = out_c0;
+    const uint32_t stage_bytes = xb_conv_stage_bytes(N);
+    int stages = (int)((200u * 1024u) / stage_bytes);
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 2) return XB_ERANGE;
+    p.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr = true;
+    }
+    const int64_t tiles = (p.M + TILE_M - 1) / TILE_M;
+    const int grid = (int)(tiles < xb_sm_count() ? tiles : xb_sm_count());
+    conv_tc_kernel<<<grid, THREADS, smem, (cudaStream_t)stream>>>(p);
+    return xb_launch_status();
+}
