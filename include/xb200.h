@@ -234,14 +234,26 @@ int xb_rms_update_normalize(const float *x, int N, int64_t D, float *mean, float
  *                       columns [out_c0, out_c0+N) of row (b*out_H + y*oys+oy0)*out_W + x*oxs+ox0 of a matrix with
  *                       out_ld elements per row (out_ld % 8 == out_c0 % 8 == 0).  C % 8 == 0, (T*C) % 64 == 0,
  *                       N % 32 == 0, N <= 256, T <= 64; dy / dx are HOST arrays (copied into the launch parameters).
+ *                       relu_mask (nullable, bf16, addressed like the output): result zeroed where mask <= 0 - the ReLU
+ *                       derivative applied to a data gradient, mask = hi plane of the saved activation.
  *                       Forward conv: dy = kh - pad, (sy,sx) = stride; Linear: one tap;
- *                       data gradients: flipped taps over the output gradient, one call per stride phase. */
+ *                       data gradients: flipped taps over the output gradient, one call per stride phase.
+ * xb_wgrad_gather_tc  : weight gradient of the same gathered GEMM: partials[s, (t,c), n] = sum over the sites of split s of
+ *                       in[b, y*sy+dy[t], x*sx+dx[t], c] * G[site, n]; G = output gradient [B*OY*OX, N] as a hi / lo pair.
+ *                       Both operands are fed MN-major (16-byte units transposed into the core matrices); one CTA work
+ *                       item = (128 columns of (t,c), split).  partials: float32 [splits, T*C, N].
+ * xb_wgrad_reduce     : dw[N, C, KH, KW] (torch layout) (+)= sum_s partials[s, (kh,kw,c), n], splits added in order. */
 int xb_split_bf16(const float *x, int64_t n, void *hi, void *lo, void *stream);
 int xb_pack_conv_weight(const float *w, int N, int C, int KH, int KW, void *hi, void *lo, void *stream);
 int xb_gemm_gather_tc(const void *in_hi, const void *in_lo, const void *w_hi, const void *w_lo, const float *bias,
-                      int B, int IH, int IW, int C, int OY, int OX, int sy, int sx, int T, const int8_t *dy,
+                      const void *relu_mask, int B, int IH, int IW, int C, int OY, int OX, int sy, int sx, int T, const int8_t *dy,
                       const int8_t *dx, int N, int relu, void *out_hi, void *out_lo, float *out_f32, int out_H,
                       int out_W, int oys, int oxs, int oy0, int ox0, int64_t out_ld, int out_c0, void *stream);
+int xb_wgrad_gather_tc(const void *in_hi, const void *in_lo, const void *g_hi, const void *g_lo, int B, int IH, int IW,
+                       int C, int OY, int OX, int sy, int sx, int T, const int8_t *dy, const int8_t *dx, int N, int splits,
+                       float *partials, void *stream);
+int xb_wgrad_reduce(const float *partials, int splits, int N, int C, int KH, int KW, float *dw, int accumulate,
+                    void *stream);
 
 #ifdef __cplusplus
 }

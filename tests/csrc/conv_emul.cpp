@@ -35,29 +35,25 @@ extern "C" int emul_gemm_gather(const float *in_hi, const float *in_lo, const fl
         for (int kc = 0; kc < n_chunks; ++kc, ++it) {
             const uint32_t base = (it % stages) * stage_bytes;
             for (uint32_t i = 0; i < stage_bytes / 2; ++i) smem[base / 2 + i] = nan;     // poison the stage
-            // ---- producer (conv_tc.cu, warps 5-8): thread = row
+            // ---- producer (conv_tc.cu, warps 5-8): thread = row; the staging routine is the kernel's own
             for (int row = 0; row < TM; ++row) {
                 const int64_t m = tile * TM + row;
                 const bool live = m < M;
                 int b = 0, y = 0, x = 0;
                 if (live) xb_conv_site(g, m, b, y, x);
-                for (int u = 0; u < KC / 8; ++u) {
-                    const int64_t off = live ? xb_conv_unit_src(g, b, y, x, kc * KC + u * 8) : -1;
-                    const uint32_t dst = base + xb_canon_off(row, u * 8, KC);
+                auto emit_a = [&](uint32_t dst, int64_t src) {
                     for (int j = 0; j < 8; ++j) {
-                        at(smem, dst + 2 * j) = off >= 0 ? in_hi[off + j] : 0.f;
-                        at(smem, dst + a_plane + 2 * j) = off >= 0 ? in_lo[off + j] : 0.f;
+                        at(smem, base + dst + 2 * j) = src >= 0 ? in_hi[src + j] : 0.f;
+                        at(smem, base + a_plane + dst + 2 * j) = src >= 0 ? in_lo[src + j] : 0.f;
                     }
-                }
-                for (int idx = row; idx < N * (KC / 8); idx += TM) {
-                    const int n = idx >> 3, u = idx & 7;
-                    const int64_t src = (int64_t)n * K + kc * KC + u * 8;
-                    const uint32_t dst = base + 2 * a_plane + xb_canon_off(n, u * 8, KC);
+                };
+                auto emit_w = [&](uint32_t dst, int64_t src) {
                     for (int j = 0; j < 8; ++j) {
-                        at(smem, dst + 2 * j) = w_hi[src + j];
-                        at(smem, dst + w_plane + 2 * j) = w_lo[src + j];
+                        at(smem, base + 2 * a_plane + dst + 2 * j) = src >= 0 ? w_hi[src + j] : 0.f;
+                        at(smem, base + 2 * a_plane + w_plane + dst + 2 * j) = src >= 0 ? w_lo[src + j] : 0.f;
                     }
-                }
+                };
+                xb_stage_fwd(g, row, live, b, y, x, kc, emit_a, emit_w);
             }
             // ---- tensor core: three products, K 16 per instruction, operands located through the descriptor fields
             const uint32_t LBO = 128, SBO = (KC / 8) * 128;
@@ -96,4 +92,85 @@ extern "C" int emul_gemm_gather(const float *in_hi, const float *in_lo, const fl
 extern "C" void emul_pack_weight(const float *w, int N, int C, int KH, int KW, float *packed) {
     const int64_t total = (int64_t)N * C * KH * KW;
     for (int64_t i = 0; i < total; ++i) packed[i] = w[xb_pack_weight_src(i, C, KH, KW)];
+}
+
+// weight gradient (conv_tc_kernel<true>): partials[split, (t,c), n]; MN-major operands: the "tensor core" locates element
+// (mn, k) at start + (mn/8)*SBO + (k/8)*LBO + (k%8)*16 + (mn%8)*2
+extern "C" int emul_wgrad(const float *in_hi, const float *in_lo, const float *g_hi, const float *g_lo, int B, int IH,
+                          int IW, int C, int OY, int OX, int sy, int sx, int T, const int8_t *dy, const int8_t *dx, int N,
+                          int splits, int stages, double *partials) {
+    XbConvGeom g;
+    g.B = B, g.IH = IH, g.IW = IW, g.C = C, g.OY = OY, g.OX = OX, g.sy = sy, g.sx = sx, g.T = T, g.N = N;
+    for (int t = 0; t < XB_CONV_MAX_TAPS; ++t) g.dy[t] = t < T ? dy[t] : 0, g.dx[t] = t < T ? dx[t] : 0;
+    const int KC = XB_CONV_KC, TM = XB_CONV_TILE_M, K = T * C;
+    const int64_t M = (int64_t)B * OY * OX;
+    const int64_t per = xb_wgrad_sites_per_split(M, splits);
+    if (per == 0 || C % 8 || N % 8) return -1;
+    const uint32_t stage_bytes = xb_conv_stage_bytes(N), a_plane = xb_conv_a_plane_bytes(), w_plane = xb_conv_w_plane_bytes(N);
+    std::vector<float> smem((size_t)stages * stage_bytes / 2);
+    const float nan = std::numeric_limits<float>::quiet_NaN();
+    const int64_t m_tiles = (K + TM - 1) / TM;
+    std::vector<double> acc((size_t)TM * N);
+    uint32_t it = 0;
+    for (int64_t w = 0; w < m_tiles * splits; ++w) {
+        const int64_t mt = w % m_tiles, sp = w / m_tiles;
+        const int64_t s0 = sp * per, site_end = (s0 + per < M) ? s0 + per : M;
+        const int n_chunks = (int)((site_end - s0 + KC - 1) / KC);
+        std::fill(acc.begin(), acc.end(), 0.0);
+        for (int kc = 0; kc < n_chunks; ++kc, ++it) {
+            const uint32_t base = (it % stages) * stage_bytes;
+            for (uint32_t i = 0; i < stage_bytes / 2; ++i) smem[base / 2 + i] = nan;
+            for (int row = 0; row < TM; ++row) {
+                auto emit_a = [&](uint32_t dst, int64_t src) {
+                    for (int j = 0; j < 8; ++j) {
+                        at(smem, base + dst + 2 * j) = src >= 0 ? in_hi[src + j] : 0.f;
+                        at(smem, base + a_plane + dst + 2 * j) = src >= 0 ? in_lo[src + j] : 0.f;
+                    }
+                };
+                auto emit_g = [&](uint32_t dst, int64_t src) {
+                    for (int j = 0; j < 8; ++j) {
+                        at(smem, base + 2 * a_plane + dst + 2 * j) = src >= 0 ? g_hi[src + j] : 0.f;
+                        at(smem, base + 2 * a_plane + w_plane + dst + 2 * j) = src >= 0 ? g_lo[src + j] : 0.f;
+                    }
+                };
+                xb_stage_wgrad(g, row, mt, s0 + (int64_t)kc * KC, site_end, emit_a, emit_g);
+            }
+            const uint32_t LBO = 128, SBO = (KC / 8) * 128;
+            const uint32_t a_addr[2] = {base, base + a_plane};
+            const uint32_t w_addr[2] = {base + 2 * a_plane, base + 2 * a_plane + w_plane};
+            for (int pa = 0; pa < 2; ++pa)
+                for (int pb = 0; pb < 2 - pa; ++pb)
+                    for (int ks = 0; ks < KC / 16; ++ks) {
+                        const uint32_t sa = a_addr[pa] + ks * 256, sb = w_addr[pb] + ks * 256;
+                        for (int r = 0; r < TM; ++r)
+                            for (int n = 0; n < N; ++n) {
+                                double s = 0.0;
+                                for (int kk = 0; kk < 16; ++kk) {
+                                    const uint32_t inner = (kk >> 3) * LBO + (kk & 7) * 16;
+                                    const float av = at(smem, sa + (r >> 3) * SBO + inner + (r & 7) * 2);
+                                    const float bv = at(smem, sb + (n >> 3) * SBO + inner + (n & 7) * 2);
+                                    s += (double)av * (double)bv;
+                                }
+                                acc[(size_t)r * N + n] += s;
+                            }
+                    }
+        }
+        for (int r = 0; r < TM; ++r) {
+            const int64_t kcol = mt * TM + r;
+            if (kcol >= K) continue;
+            for (int n = 0; n < N; ++n) partials[((int64_t)sp * K + kcol) * N + n] = acc[(size_t)r * N + n];
+        }
+    }
+    return 0;
+}
+
+// xb_wgrad_reduce: packed-layout partial sums -> torch [N, C, KH, KW]
+extern "C" void emul_wgrad_reduce(const double *partials, int splits, int N, int C, int KH, int KW, double *dw) {
+    const int64_t K = (int64_t)C * KH * KW, total = (int64_t)N * K;
+    for (int64_t i = 0; i < total; ++i) {
+        const int64_t n = i / K, k = i - n * K;
+        double s = 0.0;
+        for (int sp = 0; sp < splits; ++sp) s += partials[((int64_t)sp * K + k) * N + n];
+        dw[xb_pack_weight_src(i, C, KH, KW)] = s;
+    }
 }

@@ -30,6 +30,9 @@ def emul():
     lib.emul_gemm_gather.argtypes = [P, P, P, P] + [i] * 9 + [P, P] + [i] * 7 + [l, i, i, P]
     lib.emul_gemm_gather.restype = i
     lib.emul_pack_weight.argtypes = [P, i, i, i, i, P]
+    lib.emul_wgrad.argtypes = [P, P, P, P] + [i] * 9 + [P, P] + [i] * 3 + [P]
+    lib.emul_wgrad.restype = i
+    lib.emul_wgrad_reduce.argtypes = [P, i, i, i, i, i, P]
     return lib
 
 
@@ -116,3 +119,164 @@ def test_data_gradient_phases(emul, name, B, H, W, C, N, k, s):
     for g, taps in phases:
         _run(emul, g, gy_nhwc, tc.dgrad_weight_matrix(w, taps), out, C)
     np.testing.assert_allclose(out.reshape(B, H, W, C).permute(0, 3, 1, 2).numpy(), want.numpy(), **TOL)
+
+
+@pytest.mark.parametrize("name,B,H,W,C,N,k,s,splits", [("conv1", 2, 84, 84, 4, 32, 8, 4, 3), ("conv2", 4, 21, 21, 32, 64, 4, 2, 3),
+                                                       ("conv3", 3, 10, 10, 64, 64, 3, 1, 2), ("conv3_1split", 1, 10, 10, 64, 64, 3, 1, 1)])
+def test_weight_gradient(emul, name, B, H, W, C, N, k, s, splits):
+    """grad_weight as the MN-major gathered GEMM (split over sites, then reduced into torch's [N, C, KH, KW]) vs autograd.
+    conv3 has K = 576 = 4.5 column tiles (a half-empty tile); conv1 runs on the pixel-folded view."""
+    torch.manual_seed(2)
+    pad = (k - s) // 2
+    x = torch.rand(B, C, H, W, dtype=torch.float64)
+    w = (torch.randn(N, C, k, k, dtype=torch.float64) / np.sqrt(C * k * k)).requires_grad_(True)
+    y = F.conv2d(x, w, stride=s, padding=pad)
+    gy = torch.randn_like(y) / np.sqrt(y[0, 0].numel())
+    (want,) = torch.autograd.grad(y, w, gy)
+    g = tc.conv_forward_geometry(B, H, W, C, k, k, s, pad)             # the weight gradient gathers like the forward
+    xh, xl = _split(x.permute(0, 2, 3, 1).contiguous())
+    gh, gl = _split(gy.permute(0, 2, 3, 1).reshape(g.M, N).contiguous())
+    partials = torch.full((splits, g.K, N), float("nan"), dtype=torch.float64)
+    dy, dx = np.asarray(g.dy, np.int8), np.asarray(g.dx, np.int8)
+    rc = emul.emul_wgrad(xh.data_ptr(), xl.data_ptr(), gh.data_ptr(), gl.data_ptr(), g.B, g.IH, g.IW, g.C, g.OY, g.OX, g.sy,
+                         g.sx, g.T, dy.ctypes.data, dx.ctypes.data, N, splits, 3, partials.data_ptr())
+    assert rc == 0 and not torch.isnan(partials).any()
+    dw = torch.full((N, C, k, k), float("nan"), dtype=torch.float64)
+    emul.emul_wgrad_reduce(partials.data_ptr(), splits, N, C, k, k, dw.data_ptr())
+    np.testing.assert_allclose(dw.numpy(), want.numpy(), **TOL)
+
+
+def test_linear_weight_gradient(emul):
+    """dW of Linear(6400 -> 256 columns of the 512) : sites = batch rows, one tap, 50 column tiles."""
+    torch.manual_seed(3)
+    Bn, K, N = 70, 6400, 64
+    x = torch.rand(Bn, K, dtype=torch.float64)
+    gy = torch.randn(Bn, N, dtype=torch.float64) / 8
+    g = tc.linear_geometry(Bn, K)
+    xh, xl = _split(x)
+    gh, gl = _split(gy)
+    partials = torch.full((2, K, N), float("nan"), dtype=torch.float64)
+    dy, dx = np.zeros(1, np.int8), np.zeros(1, np.int8)
+    rc = emul.emul_wgrad(xh.data_ptr(), xl.data_ptr(), gh.data_ptr(), gl.data_ptr(), g.B, 1, 1, K, 1, 1, 1, 1, 1,
+                         dy.ctypes.data, dx.ctypes.data, N, 2, 2, partials.data_ptr())
+    assert rc == 0
+    np.testing.assert_allclose(partials.sum(0).t().numpy(), (gy.t() @ x).numpy(), **TOL)
+
+
+def test_wgrad_split_rule():
+    """xb_wgrad_sites_per_split (mirrored here): runs are multiples of 64 sites and never empty."""
+    def per(M, splits):
+        p = -(-M // splits)
+        p = -(-p // 64) * 64
+        return 0 if (splits - 1) * p >= M else p
+    assert per(882, 3) == 320 and per(200, 5) == 0 and per(64, 1) == 64 and per(8192 * 100, 37) % 64 == 0
+
+
+class EmulBackend:
+    """``TensorCoreNatureCNN`` backend that runs every K12 launch through the host emulator (CPU float32 tensors holding
+    bf16-representable values stand in for the bf16 planes).  The epilogue (bias, ReLU, mask, output formats) is restated
+    here; staging, operand layouts and work decomposition are the kernel's own code (conv_index.h)."""
+
+    def __init__(self, lib):
+        self.lib = lib
+
+    def split(self, x):
+        return _split(x)
+
+    def pack_weight(self, w4d):
+        N = w4d.shape[0]
+        return _split(w4d.permute(0, 2, 3, 1).reshape(N, -1))
+
+    def empty_pair(self, shape, like):
+        return torch.full(shape, float("nan")), torch.full(shape, float("nan"))
+
+    def empty_f32(self, shape, like):
+        return torch.full(shape, float("nan"))
+
+    def to_float(self, pair):
+        return pair[0] + pair[1]
+
+    def colsum(self, g_pair):
+        return (g_pair[0].double() + g_pair[1].double()).sum(0).float()
+
+    def gemm(self, x_pair, w_pair, geom, bias=None, relu=False, out_f32=None, out_pair=None, out_ld=None, out_c0=0, mask=None):
+        N = w_pair[0].shape[0]
+        out_ld = N if out_ld is None else out_ld
+        rows = geom.B * geom.out_H * geom.out_W
+        tmp = torch.full((rows, out_ld), float("nan"), dtype=torch.float64)
+        xh, xl = x_pair[0].contiguous(), x_pair[1].contiguous()
+        wh, wl = w_pair[0].contiguous(), w_pair[1].contiguous()
+        dy, dx = np.asarray(geom.dy, np.int8), np.asarray(geom.dx, np.int8)
+        rc = self.lib.emul_gemm_gather(xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), geom.B, geom.IH, geom.IW,
+                                       geom.C, geom.OY, geom.OX, geom.sy, geom.sx, geom.T, dy.ctypes.data, dx.ctypes.data, N,
+                                       geom.out_H, geom.out_W, geom.oys, geom.oxs, geom.oy0, geom.ox0, out_ld, out_c0, 3,
+                                       tmp.data_ptr())
+        assert rc == 0
+        blk = tmp[:, out_c0:out_c0 + N]
+        written = ~torch.isnan(blk[:, 0])
+        assert int(written.sum()) == geom.M
+        v = blk[written]
+        if bias is not None:
+            v = v + bias.double()
+        if relu:
+            v = v.clamp_min(0)
+        if mask is not None:
+            v = torch.where(mask.reshape(rows, out_ld)[written, out_c0:out_c0 + N] > 0, v, torch.zeros_like(v))
+        v = v.float()
+        if out_f32 is not None:
+            out_f32.view(rows, out_ld)[written, out_c0:out_c0 + N] = v
+        if out_pair is not None:
+            hi, lo = _split(v)
+            out_pair[0].view(rows, out_ld)[written, out_c0:out_c0 + N] = hi
+            out_pair[1].view(rows, out_ld)[written, out_c0:out_c0 + N] = lo
+
+    def wgrad(self, x_pair, g_pair, geom, N, C, KH, KW):
+        splits = 2 if geom.M > 128 else 1
+        partials = torch.full((splits, geom.K, N), float("nan"), dtype=torch.float64)
+        dy, dx = np.asarray(geom.dy, np.int8), np.asarray(geom.dx, np.int8)
+        xh, xl, gh, gl = (t.contiguous() for t in (*x_pair, *g_pair))
+        rc = self.lib.emul_wgrad(xh.data_ptr(), xl.data_ptr(), gh.data_ptr(), gl.data_ptr(), geom.B, geom.IH, geom.IW, geom.C,
+                                 geom.OY, geom.OX, geom.sy, geom.sx, geom.T, dy.ctypes.data, dx.ctypes.data, N, splits, 3,
+                                 partials.data_ptr())
+        assert rc == 0
+        dw = torch.full((N, C, KH, KW), float("nan"), dtype=torch.float64)
+        self.lib.emul_wgrad_reduce(partials.data_ptr(), splits, N, C, KH, KW, dw.data_ptr())
+        return dw.float()
+
+
+def test_nature_cnn_forward_backward_orchestration(emul):
+    """The whole encoder (3 convs + Linear, cnn.py:84-101) forward and backward through TensorCoreNatureCNN with the
+    emulated backend vs torch autograd in float64: layer chaining, NHWC <-> NCHW-flatten weight permutation, ReLU masks in
+    the data-gradient epilogues, stride-phase data gradients, column-split Linear (320 = 256 + 64 outputs)."""
+    import torch.nn as nn
+    torch.manual_seed(7)
+    B, hidden = 2, 320
+    convs = [nn.Conv2d(4, 32, 8, 4, padding=2), nn.Conv2d(32, 64, 4, 2, padding=1), nn.Conv2d(64, 64, 3, 1, padding=1)]
+    fc = nn.Linear(6400, hidden)
+    for m in convs + [fc]:
+        nn.init.orthogonal_(m.weight, gain=np.sqrt(2))
+        nn.init.uniform_(m.bias, -0.05, 0.05)
+    obs = torch.randint(0, 256, (B, 84, 84, 4), dtype=torch.uint8)
+    x = obs.float() / 255.0
+    R = torch.randn(B, hidden)
+    # reference: torch autograd in float64, NCHW
+    ref = [nn.Conv2d(4, 32, 8, 4, padding=2), nn.Conv2d(32, 64, 4, 2, padding=1), nn.Conv2d(64, 64, 3, 1, padding=1),
+           nn.Linear(6400, hidden)]
+    for r, m in zip(ref, convs + [fc]):
+        r.load_state_dict(m.state_dict())
+        r.double()
+    h = x.double().permute(0, 3, 1, 2)
+    for r in ref[:3]:
+        h = torch.relu(r(h))
+    z_ref = torch.relu(ref[3](h.flatten(1)))
+    (z_ref * R.double()).sum().backward()
+    # K12 path on the emulator
+    enc = tc.TensorCoreNatureCNN(convs, fc, (84, 84, 4), backend=EmulBackend(emul))
+    z = tc.tc_encode(enc, _split(x), B)
+    np.testing.assert_allclose(z.detach().numpy(), z_ref.detach().numpy(), rtol=1e-4, atol=1e-4)
+    (z * R).sum().backward()
+    for (m, r), name in zip(zip(convs + [fc], ref), ("conv1", "conv2", "conv3", "fc")):
+        scale = float(r.weight.grad.abs().max())
+        np.testing.assert_allclose(m.weight.grad.numpy(), r.weight.grad.numpy(), rtol=0, atol=2e-4 * scale, err_msg=name)
+        np.testing.assert_allclose(m.bias.grad.numpy(), r.bias.grad.numpy(), rtol=0,
+                                   atol=2e-4 * float(r.bias.grad.abs().max()), err_msg=name + ".bias")

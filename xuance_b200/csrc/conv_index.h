@@ -42,6 +42,14 @@ XB_HD uint32_t xb_canon_off(int r, int k, int KP) {
     return (uint32_t)((r >> 3) * (KP >> 3) * 128 + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2);
 }
 
+// byte offset of element (mn, k) of a [MN x KP] bf16 operand in the MN-major no-swizzle canonical layout: a core matrix
+// is 8 k-rows of 16 bytes (8 consecutive mn elements); K-adjacent cores 128 B apart (descriptor LBO), 8-mn groups
+// KP/8*128 B apart (descriptor SBO) - the transpose of xb_canon_off inside each core matrix, same core placement.
+// (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>, LayoutType::INTERLEAVE: ((T,1,m),(8,k)):((1,T,SBO),(1T,LBO)))
+XB_HD uint32_t xb_canon_off_mn(int mn, int k, int KP) {
+    return (uint32_t)((mn >> 3) * (KP >> 3) * 128 + (k >> 3) * 128 + (k & 7) * 16 + (mn & 7) * 2);
+}
+
 // site m -> (b, y, x)
 XB_HD void xb_conv_site(const XbConvGeom &g, int64_t m, int &b, int &y, int &x) {
     const int per_img = g.OY * g.OX;
@@ -71,6 +79,55 @@ XB_HD int64_t xb_pack_weight_src(int64_t i, int C, int KH, int KW) {
     r /= C;
     const int kw = (int)(r % KW), kh = (int)(r / KW);
     return ((n * C + c) * KH + kh) * KW + kw;
+}
+
+// sites per split of the weight-gradient reduction: a multiple of the chunk length; 0 if `splits` would leave one empty
+XB_HD int64_t xb_wgrad_sites_per_split(int64_t M, int splits) {
+    int64_t per = (M + splits - 1) / splits;
+    per = (per + XB_CONV_KC - 1) / XB_CONV_KC * XB_CONV_KC;
+    return ((int64_t)(splits - 1) * per >= M) ? 0 : per;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// What ONE producer thread (`row` in [0,128)) stages for one K chunk.  emit_a / emit_w receive (byte offset of the 16-byte
+// unit inside the stage's hi plane of that operand, element offset of its 8 source values or -1 for a zero unit).
+// The kernel turns each call into two cp.async (hi and lo plane); the host test writes an emulated shared memory.
+// ---------------------------------------------------------------------------------------------------------------------
+// forward / data-gradient GEMM: thread = site (b, y, x) (live = inside the problem); K-major operands
+template <class EmitA, class EmitW>
+XB_HD void xb_stage_fwd(const XbConvGeom &g, int row, bool live, int b, int y, int x, int kc, EmitA &&emit_a,
+                        EmitW &&emit_w) {
+    const int K = g.T * g.C;
+    for (int u = 0; u < XB_CONV_KC / 8; ++u) {
+        const int64_t off = live ? xb_conv_unit_src(g, b, y, x, kc * XB_CONV_KC + u * 8) : -1;
+        emit_a(xb_canon_off(row, u * 8, XB_CONV_KC), off);
+    }
+    for (int idx = row; idx < g.N * (XB_CONV_KC / 8); idx += XB_CONV_TILE_M) {
+        const int n = idx >> 3, u = idx & 7;
+        emit_w(xb_canon_off(n, u * 8, XB_CONV_KC), (int64_t)n * K + kc * XB_CONV_KC + u * 8);
+    }
+}
+
+// weight-gradient GEMM: the chunk holds 64 consecutive sites starting at chunk_site0 (sites >= site_end are zero);
+// thread = (site pp = row & 63, half uh = row >> 6 of the tile's 16 column units); MN-major operands;
+// the second operand is the output gradient G[site, n]
+template <class EmitA, class EmitG>
+XB_HD void xb_stage_wgrad(const XbConvGeom &g, int row, int64_t mt, int64_t chunk_site0, int64_t site_end, EmitA &&emit_a,
+                          EmitG &&emit_g) {
+    const int K = g.T * g.C;
+    const int pp = row & (XB_CONV_KC - 1), uh = row >> 6;
+    const int64_t site = chunk_site0 + pp;
+    const bool in_run = site < site_end;
+    int b = 0, y = 0, x = 0;
+    if (in_run) xb_conv_site(g, site, b, y, x);
+    for (int j = 0; j < 8; ++j) {
+        const int u = uh * 8 + j;
+        const int64_t kcol = mt * XB_CONV_TILE_M + u * 8;
+        const int64_t off = (in_run && kcol < K) ? xb_conv_unit_src(g, b, y, x, (int)kcol) : -1;
+        emit_a(xb_canon_off_mn(u * 8, pp, XB_CONV_KC), off);
+    }
+    for (int j = uh; j < g.N / 8; j += 2)
+        emit_g(xb_canon_off_mn(j * 8, pp, XB_CONV_KC), in_run ? site * g.N + j * 8 : (int64_t)-1);
 }
 
 // shared-memory bytes of one pipeline stage: A hi | A lo | W hi | W lo

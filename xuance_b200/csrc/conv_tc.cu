@@ -32,17 +32,22 @@ constexpr int MAX_STAGES = 6;
 struct ConvParams {
     XbConvGeom g;
     const __nv_bfloat16 *in_hi, *in_lo;    // [B, IH, IW, C]
-    const __nv_bfloat16 *w_hi, *w_lo;      // [N, K]
-    const float *bias;                     // [N] or null
-    __nv_bfloat16 *out_hi, *out_lo;        // nullable pair
-    float *out_f32;                        // nullable
-    int64_t M;                             // B * OY * OX
+    const __nv_bfloat16 *w_hi, *w_lo;      // forward: weight [N, K].  weight gradient: output gradient [P, N]
+    const float *bias;                     // [N] or null (forward)
+    const __nv_bfloat16 *mask;             // forward, nullable: result elements are zeroed where mask <= 0; same
+                                           // addressing as the output (the ReLU derivative of a saved activation's hi plane)
+    __nv_bfloat16 *out_hi, *out_lo;        // nullable pair (forward)
+    float *out_f32;                        // forward: nullable.  weight gradient: partials [splits, K, N]
+    int64_t M;                             // sites B * OY * OX (GEMM rows forward, reduction length for the weight gradient)
     int relu, stages;
-    // placement of site (b, y, x): row ((b*out_H + y*oys + oy0)*out_W + x*oxs + ox0) of an output matrix whose rows are
-    // out_ld elements apart; this call fills columns [out_c0, out_c0 + N)
+    // forward: placement of site (b, y, x): row ((b*out_H + y*oys + oy0)*out_W + x*oxs + ox0) of an output matrix whose
+    // rows are out_ld elements apart; this call fills columns [out_c0, out_c0 + N)
     int out_H, out_W, oys, oxs, oy0, ox0;
     int64_t out_ld;
     int out_c0;
+    // weight gradient: sites are cut into `splits` runs of sites_per_split (a multiple of KC)
+    int splits;
+    int64_t sites_per_split;
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
@@ -54,6 +59,12 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// kind::f16 instruction descriptor with both operands MN-major (bits 15 / 16; cute/arch/mma_sm100_desc.hpp)
+__device__ __forceinline__ uint32_t make_idesc_mn(int M, int N) { return make_idesc(M, N) | (1u << 15) | (1u << 16); }
+
+// WGRAD = false:  D[site, n]  = sum_k A[site, k] W[n, k]            work item = 128-site tile,        K-major operands
+// WGRAD = true :  D[kcol, n]  = sum_site A[site, kcol] G[site, n]   work item = (128-kcol tile, split), MN-major operands
+template <bool WGRAD>
 __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_full[2], acc_empty[2];
@@ -62,10 +73,18 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const XbConvGeom &g = p.g;
-    const int N = g.N, K = g.T * g.C, n_chunks = K / KC, S = p.stages;
+    const int N = g.N, K = g.T * g.C, S = p.stages;
     const uint32_t stage_bytes = xb_conv_stage_bytes(N);
     const uint32_t a_plane = xb_conv_a_plane_bytes(), w_plane = xb_conv_w_plane_bytes(N);
-    const int64_t n_tiles = (p.M + TILE_M - 1) / TILE_M;
+    const int64_t m_tiles = WGRAD ? (K + TILE_M - 1) / TILE_M : (p.M + TILE_M - 1) / TILE_M;
+    const int64_t n_work = WGRAD ? m_tiles * p.splits : m_tiles;
+    // chunks of one work item
+    auto chunks_of = [&](int64_t w) -> int {
+        if (!WGRAD) return K / KC;
+        const int64_t sp = w / m_tiles, s0 = sp * p.sites_per_split;
+        const int64_t cnt = (p.M - s0) < p.sites_per_split ? (p.M - s0) : p.sites_per_split;
+        return (int)((cnt + KC - 1) / KC);
+    };
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < 2 * N) tmem_cols <<= 1;
 
@@ -85,7 +104,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                      "r"(tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    for (int i = tid; i < N; i += THREADS) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    for (int i = tid; i < N; i += THREADS) s_bias[i] = (!WGRAD && p.bias) ? p.bias[i] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -96,54 +115,55 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
         // ------------------------------------------------------------------ producers
         const int row = tid - (MMA_WARP + 1) * 32;    // 0..127
         uint32_t it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int64_t m = tile * TILE_M + row;
-            const bool live = m < p.M;
+        auto publish_previous = [&](bool drain) {
+            if (drain) cp_async_wait<0>();
+            else cp_async_wait<1>();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[(it - 1) % (uint32_t)S]);
+        };
+        for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+            const int n_chunks = chunks_of(w);
+            // forward: this thread's site, fixed for the tile
+            const int64_t m = w * TILE_M + row;
+            const bool live = !WGRAD && m < p.M;
             int b = 0, y = 0, x = 0;
             if (live) xb_conv_site(g, m, b, y, x);
+            // weight gradient: this thread's site changes with the chunk; its kcol units are fixed for the tile
+            const int64_t mt = w % m_tiles, sp = w / m_tiles;
+            const int64_t site_end = WGRAD ? ((sp + 1) * p.sites_per_split < p.M ? (sp + 1) * p.sites_per_split : p.M) : 0;
             for (int kc = 0; kc < n_chunks; ++kc) {
                 const int stage = (int)(it % (uint32_t)S);
                 mbar_wait(&empty_bar[stage], ((it / (uint32_t)S) & 1u) ^ 1u);
                 const uint32_t base = smem_base + (uint32_t)stage * stage_bytes;
-#pragma unroll
-                for (int u = 0; u < KC / 8; ++u) {
-                    const int64_t off = live ? xb_conv_unit_src(g, b, y, x, kc * KC + u * 8) : -1;
-                    const uint32_t dst = base + xb_canon_off(row, u * 8, KC);
-                    const uint32_t nbytes = off >= 0 ? 16u : 0u;      // 0: the 16 destination bytes are zero-filled
-                    const int64_t o = off >= 0 ? off : 0;
-                    cp_async16(dst, p.in_hi + o, nbytes);
-                    cp_async16(dst + a_plane, p.in_lo + o, nbytes);
-                }
                 const uint32_t wbase = base + 2 * a_plane;
-                for (int idx = row; idx < N * (KC / 8); idx += PROD_WARPS * 32) {
-                    const int n = idx >> 3, u = idx & 7;
-                    const int64_t src = (int64_t)n * K + kc * KC + u * 8;
-                    const uint32_t dst = wbase + xb_canon_off(n, u * 8, KC);
-                    cp_async16(dst, p.w_hi + src, 16u);
-                    cp_async16(dst + w_plane, p.w_lo + src, 16u);
-                }
+                auto emit_a = [&](uint32_t dst_off, int64_t src) {       // src < 0: the 16 bytes are zero-filled
+                    const uint32_t nbytes = src >= 0 ? 16u : 0u;
+                    const int64_t o = src >= 0 ? src : 0;
+                    cp_async16(base + dst_off, p.in_hi + o, nbytes);
+                    cp_async16(base + a_plane + dst_off, p.in_lo + o, nbytes);
+                };
+                auto emit_w = [&](uint32_t dst_off, int64_t src) {
+                    const uint32_t nbytes = src >= 0 ? 16u : 0u;
+                    const int64_t o = src >= 0 ? src : 0;
+                    cp_async16(wbase + dst_off, p.w_hi + o, nbytes);
+                    cp_async16(wbase + w_plane + dst_off, p.w_lo + o, nbytes);
+                };
+                if (!WGRAD) xb_stage_fwd(g, row, live, b, y, x, kc, emit_a, emit_w);
+                else xb_stage_wgrad(g, row, mt, sp * p.sites_per_split + (int64_t)kc * KC, site_end, emit_a, emit_w);
                 cp_async_commit();
-                if (it > 0) {            // publish the previous chunk; this one stays in flight
-                    cp_async_wait<1>();
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&full_bar[(it - 1) % (uint32_t)S]);
-                }
+                if (it > 0) publish_previous(false);     // this chunk stays in flight
                 ++it;
             }
         }
-        if (it > 0) {
-            cp_async_wait<0>();
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full_bar[(it - 1) % (uint32_t)S]);
-        }
+        if (it > 0) publish_previous(true);
     } else if (warp == MMA_WARP) {
         // ------------------------------------------------------------------ MMA issue (one thread)
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(TILE_M, N);
+            const uint32_t idesc = WGRAD ? make_idesc_mn(TILE_M, N) : make_idesc(TILE_M, N);
             uint32_t it = 0, tcount = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int n_chunks = chunks_of(w);
                 const uint32_t a = tcount & 1u;
                 mbar_wait(&acc_empty[a], ((tcount >> 1) & 1u) ^ 1u);     // epilogue drained this accumulator
                 tc_fence_after();
@@ -176,25 +196,50 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
         // ------------------------------------------------------------------ epilogue: thread = row = TMEM lane
         const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
         uint32_t tcount = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
             const uint32_t a = tcount & 1u;
             mbar_wait(&acc_full[a], (tcount >> 1) & 1u);
             tc_fence_after();
-            const int64_t m = tile * TILE_M + tid;
-            const bool live = m < p.M;
+            bool live;
             int64_t orow = 0;
-            if (live) {
-                int b, y, x;
-                xb_conv_site(g, m, b, y, x);
-                orow = (((int64_t)b * p.out_H + (y * p.oys + p.oy0)) * p.out_W + (x * p.oxs + p.ox0)) * p.out_ld + p.out_c0;
+            if (!WGRAD) {
+                const int64_t m = w * TILE_M + tid;
+                live = m < p.M;
+                if (live) {
+                    int b, y, x;
+                    xb_conv_site(g, m, b, y, x);
+                    orow = (((int64_t)b * p.out_H + (y * p.oys + p.oy0)) * p.out_W + (x * p.oxs + p.ox0)) * p.out_ld + p.out_c0;
+                }
+            } else {
+                const int64_t mt = w % m_tiles, sp = w / m_tiles;
+                const int64_t kcol = mt * TILE_M + tid;
+                live = kcol < K;
+                orow = (sp * K + kcol) * N;                       // partials [splits, K, N]
             }
             for (int c0 = 0; c0 < N; c0 += 32) {
                 float v[32];
                 tmem_ld32(lane_addr + a * (uint32_t)N + c0, v);
+                if (!WGRAD) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    v[j] += s_bias[c0 + j];
-                    if (p.relu) v[j] = fmaxf(v[j], 0.f);
+                    for (int j = 0; j < 32; ++j) {
+                        v[j] += s_bias[c0 + j];
+                        if (p.relu) v[j] = fmaxf(v[j], 0.f);
+                    }
+                }
+                if (!WGRAD && p.mask && live) {
+                    const uint4 *mk = reinterpret_cast<const uint4 *>(p.mask + orow + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 q = mk[j];
+                        const uint32_t ws[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            // bf16 > 0  <=>  sign bit clear and not (+)zero
+                            const uint32_t lo16 = ws[i] & 0xffffu, hi16 = ws[i] >> 16;
+                            if (!(lo16 != 0u && lo16 < 0x8000u)) v[8 * j + 2 * i] = 0.f;
+                            if (!(hi16 != 0u && hi16 < 0x8000u)) v[8 * j + 2 * i + 1] = 0.f;
+                        }
+                    }
                 }
                 if (live) {
                     if (p.out_f32) {
@@ -202,7 +247,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     }
-                    if (p.out_hi) {
+                    if (!WGRAD && p.out_hi) {
                         uint4 *oh = reinterpret_cast<uint4 *>(p.out_hi + orow + c0);
                         uint4 *ol = reinterpret_cast<uint4 *>(p.out_lo + orow + c0);
 #pragma unroll
@@ -227,6 +272,20 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
     __syncthreads();
     if (warp == MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols));
+    }
+}
+
+// weight-gradient finish: sum the split partials [splits, K, N] in split order and scatter to torch's [N, C, KH, KW]
+// (column k = (kh, kw, c) of the packed layout -> xb_pack_weight_src); accumulate != 0 adds to dw (autograd .grad)
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restrict__ ws, int splits, int N, int C, int KH,
+                                                           int KW, float *__restrict__ dw, int accumulate) {
+    const int64_t K = (int64_t)C * KH * KW, total = (int64_t)N * K;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = i / K, k = i - n * K;              // i indexes the PACKED layout [N, (kh, kw, c)]
+        float s = 0.f;
+        for (int sp = 0; sp < splits; ++sp) s += ws[((int64_t)sp * K + k) * N + n];
+        const int64_t dst = xb_pack_weight_src(i, C, KH, KW);
+        dw[dst] = accumulate ? dw[dst] + s : s;
     }
 }
 
@@ -289,7 +348,7 @@ extern "C" int xb_pack_conv_weight(const float *w, int N, int C, int KH, int KW,
 }
 
 extern "C" int xb_gemm_gather_tc(const void *in_hi, const void *in_lo, const void *w_hi, const void *w_lo,
-                                 const float *bias, int B, int IH, int IW, int C, int OY, int OX, int sy, int sx, int T,
+                                 const float *bias, const void *relu_mask, int B, int IH, int IW, int C, int OY, int OX, int sy, int sx, int T,
                                  const int8_t *dy, const int8_t *dx, int N, int relu, void *out_hi, void *out_lo,
                                  float *out_f32, int out_H, int out_W, int oys, int oxs, int oy0, int ox0,
                                  int64_t out_ld, int out_c0, void *stream) {
@@ -303,7 +362,8 @@ extern "C" int xb_gemm_gather_tc(const void *in_hi, const void *in_lo, const voi
         return XB_EINVAL;
     if (out_ld % 8 != 0 || out_c0 % 8 != 0) return XB_EALIGN;   // 16-byte row segments in both output formats
     if (!xb_aligned(in_hi, 16) || !xb_aligned(in_lo, 16) || !xb_aligned(w_hi, 16) || !xb_aligned(w_lo, 16) ||
-        (out_hi && (!xb_aligned(out_hi, 16) || !xb_aligned(out_lo, 16))) || (out_f32 && !xb_aligned(out_f32, 16)))
+        (out_hi && (!xb_aligned(out_hi, 16) || !xb_aligned(out_lo, 16))) || (out_f32 && !xb_aligned(out_f32, 16)) ||
+        (relu_mask && !xb_aligned(relu_mask, 16)))
         return XB_EALIGN;
     ConvParams p;
     p.g.B = B, p.g.IH = IH, p.g.IW = IW, p.g.C = C, p.g.OY = OY, p.g.OX = OX, p.g.sy = sy, p.g.sx = sx, p.g.T = T, p.g.N = N;
@@ -311,11 +371,13 @@ extern "C" int xb_gemm_gather_tc(const void *in_hi, const void *in_lo, const voi
     p.in_hi = (const __nv_bfloat16 *)in_hi, p.in_lo = (const __nv_bfloat16 *)in_lo;
     p.w_hi = (const __nv_bfloat16 *)w_hi, p.w_lo = (const __nv_bfloat16 *)w_lo;
     p.bias = bias;
+    p.mask = (const __nv_bfloat16 *)relu_mask;
     p.out_hi = (__nv_bfloat16 *)out_hi, p.out_lo = (__nv_bfloat16 *)out_lo, p.out_f32 = out_f32;
     p.M = (int64_t)B * OY * OX;
     p.relu = relu;
     p.out_H = out_H, p.out_W = out_W, p.oys = oys, p.oxs = oxs, p.oy0 = oy0, p.ox0 = ox0;
     p.out_ld = out_ld, p.out_c0 = out_c0;
+    p.splits = 1, p.sites_per_split = 0;
     const uint32_t stage_bytes = xb_conv_stage_bytes(N);
     int stages = (int)((200u * 1024u) / stage_bytes);
     if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -324,11 +386,59 @@ extern "C" int xb_gemm_gather_tc(const void *in_hi, const void *in_lo, const voi
     const size_t smem = (size_t)stages * stage_bytes;
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr = true;
     }
     const int64_t tiles = (p.M + TILE_M - 1) / TILE_M;
     const int grid = (int)(tiles < xb_sm_count() ? tiles : xb_sm_count());
-    conv_tc_kernel<<<grid, THREADS, smem, (cudaStream_t)stream>>>(p);
+    conv_tc_kernel<false><<<grid, THREADS, smem, (cudaStream_t)stream>>>(p);
+    return xb_launch_status();
+}
+
+extern "C" int xb_wgrad_gather_tc(const void *in_hi, const void *in_lo, const void *g_hi, const void *g_lo, int B, int IH,
+                                  int IW, int C, int OY, int OX, int sy, int sx, int T, const int8_t *dy, const int8_t *dx,
+                                  int N, int splits, float *partials, void *stream) {
+    if (!in_hi || !in_lo || !g_hi || !g_lo || !dy || !dx || !partials) return XB_EINVAL;
+    if (B <= 0 || IH <= 0 || IW <= 0 || OY <= 0 || OX <= 0 || sy <= 0 || sx <= 0 || T <= 0 || splits <= 0) return XB_EINVAL;
+    if (T > XB_CONV_MAX_TAPS || N > 256 || N % 32 != 0 || C % 8 != 0) return XB_ERANGE;
+    if (!xb_aligned(in_hi, 16) || !xb_aligned(in_lo, 16) || !xb_aligned(g_hi, 16) || !xb_aligned(g_lo, 16) ||
+        !xb_aligned(partials, 16))
+        return XB_EALIGN;
+    ConvParams p;
+    p.g.B = B, p.g.IH = IH, p.g.IW = IW, p.g.C = C, p.g.OY = OY, p.g.OX = OX, p.g.sy = sy, p.g.sx = sx, p.g.T = T, p.g.N = N;
+    for (int t = 0; t < XB_CONV_MAX_TAPS; ++t) p.g.dy[t] = t < T ? dy[t] : 0, p.g.dx[t] = t < T ? dx[t] : 0;
+    p.in_hi = (const __nv_bfloat16 *)in_hi, p.in_lo = (const __nv_bfloat16 *)in_lo;
+    p.w_hi = (const __nv_bfloat16 *)g_hi, p.w_lo = (const __nv_bfloat16 *)g_lo;
+    p.bias = nullptr, p.mask = nullptr, p.out_hi = nullptr, p.out_lo = nullptr, p.out_f32 = partials;
+    p.M = (int64_t)B * OY * OX;
+    p.relu = 0;
+    p.out_H = p.out_W = p.oys = p.oxs = 1, p.oy0 = p.ox0 = 0, p.out_ld = N, p.out_c0 = 0;
+    // sites per split: a multiple of the chunk length, every split non-empty
+    const int64_t per = xb_wgrad_sites_per_split(p.M, splits);
+    if (per == 0) return XB_EINVAL;     // too many splits for this many sites
+    p.splits = splits, p.sites_per_split = per;
+    const uint32_t stage_bytes = xb_conv_stage_bytes(N);
+    int stages = (int)((200u * 1024u) / stage_bytes);
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 2) return XB_ERANGE;
+    p.stages = stages;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr = true;
+    }
+    const int64_t K = (int64_t)T * C, work = (K + TILE_M - 1) / TILE_M * splits;
+    const int grid = (int)(work < xb_sm_count() ? work : xb_sm_count());
+    conv_tc_kernel<true><<<grid, THREADS, (size_t)stages * stage_bytes, (cudaStream_t)stream>>>(p);
+    return xb_launch_status();
+}
+
+extern "C" int xb_wgrad_reduce(const float *partials, int splits, int N, int C, int KH, int KW, float *dw, int accumulate,
+                               void *stream) {
+    if (!partials || !dw || splits <= 0 || N <= 0 || C <= 0 || KH <= 0 || KW <= 0) return XB_EINVAL;
+    const int64_t total = (int64_t)N * C * KH * KW;
+    int64_t want = (total + 255) / 256;
+    const int grid = (int)(want < (int64_t)xb_sm_count() * 8 ? want : (int64_t)xb_sm_count() * 8);
+    wgrad_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(partials, splits, N, C, KH, KW, dw, accumulate);
     return xb_launch_status();
 }
