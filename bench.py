@@ -222,8 +222,8 @@ def run_own_arm(args):
         assert world == args.gpus, "torchrun world size must equal --gpus"
     torch.cuda.set_device(local_rank)
     device = "cuda:%d" % local_rank
-    torch.backends.cudnn.allow_tf32 = args.compute not in ("fp32", "fp32_cl")
-    torch.backends.cuda.matmul.allow_tf32 = args.compute not in ("fp32", "fp32_cl")
+    torch.backends.cudnn.allow_tf32 = args.compute not in ("fp32", "fp32_cl", "tc")
+    torch.backends.cuda.matmul.allow_tf32 = args.compute not in ("fp32", "fp32_cl", "tc")
     torch.backends.cudnn.benchmark = True
     assert N_ENVS % world == 0
     n_local = N_ENVS // world
@@ -354,7 +354,7 @@ def run_own_arm(args):
     peak, peak_src = measured_peaks()
     B_local = (N_ENVS * T // N_MINIBATCH) // world
     obs_bytes = int(np.prod(OBS_SHAPE))
-    out_w = {"fp32": 4, "fp32_cl": 4, "tf32": 4, "bf16": 2}[args.compute]
+    out_w = {"fp32": 4, "fp32_cl": 4, "tf32": 4, "bf16": 2, "tc": 4}[args.compute]
     alg_bytes = B_local * obs_bytes * (1 + out_w) + 8 * B_local
     roofline = None
     if k3_ms:
@@ -382,7 +382,8 @@ def run_own_arm(args):
             "config": {"workload": WORKLOAD, "global_minibatch": N_ENVS * T // N_MINIBATCH,
                        "parallelism": "dp%d (envs sharded, 1 NCCL grad all-reduce/update)" % world,
                        "compute": {"fp32": "fp32, TF32 disabled (reference arithmetic)", "fp32_cl": "fp32, TF32 disabled, channels-last convolutions", "tf32": "fp32 storage, TF32 convs/matmuls",
-                                   "bf16": "bf16 autocast convs, fp32 master weights"}[args.compute],
+                                   "bf16": "bf16 autocast convs, fp32 master weights",
+                                   "tc": "EXPERIMENTAL: split-bf16 (hi+lo) tcgen05 layers, fp32 accumulation, fp32-level accuracy"}[args.compute],
                        "l2": "inputs (925 MB uint8 rollout / G) exceed the 126 MB L2; no explicit flush",
                        "cuda_graph": bool(cfg.use_cuda_graph)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
@@ -396,7 +397,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="xuance_b200", choices=["xuance_b200", "reference"])
-    ap.add_argument("--compute", default="fp32", choices=["fp32", "fp32_cl", "tf32", "bf16"])
+    ap.add_argument("--compute", default="fp32", choices=["fp32", "fp32_cl", "tf32", "bf16", "tc"],
+                    help="'tc' = EXPERIMENTAL split-bf16 tcgen05 layers (K12); not a default, see DESIGN.md section 9")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", type=int, default=-1, help="CUDA-graph the minibatch update: 1/0; default: on when --gpus > 1")

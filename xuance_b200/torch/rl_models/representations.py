@@ -50,9 +50,11 @@ class _PixelEncoder(nn.Module):
     compute = "fp32"
 
     def set_compute(self, mode):
-        assert mode in ("fp32", "fp32_cl", "tf32", "bf16")
+        assert mode in ("fp32", "fp32_cl", "tf32", "bf16", "tc")
+        if mode == "tc":
+            self._build_tc()
         self.compute = mode
-        fmt = torch.channels_last if mode != "fp32" else torch.contiguous_format
+        fmt = torch.channels_last if mode not in ("fp32", "tc") else torch.contiguous_format
         for m in self.model:
             if isinstance(m, nn.Conv2d):
                 m.to(memory_format=fmt)
@@ -61,7 +63,35 @@ class _PixelEncoder(nn.Module):
     def preferred_obs_format(self):
         """K3 output format this encoder consumes without any further copy."""
         return {"fp32": _lib.OBS_F32_NCHW, "fp32_cl": _lib.OBS_F32_NHWC, "tf32": _lib.OBS_F32_NHWC,
-                "bf16": _lib.OBS_BF16_NHWC}[self.compute]
+                "bf16": _lib.OBS_BF16_NHWC, "tc": _lib.OBS_F32_NHWC}[self.compute]
+
+    # ---- EXPERIMENTAL "tc" mode: the conv stack + hidden layer as K12 launches (split-bf16 tcgen05 GEMMs with fp32-level
+    # accuracy, utils/tc_conv.py).  Host-verified only (tests/test_conv_index.py); see DESIGN.md section 9.
+    def _build_tc(self):
+        from ..utils.tc_conv import TensorCoreNatureCNN
+        mods = list(self.model)
+        convs, fc, i = [], None, 0
+        while i + 1 < len(mods) and isinstance(mods[i], nn.Conv2d) and isinstance(mods[i + 1], nn.ReLU):
+            convs.append(mods[i])
+            i += 2
+        rest = mods[i:]
+        ok = (len(convs) > 0 and len(rest) == 3 and isinstance(rest[0], nn.Flatten) and isinstance(rest[1], nn.Linear)
+              and isinstance(rest[2], nn.ReLU))
+        if not ok:
+            raise NotImplementedError("compute='tc' covers Conv2d+ReLU stacks followed by Flatten, Linear, ReLU "
+                                      "(AC_CNN_Atari with one hidden layer)")
+        C, H, W = self.input_shape
+        self._tc = TensorCoreNatureCNN(convs, rest[1], (H, W, C))
+
+    def _run_tc(self, x_nchw_view):
+        from ..utils import tc_conv
+        x = x_nchw_view.permute(0, 2, 3, 1)
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        pair = tc_conv.split_bf16(x)
+        if torch.is_grad_enabled():
+            return tc_conv.tc_encode(self._tc, pair, x.shape[0])
+        return self._tc.forward(pair, x.shape[0])
 
     def _as_input(self, observations):
         fmt = self.preferred_obs_format()
@@ -146,7 +176,8 @@ class AC_CNN_Atari(_PixelEncoder):
         return layer
 
     def forward(self, observations, **kwargs):
-        return RepresentationOutput(embeddings=self._run(self._as_input(observations)))
+        x = self._as_input(observations)
+        return RepresentationOutput(embeddings=self._run_tc(x) if self.compute == "tc" else self._run(x))
 
 
 REGISTRY_Representation = {
