@@ -223,8 +223,8 @@ int xb_rms_update_normalize(const float *x, int N, int64_t D, float *mean, float
                             float *out, float clip_range, float eps, void *stream);
 
 /* ---------------------------------------------------------------- K12 (EXPERIMENTAL): tensor-core layers ------
- * Not on any default path; compiled and host-verified (tests/test_conv_index.py), hardware bring-up is round-2 work
- * (DESIGN.md section 9).  Target: the NatureCNN layers of AC_CNN_Atari / Basic_CNN (rl_models/representations/cnn.py:
+ * Not on any default path.  Host-verified (tests/test_conv_index.py); on B200 the forward GEMM passes its parity tests
+ * (tests/test_gpu_tc_conv.py), the two gradient modes have run but are not yet parity-pinned.  Target: the NatureCNN layers of AC_CNN_Atari / Basic_CNN (rl_models/representations/cnn.py:
  * 45-50, 84-101; layers.py:16-65) that cuDNN runs as CUDA-core fp32 convolutions.
  * xb_split_bf16       : x (float32[n]) -> hi = bf16(x), lo = bf16(x - hi)            (n*4 B read, n*4 B written)
  * xb_pack_conv_weight : torch [N, C, KH, KW] float32 -> [N, (kh, kw, c)] hi / lo bf16 (also Linear over a [C,H,W] flatten)

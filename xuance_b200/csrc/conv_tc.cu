@@ -1,4 +1,6 @@
-// K12 (EXPERIMENTAL - compiled and host-verified, not yet run on hardware; nothing on the default path calls it):
+// K12 (EXPERIMENTAL; nothing on the default path calls it.  Status after round 1: the forward GEMM passed on B200 -
+// tests/test_gpu_tc_conv.py, profiles/r01_k12_bringup_forward.log; the data-gradient and weight-gradient modes ran on
+// hardware inside the whole-encoder backward and agreed with cuDNN fp32 to ~4e-3 of max|grad|, per-layer parity pending):
 // gathered-operand GEMM on the 5th-generation tensor cores for the NatureCNN layers (cnn.py:45-50, 84-101) - the 85 %
 // of the fp32 PPO step that cuDNN's CUDA-core fp32 convolutions take.
 //

@@ -66,7 +66,7 @@ class _PixelEncoder(nn.Module):
                 "bf16": _lib.OBS_BF16_NHWC, "tc": _lib.OBS_F32_NHWC}[self.compute]
 
     # ---- EXPERIMENTAL "tc" mode: the conv stack + hidden layer as K12 launches (split-bf16 tcgen05 GEMMs with fp32-level
-    # accuracy, utils/tc_conv.py).  Host-verified only (tests/test_conv_index.py); see DESIGN.md section 9.
+    # accuracy, utils/tc_conv.py).  Forward parity-tested on B200, backward not yet pinned; see DESIGN.md section 9.
     def _build_tc(self):
         from ..utils.tc_conv import TensorCoreNatureCNN
         mods = list(self.model)
