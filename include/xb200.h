@@ -226,8 +226,8 @@ int xb_rms_update_normalize(const float *x, int N, int64_t D, float *mean, float
  * Not on any default path.  Host-verified (tests/test_conv_index.py); on B200 the forward GEMM passes its parity tests
  * (tests/test_gpu_tc_conv.py), the two gradient modes have run but are not yet parity-pinned.  Target: the NatureCNN layers of AC_CNN_Atari / Basic_CNN (rl_models/representations/cnn.py:
  * 45-50, 84-101; layers.py:16-65) that cuDNN runs as CUDA-core fp32 convolutions.
- * xb_split_bf16       : x (float32[n]) -> hi = bf16(x), lo = bf16(x - hi)            (n*4 B read, n*4 B written)
- * xb_pack_conv_weight : torch [N, C, KH, KW] float32 -> [N, (kh, kw, c)] hi / lo bf16 (also Linear over a [C,H,W] flatten)
+ * xb_split_bf16       : x (float32[n]) -> planes[0] = bf16(x), planes[1] = bf16(x - planes[0]), [planes[2] = ...]
+ * xb_pack_conv_weight : torch [N, C, KH, KW] float32 -> bf16 planes of [N, (kh, kw, c)] (also Linear over a [C,H,W] flatten)
  * xb_gemm_gather_tc   : D[m,n] = sum_{t,c} in[b, y*sy+dy[t], x*sx+dx[t], c] * W[n, t*C+c] (+bias, ReLU), m = (b,y,x) over
  *                       [B,OY,OX]; in / W as hi / lo bf16 pairs (NHWC, [N,K]); three tcgen05.mma per product (hi.hi +
  *                       hi.lo + lo.hi, fp32 accumulation in TMEM); result as float32 and / or a hi / lo pair written to
@@ -243,13 +243,19 @@ int xb_rms_update_normalize(const float *x, int N, int64_t D, float *mean, float
  *                       Both operands are fed MN-major (16-byte units transposed into the core matrices); one CTA work
  *                       item = (128 columns of (t,c), split).  partials: float32 [splits, T*C, N].
  * xb_wgrad_reduce     : dw[N, C, KH, KW] (torch layout) (+)= sum_s partials[s, (kh,kw,c), n], splits added in order. */
-int xb_split_bf16(const float *x, int64_t n, void *hi, void *lo, void *stream);
-int xb_pack_conv_weight(const float *w, int N, int C, int KH, int KW, void *hi, void *lo, void *stream);
-int xb_gemm_gather_tc(const void *in_hi, const void *in_lo, const void *w_hi, const void *w_lo, const float *bias,
-                      const void *relu_mask, int B, int IH, int IW, int C, int OY, int OX, int sy, int sx, int T, const int8_t *dy,
-                      const int8_t *dx, int N, int relu, void *out_hi, void *out_lo, float *out_f32, int out_H,
-                      int out_W, int oys, int oxs, int oy0, int ox0, int64_t out_ld, int out_c0, void *stream);
-int xb_wgrad_gather_tc(const void *in_hi, const void *in_lo, const void *g_hi, const void *g_lo, int B, int IH, int IW,
+int xb_split_bf16(const float *x, int64_t n, int planes, void *out /* bf16 [planes, n] */, void *stream);
+int xb_pack_conv_weight(const float *w, int N, int C, int KH, int KW, int planes, void *out /* bf16 [planes, N, KH*KW*C] */,
+                        void *stream);
+/* Operands are `planes` (2 or 3) bf16 planes, plane q at base + q*plane_stride (elements): x = sum of its planes; plane 0 =
+ * bf16(x), each further plane the bf16 of the remaining residual.  2 planes: 3 products per MMA step, operands exact to
+ * 2^-17; 3 planes: 6 products, exact to 2^-24 (float32-grade; N <= 128).  out_planes (nullable) receives the result split
+ * the same way; relu_mask = plane 0 of a saved activation. */
+int xb_gemm_gather_tc(int planes, const void *in, int64_t in_plane, const void *w, int64_t w_plane, const float *bias,
+                      const void *relu_mask, int B, int IH, int IW, int C, int OY, int OX, int sy, int sx, int T,
+                      const int8_t *dy, const int8_t *dx, int N, int relu, void *out_planes, int64_t out_plane,
+                      float *out_f32, int out_H, int out_W, int oys, int oxs, int oy0, int ox0, int64_t out_ld, int out_c0,
+                      void *stream);
+int xb_wgrad_gather_tc(int planes, const void *in, int64_t in_plane, const void *g, int64_t g_plane, int B, int IH, int IW,
                        int C, int OY, int OX, int sy, int sx, int T, const int8_t *dy, const int8_t *dx, int N, int splits,
                        float *partials, void *stream);
 int xb_wgrad_reduce(const float *partials, int splits, int N, int C, int KH, int KW, float *dw, int accumulate,

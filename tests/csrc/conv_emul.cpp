@@ -14,7 +14,7 @@ namespace {
 inline float &at(std::vector<float> &smem, uint32_t byte_off) { return smem[byte_off / 2]; }   // one slot per bf16
 }
 
-extern "C" int emul_gemm_gather(const float *in_hi, const float *in_lo, const float *w_hi, const float *w_lo, int B,
+extern "C" int emul_gemm_gather(int P, const float *in, int64_t in_plane, const float *w, int64_t w_plane, int B,
                                 int IH, int IW, int C, int OY, int OX, int sy, int sx, int T, const int8_t *dy,
                                 const int8_t *dx, int N, int out_H, int out_W, int oys, int oxs, int oy0, int ox0,
                                 int64_t out_ld, int out_c0, int stages, double *out) {
@@ -24,7 +24,7 @@ extern "C" int emul_gemm_gather(const float *in_hi, const float *in_lo, const fl
     const int KC = XB_CONV_KC, TM = XB_CONV_TILE_M, K = T * C;
     if (K % KC || C % 8 || N % 8) return -1;
     const int n_chunks = K / KC;
-    const uint32_t stage_bytes = xb_conv_stage_bytes(N), a_plane = xb_conv_a_plane_bytes(), w_plane = xb_conv_w_plane_bytes(N);
+    const uint32_t stage_bytes = xb_conv_stage_bytes(N, P), a_plane = xb_conv_a_plane_bytes(), ws_plane = xb_conv_w_plane_bytes(N);
     std::vector<float> smem((size_t)stages * stage_bytes / 2);
     const int64_t M = (int64_t)B * OY * OX, n_tiles = (M + TM - 1) / TM;
     const float nan = std::numeric_limits<float>::quiet_NaN();
@@ -42,25 +42,23 @@ extern "C" int emul_gemm_gather(const float *in_hi, const float *in_lo, const fl
                 int b = 0, y = 0, x = 0;
                 if (live) xb_conv_site(g, m, b, y, x);
                 auto emit_a = [&](uint32_t dst, int64_t src) {
-                    for (int j = 0; j < 8; ++j) {
-                        at(smem, base + dst + 2 * j) = src >= 0 ? in_hi[src + j] : 0.f;
-                        at(smem, base + a_plane + dst + 2 * j) = src >= 0 ? in_lo[src + j] : 0.f;
-                    }
+                    for (int q = 0; q < P; ++q)
+                        for (int j = 0; j < 8; ++j)
+                            at(smem, base + q * a_plane + dst + 2 * j) = src >= 0 ? in[q * in_plane + src + j] : 0.f;
                 };
                 auto emit_w = [&](uint32_t dst, int64_t src) {
-                    for (int j = 0; j < 8; ++j) {
-                        at(smem, base + 2 * a_plane + dst + 2 * j) = src >= 0 ? w_hi[src + j] : 0.f;
-                        at(smem, base + 2 * a_plane + w_plane + dst + 2 * j) = src >= 0 ? w_lo[src + j] : 0.f;
-                    }
+                    for (int q = 0; q < P; ++q)
+                        for (int j = 0; j < 8; ++j)
+                            at(smem, base + P * a_plane + q * ws_plane + dst + 2 * j) = src >= 0 ? w[q * w_plane + src + j] : 0.f;
                 };
                 xb_stage_fwd(g, row, live, b, y, x, kc, emit_a, emit_w);
             }
             // ---- tensor core: three products, K 16 per instruction, operands located through the descriptor fields
             const uint32_t LBO = 128, SBO = (KC / 8) * 128;
-            const uint32_t a_addr[2] = {base, base + a_plane};
-            const uint32_t w_addr[2] = {base + 2 * a_plane, base + 2 * a_plane + w_plane};
-            for (int pa = 0; pa < 2; ++pa)
-                for (int pb = 0; pb < 2 - pa; ++pb)
+            const uint32_t a_addr[3] = {base, base + a_plane, base + 2 * a_plane};
+            const uint32_t w_addr[3] = {base + P * a_plane, base + P * a_plane + ws_plane, base + P * a_plane + 2 * ws_plane};
+            for (int pa = 0; pa < P; ++pa)
+                for (int pb = 0; pb < P - pa; ++pb)
                     for (int ks = 0; ks < KC / 16; ++ks) {
                         const uint32_t sa = a_addr[pa] + ks * 256, sb = w_addr[pb] + ks * 256;
                         for (int r = 0; r < TM; ++r)
@@ -96,7 +94,7 @@ extern "C" void emul_pack_weight(const float *w, int N, int C, int KH, int KW, f
 
 // weight gradient (conv_tc_kernel<true>): partials[split, (t,c), n]; MN-major operands: the "tensor core" locates element
 // (mn, k) at start + (mn/8)*SBO + (k/8)*LBO + (k%8)*16 + (mn%8)*2
-extern "C" int emul_wgrad(const float *in_hi, const float *in_lo, const float *g_hi, const float *g_lo, int B, int IH,
+extern "C" int emul_wgrad(int P, const float *in, int64_t in_plane, const float *gr, int64_t g_plane, int B, int IH,
                           int IW, int C, int OY, int OX, int sy, int sx, int T, const int8_t *dy, const int8_t *dx, int N,
                           int splits, int stages, double *partials) {
     XbConvGeom g;
@@ -106,7 +104,7 @@ extern "C" int emul_wgrad(const float *in_hi, const float *in_lo, const float *g
     const int64_t M = (int64_t)B * OY * OX;
     const int64_t per = xb_wgrad_sites_per_split(M, splits);
     if (per == 0 || C % 8 || N % 8) return -1;
-    const uint32_t stage_bytes = xb_conv_stage_bytes(N), a_plane = xb_conv_a_plane_bytes(), w_plane = xb_conv_w_plane_bytes(N);
+    const uint32_t stage_bytes = xb_conv_stage_bytes(N, P), a_plane = xb_conv_a_plane_bytes(), ws_plane = xb_conv_w_plane_bytes(N);
     std::vector<float> smem((size_t)stages * stage_bytes / 2);
     const float nan = std::numeric_limits<float>::quiet_NaN();
     const int64_t m_tiles = (K + TM - 1) / TM;
@@ -122,24 +120,22 @@ extern "C" int emul_wgrad(const float *in_hi, const float *in_lo, const float *g
             for (uint32_t i = 0; i < stage_bytes / 2; ++i) smem[base / 2 + i] = nan;
             for (int row = 0; row < TM; ++row) {
                 auto emit_a = [&](uint32_t dst, int64_t src) {
-                    for (int j = 0; j < 8; ++j) {
-                        at(smem, base + dst + 2 * j) = src >= 0 ? in_hi[src + j] : 0.f;
-                        at(smem, base + a_plane + dst + 2 * j) = src >= 0 ? in_lo[src + j] : 0.f;
-                    }
+                    for (int q = 0; q < P; ++q)
+                        for (int j = 0; j < 8; ++j)
+                            at(smem, base + q * a_plane + dst + 2 * j) = src >= 0 ? in[q * in_plane + src + j] : 0.f;
                 };
                 auto emit_g = [&](uint32_t dst, int64_t src) {
-                    for (int j = 0; j < 8; ++j) {
-                        at(smem, base + 2 * a_plane + dst + 2 * j) = src >= 0 ? g_hi[src + j] : 0.f;
-                        at(smem, base + 2 * a_plane + w_plane + dst + 2 * j) = src >= 0 ? g_lo[src + j] : 0.f;
-                    }
+                    for (int q = 0; q < P; ++q)
+                        for (int j = 0; j < 8; ++j)
+                            at(smem, base + P * a_plane + q * ws_plane + dst + 2 * j) = src >= 0 ? gr[q * g_plane + src + j] : 0.f;
                 };
                 xb_stage_wgrad(g, row, mt, s0 + (int64_t)kc * KC, site_end, emit_a, emit_g);
             }
             const uint32_t LBO = 128, SBO = (KC / 8) * 128;
-            const uint32_t a_addr[2] = {base, base + a_plane};
-            const uint32_t w_addr[2] = {base + 2 * a_plane, base + 2 * a_plane + w_plane};
-            for (int pa = 0; pa < 2; ++pa)
-                for (int pb = 0; pb < 2 - pa; ++pb)
+            const uint32_t a_addr[3] = {base, base + a_plane, base + 2 * a_plane};
+            const uint32_t w_addr[3] = {base + P * a_plane, base + P * a_plane + ws_plane, base + P * a_plane + 2 * ws_plane};
+            for (int pa = 0; pa < P; ++pa)
+                for (int pb = 0; pb < P - pa; ++pb)
                     for (int ks = 0; ks < KC / 16; ++ks) {
                         const uint32_t sa = a_addr[pa] + ks * 256, sb = w_addr[pb] + ks * 256;
                         for (int r = 0; r < TM; ++r)

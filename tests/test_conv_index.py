@@ -27,31 +27,37 @@ def emul():
         subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-std=c++17", "-o", so, src], check=True)
     lib = ctypes.CDLL(so)
     P, i, l = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
-    lib.emul_gemm_gather.argtypes = [P, P, P, P] + [i] * 9 + [P, P] + [i] * 7 + [l, i, i, P]
+    lib.emul_gemm_gather.argtypes = [i, P, l, P, l] + [i] * 9 + [P, P] + [i] * 7 + [l, i, i, P]
     lib.emul_gemm_gather.restype = i
     lib.emul_pack_weight.argtypes = [P, i, i, i, i, P]
-    lib.emul_wgrad.argtypes = [P, P, P, P] + [i] * 9 + [P, P] + [i] * 3 + [P]
+    lib.emul_wgrad.argtypes = [i, P, l, P, l] + [i] * 9 + [P, P] + [i] * 3 + [P]
     lib.emul_wgrad.restype = i
     lib.emul_wgrad_reduce.argtypes = [P, i, i, i, i, i, P]
     return lib
 
 
-def _split(x):
-    hi = x.float().bfloat16().float()
-    lo = (x.float() - hi).bfloat16().float()
-    return hi.contiguous(), lo.contiguous()
+def _split(x, planes=2):
+    """float -> float32 [planes, ...] of bf16-representable values: plane q = bf16 of the residual left by planes < q
+    (what xb_split_bf16 / the kernel epilogue produce)."""
+    r = x.float().clone()
+    out = []
+    for _ in range(planes):
+        h = r.bfloat16().float()
+        out.append(h)
+        r = r - h
+    return torch.stack(out).contiguous()
 
 
-def _run(lib, geom, x_nhwc, w_mat, out, out_ld, out_c0=0, stages=3):
+def _run(lib, geom, x_nhwc, w_mat, out, out_ld, out_c0=0, stages=2, planes=2):
     """x_nhwc: float64 tensor viewed as the geometry's [B, IH, IW, C]; w_mat float64 [N, K]; out float64 [rows, out_ld]."""
-    xh, xl = _split(x_nhwc)
-    wh, wl = _split(w_mat)
+    xp, wp = _split(x_nhwc, planes), _split(w_mat, planes)
     N, K = w_mat.shape
-    assert K == geom.K and xh.numel() == geom.B * geom.IH * geom.IW * geom.C
+    assert K == geom.K and xp[0].numel() == geom.B * geom.IH * geom.IW * geom.C
     dy, dx = np.asarray(geom.dy, np.int8), np.asarray(geom.dx, np.int8)
-    rc = lib.emul_gemm_gather(xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), geom.B, geom.IH, geom.IW, geom.C,
-                              geom.OY, geom.OX, geom.sy, geom.sx, geom.T, dy.ctypes.data, dx.ctypes.data, N, geom.out_H,
-                              geom.out_W, geom.oys, geom.oxs, geom.oy0, geom.ox0, out_ld, out_c0, stages, out.data_ptr())
+    rc = lib.emul_gemm_gather(planes, xp.data_ptr(), xp.stride(0), wp.data_ptr(), wp.stride(0), geom.B, geom.IH, geom.IW,
+                              geom.C, geom.OY, geom.OX, geom.sy, geom.sx, geom.T, dy.ctypes.data, dx.ctypes.data, N,
+                              geom.out_H, geom.out_W, geom.oys, geom.oxs, geom.oy0, geom.ox0, out_ld, out_c0, stages,
+                              out.data_ptr())
     assert rc == 0
 
 
@@ -68,9 +74,10 @@ def _pack(lib, w):
 TOL = dict(rtol=0, atol=4e-5)     # |x - hi - lo| <= 2^-17 |x| per operand; sums of <= 6400 products of O(1) values / sqrt(K)
 
 
+@pytest.mark.parametrize("planes", [2, 3])
 @pytest.mark.parametrize("name,B,H,W,C,N,k,s", [("conv1", 2, 84, 84, 4, 32, 8, 4), ("conv2", 2, 21, 21, 32, 64, 4, 2),
                                                 ("conv3", 3, 10, 10, 64, 64, 3, 1), ("odd", 1, 13, 9, 8, 32, 4, 2)])
-def test_forward_conv_layers(emul, name, B, H, W, C, N, k, s):
+def test_forward_conv_layers(emul, name, B, H, W, C, N, k, s, planes):
     """The three NatureCNN convolutions with the reference's padding rule (k - s)//2 (layers.py:46), NHWC input."""
     torch.manual_seed(len(name))
     pad = (k - s) // 2
@@ -79,9 +86,10 @@ def test_forward_conv_layers(emul, name, B, H, W, C, N, k, s):
     g = tc.conv_forward_geometry(B, H, W, C, k, k, s, pad)
     assert g.K == C * k * k and (g.fold == 2) == (C == 4)
     out = torch.full((g.M, N), float("nan"), dtype=torch.float64)
-    _run(emul, g, x.permute(0, 2, 3, 1).contiguous(), _pack(emul, w), out, N)
+    _run(emul, g, x.permute(0, 2, 3, 1).contiguous(), _pack(emul, w), out, N, planes=planes)
     want = F.conv2d(x, w, stride=s, padding=pad).permute(0, 2, 3, 1).reshape(g.M, N)
-    np.testing.assert_allclose(out.numpy(), want.numpy(), **TOL)
+    # 2 planes: operands exact to 2^-17; 3 planes: to 2^-24 (the float32 inputs themselves are only exact to 2^-24)
+    np.testing.assert_allclose(out.numpy(), want.numpy(), rtol=0, atol=4e-5 if planes == 2 else 6e-7)
 
 
 def test_linear_layer_with_column_split_and_row_tail(emul):
@@ -134,12 +142,13 @@ def test_weight_gradient(emul, name, B, H, W, C, N, k, s, splits):
     gy = torch.randn_like(y) / np.sqrt(y[0, 0].numel())
     (want,) = torch.autograd.grad(y, w, gy)
     g = tc.conv_forward_geometry(B, H, W, C, k, k, s, pad)             # the weight gradient gathers like the forward
-    xh, xl = _split(x.permute(0, 2, 3, 1).contiguous())
-    gh, gl = _split(gy.permute(0, 2, 3, 1).reshape(g.M, N).contiguous())
+    planes = 3 if name == "conv3" else 2
+    xp = _split(x.permute(0, 2, 3, 1).contiguous(), planes)
+    gp = _split(gy.permute(0, 2, 3, 1).reshape(g.M, N).contiguous(), planes)
     partials = torch.full((splits, g.K, N), float("nan"), dtype=torch.float64)
     dy, dx = np.asarray(g.dy, np.int8), np.asarray(g.dx, np.int8)
-    rc = emul.emul_wgrad(xh.data_ptr(), xl.data_ptr(), gh.data_ptr(), gl.data_ptr(), g.B, g.IH, g.IW, g.C, g.OY, g.OX, g.sy,
-                         g.sx, g.T, dy.ctypes.data, dx.ctypes.data, N, splits, 3, partials.data_ptr())
+    rc = emul.emul_wgrad(planes, xp.data_ptr(), xp.stride(0), gp.data_ptr(), gp.stride(0), g.B, g.IH, g.IW, g.C, g.OY, g.OX,
+                         g.sy, g.sx, g.T, dy.ctypes.data, dx.ctypes.data, N, splits, 2, partials.data_ptr())
     assert rc == 0 and not torch.isnan(partials).any()
     dw = torch.full((N, C, k, k), float("nan"), dtype=torch.float64)
     emul.emul_wgrad_reduce(partials.data_ptr(), splits, N, C, k, k, dw.data_ptr())
@@ -153,11 +162,10 @@ def test_linear_weight_gradient(emul):
     x = torch.rand(Bn, K, dtype=torch.float64)
     gy = torch.randn(Bn, N, dtype=torch.float64) / 8
     g = tc.linear_geometry(Bn, K)
-    xh, xl = _split(x)
-    gh, gl = _split(gy)
+    xp, gp = _split(x), _split(gy)
     partials = torch.full((2, K, N), float("nan"), dtype=torch.float64)
     dy, dx = np.zeros(1, np.int8), np.zeros(1, np.int8)
-    rc = emul.emul_wgrad(xh.data_ptr(), xl.data_ptr(), gh.data_ptr(), gl.data_ptr(), g.B, 1, 1, K, 1, 1, 1, 1, 1,
+    rc = emul.emul_wgrad(2, xp.data_ptr(), xp.stride(0), gp.data_ptr(), gp.stride(0), g.B, 1, 1, K, 1, 1, 1, 1, 1,
                          dy.ctypes.data, dx.ctypes.data, N, 2, 2, partials.data_ptr())
     assert rc == 0
     np.testing.assert_allclose(partials.sum(0).t().numpy(), (gy.t() @ x).numpy(), **TOL)
@@ -177,40 +185,40 @@ class EmulBackend:
     bf16-representable values stand in for the bf16 planes).  The epilogue (bias, ReLU, mask, output formats) is restated
     here; staging, operand layouts and work decomposition are the kernel's own code (conv_index.h)."""
 
-    def __init__(self, lib):
-        self.lib = lib
+    def __init__(self, lib, planes=2):
+        self.lib, self.planes = lib, planes
+        self.n_tile = 256 if planes == 2 else 128
 
     def split(self, x):
-        return _split(x)
+        return _split(x, self.planes)
 
     def pack_weight(self, w4d):
         N = w4d.shape[0]
-        return _split(w4d.permute(0, 2, 3, 1).reshape(N, -1))
+        return _split(w4d.permute(0, 2, 3, 1).reshape(N, -1), self.planes)
 
-    def empty_pair(self, shape, like):
-        return torch.full(shape, float("nan")), torch.full(shape, float("nan"))
+    def empty_planes(self, shape, like):
+        return torch.full((self.planes,) + tuple(shape), float("nan"))
 
     def empty_f32(self, shape, like):
         return torch.full(shape, float("nan"))
 
-    def to_float(self, pair):
-        return pair[0] + pair[1]
+    def to_float(self, pl):
+        return pl.sum(0)
 
-    def colsum(self, g_pair):
-        return (g_pair[0].double() + g_pair[1].double()).sum(0).float()
+    def colsum(self, g_pl):
+        return g_pl.double().sum(dim=(0, 1)).float()
 
-    def gemm(self, x_pair, w_pair, geom, bias=None, relu=False, out_f32=None, out_pair=None, out_ld=None, out_c0=0, mask=None):
-        N = w_pair[0].shape[0]
+    def gemm(self, x_pl, w_pl, geom, bias=None, relu=False, out_f32=None, out_pl=None, out_ld=None, out_c0=0, mask=None):
+        P, N = w_pl.shape[0], w_pl.shape[1]
         out_ld = N if out_ld is None else out_ld
         rows = geom.B * geom.out_H * geom.out_W
         tmp = torch.full((rows, out_ld), float("nan"), dtype=torch.float64)
-        xh, xl = x_pair[0].contiguous(), x_pair[1].contiguous()
-        wh, wl = w_pair[0].contiguous(), w_pair[1].contiguous()
+        x_pl, w_pl = x_pl.contiguous(), w_pl.contiguous()
         dy, dx = np.asarray(geom.dy, np.int8), np.asarray(geom.dx, np.int8)
-        rc = self.lib.emul_gemm_gather(xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), geom.B, geom.IH, geom.IW,
-                                       geom.C, geom.OY, geom.OX, geom.sy, geom.sx, geom.T, dy.ctypes.data, dx.ctypes.data, N,
-                                       geom.out_H, geom.out_W, geom.oys, geom.oxs, geom.oy0, geom.ox0, out_ld, out_c0, 3,
-                                       tmp.data_ptr())
+        rc = self.lib.emul_gemm_gather(P, x_pl.data_ptr(), x_pl.stride(0), w_pl.data_ptr(), w_pl.stride(0), geom.B, geom.IH,
+                                       geom.IW, geom.C, geom.OY, geom.OX, geom.sy, geom.sx, geom.T, dy.ctypes.data,
+                                       dx.ctypes.data, N, geom.out_H, geom.out_W, geom.oys, geom.oxs, geom.oy0, geom.ox0,
+                                       out_ld, out_c0, 2, tmp.data_ptr())
         assert rc == 0
         blk = tmp[:, out_c0:out_c0 + N]
         written = ~torch.isnan(blk[:, 0])
@@ -225,26 +233,26 @@ class EmulBackend:
         v = v.float()
         if out_f32 is not None:
             out_f32.view(rows, out_ld)[written, out_c0:out_c0 + N] = v
-        if out_pair is not None:
-            hi, lo = _split(v)
-            out_pair[0].view(rows, out_ld)[written, out_c0:out_c0 + N] = hi
-            out_pair[1].view(rows, out_ld)[written, out_c0:out_c0 + N] = lo
+        if out_pl is not None:
+            out_pl.view(P, rows, out_ld)[:, written, out_c0:out_c0 + N] = _split(v, P)
 
-    def wgrad(self, x_pair, g_pair, geom, N, C, KH, KW):
+    def wgrad(self, x_pl, g_pl, geom, N, C, KH, KW):
+        P = g_pl.shape[0]
         splits = 2 if geom.M > 128 else 1
         partials = torch.full((splits, geom.K, N), float("nan"), dtype=torch.float64)
         dy, dx = np.asarray(geom.dy, np.int8), np.asarray(geom.dx, np.int8)
-        xh, xl, gh, gl = (t.contiguous() for t in (*x_pair, *g_pair))
-        rc = self.lib.emul_wgrad(xh.data_ptr(), xl.data_ptr(), gh.data_ptr(), gl.data_ptr(), geom.B, geom.IH, geom.IW, geom.C,
-                                 geom.OY, geom.OX, geom.sy, geom.sx, geom.T, dy.ctypes.data, dx.ctypes.data, N, splits, 3,
-                                 partials.data_ptr())
+        x_pl, g_pl = x_pl.contiguous(), g_pl.contiguous()
+        rc = self.lib.emul_wgrad(P, x_pl.data_ptr(), x_pl.stride(0), g_pl.data_ptr(), g_pl.stride(0), geom.B, geom.IH,
+                                 geom.IW, geom.C, geom.OY, geom.OX, geom.sy, geom.sx, geom.T, dy.ctypes.data, dx.ctypes.data,
+                                 N, splits, 2, partials.data_ptr())
         assert rc == 0
         dw = torch.full((N, C, KH, KW), float("nan"), dtype=torch.float64)
         self.lib.emul_wgrad_reduce(partials.data_ptr(), splits, N, C, KH, KW, dw.data_ptr())
         return dw.float()
 
 
-def test_nature_cnn_forward_backward_orchestration(emul):
+@pytest.mark.parametrize("planes", [2, 3])
+def test_nature_cnn_forward_backward_orchestration(emul, planes):
     """The whole encoder (3 convs + Linear, cnn.py:84-101) forward and backward through TensorCoreNatureCNN with the
     emulated backend vs torch autograd in float64: layer chaining, NHWC <-> NCHW-flatten weight permutation, ReLU masks in
     the data-gradient epilogues, stride-phase data gradients, column-split Linear (320 = 256 + 64 outputs)."""
@@ -271,8 +279,8 @@ def test_nature_cnn_forward_backward_orchestration(emul):
     z_ref = torch.relu(ref[3](h.flatten(1)))
     (z_ref * R.double()).sum().backward()
     # K12 path on the emulator
-    enc = tc.TensorCoreNatureCNN(convs, fc, (84, 84, 4), backend=EmulBackend(emul))
-    z = tc.tc_encode(enc, _split(x), B)
+    enc = tc.TensorCoreNatureCNN(convs, fc, (84, 84, 4), backend=EmulBackend(emul, planes))
+    z = tc.tc_encode(enc, _split(x, planes), B)
     np.testing.assert_allclose(z.detach().numpy(), z_ref.detach().numpy(), rtol=1e-4, atol=1e-4)
     (z * R).sum().backward()
     for (m, r), name in zip(zip(convs + [fc], ref), ("conv1", "conv2", "conv3", "fc")):

@@ -17,20 +17,26 @@ bringup = pytest.mark.skipif(os.environ.get("XB_EXPERIMENTAL_TC") != "1", reason
 DEV = "cuda:0"
 
 
-def test_split_and_pack():
+def _planes_ref(x, planes):
+    r, out = x.clone(), []
+    for _ in range(planes):
+        h = r.bfloat16()
+        out.append(h)
+        r = r - h.float()
+    return torch.stack(out)
+
+
+@pytest.mark.parametrize("planes", [2, 3])
+def test_split_and_pack(planes):
     from xuance_b200.torch.utils import tc_conv as tc
-    x = torch.randn(1000, 37, device=DEV)
-    hi, lo = tc.split_bf16(x)
-    assert torch.equal(hi, x.bfloat16()) and torch.equal(lo, (x - hi.float()).bfloat16())
+    for shape in ((1000, 37), (4099,), (8, 8)):                      # 37000 = 8*4625, a ragged length, one vector
+        x = torch.randn(*shape, device=DEV)
+        assert torch.equal(tc.split_bf16(x, planes), _planes_ref(x, planes))
     w = torch.randn(32, 4, 8, 8, device=DEV)
-    wh, wl = tc.pack_conv_weight(w)
-    ref = w.permute(0, 2, 3, 1).reshape(32, -1)
-    assert torch.equal(wh, ref.bfloat16()) and torch.equal(wl, (ref - wh.float()).bfloat16())
+    assert torch.equal(tc.pack_conv_weight(w, planes), _planes_ref(w.permute(0, 2, 3, 1).reshape(32, -1), planes))
 
 
-@pytest.mark.parametrize("B,H,W,C,N,k,s", [(2, 84, 84, 4, 32, 8, 4), (3, 21, 21, 32, 64, 4, 2), (5, 10, 10, 64, 64, 3, 1),
-                                            (256, 21, 21, 32, 64, 4, 2)])
-def test_forward_conv(B, H, W, C, N, k, s):
+def _forward_conv(B, H, W, C, N, k, s, planes, atol):
     from xuance_b200.torch.utils import tc_conv as tc
     torch.backends.cudnn.allow_tf32 = False
     torch.manual_seed(0)
@@ -40,12 +46,26 @@ def test_forward_conv(B, H, W, C, N, k, s):
     b = torch.randn(N, device=DEV) * 0.1
     g = tc.conv_forward_geometry(B, H, W, C, k, k, s, pad)
     out = torch.full((g.M, N), float("nan"), device=DEV)
-    oh, ol = torch.zeros((g.M, N), dtype=torch.bfloat16, device=DEV), torch.zeros((g.M, N), dtype=torch.bfloat16, device=DEV)
-    tc.gemm_gather(*tc.split_bf16(x), *tc.pack_conv_weight(w), g, bias=b, relu=True, out_f32=out, out_hi=oh, out_lo=ol)
+    opl = torch.zeros((planes, g.M, N), dtype=torch.bfloat16, device=DEV)
+    tc.gemm_gather(tc.split_bf16(x, planes), tc.pack_conv_weight(w, planes), g, bias=b, relu=True, out_f32=out, out_pl=opl)
     want = F.relu(F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), stride=s, padding=pad))
     want = want.permute(0, 2, 3, 1).reshape(g.M, N)
-    np.testing.assert_allclose(out.cpu().numpy(), want.cpu().numpy(), rtol=0, atol=5e-5)
-    np.testing.assert_allclose((oh.float() + ol.float()).cpu().numpy(), out.cpu().numpy(), rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(out.cpu().numpy(), want.cpu().numpy(), rtol=0, atol=atol)
+    np.testing.assert_allclose(opl.float().sum(0).cpu().numpy(), out.cpu().numpy(), rtol=2e-5 if planes == 2 else 3e-7, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,H,W,C,N,k,s", [(2, 84, 84, 4, 32, 8, 4), (3, 21, 21, 32, 64, 4, 2), (5, 10, 10, 64, 64, 3, 1),
+                                            (256, 21, 21, 32, 64, 4, 2)])
+def test_forward_conv(B, H, W, C, N, k, s):
+    """Two planes per operand (hi, lo): the configuration that passed on B200 in round 1."""
+    _forward_conv(B, H, W, C, N, k, s, 2, 5e-5)
+
+
+@bringup
+@pytest.mark.parametrize("B,H,W,C,N,k,s", [(2, 84, 84, 4, 32, 8, 4), (3, 21, 21, 32, 64, 4, 2), (64, 10, 10, 64, 64, 3, 1)])
+def test_forward_conv_three_planes(B, H, W, C, N, k, s):
+    """Three planes (hi, mid, lo), six products: float32-grade (fp32 accumulation in TMEM bounds it, not the operands)."""
+    _forward_conv(B, H, W, C, N, k, s, 3, 2e-6)
 
 
 @bringup
@@ -64,13 +84,11 @@ def test_data_gradient_with_mask(B, H, W, C, N, k, s):
     act = torch.randn(B, H, W, C, device=DEV)                      # the "saved activation": mask = act > 0
     act_hi = act.bfloat16()
     want = want.permute(0, 2, 3, 1) * (act_hi.float() > 0)
-    g_pair = tc.split_bf16(gy.permute(0, 2, 3, 1).reshape(-1, N).contiguous())
-    oh = torch.full((B * H * W, C), float("nan"), dtype=torch.bfloat16, device=DEV)
-    ol = torch.full_like(oh, float("nan"))
+    g_pl = tc.split_bf16(gy.permute(0, 2, 3, 1).reshape(-1, N).contiguous())
+    opl = torch.full((2, B * H * W, C), float("nan"), dtype=torch.bfloat16, device=DEV)
     for geom, taps in tc.conv_dgrad_geometries(B, H, W, C, k, k, s, pad, N):
-        w_pair = tc.split_bf16(tc.dgrad_weight_matrix(w, taps))
-        tc.gemm_gather(g_pair[0], g_pair[1], w_pair[0], w_pair[1], geom, out_hi=oh, out_lo=ol, out_ld=C, relu_mask=act_hi)
-    got = (oh.float() + ol.float()).reshape(B, H, W, C)
+        tc.gemm_gather(g_pl, tc.split_bf16(tc.dgrad_weight_matrix(w, taps)), geom, out_pl=opl, out_ld=C, relu_mask=act_hi)
+    got = opl.float().sum(0).reshape(B, H, W, C)
     np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=0, atol=5e-5)
 
 
@@ -88,18 +106,23 @@ def test_weight_gradient(B, H, W, C, N, k, s):
     gy = torch.randn(y.shape, device=DEV) / np.sqrt(y[0, 0].numel() * B)
     (want,) = torch.autograd.grad(y, w, gy.double())
     g = tc.conv_forward_geometry(B, H, W, C, k, k, s, pad)
-    x_pair = tc.split_bf16(x)
-    g_pair = tc.split_bf16(gy.permute(0, 2, 3, 1).reshape(g.M, N).contiguous())
-    for splits in sorted({1, tc.wgrad_splits(g.M, g.K)}):
-        dw = tc.wgrad_reduce(tc.wgrad_gather(x_pair[0], x_pair[1], g_pair[0], g_pair[1], g, splits), N, C, k, k)
-        np.testing.assert_allclose(dw.cpu().numpy(), want.cpu().numpy(), rtol=0, atol=5e-5, err_msg="splits=%d" % splits)
+    for planes, atol in ((2, 5e-5), (3, 2e-6)):
+        x_pl = tc.split_bf16(x, planes)
+        g_pl = tc.split_bf16(gy.permute(0, 2, 3, 1).reshape(g.M, N).contiguous(), planes)
+        for splits in sorted({1, tc.wgrad_splits(g.M, g.K)}):
+            dw = tc.wgrad_reduce(tc.wgrad_gather(x_pl, g_pl, g, splits), N, C, k, k)
+            np.testing.assert_allclose(dw.cpu().numpy(), want.cpu().numpy(), rtol=0, atol=atol,
+                                       err_msg="planes=%d splits=%d" % (planes, splits))
 
 
 @bringup
-def test_encoder_matches_cudnn_fp32():
-    """Whole encoder forward + backward vs the cuDNN fp32 path.  Forward is elementwise-tight.  The backward comparison is
-    made in norm: ReLU derivatives are discontinuous, so an activation within rounding distance of zero may take a different
-    side in the two implementations and shift every upstream gradient by O(1/B) - per-layer tests above are the tight ones."""
+@pytest.mark.parametrize("planes,fwd_tol,grad_tol", [(2, 1e-4, 1e-2), (3, 5e-6, 2e-5)])
+def test_encoder_matches_cudnn_fp32(planes, fwd_tol, grad_tol):
+    """Whole encoder forward + backward vs the cuDNN fp32 path.  With two planes the forward is within ~1e-5, which lets an
+    activation that close to zero take the other side of its ReLU than in the float32 network: one such flip shifts the
+    upstream gradients by O(1/B) (host emulation at B = 64: 3e-3 relative on the first layer), so
+    that comparison is made in norm with a loose bound.  With three planes the operands are exact to 2^-24 and the
+    gradients agree to float32 rounding."""
     from helpers import build_product_ppo_model
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -107,14 +130,15 @@ def test_encoder_matches_cudnn_fp32():
     m_ref = build_product_ppo_model(4, DEV).to(DEV)
     m_tc = build_product_ppo_model(4, DEV).to(DEV)
     m_tc.load_state_dict(m_ref.state_dict())
+    m_tc.representation.tc_planes = planes
     m_tc.representation.set_compute("tc")
     obs = torch.randint(0, 256, (64, 84, 84, 4), dtype=torch.uint8, device=DEV)
     R = torch.randn(64, 512, device=DEV)
     z_ref = m_ref.representation(obs).embeddings
     z_tc = m_tc.representation(obs).embeddings
-    np.testing.assert_allclose(z_tc.detach().cpu().numpy(), z_ref.detach().cpu().numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(z_tc.detach().cpu().numpy(), z_ref.detach().cpu().numpy(), rtol=fwd_tol, atol=fwd_tol)
     (z_ref * R).sum().backward()
     (z_tc * R).sum().backward()
     for (k, p), (_, q) in zip(m_ref.representation.named_parameters(), m_tc.representation.named_parameters()):
         rel = float((q.grad - p.grad).norm() / p.grad.norm())
-        assert rel < 1e-2, (k, rel)
+        assert rel < grad_tol, (k, rel)

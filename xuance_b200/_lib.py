@@ -35,10 +35,11 @@ _SIGNATURES = {
     "xb_adam_step": (c_int, [_P, _P, _P, _P, c_int64, _P, c_float, c_float, c_float, c_float, _P, c_float,
                              c_int, _P]),
     "xb_soft_update": (c_int, [_P, _P, c_int64, c_float, _P]),
-    "xb_split_bf16": (c_int, [_P, c_int64, _P, _P, _P]),
-    "xb_pack_conv_weight": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P]),
-    "xb_gemm_gather_tc": (c_int, [_P, _P, _P, _P, _P, _P] + [c_int] * 9 + [_P, _P, c_int, c_int, _P, _P, _P] + [c_int] * 6 + [c_int64, c_int, _P]),
-    "xb_wgrad_gather_tc": (c_int, [_P, _P, _P, _P] + [c_int] * 9 + [_P, _P, c_int, c_int, _P, _P]),
+    "xb_split_bf16": (c_int, [_P, c_int64, c_int, _P, _P]),
+    "xb_pack_conv_weight": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "xb_gemm_gather_tc": (c_int, [c_int, _P, c_int64, _P, c_int64, _P, _P] + [c_int] * 9 + [_P, _P, c_int, c_int, _P, c_int64,
+                                  _P] + [c_int] * 6 + [c_int64, c_int, _P]),
+    "xb_wgrad_gather_tc": (c_int, [c_int, _P, c_int64, _P, c_int64] + [c_int] * 9 + [_P, _P, c_int, c_int, _P, _P]),
     "xb_wgrad_reduce": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P]),
     "xb_categorical_act": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P]),
     "xb_rms_update_normalize": (c_int, [_P, c_int, c_int64, _P, _P, c_double, c_int, _P, c_float, c_float, _P]),

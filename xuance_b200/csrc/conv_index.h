@@ -130,7 +130,10 @@ XB_HD void xb_stage_wgrad(const XbConvGeom &g, int row, int64_t mt, int64_t chun
         emit_g(xb_canon_off_mn(j * 8, pp, XB_CONV_KC), in_run ? site * g.N + j * 8 : (int64_t)-1);
 }
 
-// shared-memory bytes of one pipeline stage: A hi | A lo | W hi | W lo
-XB_HD uint32_t xb_conv_stage_bytes(int N) { return (uint32_t)(2 * XB_CONV_TILE_M * XB_CONV_KC * 2 + 2 * N * XB_CONV_KC * 2); }
+// shared-memory bytes of one pipeline stage: the P planes of A (hi | [mid |] lo) followed by the P planes of W.
+// P = 2: x = hi + lo (|err| <= 2^-17 |x|, 3 products);  P = 3: x = hi + mid + lo (<= 2^-24 |x|, 6 products)
+XB_HD uint32_t xb_conv_stage_bytes(int N, int P = 2) {
+    return (uint32_t)(P * XB_CONV_TILE_M * XB_CONV_KC * 2 + P * N * XB_CONV_KC * 2);
+}
 XB_HD uint32_t xb_conv_a_plane_bytes() { return (uint32_t)(XB_CONV_TILE_M * XB_CONV_KC * 2); }
 XB_HD uint32_t xb_conv_w_plane_bytes(int N) { return (uint32_t)(N * XB_CONV_KC * 2); }

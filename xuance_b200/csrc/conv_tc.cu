@@ -50,6 +50,9 @@ struct ConvParams {
     // weight gradient: sites are cut into `splits` runs of sites_per_split (a multiple of KC)
     int splits;
     int64_t sites_per_split;
+    // third plane of each operand / output for the 3-way split (P = 3); appended so the P = 2 layout is unchanged
+    const __nv_bfloat16 *in_p2, *w_p2;
+    __nv_bfloat16 *out_p2;
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
@@ -61,12 +64,22 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// x = hi + mid + lo, three bf16 values: 24 mantissa bits, |x - hi - mid - lo| <= 2^-24 |x|
+__device__ __forceinline__ void split3_bf16(float x, __nv_bfloat16 &hi, __nv_bfloat16 &mid, __nv_bfloat16 &lo) {
+    hi = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(hi);
+    mid = __float2bfloat16_rn(r1);
+    lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+}
+
 // kind::f16 instruction descriptor with both operands MN-major (bits 15 / 16; cute/arch/mma_sm100_desc.hpp)
 __device__ __forceinline__ uint32_t make_idesc_mn(int M, int N) { return make_idesc(M, N) | (1u << 15) | (1u << 16); }
 
 // WGRAD = false:  D[site, n]  = sum_k A[site, k] W[n, k]            work item = 128-site tile,        K-major operands
 // WGRAD = true :  D[kcol, n]  = sum_site A[site, kcol] G[site, n]   work item = (128-kcol tile, split), MN-major operands
-template <bool WGRAD>
+// P: planes per operand.  P = 2: (hi, lo), products hi.hi + hi.lo + lo.hi.  P = 3: (hi, mid, lo), the six products with
+// plane indices summing to <= 2 - operands exact to 2^-24, i.e. float32-grade results (ReLU masks included).
+template <bool WGRAD, int P>
 __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_full[2], acc_empty[2];
@@ -76,7 +89,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const XbConvGeom &g = p.g;
     const int N = g.N, K = g.T * g.C, S = p.stages;
-    const uint32_t stage_bytes = xb_conv_stage_bytes(N);
+    const uint32_t stage_bytes = xb_conv_stage_bytes(N, P);
     const uint32_t a_plane = xb_conv_a_plane_bytes(), w_plane = xb_conv_w_plane_bytes(N);
     const int64_t m_tiles = WGRAD ? (K + TILE_M - 1) / TILE_M : (p.M + TILE_M - 1) / TILE_M;
     const int64_t n_work = WGRAD ? m_tiles * p.splits : m_tiles;
@@ -138,18 +151,20 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                 const int stage = (int)(it % (uint32_t)S);
                 mbar_wait(&empty_bar[stage], ((it / (uint32_t)S) & 1u) ^ 1u);
                 const uint32_t base = smem_base + (uint32_t)stage * stage_bytes;
-                const uint32_t wbase = base + 2 * a_plane;
+                const uint32_t wbase = base + P * a_plane;
                 auto emit_a = [&](uint32_t dst_off, int64_t src) {       // src < 0: the 16 bytes are zero-filled
                     const uint32_t nbytes = src >= 0 ? 16u : 0u;
                     const int64_t o = src >= 0 ? src : 0;
                     cp_async16(base + dst_off, p.in_hi + o, nbytes);
                     cp_async16(base + a_plane + dst_off, p.in_lo + o, nbytes);
+                    if (P == 3) cp_async16(base + 2 * a_plane + dst_off, p.in_p2 + o, nbytes);
                 };
                 auto emit_w = [&](uint32_t dst_off, int64_t src) {
                     const uint32_t nbytes = src >= 0 ? 16u : 0u;
                     const int64_t o = src >= 0 ? src : 0;
                     cp_async16(wbase + dst_off, p.w_hi + o, nbytes);
                     cp_async16(wbase + w_plane + dst_off, p.w_lo + o, nbytes);
+                    if (P == 3) cp_async16(wbase + 2 * w_plane + dst_off, p.w_p2 + o, nbytes);
                 };
                 if (!WGRAD) xb_stage_fwd(g, row, live, b, y, x, kc, emit_a, emit_w);
                 else xb_stage_wgrad(g, row, mt, sp * p.sites_per_split + (int64_t)kc * KC, site_end, emit_a, emit_w);
@@ -176,10 +191,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                     mbar_wait(&full_bar[stage], (it / (uint32_t)S) & 1u);
                     tc_fence_after();
                     const uint32_t base = smem_base + (uint32_t)stage * stage_bytes;
-                    const uint32_t a_addr[2] = {base, base + a_plane};
-                    const uint32_t w_addr[2] = {base + 2 * a_plane, base + 2 * a_plane + w_plane};
-                    for (int pa = 0; pa < 2; ++pa)
-                        for (int pb = 0; pb < 2 - pa; ++pb)            // (hi,hi) (hi,lo) (lo,hi)
+                    const uint32_t a_addr[3] = {base, base + a_plane, base + 2 * a_plane};
+                    const uint32_t w_addr[3] = {base + P * a_plane, base + P * a_plane + w_plane,
+                                                base + P * a_plane + 2 * w_plane};
+                    for (int pa = 0; pa < P; ++pa)
+                        for (int pb = 0; pb < P - pa; ++pb)            // P = 2: (hi,hi) (hi,lo) (lo,hi)
 #pragma unroll
                             for (int ks = 0; ks < KC / 16; ++ks) {
                                 mma_bf16(d_tmem, make_desc(a_addr[pa] + ks * 256, KC), make_desc(w_addr[pb] + ks * 256, KC),
@@ -255,8 +271,16 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             __nv_bfloat16 h[8], l[8];
+                            if (P == 2) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) split_bf16(v[8 * j + i], h[i], l[i]);
+                                for (int i = 0; i < 8; ++i) split_bf16(v[8 * j + i], h[i], l[i]);
+                            } else {                               // planes 0 | 1 | 2 = hi | mid | lo (out_lo holds plane 1)
+                                __nv_bfloat16 t[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) split3_bf16(v[8 * j + i], h[i], l[i], t[i]);
+                                reinterpret_cast<uint4 *>(p.out_p2 + orow + c0)[j] =
+                                    make_uint4(pack2(t[0], t[1]), pack2(t[2], t[3]), pack2(t[4], t[5]), pack2(t[6], t[7]));
+                            }
                             oh[j] = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
                             ol[j] = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
                         }
@@ -292,147 +316,158 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restri
 }
 
 // ---------------------------------------------------------------- operand preparation (HBM-bound, elementwise)
+// planes: out is [P, n] bf16; plane 0 = bf16(x), plane q = bf16 of the residual left by planes < q
+template <int P>
 __global__ void __launch_bounds__(256) split_bf16_kernel(const float *__restrict__ x, int64_t n8, int64_t n,
-                                                         __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo) {
+                                                         __nv_bfloat16 *__restrict__ out) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
         float v[8];
         const int64_t e = i * 8;
-        if (e + 8 <= n) {
+        const bool full = e + 8 <= n;
+        if (full) {
             const float4 a = reinterpret_cast<const float4 *>(x + e)[0], b = reinterpret_cast<const float4 *>(x + e)[1];
             v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
         } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = e + j < n ? x[e + j] : 0.f;
         }
-        __nv_bfloat16 h[8], l[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) split_bf16(v[j], h[j], l[j]);
-        if (e + 8 <= n) {
-            *reinterpret_cast<uint4 *>(hi + e) = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
-            *reinterpret_cast<uint4 *>(lo + e) = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
-        } else {
-            for (int j = 0; j < 8 && e + j < n; ++j) hi[e + j] = h[j], lo[e + j] = l[j];
+        for (int q = 0; q < P; ++q) {
+            __nv_bfloat16 h[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                h[j] = __float2bfloat16_rn(v[j]);
+                v[j] -= __bfloat162float(h[j]);
+            }
+            __nv_bfloat16 *dst = out + (int64_t)q * n + e;
+            if (full && ((n & 7) == 0)) {
+                *reinterpret_cast<uint4 *>(dst) = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
+            } else {
+                for (int j = 0; j < 8 && e + j < n; ++j) dst[j] = h[j];
+            }
         }
     }
 }
 
-// torch weight [N, C, KH, KW] (also a Linear over a flattened [C, H, W] feature map) -> [N, (kh, kw, c)] hi / lo
+// torch weight [N, C, KH, KW] (also a Linear over a flattened [C, H, W] feature map) -> [P, N, (kh, kw, c)] bf16 planes
+template <int P>
 __global__ void __launch_bounds__(256) pack_weight_kernel(const float *__restrict__ w, int N, int C, int KH, int KW,
-                                                          __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo) {
+                                                          __nv_bfloat16 *__restrict__ out) {
     const int64_t total = (int64_t)N * C * KH * KW;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const float v = w[xb_pack_weight_src(i, C, KH, KW)];
-        __nv_bfloat16 h, l;
-        split_bf16(v, h, l);
-        hi[i] = h, lo[i] = l;
+        float v = w[xb_pack_weight_src(i, C, KH, KW)];
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            out[(int64_t)q * total + i] = h;
+            v -= __bfloat162float(h);
+        }
     }
+}
+
+int fill_params(ConvParams &p, int planes, const void *in, int64_t in_plane, const void *w, int64_t w_plane, int B, int IH,
+                int IW, int C, int OY, int OX, int sy, int sx, int T, const int8_t *dy, const int8_t *dx, int N) {
+    if (planes != 2 && planes != 3) return XB_EINVAL;
+    if (!in || !w || !dy || !dx) return XB_EINVAL;
+    if (B <= 0 || IH <= 0 || IW <= 0 || OY <= 0 || OX <= 0 || sy <= 0 || sx <= 0 || T <= 0) return XB_EINVAL;
+    if (T > XB_CONV_MAX_TAPS || N > 256 || N % 32 != 0 || C % 8 != 0) return XB_ERANGE;
+    if (!xb_aligned(in, 16) || !xb_aligned(w, 16) || in_plane % 8 != 0 || w_plane % 8 != 0) return XB_EALIGN;
+    p.g.B = B, p.g.IH = IH, p.g.IW = IW, p.g.C = C, p.g.OY = OY, p.g.OX = OX, p.g.sy = sy, p.g.sx = sx, p.g.T = T, p.g.N = N;
+    for (int t = 0; t < XB_CONV_MAX_TAPS; ++t) p.g.dy[t] = t < T ? dy[t] : 0, p.g.dx[t] = t < T ? dx[t] : 0;
+    const __nv_bfloat16 *ib = (const __nv_bfloat16 *)in, *wb = (const __nv_bfloat16 *)w;
+    p.in_hi = ib, p.in_lo = ib + in_plane, p.in_p2 = planes == 3 ? ib + 2 * in_plane : nullptr;
+    p.w_hi = wb, p.w_lo = wb + w_plane, p.w_p2 = planes == 3 ? wb + 2 * w_plane : nullptr;
+    p.M = (int64_t)B * OY * OX;
+    const uint32_t stage_bytes = xb_conv_stage_bytes(N, planes);
+    int stages = (int)((200u * 1024u) / stage_bytes);
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 2) return XB_ERANGE;      // P = 3 needs N <= 128
+    p.stages = stages;
+    return XB_OK;
+}
+
+template <bool WGRAD, int P>
+int launch(const ConvParams &p, int64_t work, void *stream) {
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(conv_tc_kernel<WGRAD, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr = true;
+    }
+    const int grid = (int)(work < xb_sm_count() ? work : xb_sm_count());
+    const size_t smem = (size_t)p.stages * xb_conv_stage_bytes(p.g.N, P);
+    conv_tc_kernel<WGRAD, P><<<grid, THREADS, smem, (cudaStream_t)stream>>>(p);
+    return xb_launch_status();
 }
 
 }  // namespace
 
-extern "C" int xb_split_bf16(const float *x, int64_t n, void *hi, void *lo, void *stream) {
-    if (!x || !hi || !lo || n <= 0) return XB_EINVAL;
-    if (!xb_aligned(x, 16) || !xb_aligned(hi, 16) || !xb_aligned(lo, 16)) return XB_EALIGN;
+extern "C" int xb_split_bf16(const float *x, int64_t n, int planes, void *out, void *stream) {
+    if (!x || !out || n <= 0 || (planes != 2 && planes != 3)) return XB_EINVAL;
+    if (!xb_aligned(x, 16) || !xb_aligned(out, 16)) return XB_EALIGN;
     const int64_t n8 = (n + 7) / 8;
     int64_t want = (n8 + 255) / 256;
     const int grid = (int)(want < (int64_t)xb_sm_count() * 8 ? want : (int64_t)xb_sm_count() * 8);
-    split_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n8, n, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo);
+    if (planes == 2) split_bf16_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(x, n8, n, (__nv_bfloat16 *)out);
+    else split_bf16_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(x, n8, n, (__nv_bfloat16 *)out);
     return xb_launch_status();
 }
 
-extern "C" int xb_pack_conv_weight(const float *w, int N, int C, int KH, int KW, void *hi, void *lo, void *stream) {
-    if (!w || !hi || !lo || N <= 0 || C <= 0 || KH <= 0 || KW <= 0) return XB_EINVAL;
+extern "C" int xb_pack_conv_weight(const float *w, int N, int C, int KH, int KW, int planes, void *out, void *stream) {
+    if (!w || !out || N <= 0 || C <= 0 || KH <= 0 || KW <= 0 || (planes != 2 && planes != 3)) return XB_EINVAL;
     const int64_t total = (int64_t)N * C * KH * KW;
     int64_t want = (total + 255) / 256;
     const int grid = (int)(want < (int64_t)xb_sm_count() * 8 ? want : (int64_t)xb_sm_count() * 8);
-    pack_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, N, C, KH, KW, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo);
+    if (planes == 2) pack_weight_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(w, N, C, KH, KW, (__nv_bfloat16 *)out);
+    else pack_weight_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(w, N, C, KH, KW, (__nv_bfloat16 *)out);
     return xb_launch_status();
 }
 
-extern "C" int xb_gemm_gather_tc(const void *in_hi, const void *in_lo, const void *w_hi, const void *w_lo,
-                                 const float *bias, const void *relu_mask, int B, int IH, int IW, int C, int OY, int OX, int sy, int sx, int T,
-                                 const int8_t *dy, const int8_t *dx, int N, int relu, void *out_hi, void *out_lo,
-                                 float *out_f32, int out_H, int out_W, int oys, int oxs, int oy0, int ox0,
+extern "C" int xb_gemm_gather_tc(int planes, const void *in, int64_t in_plane, const void *w, int64_t w_plane,
+                                 const float *bias, const void *relu_mask, int B, int IH, int IW, int C, int OY, int OX,
+                                 int sy, int sx, int T, const int8_t *dy, const int8_t *dx, int N, int relu, void *out_planes,
+                                 int64_t out_plane, float *out_f32, int out_H, int out_W, int oys, int oxs, int oy0, int ox0,
                                  int64_t out_ld, int out_c0, void *stream) {
-    if (!in_hi || !in_lo || !w_hi || !w_lo || !dy || !dx) return XB_EINVAL;
-    if ((out_hi == nullptr) != (out_lo == nullptr) || (!out_hi && !out_f32)) return XB_EINVAL;
-    if (B <= 0 || IH <= 0 || IW <= 0 || OY <= 0 || OX <= 0 || sy <= 0 || sx <= 0 || T <= 0) return XB_EINVAL;
-    if (T > XB_CONV_MAX_TAPS || N > 256 || N % 32 != 0 || C % 8 != 0 || ((int64_t)T * C) % XB_CONV_KC != 0)
-        return XB_ERANGE;
+    ConvParams p;
+    const int rc = fill_params(p, planes, in, in_plane, w, w_plane, B, IH, IW, C, OY, OX, sy, sx, T, dy, dx, N);
+    if (rc != XB_OK) return rc;
+    if (!out_planes && !out_f32) return XB_EINVAL;
+    if (((int64_t)T * C) % XB_CONV_KC != 0) return XB_ERANGE;
     if (out_H <= 0 || out_W <= 0 || oys <= 0 || oxs <= 0 || oy0 < 0 || ox0 < 0 || (OY - 1) * oys + oy0 >= out_H ||
         (OX - 1) * oxs + ox0 >= out_W || out_c0 < 0 || out_ld < (int64_t)out_c0 + N)
         return XB_EINVAL;
-    if (out_ld % 8 != 0 || out_c0 % 8 != 0) return XB_EALIGN;   // 16-byte row segments in both output formats
-    if (!xb_aligned(in_hi, 16) || !xb_aligned(in_lo, 16) || !xb_aligned(w_hi, 16) || !xb_aligned(w_lo, 16) ||
-        (out_hi && (!xb_aligned(out_hi, 16) || !xb_aligned(out_lo, 16))) || (out_f32 && !xb_aligned(out_f32, 16)) ||
+    if (out_ld % 8 != 0 || out_c0 % 8 != 0 || out_plane % 8 != 0) return XB_EALIGN;   // 16-byte row segments
+    if ((out_planes && !xb_aligned(out_planes, 16)) || (out_f32 && !xb_aligned(out_f32, 16)) ||
         (relu_mask && !xb_aligned(relu_mask, 16)))
         return XB_EALIGN;
-    ConvParams p;
-    p.g.B = B, p.g.IH = IH, p.g.IW = IW, p.g.C = C, p.g.OY = OY, p.g.OX = OX, p.g.sy = sy, p.g.sx = sx, p.g.T = T, p.g.N = N;
-    for (int t = 0; t < XB_CONV_MAX_TAPS; ++t) p.g.dy[t] = t < T ? dy[t] : 0, p.g.dx[t] = t < T ? dx[t] : 0;
-    p.in_hi = (const __nv_bfloat16 *)in_hi, p.in_lo = (const __nv_bfloat16 *)in_lo;
-    p.w_hi = (const __nv_bfloat16 *)w_hi, p.w_lo = (const __nv_bfloat16 *)w_lo;
     p.bias = bias;
     p.mask = (const __nv_bfloat16 *)relu_mask;
-    p.out_hi = (__nv_bfloat16 *)out_hi, p.out_lo = (__nv_bfloat16 *)out_lo, p.out_f32 = out_f32;
-    p.M = (int64_t)B * OY * OX;
+    __nv_bfloat16 *ob = (__nv_bfloat16 *)out_planes;
+    p.out_hi = ob, p.out_lo = ob ? ob + out_plane : nullptr, p.out_p2 = (ob && planes == 3) ? ob + 2 * out_plane : nullptr;
+    p.out_f32 = out_f32;
     p.relu = relu;
     p.out_H = out_H, p.out_W = out_W, p.oys = oys, p.oxs = oxs, p.oy0 = oy0, p.ox0 = ox0;
     p.out_ld = out_ld, p.out_c0 = out_c0;
     p.splits = 1, p.sites_per_split = 0;
-    const uint32_t stage_bytes = xb_conv_stage_bytes(N);
-    int stages = (int)((200u * 1024u) / stage_bytes);
-    if (stages > MAX_STAGES) stages = MAX_STAGES;
-    if (stages < 2) return XB_ERANGE;
-    p.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr = true;
-    }
     const int64_t tiles = (p.M + TILE_M - 1) / TILE_M;
-    const int grid = (int)(tiles < xb_sm_count() ? tiles : xb_sm_count());
-    conv_tc_kernel<false><<<grid, THREADS, smem, (cudaStream_t)stream>>>(p);
-    return xb_launch_status();
+    return planes == 2 ? launch<false, 2>(p, tiles, stream) : launch<false, 3>(p, tiles, stream);
 }
 
-extern "C" int xb_wgrad_gather_tc(const void *in_hi, const void *in_lo, const void *g_hi, const void *g_lo, int B, int IH,
+extern "C" int xb_wgrad_gather_tc(int planes, const void *in, int64_t in_plane, const void *g, int64_t g_plane, int B, int IH,
                                   int IW, int C, int OY, int OX, int sy, int sx, int T, const int8_t *dy, const int8_t *dx,
                                   int N, int splits, float *partials, void *stream) {
-    if (!in_hi || !in_lo || !g_hi || !g_lo || !dy || !dx || !partials) return XB_EINVAL;
-    if (B <= 0 || IH <= 0 || IW <= 0 || OY <= 0 || OX <= 0 || sy <= 0 || sx <= 0 || T <= 0 || splits <= 0) return XB_EINVAL;
-    if (T > XB_CONV_MAX_TAPS || N > 256 || N % 32 != 0 || C % 8 != 0) return XB_ERANGE;
-    if (!xb_aligned(in_hi, 16) || !xb_aligned(in_lo, 16) || !xb_aligned(g_hi, 16) || !xb_aligned(g_lo, 16) ||
-        !xb_aligned(partials, 16))
-        return XB_EALIGN;
     ConvParams p;
-    p.g.B = B, p.g.IH = IH, p.g.IW = IW, p.g.C = C, p.g.OY = OY, p.g.OX = OX, p.g.sy = sy, p.g.sx = sx, p.g.T = T, p.g.N = N;
-    for (int t = 0; t < XB_CONV_MAX_TAPS; ++t) p.g.dy[t] = t < T ? dy[t] : 0, p.g.dx[t] = t < T ? dx[t] : 0;
-    p.in_hi = (const __nv_bfloat16 *)in_hi, p.in_lo = (const __nv_bfloat16 *)in_lo;
-    p.w_hi = (const __nv_bfloat16 *)g_hi, p.w_lo = (const __nv_bfloat16 *)g_lo;
-    p.bias = nullptr, p.mask = nullptr, p.out_hi = nullptr, p.out_lo = nullptr, p.out_f32 = partials;
-    p.M = (int64_t)B * OY * OX;
+    const int rc = fill_params(p, planes, in, in_plane, g, g_plane, B, IH, IW, C, OY, OX, sy, sx, T, dy, dx, N);
+    if (rc != XB_OK) return rc;
+    if (!partials || splits <= 0) return XB_EINVAL;
+    if (!xb_aligned(partials, 16)) return XB_EALIGN;
+    p.bias = nullptr, p.mask = nullptr, p.out_hi = nullptr, p.out_lo = nullptr, p.out_p2 = nullptr, p.out_f32 = partials;
     p.relu = 0;
     p.out_H = p.out_W = p.oys = p.oxs = 1, p.oy0 = p.ox0 = 0, p.out_ld = N, p.out_c0 = 0;
-    // sites per split: a multiple of the chunk length, every split non-empty
     const int64_t per = xb_wgrad_sites_per_split(p.M, splits);
     if (per == 0) return XB_EINVAL;     // too many splits for this many sites
     p.splits = splits, p.sites_per_split = per;
-    const uint32_t stage_bytes = xb_conv_stage_bytes(N);
-    int stages = (int)((200u * 1024u) / stage_bytes);
-    if (stages > MAX_STAGES) stages = MAX_STAGES;
-    if (stages < 2) return XB_ERANGE;
-    p.stages = stages;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr = true;
-    }
     const int64_t K = (int64_t)T * C, work = (K + TILE_M - 1) / TILE_M * splits;
-    const int grid = (int)(work < xb_sm_count() ? work : xb_sm_count());
-    conv_tc_kernel<true><<<grid, THREADS, (size_t)stages * stage_bytes, (cudaStream_t)stream>>>(p);
-    return xb_launch_status();
+    return planes == 2 ? launch<true, 2>(p, work, stream) : launch<true, 3>(p, work, stream);
 }
 
 extern "C" int xb_wgrad_reduce(const float *partials, int splits, int N, int C, int KH, int KW, float *dw, int accumulate,

@@ -68,7 +68,7 @@ class _PixelEncoder(nn.Module):
     # ---- EXPERIMENTAL "tc" mode: the conv stack + hidden layer as K12 launches (split-bf16 tcgen05 GEMMs with fp32-level
     # accuracy, utils/tc_conv.py).  Forward parity-tested on B200, backward not yet pinned; see DESIGN.md section 9.
     def _build_tc(self):
-        from ..utils.tc_conv import TensorCoreNatureCNN
+        from ..utils.tc_conv import TensorCoreNatureCNN, CudaBackend
         mods = list(self.model)
         convs, fc, i = [], None, 0
         while i + 1 < len(mods) and isinstance(mods[i], nn.Conv2d) and isinstance(mods[i + 1], nn.ReLU):
@@ -81,17 +81,17 @@ class _PixelEncoder(nn.Module):
             raise NotImplementedError("compute='tc' covers Conv2d+ReLU stacks followed by Flatten, Linear, ReLU "
                                       "(AC_CNN_Atari with one hidden layer)")
         C, H, W = self.input_shape
-        self._tc = TensorCoreNatureCNN(convs, rest[1], (H, W, C))
+        self._tc = TensorCoreNatureCNN(convs, rest[1], (H, W, C), backend=CudaBackend(planes=getattr(self, "tc_planes", 2)))
 
     def _run_tc(self, x_nchw_view):
         from ..utils import tc_conv
         x = x_nchw_view.permute(0, 2, 3, 1)
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
-        pair = tc_conv.split_bf16(x)
+        planes = tc_conv.split_bf16(x, self._tc.be.planes)
         if torch.is_grad_enabled():
-            return tc_conv.tc_encode(self._tc, pair, x.shape[0])
-        return self._tc.forward(pair, x.shape[0])
+            return tc_conv.tc_encode(self._tc, planes, x.shape[0])
+        return self._tc.forward(planes, x.shape[0])
 
     def _as_input(self, observations):
         fmt = self.preferred_obs_format()

@@ -131,53 +131,63 @@ def dgrad_weight_matrix(w, taps):
 
 
 # ------------------------------------------------------------------------------------------------ device wrappers
-def split_bf16(x):
-    """float32 CUDA tensor -> (hi, lo) bfloat16 tensors of the same shape, x ~= hi + lo to 2^-17 relative."""
+# Operands are "plane tensors": bfloat16 [P, ...] with x = planes.sum(0) - P = 2 (hi, lo; exact to 2^-17, three products
+# per MMA step) or P = 3 (hi, mid, lo; exact to 2^-24, six products: float32-grade results, including which side of
+# zero a ReLU input falls on - with P = 2 an activation within ~1e-5 of zero can take the other side than the float32
+# network does and shift the upstream gradients by O(1/batch)).
+def split_bf16(x, planes=2):
+    """float32 CUDA tensor -> bfloat16 [planes, *x.shape]."""
     x = x.contiguous()
-    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    lo = torch.empty_like(hi)
-    _lib.call("xb_split_bf16", _lib.ptr(x), x.numel(), _lib.ptr(hi), _lib.ptr(lo))
-    return hi, lo
+    out = torch.empty((planes,) + tuple(x.shape), dtype=torch.bfloat16, device=x.device)
+    _lib.call("xb_split_bf16", _lib.ptr(x), x.numel(), planes, _lib.ptr(out))
+    return out
 
 
-def pack_conv_weight(w):
-    """[N, C, KH, KW] float32 CUDA -> (hi, lo) bfloat16 [N, KH*KW*C] in (kh, kw, c) column order."""
+def pack_conv_weight(w, planes=2):
+    """[N, C, KH, KW] float32 CUDA -> bfloat16 [planes, N, KH*KW*C] in (kh, kw, c) column order."""
     w = w.contiguous()
     N, C, KH, KW = w.shape
-    hi = torch.empty((N, KH * KW * C), dtype=torch.bfloat16, device=w.device)
-    lo = torch.empty_like(hi)
-    _lib.call("xb_pack_conv_weight", _lib.ptr(w), N, C, KH, KW, _lib.ptr(hi), _lib.ptr(lo))
-    return hi, lo
+    out = torch.empty((planes, N, KH * KW * C), dtype=torch.bfloat16, device=w.device)
+    _lib.call("xb_pack_conv_weight", _lib.ptr(w), N, C, KH, KW, planes, _lib.ptr(out))
+    return out
 
 
-def gemm_gather(in_hi, in_lo, w_hi, w_lo, geom, bias=None, relu=False, out_f32=None, out_hi=None, out_lo=None,
-                out_ld=None, out_c0=0, relu_mask=None):
-    """One K12 launch.  ``w_hi/w_lo`` [N, K]; outputs are caller-allocated matrices with ``out_ld`` elements per row
-    (default N)."""
-    N, K = w_hi.shape
-    assert K == geom.K, (K, geom.K)
+def _plane_arg(t):
+    """(pointer of plane 0, plane stride in elements) of a plane tensor whose planes are each contiguous."""
+    assert t[0].is_contiguous(), "each plane must be contiguous"
+    return _lib.ptr(t[0]), t.stride(0)
+
+
+def gemm_gather(x_pl, w_pl, geom, bias=None, relu=False, out_f32=None, out_pl=None, out_ld=None, out_c0=0, relu_mask=None):
+    """One K12 launch.  ``x_pl`` [P, B, IH, IW, C] (any shape with that element order), ``w_pl`` [P, N, K] (row slices
+    allowed); outputs are caller-allocated: ``out_f32`` [rows, out_ld] and / or ``out_pl`` [P, rows, out_ld]."""
+    P, N, K = w_pl.shape
+    assert K == geom.K and x_pl.shape[0] == P, (K, geom.K, x_pl.shape[0], P)
     out_ld = N if out_ld is None else out_ld
     dy = torch.tensor(geom.dy, dtype=torch.int8)
     dx = torch.tensor(geom.dx, dtype=torch.int8)
-    _lib.call("xb_gemm_gather_tc", _lib.ptr(in_hi), _lib.ptr(in_lo), _lib.ptr(w_hi), _lib.ptr(w_lo),
-              _lib.ptr(bias) if bias is not None else None, _lib.ptr(relu_mask) if relu_mask is not None else None, geom.B, geom.IH, geom.IW, geom.C, geom.OY, geom.OX, geom.sy,
-              geom.sx, geom.T, dy.data_ptr(), dx.data_ptr(), N, 1 if relu else 0,
-              _lib.ptr(out_hi) if out_hi is not None else None, _lib.ptr(out_lo) if out_lo is not None else None,
+    xp, xs = _plane_arg(x_pl)
+    wp, ws = _plane_arg(w_pl)
+    op, os_ = _plane_arg(out_pl) if out_pl is not None else (None, 0)
+    _lib.call("xb_gemm_gather_tc", P, xp, xs, wp, ws, _lib.ptr(bias) if bias is not None else None,
+              _lib.ptr(relu_mask) if relu_mask is not None else None, geom.B, geom.IH, geom.IW, geom.C, geom.OY, geom.OX,
+              geom.sy, geom.sx, geom.T, dy.data_ptr(), dx.data_ptr(), N, 1 if relu else 0, op, os_,
               _lib.ptr(out_f32) if out_f32 is not None else None, geom.out_H, geom.out_W, geom.oys, geom.oxs, geom.oy0,
               geom.ox0, out_ld, out_c0)
-    return out_f32, out_hi, out_lo
+    return out_f32, out_pl
 
 
-def wgrad_gather(in_hi, in_lo, g_hi, g_lo, geom, splits):
-    """Partial weight gradients [splits, K, N] (float32) of the gathered GEMM ``geom`` for the output gradient
-    ``g_hi/g_lo`` [sites, N]."""
-    N = g_hi.shape[1]
-    partials = torch.empty((splits, geom.K, N), dtype=torch.float32, device=g_hi.device)
+def wgrad_gather(x_pl, g_pl, geom, splits):
+    """Partial weight gradients [splits, K, N] (float32) of the gathered GEMM ``geom`` for the output gradient planes
+    ``g_pl`` [P, sites, N]."""
+    P, _, N = g_pl.shape
+    partials = torch.empty((splits, geom.K, N), dtype=torch.float32, device=g_pl.device)
     dy = torch.tensor(geom.dy, dtype=torch.int8)
     dx = torch.tensor(geom.dx, dtype=torch.int8)
-    _lib.call("xb_wgrad_gather_tc", _lib.ptr(in_hi), _lib.ptr(in_lo), _lib.ptr(g_hi), _lib.ptr(g_lo), geom.B, geom.IH,
-              geom.IW, geom.C, geom.OY, geom.OX, geom.sy, geom.sx, geom.T, dy.data_ptr(), dx.data_ptr(), N, splits,
-              _lib.ptr(partials))
+    xp, xs = _plane_arg(x_pl)
+    gp, gs = _plane_arg(g_pl)
+    _lib.call("xb_wgrad_gather_tc", P, xp, xs, gp, gs, geom.B, geom.IH, geom.IW, geom.C, geom.OY, geom.OX, geom.sy, geom.sx,
+              geom.T, dy.data_ptr(), dx.data_ptr(), N, splits, _lib.ptr(partials))
     return partials
 
 
@@ -205,43 +215,44 @@ class CudaBackend:
     """The product backend of ``TensorCoreNatureCNN``: every method is one or a few C-ABI launches (K12).  The host test
     substitutes an emulated backend with the same methods (tests/test_conv_index.py) to check the orchestration."""
 
+    def __init__(self, planes=2):
+        self.planes = planes
+        self.n_tile = 256 if planes == 2 else 128        # output columns per launch (shared-memory stage size)
+
     def split(self, x):
-        return split_bf16(x)
+        return split_bf16(x, self.planes)
 
     def pack_weight(self, w4d):
-        return pack_conv_weight(w4d)
+        return pack_conv_weight(w4d, self.planes)
 
-    def empty_pair(self, shape, like):
-        hi = torch.empty(shape, dtype=torch.bfloat16, device=like.device)
-        return hi, torch.empty_like(hi)
+    def empty_planes(self, shape, like):
+        return torch.empty((self.planes,) + tuple(shape), dtype=torch.bfloat16, device=like.device)
 
     def empty_f32(self, shape, like):
         return torch.empty(shape, dtype=torch.float32, device=like.device)
 
-    def gemm(self, x_pair, w_pair, geom, bias=None, relu=False, out_f32=None, out_pair=None, out_ld=None, out_c0=0,
-             mask=None):
-        gemm_gather(x_pair[0], x_pair[1], w_pair[0], w_pair[1], geom, bias=bias, relu=relu, out_f32=out_f32,
-                    out_hi=None if out_pair is None else out_pair[0], out_lo=None if out_pair is None else out_pair[1],
-                    out_ld=out_ld, out_c0=out_c0, relu_mask=mask)
+    def gemm(self, x_pl, w_pl, geom, bias=None, relu=False, out_f32=None, out_pl=None, out_ld=None, out_c0=0, mask=None):
+        gemm_gather(x_pl, w_pl, geom, bias=bias, relu=relu, out_f32=out_f32, out_pl=out_pl, out_ld=out_ld, out_c0=out_c0,
+                    relu_mask=mask)
 
-    def wgrad(self, x_pair, g_pair, geom, N, C, KH, KW):
+    def wgrad(self, x_pl, g_pl, geom, N, C, KH, KW):
         splits = wgrad_splits(geom.M, geom.K)
-        return wgrad_reduce(wgrad_gather(x_pair[0], x_pair[1], g_pair[0], g_pair[1], geom, splits), N, C, KH, KW)
+        return wgrad_reduce(wgrad_gather(x_pl, g_pl, geom, splits), N, C, KH, KW)
 
-    def colsum(self, g_pair):
-        return g_pair[0].float().sum(0) + g_pair[1].float().sum(0)
+    def colsum(self, g_pl):
+        return g_pl.float().sum(dim=(0, 1))
 
-    def to_float(self, pair):
-        return pair[0].float() + pair[1].float()
+    def to_float(self, pl):
+        return pl.float().sum(0)
 
 
 class TensorCoreNatureCNN:
     """The convolution stack + hidden layer of AC_CNN_Atari / Basic_CNN's conv part (cnn.py:45-50, 84-101) as K12 launches,
-    forward AND backward, for one batch size.  Activations live as hi / lo bf16 NHWC pairs between layers; the ReLU
-    derivative is applied inside the data-gradient GEMM's epilogue from the saved activation's hi plane.
+    forward AND backward, for one batch size.  Activations live as bf16 plane tensors (NHWC) between layers; the ReLU
+    derivative is applied inside the data-gradient GEMM's epilogue from plane 0 of the saved activation.
 
     ``convs``: nn.Conv2d modules (padding (k - s)//2 as layers.py:46 builds them), each followed by ReLU;
-    ``fc``: nn.Linear over the NCHW-flattened last feature map (or None), followed by ReLU."""
+    ``fc``: nn.Linear over the NCHW-flattened last feature map, followed by ReLU."""
 
     def __init__(self, convs, fc, in_hwc, backend=None):
         self.convs, self.fc = list(convs), fc
@@ -268,34 +279,33 @@ class TensorCoreNatureCNN:
             assert Cw == C and conv.stride[0] == conv.stride[1] and conv.padding[0] == conv.padding[1]
             fwd = conv_forward_geometry(B, H, W, C, KH, KW, s, p)
             dgrad = conv_dgrad_geometries(B, H, W, C, KH, KW, s, p, N) if layers else None   # no gradient w.r.t. pixels
-            layers.append(dict(kind="conv", N=N, C=C, KH=KH, KW=KW, fwd=fwd, dgrad=dgrad, in_shape=(B, H, W, C)))
+            layers.append(dict(kind="conv", N=N, C=C, KH=KH, KW=KW, fwd=fwd, dgrad=dgrad))
             H, W, C = fwd.OY, fwd.OX, N
         if self.fc is not None:
             N, K = self.fc.weight.shape
             assert K == H * W * C
-            layers.append(dict(kind="fc", N=N, C=C, KH=H, KW=W, fwd=linear_geometry(B, K), dgrad=linear_geometry(B, N),
-                               in_shape=(B, H, W, C)))
+            layers.append(dict(kind="fc", N=N, C=C, KH=H, KW=W, fwd=linear_geometry(B, K), dgrad=linear_geometry(B, N)))
         self._plans[B] = layers
         return layers
 
     # ---- forward: returns float32 [sites of the last layer, features]; keeps what backward needs
-    def forward(self, x_pair, B):
+    def forward(self, x_pl, B):
         be, plan = self.be, self._plan(B)
-        saved, cur, out_f32 = [], x_pair, None
+        saved, cur, out_f32 = [], x_pl, None
         for li, L in enumerate(plan):
             mod = self.convs[li] if L["kind"] == "conv" else self.fc
             N, g = L["N"], L["fwd"]
             w4 = (mod.weight if L["kind"] == "conv" else mod.weight.reshape(N, L["C"], L["KH"], L["KW"])).detach()
-            w_pair = be.pack_weight(w4)
+            w_pl = be.pack_weight(w4)
             bias = mod.bias.detach()
-            out_pair = be.empty_pair((g.M, N), cur[0])
-            out_f32 = be.empty_f32((g.M, N), cur[0]) if li == len(plan) - 1 else None
-            for c0 in range(0, N, 256):
-                n1 = min(N, c0 + 256)
-                be.gemm(cur, (w_pair[0][c0:n1], w_pair[1][c0:n1]), g, bias=bias[c0:n1], relu=True, out_f32=out_f32,
-                        out_pair=out_pair, out_ld=N, out_c0=c0)
-            saved.append(dict(x=cur, y=out_pair, w4=w4))
-            cur = out_pair
+            out_pl = be.empty_planes((g.M, N), cur)
+            out_f32 = be.empty_f32((g.M, N), cur) if li == len(plan) - 1 else None
+            for c0 in range(0, N, be.n_tile):
+                n1 = min(N, c0 + be.n_tile)
+                be.gemm(cur, w_pl[:, c0:n1], g, bias=bias[c0:n1], relu=True, out_f32=out_f32, out_pl=out_pl, out_ld=N,
+                        out_c0=c0)
+            saved.append(dict(x=cur, y=out_pl, w4=w4))
+            cur = out_pl
         self._saved = (B, saved)
         return out_f32
 
@@ -306,53 +316,50 @@ class TensorCoreNatureCNN:
         plan = self._plan(B)
         grads = [None] * (2 * len(plan))
         y_last = saved[-1]["y"]
-        g_pair = be.split(dz * (be.to_float(y_last) > 0).to(dz.dtype))          # ReLU derivative of the last layer
+        g_pl = be.split(dz * (be.to_float(y_last) > 0).to(dz.dtype))            # ReLU derivative of the last layer
         for li in range(len(plan) - 1, -1, -1):
             L, sv = plan[li], saved[li]
             N, C, KH, KW = L["N"], L["C"], L["KH"], L["KW"]
             # -- weight and bias gradients (the weight gradient gathers exactly like the forward)
-            if N <= 256:
-                dw = be.wgrad(sv["x"], g_pair, L["fwd"], N, C, KH, KW)
+            if N <= be.n_tile:
+                dw = be.wgrad(sv["x"], g_pl, L["fwd"], N, C, KH, KW)
             else:
                 dw = be.empty_f32((N, C, KH, KW), dz)
-                for c0 in range(0, N, 256):
-                    n1 = min(N, c0 + 256)
-                    gp = (g_pair[0][:, c0:n1].contiguous(), g_pair[1][:, c0:n1].contiguous())
-                    dw[c0:n1] = be.wgrad(sv["x"], gp, L["fwd"], n1 - c0, C, KH, KW)
+                for c0 in range(0, N, be.n_tile):
+                    n1 = min(N, c0 + be.n_tile)
+                    dw[c0:n1] = be.wgrad(sv["x"], g_pl[:, :, c0:n1].contiguous(), L["fwd"], n1 - c0, C, KH, KW)
             grads[2 * li] = dw if L["kind"] == "conv" else dw.reshape(N, C * KH * KW)
-            grads[2 * li + 1] = be.colsum(g_pair)
+            grads[2 * li + 1] = be.colsum(g_pl)
             if li == 0:
                 break
             # -- data gradient, masked by the previous activation's ReLU derivative inside the GEMM epilogue
-            prev_y = saved[li - 1]["y"]                   # [sites_prev, C] == NHWC input of this layer
-            out_pair = be.empty_pair(tuple(prev_y[0].shape), prev_y[0])
+            prev_y = saved[li - 1]["y"]                   # [P, sites_prev, C] == NHWC input planes of this layer
+            out_pl = be.empty_planes(tuple(prev_y.shape[1:]), prev_y)
             if L["kind"] == "conv":
                 for geom, taps in L["dgrad"]:
-                    w_pair = be.split(dgrad_weight_matrix(sv["w4"], taps))        # [C, (tap, n)]
-                    be.gemm(g_pair, w_pair, geom, out_pair=out_pair, out_ld=C, mask=prev_y[0])
+                    w_pl = be.split(dgrad_weight_matrix(sv["w4"], taps))          # [P, C, (tap, n)]
+                    be.gemm(g_pl, w_pl, geom, out_pl=out_pl, out_ld=C, mask=prev_y[0])
             else:
                 K = C * KH * KW
-                wd = sv["w4"].permute(0, 2, 3, 1).reshape(N, K).t().contiguous()  # [K (h,w,c), N]
-                w_pair = be.split(wd)
-                for c0 in range(0, K, 256):
-                    n1 = min(K, c0 + 256)
-                    be.gemm(g_pair, (w_pair[0][c0:n1], w_pair[1][c0:n1]), L["dgrad"], out_pair=out_pair, out_ld=K, out_c0=c0,
-                            mask=prev_y[0])
-            g_pair = out_pair
+                w_pl = be.split(sv["w4"].permute(0, 2, 3, 1).reshape(N, K).t().contiguous())   # [P, K (h,w,c), N]
+                for c0 in range(0, K, be.n_tile):
+                    n1 = min(K, c0 + be.n_tile)
+                    be.gemm(g_pl, w_pl[:, c0:n1], L["dgrad"], out_pl=out_pl, out_ld=K, out_c0=c0, mask=prev_y[0])
+            g_pl = out_pl
         return grads
 
 
 class _TCEncoderFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, enc, x_hi, x_lo, B, *params):
+    def forward(ctx, enc, x_pl, B, *params):
         ctx.enc = enc
-        return enc.forward((x_hi, x_lo), B)
+        return enc.forward(x_pl, B)
 
     @staticmethod
     def backward(ctx, dz):
-        return (None, None, None, None, *ctx.enc.backward(dz.contiguous()))
+        return (None, None, None, *ctx.enc.backward(dz.contiguous()))
 
 
-def tc_encode(enc, x_pair, B):
+def tc_encode(enc, x_pl, B):
     """Differentiable call of a ``TensorCoreNatureCNN``: gradients reach the conv / linear parameters."""
-    return _TCEncoderFn.apply(enc, x_pair[0], x_pair[1], B, *enc.parameters())
+    return _TCEncoderFn.apply(enc, x_pl, B, *enc.parameters())
