@@ -244,6 +244,10 @@ int xb_rms_update_normalize(const float *x, int N, int64_t D, float *mean, float
  *                       item = (128 columns of (t,c), split).  partials: float32 [splits, T*C, N].
  * xb_wgrad_reduce     : dw[N, C, KH, KW] (torch layout) (+)= sum_s partials[s, (kh,kw,c), n], splits added in order. */
 int xb_split_bf16(const float *x, int64_t n, int planes, void *out /* bf16 [planes, n] */, void *stream);
+/* K3 variant that feeds K12: gathers uint8 rows (sample_batch, memory_tools.py:64-84; idx NULL = rows 0..B-1) and writes
+ * dst[q, b, :] = plane q of float32(x)/255.0f for q < planes (bf16 [planes, B, row_bytes]); row_bytes % 16 == 0. */
+int xb_gather_obs_planes(const uint8_t *src, const int64_t *idx, int64_t B, int64_t row_bytes, int planes, void *dst,
+                         void *stream);
 int xb_pack_conv_weight(const float *w, int N, int C, int KH, int KW, int planes, void *out /* bf16 [planes, N, KH*KW*C] */,
                         void *stream);
 /* Operands are `planes` (2 or 3) bf16 planes, plane q at base + q*plane_stride (elements): x = sum of its planes; plane 0 =

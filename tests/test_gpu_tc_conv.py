@@ -142,3 +142,49 @@ def test_encoder_matches_cudnn_fp32(planes, fwd_tol, grad_tol):
     for (k, p), (_, q) in zip(m_ref.representation.named_parameters(), m_tc.representation.named_parameters()):
         rel = float((q.grad - p.grad).norm() / p.grad.norm())
         assert rel < grad_tol, (k, rel)
+
+
+@bringup
+@pytest.mark.parametrize("planes", [2, 3])
+def test_gather_obs_planes(planes):
+    """K3-P: uint8 rows gathered straight into the bf16 planes of x/255 (bit-exact vs gather + true division + split)."""
+    from xuance_b200 import _lib
+    buf = torch.randint(0, 256, (6, 5, 84, 84, 4), dtype=torch.uint8, device=DEV)
+    idx = torch.tensor([29, 0, 7, 7, 13, 1, 28], dtype=torch.int64, device=DEV)
+    out = torch.empty((planes, idx.numel(), 84, 84, 4), dtype=torch.bfloat16, device=DEV)
+    _lib.call("xb_gather_obs_planes", _lib.ptr(buf), _lib.ptr(idx), idx.numel(), 84 * 84 * 4, planes, _lib.ptr(out))
+    ref = _planes_ref(buf.reshape(-1, 84, 84, 4)[idx].float() / 255.0, planes)
+    assert torch.equal(out, ref)
+    out2 = torch.empty((planes, 30, 84, 84, 4), dtype=torch.bfloat16, device=DEV)
+    _lib.call("xb_gather_obs_planes", _lib.ptr(buf), None, 30, 84 * 84 * 4, planes, _lib.ptr(out2))
+    assert torch.equal(out2, _planes_ref(buf.reshape(-1, 84, 84, 4).float() / 255.0, planes))
+
+
+@bringup
+def test_ppo_update_tc_three_planes_matches_fp32():
+    """PPO_Learner.update with compute='tc' (three planes) next to the cuDNN fp32 learner: same losses, same parameters."""
+    from helpers import build_product_ppo_model, ppo_config
+    from xuance_b200.common import BaseCallback
+    from xuance_b200.torch.learners import PPO_Learner
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(3)
+    A, B = 6, 256
+    m_ref = build_product_ppo_model(A, DEV)
+    m_tc = build_product_ppo_model(A, DEV)
+    m_tc.load_state_dict(m_ref.state_dict())
+    m_tc.representation.tc_planes = 3
+    m_tc.representation.set_compute("tc")
+    cfg = ppo_config(DEV, running_steps=256 * 128 * 10)
+    l_ref, l_tc = PPO_Learner(cfg, m_ref, BaseCallback()), PPO_Learner(cfg, m_tc, BaseCallback())
+    rng = np.random.default_rng(5)
+    for it in range(3):
+        s = {"obs": torch.from_numpy(rng.integers(0, 256, size=(B, 84, 84, 4), dtype=np.uint8)).cuda(),
+             "actions": rng.integers(0, A, size=B).astype(np.float32), "returns": rng.normal(size=B).astype(np.float32),
+             "advantages": rng.normal(size=B).astype(np.float32),
+             "aux_batch": {"old_logp": (rng.normal(size=B) * 0.05 - np.log(A)).astype(np.float32)}}
+        i_ref, i_tc = l_ref.update(**s), l_tc.update(**s)
+        for k in ("actor_loss", "critic_loss", "entropy", "predict_value"):
+            np.testing.assert_allclose(i_tc[k], i_ref[k], rtol=2e-4, atol=1e-5, err_msg=k)
+    for (k, p), (_, q) in zip(m_ref.state_dict().items(), m_tc.state_dict().items()):
+        np.testing.assert_allclose(q.cpu().numpy(), p.cpu().numpy(), rtol=1e-3, atol=1e-4, err_msg=k)

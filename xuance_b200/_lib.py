@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libxb200.so")
 
 OBS_U8, OBS_F32_NHWC, OBS_F32_NCHW, OBS_BF16_NHWC, OBS_F16_NHWC = 0, 1, 2, 3, 4
+OBS_PLANES2, OBS_PLANES3 = 5, 6   # bf16 plane tensors [P, B, H, W, C] for the experimental K12 layers (xb_gather_obs_planes)
 
 _P = c_void_p
 _SIGNATURES = {
@@ -36,6 +37,7 @@ _SIGNATURES = {
                              c_int, _P]),
     "xb_soft_update": (c_int, [_P, _P, c_int64, c_float, _P]),
     "xb_split_bf16": (c_int, [_P, c_int64, c_int, _P, _P]),
+    "xb_gather_obs_planes": (c_int, [_P, _P, c_int64, c_int64, c_int, _P, _P]),
     "xb_pack_conv_weight": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "xb_gemm_gather_tc": (c_int, [c_int, _P, c_int64, _P, c_int64, _P, _P] + [c_int] * 9 + [_P, _P, c_int, c_int, _P, c_int64,
                                   _P] + [c_int] * 6 + [c_int64, c_int, _P]),

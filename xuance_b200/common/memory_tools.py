@@ -38,10 +38,11 @@ class PreparedObs:
 
     def __init__(self, tensor, fmt, hwc):
         self.tensor, self.fmt, self.hwc = tensor, fmt, hwc
-        self.shape = (tensor.shape[0],) + tuple(hwc)
+        self._n = tensor.shape[1] if fmt in (_lib.OBS_PLANES2, _lib.OBS_PLANES3) else tensor.shape[0]
+        self.shape = (self._n,) + tuple(hwc)
 
     def __len__(self):
-        return self.tensor.shape[0]
+        return self._n
 
 
 class Buffer(ABC):
@@ -437,6 +438,11 @@ class DummyOnPolicyBuffer(Buffer):
         idx_t = self._index_tensor(indexes)
         H, W, C = self._obs_shape
         B = idx_t.numel()
+        if fmt in (_lib.OBS_PLANES2, _lib.OBS_PLANES3):        # experimental K12 input: bf16 planes of u8/255
+            P = 2 if fmt == _lib.OBS_PLANES2 else 3
+            out = torch.empty((P, B, H, W, C), dtype=torch.bfloat16, device=self.device)
+            _lib.call("xb_gather_obs_planes", _lib.ptr(self._obs), _lib.ptr(idx_t), B, H * W * C, P, _lib.ptr(out))
+            return self._assemble(PreparedObs(out, fmt, (H, W, C)), idx_t, self._gather_fields(idx_t))
         dt = {_lib.OBS_F32_NHWC: torch.float32, _lib.OBS_F32_NCHW: torch.float32,
               _lib.OBS_BF16_NHWC: torch.bfloat16, _lib.OBS_F16_NHWC: torch.float16}[fmt]
         shape = (B, C, H, W) if fmt == _lib.OBS_F32_NCHW else (B, H, W, C)

@@ -62,8 +62,10 @@ class _PixelEncoder(nn.Module):
 
     def preferred_obs_format(self):
         """K3 output format this encoder consumes without any further copy."""
+        if self.compute == "tc":
+            return _lib.OBS_PLANES2 if self._tc.be.planes == 2 else _lib.OBS_PLANES3
         return {"fp32": _lib.OBS_F32_NCHW, "fp32_cl": _lib.OBS_F32_NHWC, "tf32": _lib.OBS_F32_NHWC,
-                "bf16": _lib.OBS_BF16_NHWC, "tc": _lib.OBS_F32_NHWC}[self.compute]
+                "bf16": _lib.OBS_BF16_NHWC}[self.compute]
 
     # ---- EXPERIMENTAL "tc" mode: the conv stack + hidden layer as K12 launches (split-bf16 tcgen05 GEMMs with fp32-level
     # accuracy, utils/tc_conv.py).  Forward parity-tested on B200, backward not yet pinned; see DESIGN.md section 9.
@@ -83,15 +85,31 @@ class _PixelEncoder(nn.Module):
         C, H, W = self.input_shape
         self._tc = TensorCoreNatureCNN(convs, rest[1], (H, W, C), backend=CudaBackend(planes=getattr(self, "tc_planes", 2)))
 
-    def _run_tc(self, x_nchw_view):
+    def _run_tc(self, observations):
         from ..utils import tc_conv
-        x = x_nchw_view.permute(0, 2, 3, 1)
-        if x.dtype != torch.float32 or not x.is_contiguous():
-            x = x.float().contiguous()
-        planes = tc_conv.split_bf16(x, self._tc.be.planes)
+        P = self._tc.be.planes
+        if isinstance(observations, PreparedObs) and observations.fmt in (_lib.OBS_PLANES2, _lib.OBS_PLANES3):
+            planes = observations.tensor                                   # K3-P already produced [P, B, H, W, C]
+        elif isinstance(observations, torch.Tensor) and observations.is_cuda and observations.dtype == torch.uint8:
+            obs = observations.contiguous()
+            planes = torch.empty((P,) + tuple(obs.shape), dtype=torch.bfloat16, device=obs.device)
+            _lib.call("xb_gather_obs_planes", _lib.ptr(obs), None, obs.shape[0], obs[0].numel(), P, _lib.ptr(planes))
+        else:
+            x = self._as_input_f32_nhwc(observations)
+            planes = tc_conv.split_bf16(x, P)
+        B = planes.shape[1]
         if torch.is_grad_enabled():
-            return tc_conv.tc_encode(self._tc, planes, x.shape[0])
-        return self._tc.forward(planes, x.shape[0])
+            return tc_conv.tc_encode(self._tc, planes, B)
+        return self._tc.forward(planes, B)
+
+    def _as_input_f32_nhwc(self, observations):
+        """float32 NHWC u8/255 for inputs that are neither a planes batch nor a CUDA uint8 tensor (host arrays, floats)."""
+        if isinstance(observations, PreparedObs):
+            x = observations.tensor if observations.fmt != _lib.OBS_F32_NCHW else observations.tensor.permute(0, 2, 3, 1)
+            return x.float().contiguous()
+        if isinstance(observations, np.ndarray):
+            observations = torch.from_numpy(observations).to(self.device)
+        return (observations / 255.0).to(dtype=torch.float32, device=self.device).contiguous()
 
     def _as_input(self, observations):
         fmt = self.preferred_obs_format()
@@ -176,8 +194,9 @@ class AC_CNN_Atari(_PixelEncoder):
         return layer
 
     def forward(self, observations, **kwargs):
-        x = self._as_input(observations)
-        return RepresentationOutput(embeddings=self._run_tc(x) if self.compute == "tc" else self._run(x))
+        if self.compute == "tc":
+            return RepresentationOutput(embeddings=self._run_tc(observations))
+        return RepresentationOutput(embeddings=self._run(self._as_input(observations)))
 
 
 REGISTRY_Representation = {
