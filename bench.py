@@ -228,6 +228,7 @@ def run_own_arm(args):
     assert N_ENVS % world == 0
     n_local = N_ENVS // world
     cfg = ppo_namespace(device, n_local, world > 1, args.compute)
+    cfg.tc_planes = args.tc_planes
     cfg.use_cuda_graph = bool(args.graph) if args.graph >= 0 else world > 1
     obs_space, act_space = Box(0, 255, OBS_SHAPE, np.uint8), Discrete(N_ACTIONS)
     agent = PPO_Agent(cfg, envs=None, observation_space=obs_space, action_space=act_space)  # buffer: n_local envs
@@ -399,6 +400,8 @@ def main():
     ap.add_argument("--impl", default="xuance_b200", choices=["xuance_b200", "reference"])
     ap.add_argument("--compute", default="fp32", choices=["fp32", "fp32_cl", "tf32", "bf16", "tc"],
                     help="'tc' = EXPERIMENTAL split-bf16 tcgen05 layers (K12); not a default, see DESIGN.md section 9")
+    ap.add_argument("--tc-planes", type=int, default=3, choices=[2, 3],
+                    help="with --compute tc: bf16 planes per operand (3 = float32-grade, 2 = ~1e-5 forward error)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", type=int, default=-1, help="CUDA-graph the minibatch update: 1/0; default: on when --gpus > 1")
