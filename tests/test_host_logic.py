@@ -114,20 +114,66 @@ def _grad_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_sharded_gradient_identity_gloo_world2():
-    """sum over ranks of grad(local rows / B_total) == grad of the global minibatch: the identity the single
-    NCCL all-reduce of the flat bucket relies on (K4/K6 take B_total for exactly this)."""
+def _offpolicy_grad_worker(rank, world, port, out):
+    """DQN: mean squared TD error over the GLOBAL batch (dqn_learner.py:41-46; K6 scales by 1/B_total).  QMIX: masked
+    squared TD error over the GLOBAL sum(filled) (qmix_learner.py:74-84) - the denominator is itself all-reduced."""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    B, A = 48, 5
+    net = torch.nn.Linear(6, A)
+    x, act = torch.randn(B, 6), torch.randint(0, A, (B,))
+    y, filled = torch.randn(B), (torch.rand(B) < 0.7).float()
+    lo, hi = rank * B // world, (rank + 1) * B // world
+    errs = []
+    for kind in ("dqn", "qmix"):
+        net.zero_grad()
+        pred = net(x[lo:hi]).gather(1, act[lo:hi, None]).squeeze(1)
+        if kind == "dqn":
+            loss = ((pred - y[lo:hi]) ** 2).sum() / B
+        else:
+            denom = filled[lo:hi].sum().clone()
+            dist.all_reduce(denom)                                   # global sum(filled): one float
+            loss = (((pred - y[lo:hi]) * filled[lo:hi]) ** 2).sum() / denom
+        loss.backward()
+        flat = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+        dist.all_reduce(flat)
+        if rank == 0:
+            net.zero_grad()
+            pred = net(x).gather(1, act[:, None]).squeeze(1)
+            full_loss = ((pred - y) ** 2).mean() if kind == "dqn" else (((pred - y) * filled) ** 2).sum() / filled.sum()
+            full_loss.backward()
+            full = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+            errs.append(float((flat - full).abs().max()))
+    if rank == 0:
+        out.put(max(errs))
+    dist.destroy_process_group()
+
+
+def _run_world2(worker, port_base):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = port_base + os.getpid() % 2000
+    procs = [ctx.Process(target=worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
     err = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
-    assert err < 1e-6, err
+    return err
+
+
+def test_sharded_gradient_identity_gloo_world2():
+    """sum over ranks of grad(local rows / B_total) == grad of the global minibatch: the identity the single
+    NCCL all-reduce of the flat bucket relies on (K4/K6 take B_total for exactly this)."""
+    assert _run_world2(_grad_worker, 29500) < 1e-6
+
+
+def test_sharded_offpolicy_gradient_identities_gloo_world2():
+    """The same identity for the DQN loss and for QMIX's masked loss with an all-reduced denominator."""
+    assert _run_world2(_offpolicy_grad_worker, 31500) < 1e-6
 
 
 def test_vector_envs_agree_step_for_step():
