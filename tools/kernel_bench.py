@@ -4,7 +4,7 @@ shapes (SURVEY.md section 7 "hard parts": at the named PPO shape K2/K4/K5 move <
 bandwidth fraction is also reported at a scaled shape).  CUDA events on the launching stream, >= 3 warm-ups, L2
 flushed between timed launches (256 MB memset).  Prints one JSON object; profiles/rNN_kernels.json keeps a copy.
 
-    python tools/kernel_bench.py [--only k2,k4] [--reps 20]
+    python tools/kernel_bench.py [--only k2,k4] [--reps 20]      (k12 / k3p: experimental tensor-core layers)
 """
 import argparse
 import json
@@ -214,6 +214,81 @@ def main():
                       Rr * (S + n + 1) * 4, hbm, flops, tpk)
             e["vs_cublas_plus_epilogue_us"] = round(us_lib, 2)
             add(e)
+
+    if want("k10"):
+        for N, A in ((256, 4), (1 << 20, 4), (1 << 20, 18)):
+            logits = torch.randn((N, A), device=DEV, generator=g)
+            u = torch.rand(N, device=DEV, generator=g)
+            af, ai, lp = torch.empty(N, device=DEV), torch.empty(N, dtype=torch.int32, device=DEV), torch.empty(N, device=DEV)
+            us = timeit(lambda: _lib.call("xb_categorical_act", _lib.ptr(logits), _lib.ptr(u), None, N, A, _lib.ptr(af),
+                                          _lib.ptr(ai), _lib.ptr(lp), None), R)
+            add(entry("K10 xb_categorical_act", f"{N}x{A}", us, N * ((A + 1) * 4 + 12), hbm))
+
+    if want("k11"):
+        for N, D in ((8, 4), (256, 28224), (256, 1 << 20)):
+            x = torch.randn((N, D), device=DEV, generator=g)
+            mean, var, y = torch.zeros(D, device=DEV), torch.ones(D, device=DEV), torch.empty_like(x)
+            us = timeit(lambda: _lib.call("xb_rms_update_normalize", _lib.ptr(x), N, D, _lib.ptr(mean), _lib.ptr(var), 1e-4, 1,
+                                          _lib.ptr(y), 5.0, 1e-8), R)
+            add(entry("K11 xb_rms_update_normalize", f"{N}x{D}", us, N * D * 4 * 2, hbm))     # one read + one write (algorithmic)
+
+    if want("k3p"):
+        from xuance_b200 import _lib as L
+        Nn, T, rb, B = 256, 128, 28224, 8192
+        buf = torch.randint(0, 256, (Nn * T, rb), dtype=torch.uint8, device=DEV, generator=g)
+        idx = torch.randperm(Nn * T, device=DEV, generator=g)[:B].contiguous()
+        for P in (2, 3):
+            out = torch.empty((P, B, rb), dtype=torch.bfloat16, device=DEV)
+            us = timeit(lambda: L.call("xb_gather_obs_planes", L.ptr(buf), L.ptr(idx), B, rb, P, L.ptr(out)), R)
+            add(entry(f"K3-P xb_gather_obs_planes (P={P})", f"{B} rows x {rb} B", us, B * rb * (1 + 2 * P) + 8 * B, hbm))
+
+    if want("k12"):
+        # EXPERIMENTAL tensor-core layers at the PPO minibatch (8192 samples): forward, data gradient, weight gradient.
+        # flops = fp32-equivalent 2*M*N*K of the layer (the tensor pipe executes 3x / 6x that in bf16 MMAs)
+        from xuance_b200.torch.utils import tc_conv as tc
+        B = 8192
+        layers = (("conv1", 84, 84, 4, 32, 8, 4), ("conv2", 21, 21, 32, 64, 4, 2), ("conv3", 10, 10, 64, 64, 3, 1))
+        for P in (2, 3):
+            for name, H, W, C, N, k, s in layers:
+                pad = (k - s) // 2
+                geom = tc.conv_forward_geometry(B, H, W, C, k, k, s, pad)
+                x = torch.rand((B, H, W, C), device=DEV, generator=g)
+                w = torch.randn((N, C, k, k), device=DEV, generator=g) / np.sqrt(C * k * k)
+                x_pl, w_pl = tc.split_bf16(x, P), tc.pack_conv_weight(w, P)
+                out_pl = torch.empty((P, geom.M, N), dtype=torch.bfloat16, device=DEV)
+                fl = 2.0 * geom.M * N * geom.K
+                byts = x_pl.numel() * 2 + w_pl.numel() * 2 + out_pl.numel() * 2
+                us = timeit(lambda: tc.gemm_gather(x_pl, w_pl, geom, relu=True, out_pl=out_pl), R)
+                add(entry(f"K12 forward {name} (P={P})", f"M={geom.M} N={N} K={geom.K}", us, byts, hbm, fl, tpk))
+                g_pl = tc.split_bf16(torch.randn((geom.M, N), device=DEV, generator=g), P)
+                splits = tc.wgrad_splits(geom.M, geom.K)
+                us = timeit(lambda: tc.wgrad_reduce(tc.wgrad_gather(x_pl, g_pl, geom, splits), N, C, k, k), R)
+                add(entry(f"K12 weight gradient {name} (P={P}, {splits} splits)", f"M={geom.M} N={N} K={geom.K}", us,
+                          x_pl.numel() * 2 + g_pl.numel() * 2, hbm, fl, tpk))
+                if name != "conv1":
+                    phases = tc.conv_dgrad_geometries(B, H, W, C, k, k, s, pad, N)
+                    wds = [tc.split_bf16(tc.dgrad_weight_matrix(w, taps), P) for _, taps in phases]
+                    dx_pl = torch.empty((P, B * H * W, C), dtype=torch.bfloat16, device=DEV)
+
+                    def run_dgrad():
+                        for (gm, _), wd in zip(phases, wds):
+                            tc.gemm_gather(g_pl, wd, gm, out_pl=dx_pl, out_ld=C, relu_mask=x_pl[0].reshape(-1, C))
+                    us = timeit(run_dgrad, R)
+                    add(entry(f"K12 data gradient {name} (P={P}, {len(phases)} phases)", f"M={B * H * W} N={C}", us,
+                              g_pl.numel() * 2 + dx_pl.numel() * 2, hbm, fl, tpk))
+            # the hidden layer 6400 -> 512
+            geom = tc.linear_geometry(B, 6400)
+            x_pl = tc.split_bf16(torch.rand((B, 6400), device=DEV, generator=g), P)
+            w_pl = tc.pack_conv_weight(torch.randn((512, 64, 10, 10), device=DEV, generator=g) / 80.0, P)
+            out = torch.empty((B, 512), device=DEV)
+            nt = 256 if P == 2 else 128
+
+            def run_fc():
+                for c0 in range(0, 512, nt):
+                    tc.gemm_gather(x_pl, w_pl[:, c0:c0 + nt], geom, relu=True, out_f32=out, out_ld=512, out_c0=c0)
+            us = timeit(run_fc, R)
+            add(entry(f"K12 forward fc 6400->512 (P={P}, {512 // nt} launches)", f"M={B} N=512 K=6400", us,
+                      x_pl.numel() * 2 + w_pl.numel() * 2 + out.numel() * 4, hbm, 2.0 * B * 512 * 6400, tpk))
     print(json.dumps(out))
 
 
