@@ -96,5 +96,34 @@ def test_every_entry_point_validates_before_touching_the_device():
     assert lib.xb_qmix_mix_fused_fwd(junk, junk, four, four, junk, junk, junk, junk, junk, junk, 128, 98, 5, 64, 32, junk, None) == ERANGE
     assert lib.xb_qmix_mix_fused_fwd(junk, junk, four, four, junk, junk, junk, junk, junk, junk, 128, 160, 5, 32, 32, junk, None) == ERANGE  # smem
     assert lib.xb_powf_libm(None, 0.5, junk, 4, None) == EINVAL
+    # K10 / K11: rollout glue
+    assert lib.xb_categorical_act(junk, junk, None, 8, 65, junk, None, junk, None, None) == ERANGE       # A > 64
+    assert lib.xb_categorical_act(junk, junk, None, 8, 4, None, None, None, None, None) == EINVAL        # no output
+    assert lib.xb_categorical_act(None, junk, None, 8, 4, junk, None, junk, None, None) == EINVAL
+    assert lib.xb_rms_update_normalize(junk, 0, 4, junk, junk, 1e-4, 1, junk, 5.0, 1e-8, None) == EINVAL
+    assert lib.xb_rms_update_normalize(junk, 8, 4, junk, junk, 1e-4, 0, None, 5.0, 1e-8, None) == EINVAL  # nothing to do
+    # K12 (experimental tensor-core layers) and its operand preparation
+    taps = (ctypes.c_int8 * 64)()
+    gg = lambda planes=2, C=32, T=16, N=64, ld=64, c0=0, w=junk: lib.xb_gemm_gather_tc(
+        planes, junk, 1024, w, 1024, None, None, 2, 21, 21, C, 10, 10, 2, 2, T, taps, taps, N, 1, junk, 1024, None, 10, 10,
+        1, 1, 0, 0, ld, c0, None)
+    assert gg(planes=4) == EINVAL                      # 2 or 3 planes
+    assert gg(C=12) == ERANGE                          # channels per tap: multiple of 8 (one 16-byte unit)
+    assert gg(T=65) == ERANGE                          # tap table
+    assert gg(N=48) == ERANGE                          # N % 32
+    assert gg(planes=3, N=256) == ERANGE               # three planes: N <= 128 (two pipeline stages must fit)
+    assert gg(C=8, T=3) == ERANGE                      # K = T*C must be a multiple of the 64-deep stage
+    assert gg(ld=32) == EINVAL                         # output row shorter than out_c0 + N
+    assert gg(ld=68, c0=4) == EALIGN                   # 16-byte output segments
+    assert gg(w=odd) == EALIGN
+    assert lib.xb_wgrad_gather_tc(2, junk, 1024, junk, 1024, 1, 10, 10, 64, 10, 10, 1, 1, 9, taps, taps, 64, 5, junk, None) == EINVAL   # 100 sites cannot feed 5 splits
+    assert lib.xb_wgrad_gather_tc(2, junk, 1024, junk, 1024, 1, 10, 10, 64, 10, 10, 1, 1, 9, taps, taps, 64, 1, None, None) == EINVAL
+    assert lib.xb_wgrad_reduce(junk, 0, 64, 64, 3, 3, junk, 0, None) == EINVAL
+    assert lib.xb_split_bf16(junk, 64, 4, junk, None) == EINVAL
+    assert lib.xb_split_bf16(odd, 64, 2, junk, None) == EALIGN
+    assert lib.xb_pack_conv_weight(junk, 32, 4, 8, 8, 1, junk, None) == EINVAL
+    assert lib.xb_gather_obs_planes(junk, None, 4, 100, 2, junk, None) == EALIGN                        # row_bytes % 16
+    assert lib.xb_gather_obs_planes(junk, None, 4, 28224, 5, junk, None) == EINVAL
+    assert lib.xb_gather_obs_planes(junk, None, 0, 28224, 2, junk, None) == 0                           # empty batch
     for code in (EINVAL, EALIGN, ERANGE):
         assert lib.xb_error_string(code).startswith(b"xb200:")
