@@ -252,7 +252,7 @@ int xb_pack_conv_weight(const float *w, int N, int C, int KH, int KW, int planes
                         void *stream);
 /* Operands are `planes` (2 or 3) bf16 planes, plane q at base + q*plane_stride (elements): x = sum of its planes; plane 0 =
  * bf16(x), each further plane the bf16 of the remaining residual.  2 planes: 3 products per MMA step, operands exact to
- * 2^-17; 3 planes: 6 products, exact to 2^-24 (float32-grade; N <= 128).  out_planes (nullable) receives the result split
+ * 2^-16; 3 planes: 6 products, exact to 2^-24 (float32-grade; N <= 128).  out_planes (nullable) receives the result split
  * the same way; relu_mask = plane 0 of a saved activation. */
 int xb_gemm_gather_tc(int planes, const void *in, int64_t in_plane, const void *w, int64_t w_plane, const float *bias,
                       const void *relu_mask, int B, int IH, int IW, int C, int OY, int OX, int sy, int sx, int T,

@@ -14,6 +14,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from oracle.tc_numerics import split_planes
 from xuance_b200.torch.utils import tc_conv as tc
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -37,15 +38,9 @@ def emul():
 
 
 def _split(x, planes=2):
-    """float -> float32 [planes, ...] of bf16-representable values: plane q = bf16 of the residual left by planes < q
-    (what xb_split_bf16 / the kernel epilogue produce)."""
-    r = x.float().clone()
-    out = []
-    for _ in range(planes):
-        h = r.bfloat16().float()
-        out.append(h)
-        r = r - h
-    return torch.stack(out).contiguous()
+    """float -> float32 [planes, ...] of bf16-representable values (oracle/tc_numerics.py: what xb_split_bf16 and the
+    kernel epilogues produce)."""
+    return split_planes(x, planes)
 
 
 def _run(lib, geom, x_nhwc, w_mat, out, out_ld, out_c0=0, stages=2, planes=2):

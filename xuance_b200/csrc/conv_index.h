@@ -131,7 +131,7 @@ XB_HD void xb_stage_wgrad(const XbConvGeom &g, int row, int64_t mt, int64_t chun
 }
 
 // shared-memory bytes of one pipeline stage: the P planes of A (hi | [mid |] lo) followed by the P planes of W.
-// P = 2: x = hi + lo (|err| <= 2^-17 |x|, 3 products);  P = 3: x = hi + mid + lo (<= 2^-24 |x|, 6 products)
+// P = 2: x = hi + lo (|err| <= 2^-16 |x|, 3 products);  P = 3: x = hi + mid + lo (<= 2^-24 |x|, 6 products)
 XB_HD uint32_t xb_conv_stage_bytes(int N, int P = 2) {
     return (uint32_t)(P * XB_CONV_TILE_M * XB_CONV_KC * 2 + P * N * XB_CONV_KC * 2);
 }

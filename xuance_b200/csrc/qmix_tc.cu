@@ -11,7 +11,7 @@
 // the CTA then loops over its tiles (persistent grid = SM count).
 //
 // Numerics: the reference computes these layers in fp32.  The tensor pipe takes bf16 here, so every fp32 operand is
-// split x = hi + lo (two bf16 values, |x - hi - lo| <= 2^-17 |x|) and each product is the sum of the three MMAs
+// split x = hi + lo (two bf16 values, |x - hi - lo| <= 2^-16 |x|) and each product is the sum of the three MMAs
 // hi.hi + hi.lo + lo.hi (lo.lo ~ 2^-18 is below the split residual) accumulated in fp32 in TMEM: relative error ~1e-5 per layer (a plain bf16 or TF32
 // pass would be ~4e-3 / ~5e-4).  tests/test_gpu_qmix.py pins it against the fp32 oracle.
 #include "tc_common.cuh"

@@ -131,7 +131,7 @@ def dgrad_weight_matrix(w, taps):
 
 
 # ------------------------------------------------------------------------------------------------ device wrappers
-# Operands are "plane tensors": bfloat16 [P, ...] with x = planes.sum(0) - P = 2 (hi, lo; exact to 2^-17, three products
+# Operands are "plane tensors": bfloat16 [P, ...] with x = planes.sum(0) - P = 2 (hi, lo; exact to 2^-16, three products
 # per MMA step) or P = 3 (hi, mid, lo; exact to 2^-24, six products: float32-grade results, including which side of
 # zero a ReLU input falls on - with P = 2 an activation within ~1e-5 of zero can take the other side than the float32
 # network does and shift the upstream gradients by O(1/batch)).
