@@ -12,7 +12,7 @@
 //
 // Numerics: the reference computes these layers in fp32.  The tensor pipe takes bf16 here, so every fp32 operand is
 // split x = hi + lo (two bf16 values, |x - hi - lo| <= 2^-16 |x|) and each product is the sum of the three MMAs
-// hi.hi + hi.lo + lo.hi (lo.lo ~ 2^-18 is below the split residual) accumulated in fp32 in TMEM: relative error ~1e-5 per layer (a plain bf16 or TF32
+// hi.hi + hi.lo + lo.hi (lo.lo <= 2^-16 relative, the size of the split residual itself) accumulated in fp32 in TMEM: relative error ~1e-5 per layer (a plain bf16 or TF32
 // pass would be ~4e-3 / ~5e-4).  tests/test_gpu_qmix.py pins it against the fp32 oracle.
 #include "tc_common.cuh"
 
@@ -62,7 +62,7 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, const uint8_t *a_hi,
     const uint8_t *bs[2] = {b_hi, b_lo};
     uint32_t acc = 0;
     for (int pa = 0; pa < 2; ++pa)
-        for (int pb = 0; pb < 2 - pa; ++pb)   // (hi,hi) (hi,lo) (lo,hi); lo.lo ~ 2^-18 relative is dropped
+        for (int pb = 0; pb < 2 - pa; ++pb)   // (hi,hi) (hi,lo) (lo,hi); lo.lo <= 2^-16 relative is dropped
             for (int ks = 0; ks < KP / 16; ++ks) {  // one MMA = K 16 = two core matrices = 256 B along K
                 const uint64_t da = make_desc(smem_u32(as[pa]) + ks * 256, KP);
                 const uint64_t db = make_desc(smem_u32(bs[pb]) + ks * 256, KP);
