@@ -283,3 +283,33 @@ def test_nature_cnn_forward_backward_orchestration(emul, planes):
         np.testing.assert_allclose(m.weight.grad.numpy(), r.weight.grad.numpy(), rtol=0, atol=2e-4 * scale, err_msg=name)
         np.testing.assert_allclose(m.bias.grad.numpy(), r.bias.grad.numpy(), rtol=0,
                                    atol=2e-4 * float(r.bias.grad.abs().max()), err_msg=name + ".bias")
+
+
+def test_pooled_conv_stack_orchestration(emul):
+    """Basic_CNN's shape (cnn.py:11-50): three convolutions, global max pool, no hidden layer - the encoder of the DQN
+    family.  The pooled gradient reaches the K12 backward as a sparse [sites, C] array."""
+    import torch.nn as nn
+    torch.manual_seed(9)
+    B = 2
+    convs = [nn.Conv2d(4, 32, 8, 4, padding=2), nn.Conv2d(32, 64, 4, 2, padding=1), nn.Conv2d(64, 64, 3, 1, padding=1)]
+    ref = [nn.Conv2d(4, 32, 8, 4, padding=2), nn.Conv2d(32, 64, 4, 2, padding=1), nn.Conv2d(64, 64, 3, 1, padding=1)]
+    for r, m in zip(ref, convs):
+        r.load_state_dict(m.state_dict())
+        r.double()
+    x = torch.randint(0, 256, (B, 84, 84, 4), dtype=torch.uint8).float() / 255.0
+    R = torch.randn(B, 64)
+    h = x.double().permute(0, 3, 1, 2)
+    for r in ref:
+        h = torch.relu(r(h))
+    feat_ref = torch.amax(h, dim=(2, 3))
+    (feat_ref * R.double()).sum().backward()
+    enc = tc.TensorCoreNatureCNN(convs, None, (84, 84, 4), backend=EmulBackend(emul, 3))
+    z = tc.tc_encode(enc, _split(x, 3), B)
+    feat = z.view(B, -1, 64).amax(dim=1)
+    np.testing.assert_allclose(feat.detach().numpy(), feat_ref.detach().numpy(), rtol=1e-5, atol=1e-6)
+    (feat * R).sum().backward()
+    for m, r in zip(convs, ref):
+        np.testing.assert_allclose(m.weight.grad.numpy(), r.weight.grad.numpy(), rtol=0,
+                                   atol=2e-5 * float(r.weight.grad.abs().max()))
+        np.testing.assert_allclose(m.bias.grad.numpy(), r.bias.grad.numpy(), rtol=0,
+                                   atol=2e-5 * float(r.bias.grad.abs().max()))

@@ -77,13 +77,16 @@ class _PixelEncoder(nn.Module):
             convs.append(mods[i])
             i += 2
         rest = mods[i:]
-        ok = (len(convs) > 0 and len(rest) == 3 and isinstance(rest[0], nn.Flatten) and isinstance(rest[1], nn.Linear)
-              and isinstance(rest[2], nn.ReLU))
-        if not ok:
+        hidden = (len(rest) == 3 and isinstance(rest[0], nn.Flatten) and isinstance(rest[1], nn.Linear)
+                  and isinstance(rest[2], nn.ReLU))                                     # AC_CNN_Atari, one hidden layer
+        pooled = len(rest) == 2 and isinstance(rest[0], nn.AdaptiveMaxPool2d) and isinstance(rest[1], nn.Flatten)  # Basic_CNN
+        if not convs or not (hidden or pooled):
             raise NotImplementedError("compute='tc' covers Conv2d+ReLU stacks followed by Flatten, Linear, ReLU "
-                                      "(AC_CNN_Atari with one hidden layer)")
+                                      "(AC_CNN_Atari with one hidden layer) or by AdaptiveMaxPool2d(1,1), Flatten (Basic_CNN)")
         C, H, W = self.input_shape
-        self._tc = TensorCoreNatureCNN(convs, rest[1], (H, W, C), backend=CudaBackend(planes=getattr(self, "tc_planes", 2)))
+        self._tc = TensorCoreNatureCNN(convs, rest[1] if hidden else None, (H, W, C),
+                                       backend=CudaBackend(planes=getattr(self, "tc_planes", 2)))
+        self._tc_pooled = pooled
 
     def _run_tc(self, observations):
         from ..utils import tc_conv
@@ -98,9 +101,10 @@ class _PixelEncoder(nn.Module):
             x = self._as_input_f32_nhwc(observations)
             planes = tc_conv.split_bf16(x, P)
         B = planes.shape[1]
-        if torch.is_grad_enabled():
-            return tc_conv.tc_encode(self._tc, planes, B)
-        return self._tc.forward(planes, B)
+        z = tc_conv.tc_encode(self._tc, planes, B) if torch.is_grad_enabled() else self._tc.forward(planes, B)
+        if self._tc_pooled:         # [B*OY*OX, C] NHWC rows of the last convolution -> global max over the sites (cnn.py:47-48)
+            z = z.view(B, -1, z.shape[-1]).amax(dim=1)
+        return z
 
     def _as_input_f32_nhwc(self, observations):
         """float32 NHWC u8/255 for inputs that are neither a planes batch nor a CUDA uint8 tensor (host arrays, floats)."""
@@ -159,6 +163,8 @@ class Basic_CNN(_PixelEncoder):
         self.model = nn.Sequential(*layers)
 
     def forward(self, observations, **kwargs):
+        if self.compute == "tc":
+            return RepresentationOutput(embeddings=self._run_tc(observations))
         return RepresentationOutput(embeddings=self._run(self._as_input(observations)))
 
 
