@@ -17,7 +17,7 @@ inline float &at(std::vector<float> &smem, uint32_t byte_off) { return smem[byte
 extern "C" int emul_gemm_gather(int P, const float *in, int64_t in_plane, const float *w, int64_t w_plane, int B,
                                 int IH, int IW, int C, int OY, int OX, int sy, int sx, int T, const int8_t *dy,
                                 const int8_t *dx, int N, int out_H, int out_W, int oys, int oxs, int oy0, int ox0,
-                                int64_t out_ld, int out_c0, int stages, double *out) {
+                                int64_t out_ld, int out_c0, int stages, int map, double *out) {
     XbConvGeom g;
     g.B = B, g.IH = IH, g.IW = IW, g.C = C, g.OY = OY, g.OX = OX, g.sy = sy, g.sx = sx, g.T = T, g.N = N;
     for (int t = 0; t < XB_CONV_MAX_TAPS; ++t) g.dy[t] = t < T ? dy[t] : 0, g.dx[t] = t < T ? dx[t] : 0;
@@ -51,7 +51,17 @@ extern "C" int emul_gemm_gather(int P, const float *in, int64_t in_plane, const 
                         for (int j = 0; j < 8; ++j)
                             at(smem, base + P * a_plane + q * ws_plane + dst + 2 * j) = src >= 0 ? w[q * w_plane + src + j] : 0.f;
                 };
-                xb_stage_fwd(g, row, live, b, y, x, kc, emit_a, emit_w);
+                if (map == 0) {
+                    xb_stage_fwd(g, row, live, b, y, x, kc, emit_a, emit_w);
+                } else {                                        // conv_tc.cu, MAP = 1: the thread feeds four rows
+                    int sites4[4][3];
+                    for (int gi = 0; gi < 4; ++gi) {
+                        const int64_t mm = tile * TM + xb_v2_row(row, gi);
+                        sites4[gi][0] = -1, sites4[gi][1] = 0, sites4[gi][2] = 0;
+                        if (mm < M) xb_conv_site(g, mm, sites4[gi][0], sites4[gi][1], sites4[gi][2]);
+                    }
+                    xb_stage_fwd_v2(g, row, sites4, kc, emit_a, emit_w);
+                }
             }
             // ---- tensor core: three products, K 16 per instruction, operands located through the descriptor fields
             const uint32_t LBO = 128, SBO = (KC / 8) * 128;
@@ -96,7 +106,7 @@ extern "C" void emul_pack_weight(const float *w, int N, int C, int KH, int KW, f
 // (mn, k) at start + (mn/8)*SBO + (k/8)*LBO + (k%8)*16 + (mn%8)*2
 extern "C" int emul_wgrad(int P, const float *in, int64_t in_plane, const float *gr, int64_t g_plane, int B, int IH,
                           int IW, int C, int OY, int OX, int sy, int sx, int T, const int8_t *dy, const int8_t *dx, int N,
-                          int splits, int stages, double *partials) {
+                          int splits, int stages, int map, double *partials) {
     XbConvGeom g;
     g.B = B, g.IH = IH, g.IW = IW, g.C = C, g.OY = OY, g.OX = OX, g.sy = sy, g.sx = sx, g.T = T, g.N = N;
     for (int t = 0; t < XB_CONV_MAX_TAPS; ++t) g.dy[t] = t < T ? dy[t] : 0, g.dx[t] = t < T ? dx[t] : 0;
@@ -129,7 +139,8 @@ extern "C" int emul_wgrad(int P, const float *in, int64_t in_plane, const float 
                         for (int j = 0; j < 8; ++j)
                             at(smem, base + P * a_plane + q * ws_plane + dst + 2 * j) = src >= 0 ? gr[q * g_plane + src + j] : 0.f;
                 };
-                xb_stage_wgrad(g, row, mt, s0 + (int64_t)kc * KC, site_end, emit_a, emit_g);
+                if (map == 0) xb_stage_wgrad(g, row, mt, s0 + (int64_t)kc * KC, site_end, emit_a, emit_g);
+                else xb_stage_wgrad_v2(g, row, mt, s0 + (int64_t)kc * KC, site_end, emit_a, emit_g);
             }
             const uint32_t LBO = 128, SBO = (KC / 8) * 128;
             const uint32_t a_addr[3] = {base, base + a_plane, base + 2 * a_plane};

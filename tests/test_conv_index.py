@@ -28,10 +28,10 @@ def emul():
         subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-std=c++17", "-o", so, src], check=True)
     lib = ctypes.CDLL(so)
     P, i, l = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
-    lib.emul_gemm_gather.argtypes = [i, P, l, P, l] + [i] * 9 + [P, P] + [i] * 7 + [l, i, i, P]
+    lib.emul_gemm_gather.argtypes = [i, P, l, P, l] + [i] * 9 + [P, P] + [i] * 7 + [l, i, i, i, P]
     lib.emul_gemm_gather.restype = i
     lib.emul_pack_weight.argtypes = [P, i, i, i, i, P]
-    lib.emul_wgrad.argtypes = [i, P, l, P, l] + [i] * 9 + [P, P] + [i] * 3 + [P]
+    lib.emul_wgrad.argtypes = [i, P, l, P, l] + [i] * 9 + [P, P] + [i] * 4 + [P]
     lib.emul_wgrad.restype = i
     lib.emul_wgrad_reduce.argtypes = [P, i, i, i, i, i, P]
     return lib
@@ -43,6 +43,16 @@ def _split(x, planes=2):
     return split_planes(x, planes)
 
 
+MAP = [0]      # producer mapping the emulator stages with (conv_tc.cu's MAP template parameter); set by the `mapping` fixture
+
+
+@pytest.fixture(params=[0, 1], ids=["map0", "map1"])
+def mapping(request):
+    MAP[0] = request.param
+    yield request.param
+    MAP[0] = 0
+
+
 def _run(lib, geom, x_nhwc, w_mat, out, out_ld, out_c0=0, stages=2, planes=2):
     """x_nhwc: float64 tensor viewed as the geometry's [B, IH, IW, C]; w_mat float64 [N, K]; out float64 [rows, out_ld]."""
     xp, wp = _split(x_nhwc, planes), _split(w_mat, planes)
@@ -52,7 +62,7 @@ def _run(lib, geom, x_nhwc, w_mat, out, out_ld, out_c0=0, stages=2, planes=2):
     rc = lib.emul_gemm_gather(planes, xp.data_ptr(), xp.stride(0), wp.data_ptr(), wp.stride(0), geom.B, geom.IH, geom.IW,
                               geom.C, geom.OY, geom.OX, geom.sy, geom.sx, geom.T, dy.ctypes.data, dx.ctypes.data, N,
                               geom.out_H, geom.out_W, geom.oys, geom.oxs, geom.oy0, geom.ox0, out_ld, out_c0, stages,
-                              out.data_ptr())
+                              MAP[0], out.data_ptr())
     assert rc == 0
 
 
@@ -72,7 +82,7 @@ TOL = dict(rtol=0, atol=4e-5)     # |x - hi - lo| <= 2^-17 |x| per operand; sums
 @pytest.mark.parametrize("planes", [2, 3])
 @pytest.mark.parametrize("name,B,H,W,C,N,k,s", [("conv1", 2, 84, 84, 4, 32, 8, 4), ("conv2", 2, 21, 21, 32, 64, 4, 2),
                                                 ("conv3", 3, 10, 10, 64, 64, 3, 1), ("odd", 1, 13, 9, 8, 32, 4, 2)])
-def test_forward_conv_layers(emul, name, B, H, W, C, N, k, s, planes):
+def test_forward_conv_layers(emul, mapping, name, B, H, W, C, N, k, s, planes):
     """The three NatureCNN convolutions with the reference's padding rule (k - s)//2 (layers.py:46), NHWC input."""
     torch.manual_seed(len(name))
     pad = (k - s) // 2
@@ -87,7 +97,7 @@ def test_forward_conv_layers(emul, name, B, H, W, C, N, k, s, planes):
     np.testing.assert_allclose(out.numpy(), want.numpy(), rtol=0, atol=4e-5 if planes == 2 else 6e-7)
 
 
-def test_linear_layer_with_column_split_and_row_tail(emul):
+def test_linear_layer_with_column_split_and_row_tail(emul, mapping):
     """Linear(6400 -> 512) over the NHWC-flattened conv3 output: N = 512 runs as two 256-column calls; 130 rows leave a
     2-row tail tile.  The reference flattens NCHW (cnn.py:92), so the packed weight permutes its columns to (h, w, c)."""
     torch.manual_seed(0)
@@ -106,7 +116,7 @@ def test_linear_layer_with_column_split_and_row_tail(emul):
 
 @pytest.mark.parametrize("name,B,H,W,C,N,k,s", [("conv3", 2, 10, 10, 64, 64, 3, 1), ("conv2", 2, 21, 21, 32, 64, 4, 2),
                                                 ("s4", 1, 20, 20, 8, 32, 8, 4)])
-def test_data_gradient_phases(emul, name, B, H, W, C, N, k, s):
+def test_data_gradient_phases(emul, mapping, name, B, H, W, C, N, k, s):
     """grad_input of a convolution as one gathered GEMM per stride phase over the output gradient, vs autograd."""
     torch.manual_seed(1)
     pad = (k - s) // 2
@@ -126,7 +136,7 @@ def test_data_gradient_phases(emul, name, B, H, W, C, N, k, s):
 
 @pytest.mark.parametrize("name,B,H,W,C,N,k,s,splits", [("conv1", 2, 84, 84, 4, 32, 8, 4, 3), ("conv2", 4, 21, 21, 32, 64, 4, 2, 3),
                                                        ("conv3", 3, 10, 10, 64, 64, 3, 1, 2), ("conv3_1split", 1, 10, 10, 64, 64, 3, 1, 1)])
-def test_weight_gradient(emul, name, B, H, W, C, N, k, s, splits):
+def test_weight_gradient(emul, mapping, name, B, H, W, C, N, k, s, splits):
     """grad_weight as the MN-major gathered GEMM (split over sites, then reduced into torch's [N, C, KH, KW]) vs autograd.
     conv3 has K = 576 = 4.5 column tiles (a half-empty tile); conv1 runs on the pixel-folded view."""
     torch.manual_seed(2)
@@ -143,14 +153,14 @@ def test_weight_gradient(emul, name, B, H, W, C, N, k, s, splits):
     partials = torch.full((splits, g.K, N), float("nan"), dtype=torch.float64)
     dy, dx = np.asarray(g.dy, np.int8), np.asarray(g.dx, np.int8)
     rc = emul.emul_wgrad(planes, xp.data_ptr(), xp.stride(0), gp.data_ptr(), gp.stride(0), g.B, g.IH, g.IW, g.C, g.OY, g.OX,
-                         g.sy, g.sx, g.T, dy.ctypes.data, dx.ctypes.data, N, splits, 2, partials.data_ptr())
+                         g.sy, g.sx, g.T, dy.ctypes.data, dx.ctypes.data, N, splits, 2, MAP[0], partials.data_ptr())
     assert rc == 0 and not torch.isnan(partials).any()
     dw = torch.full((N, C, k, k), float("nan"), dtype=torch.float64)
     emul.emul_wgrad_reduce(partials.data_ptr(), splits, N, C, k, k, dw.data_ptr())
     np.testing.assert_allclose(dw.numpy(), want.numpy(), **TOL)
 
 
-def test_linear_weight_gradient(emul):
+def test_linear_weight_gradient(emul, mapping):
     """dW of Linear(6400 -> 256 columns of the 512) : sites = batch rows, one tap, 50 column tiles."""
     torch.manual_seed(3)
     Bn, K, N = 70, 6400, 64
@@ -161,7 +171,7 @@ def test_linear_weight_gradient(emul):
     partials = torch.full((2, K, N), float("nan"), dtype=torch.float64)
     dy, dx = np.zeros(1, np.int8), np.zeros(1, np.int8)
     rc = emul.emul_wgrad(2, xp.data_ptr(), xp.stride(0), gp.data_ptr(), gp.stride(0), g.B, 1, 1, K, 1, 1, 1, 1, 1,
-                         dy.ctypes.data, dx.ctypes.data, N, 2, 2, partials.data_ptr())
+                         dy.ctypes.data, dx.ctypes.data, N, 2, 2, MAP[0], partials.data_ptr())
     assert rc == 0
     np.testing.assert_allclose(partials.sum(0).t().numpy(), (gy.t() @ x).numpy(), **TOL)
 
@@ -213,7 +223,7 @@ class EmulBackend:
         rc = self.lib.emul_gemm_gather(P, x_pl.data_ptr(), x_pl.stride(0), w_pl.data_ptr(), w_pl.stride(0), geom.B, geom.IH,
                                        geom.IW, geom.C, geom.OY, geom.OX, geom.sy, geom.sx, geom.T, dy.ctypes.data,
                                        dx.ctypes.data, N, geom.out_H, geom.out_W, geom.oys, geom.oxs, geom.oy0, geom.ox0,
-                                       out_ld, out_c0, 2, tmp.data_ptr())
+                                       out_ld, out_c0, 2, MAP[0], tmp.data_ptr())
         assert rc == 0
         blk = tmp[:, out_c0:out_c0 + N]
         written = ~torch.isnan(blk[:, 0])
@@ -239,7 +249,7 @@ class EmulBackend:
         x_pl, g_pl = x_pl.contiguous(), g_pl.contiguous()
         rc = self.lib.emul_wgrad(P, x_pl.data_ptr(), x_pl.stride(0), g_pl.data_ptr(), g_pl.stride(0), geom.B, geom.IH,
                                  geom.IW, geom.C, geom.OY, geom.OX, geom.sy, geom.sx, geom.T, dy.ctypes.data, dx.ctypes.data,
-                                 N, splits, 2, partials.data_ptr())
+                                 N, splits, 2, MAP[0], partials.data_ptr())
         assert rc == 0
         dw = torch.full((N, C, KH, KW), float("nan"), dtype=torch.float64)
         self.lib.emul_wgrad_reduce(partials.data_ptr(), splits, N, C, KH, KW, dw.data_ptr())
@@ -247,7 +257,7 @@ class EmulBackend:
 
 
 @pytest.mark.parametrize("planes", [2, 3])
-def test_nature_cnn_forward_backward_orchestration(emul, planes):
+def test_nature_cnn_forward_backward_orchestration(emul, mapping, planes):
     """The whole encoder (3 convs + Linear, cnn.py:84-101) forward and backward through TensorCoreNatureCNN with the
     emulated backend vs torch autograd in float64: layer chaining, NHWC <-> NCHW-flatten weight permutation, ReLU masks in
     the data-gradient epilogues, stride-phase data gradients, column-split Linear (320 = 256 + 64 outputs)."""

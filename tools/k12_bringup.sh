@@ -7,17 +7,21 @@ export XB_EXPERIMENTAL_TC=1
 mkdir -p gpurun_out
 echo "== parity tests (forward default-on, backward / 3 planes / planes gather / tc PPO update behind the env var)"
 timeout 400 python -m pytest tests/test_gpu_tc_conv.py -q -x > gpurun_out/k12_tests.log 2>&1; echo "rc=$?"; tail -15 gpurun_out/k12_tests.log
-echo "== per-kernel timings: K12 layers at the PPO minibatch, K3-P, K10, K11"
-timeout 400 python tools/kernel_bench.py --only k12,k3p,k10,k11 --reps 10 > gpurun_out/k12_kernels.json 2> gpurun_out/k12_kernels.err; echo "rc=$?"
-python - <<'PY'
-import json
+echo "== the same tests with the row-coalesced producer mapping (XB_K12_MAP=1: emulator-verified, never run on hardware)"
+XB_K12_MAP=1 timeout 400 python -m pytest tests/test_gpu_tc_conv.py -q -x > gpurun_out/k12_tests_map1.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/k12_tests_map1.log
+echo "== per-kernel timings: K12 layers at the PPO minibatch (both producer mappings), K3-P, K10, K11"
+for MAPV in 0 1; do
+  XB_K12_MAP=$MAPV timeout 400 python tools/kernel_bench.py --only k12,k3p,k10,k11 --reps 10 > gpurun_out/k12_kernels_map$MAPV.json 2> gpurun_out/k12_kernels_map$MAPV.err; echo "map=$MAPV rc=$?"
+  python - "$MAPV" <<'PY'
+import json, sys
 try:
-    d = json.load(open("gpurun_out/k12_kernels.json"))
+    d = json.load(open("gpurun_out/k12_kernels_map%s.json" % sys.argv[1]))
     for k in d["kernels"]:
         print("%-62s %-28s %9.1f us  %6.1f TF/s  hbm %.2f" % (k["kernel"][:62], k["shape"][:28], k["us"], k.get("TFLOPs", 0.0), k["frac_hbm"]))
 except Exception as e:
     print("no kernel json:", e)
 PY
+done
 echo "== headline bench through the tc encoder (3 planes = float32-grade, then 2 planes)"
 for P in 3 2; do
   timeout 400 python bench.py --compute tc --tc-planes $P --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_tc_p$P.json 2> gpurun_out/bench_tc_p$P.err

@@ -130,6 +130,59 @@ XB_HD void xb_stage_wgrad(const XbConvGeom &g, int row, int64_t mt, int64_t chun
         emit_g(xb_canon_off_mn(j * 8, pp, XB_CONV_KC), in_run ? site * g.N + j * 8 : (int64_t)-1);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Row-coalesced producer mapping (MAP = 1; same shared-memory image, different division of the units among the 128
+// producer threads).  In the canonical no-swizzle layouts the shared-memory bank of a 16-byte unit depends only on
+// (row & 7) [K-major] / (site & 7) [MN-major], so a warp instruction is conflict-free as soon as its 32 lanes hold each of
+// the 8 residues four times - which leaves the other lane bits free to walk along MEMORY-contiguous units: lane ->
+// (residue = lane & 7, unit offset = lane >> 3), i.e. 8 rows x 4 consecutive units = 8 x 64 contiguous bytes per
+// instruction instead of 32 scattered 16-byte pieces (half of every 32-byte sector wasted).
+// ---------------------------------------------------------------------------------------------------------------------
+// forward: producer thread t = (warp w, lane l) owns rows 32w + 8*gi + (l & 7), gi < 4, and units (l >> 3) and 4 + (l >> 3)
+XB_HD int xb_v2_row(int t, int gi) { return 32 * (t >> 5) + 8 * gi + (t & 7); }
+
+// sites: the thread's four sites as {b, y, x} (b < 0: row outside the problem)
+template <class EmitA, class EmitW>
+XB_HD void xb_stage_fwd_v2(const XbConvGeom &g, int t, const int (*sites)[3], int kc, EmitA &&emit_a, EmitW &&emit_w) {
+    const int K = g.T * g.C;
+    const int w = t >> 5, l = t & 31, rs = l & 7, uo = l >> 3;
+    for (int half = 0; half < 2; ++half) {
+        const int u = half * 4 + uo, k0 = kc * XB_CONV_KC + u * 8;
+        for (int gi = 0; gi < 4; ++gi) {
+            const int *s = sites[gi];
+            const int64_t off = s[0] >= 0 ? xb_conv_unit_src(g, s[0], s[1], s[2], k0) : -1;
+            emit_a(xb_canon_off(32 * w + 8 * gi + rs, u * 8, XB_CONV_KC), off);
+        }
+    }
+    for (int q = w; q < (g.N >> 3) * 2; q += 4) {            // (8-row group, half) pairs of the weight tile, dealt to the warps
+        const int n = (q >> 1) * 8 + rs, u = (q & 1) * 4 + uo;
+        emit_w(xb_canon_off(n, u * 8, XB_CONV_KC), (int64_t)n * K + kc * XB_CONV_KC + u * 8);
+    }
+}
+
+// weight gradient: thread t owns sites 16w + 8*si + (l & 7), si < 2, of the chunk and the column units 4*quad + (l >> 3)
+template <class EmitA, class EmitG>
+XB_HD void xb_stage_wgrad_v2(const XbConvGeom &g, int t, int64_t mt, int64_t chunk_site0, int64_t site_end, EmitA &&emit_a,
+                             EmitG &&emit_g) {
+    const int K = g.T * g.C;
+    const int w = t >> 5, l = t & 31, rs = l & 7, uo = l >> 3;
+    for (int si = 0; si < 2; ++si) {
+        const int pp = 16 * w + 8 * si + rs;
+        const int64_t site = chunk_site0 + pp;
+        const bool in_run = site < site_end;
+        int b = 0, y = 0, x = 0;
+        if (in_run) xb_conv_site(g, site, b, y, x);
+        for (int quad = 0; quad < 4; ++quad) {
+            const int u = quad * 4 + uo;
+            const int64_t kcol = mt * XB_CONV_TILE_M + u * 8;
+            const int64_t off = (in_run && kcol < K) ? xb_conv_unit_src(g, b, y, x, (int)kcol) : -1;
+            emit_a(xb_canon_off_mn(u * 8, pp, XB_CONV_KC), off);
+        }
+        for (int j = uo; j < (g.N >> 3); j += 4)
+            emit_g(xb_canon_off_mn(j * 8, pp, XB_CONV_KC), in_run ? site * g.N + j * 8 : (int64_t)-1);
+    }
+}
+
 // shared-memory bytes of one pipeline stage: the P planes of A (hi | [mid |] lo) followed by the P planes of W.
 // P = 2: x = hi + lo (|err| <= 2^-16 |x|, 3 products);  P = 3: x = hi + mid + lo (<= 2^-24 |x|, 6 products)
 XB_HD uint32_t xb_conv_stage_bytes(int N, int P = 2) {

@@ -19,6 +19,8 @@
 //                          empty[stage]; after the last chunk commits onto acc_full[a].  Two accumulators in TMEM.
 //   warps 0-3  epilogue  : thread = row = TMEM lane.  tcgen05.ld 32 columns at a time, bias + ReLU, then the row is
 //                          written as fp32 and / or as the hi / lo bf16 pair the next layer consumes.
+#include <cstdlib>
+
 #include "tc_common.cuh"
 #include "conv_index.h"
 
@@ -79,7 +81,9 @@ __device__ __forceinline__ uint32_t make_idesc_mn(int M, int N) { return make_id
 // WGRAD = true :  D[kcol, n]  = sum_site A[site, kcol] G[site, n]   work item = (128-kcol tile, split), MN-major operands
 // P: planes per operand.  P = 2: (hi, lo), products hi.hi + hi.lo + lo.hi.  P = 3: (hi, mid, lo), the six products with
 // plane indices summing to <= 2 - operands exact to 2^-24, i.e. float32-grade results (ReLU masks included).
-template <bool WGRAD, int P>
+// MAP: how the 16-byte units of a stage are dealt to the producer threads (conv_index.h): 0 = thread per row (the mapping
+// that passed on hardware), 1 = row-coalesced (8 rows x 4 memory-contiguous units per warp instruction).
+template <bool WGRAD, int P, int MAP>
 __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_full[2], acc_empty[2];
@@ -144,6 +148,15 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
             const bool live = !WGRAD && m < p.M;
             int b = 0, y = 0, x = 0;
             if (live) xb_conv_site(g, m, b, y, x);
+            int sites4[4][3];                                  // MAP = 1, forward: the four rows this thread feeds
+            if (MAP == 1 && !WGRAD) {
+#pragma unroll
+                for (int gi = 0; gi < 4; ++gi) {
+                    const int64_t mm = w * TILE_M + xb_v2_row(row, gi);
+                    sites4[gi][0] = -1, sites4[gi][1] = 0, sites4[gi][2] = 0;
+                    if (mm < p.M) xb_conv_site(g, mm, sites4[gi][0], sites4[gi][1], sites4[gi][2]);
+                }
+            }
             // weight gradient: this thread's site changes with the chunk; its kcol units are fixed for the tile
             const int64_t mt = w % m_tiles, sp = w / m_tiles;
             const int64_t site_end = WGRAD ? ((sp + 1) * p.sites_per_split < p.M ? (sp + 1) * p.sites_per_split : p.M) : 0;
@@ -166,8 +179,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                     cp_async16(wbase + w_plane + dst_off, p.w_lo + o, nbytes);
                     if (P == 3) cp_async16(wbase + 2 * w_plane + dst_off, p.w_p2 + o, nbytes);
                 };
-                if (!WGRAD) xb_stage_fwd(g, row, live, b, y, x, kc, emit_a, emit_w);
-                else xb_stage_wgrad(g, row, mt, sp * p.sites_per_split + (int64_t)kc * KC, site_end, emit_a, emit_w);
+                if (MAP == 0) {
+                    if (!WGRAD) xb_stage_fwd(g, row, live, b, y, x, kc, emit_a, emit_w);
+                    else xb_stage_wgrad(g, row, mt, sp * p.sites_per_split + (int64_t)kc * KC, site_end, emit_a, emit_w);
+                } else {
+                    if (!WGRAD) xb_stage_fwd_v2(g, row, sites4, kc, emit_a, emit_w);
+                    else xb_stage_wgrad_v2(g, row, mt, sp * p.sites_per_split + (int64_t)kc * KC, site_end, emit_a, emit_w);
+                }
                 cp_async_commit();
                 if (it > 0) publish_previous(false);     // this chunk stays in flight
                 ++it;
@@ -386,17 +404,29 @@ int fill_params(ConvParams &p, int planes, const void *in, int64_t in_plane, con
     return XB_OK;
 }
 
-template <bool WGRAD, int P>
-int launch(const ConvParams &p, int64_t work, void *stream) {
+template <bool WGRAD, int P, int MAP>
+int launch_map(const ConvParams &p, int64_t work, void *stream) {
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(conv_tc_kernel<WGRAD, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel<WGRAD, P, MAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr = true;
     }
     const int grid = (int)(work < xb_sm_count() ? work : xb_sm_count());
     const size_t smem = (size_t)p.stages * xb_conv_stage_bytes(p.g.N, P);
-    conv_tc_kernel<WGRAD, P><<<grid, THREADS, smem, (cudaStream_t)stream>>>(p);
+    conv_tc_kernel<WGRAD, P, MAP><<<grid, THREADS, smem, (cudaStream_t)stream>>>(p);
     return xb_launch_status();
+}
+
+// XB_K12_MAP=1 selects the row-coalesced producer mapping (emulator-verified, not yet timed); default 0 = the mapping that
+// passed on hardware
+template <bool WGRAD, int P>
+int launch(const ConvParams &p, int64_t work, void *stream) {
+    static int map = -1;
+    if (map < 0) {
+        const char *e = getenv("XB_K12_MAP");
+        map = (e && e[0] == '1') ? 1 : 0;
+    }
+    return map == 1 ? launch_map<WGRAD, P, 1>(p, work, stream) : launch_map<WGRAD, P, 0>(p, work, stream);
 }
 
 }  // namespace
