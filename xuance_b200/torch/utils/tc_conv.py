@@ -240,7 +240,8 @@ class CudaBackend:
         return wgrad_reduce(wgrad_gather(x_pl, g_pl, geom, splits), N, C, KH, KW)
 
     def colsum(self, g_pl):
-        return g_pl.float().sum(dim=(0, 1))
+        # bias gradient: reduce the bf16 planes straight into float32 (no float32 copy of the [P, sites, N] tensor)
+        return g_pl.sum(dim=1, dtype=torch.float32).sum(0)
 
     def to_float(self, pl):
         return pl.float().sum(0)
