@@ -136,14 +136,18 @@ int xb_dqn_td_fwd_bwd(const float *q_eval, const float *q_next, const float *q_s
  *           q_all[B,n,T+1,A], the double-Q / max next value from the target outputs q_tgt at step t+1, both
  *           multiplied by agent_mask*filled and written agent-minor [B*T, n] (the layout Q_tot concatenates,
  *           value_factorization.py:137-142); also filled_sum[0] = sum(filled).  actions/masks are float32.
+ *           avail (nullable; use_actions_mask, iql_learner.py:60-81 + value_factorization.py:86-89): uint8
+ *           [B,n,T+1,avail_ld], unavailable actions count as -1e10 in the double-Q arg-max over the eval values
+ *           and in the target values of step t+1.
  *           select_bwd scatters d(q_eval_taken) back into a zeroed dq_all.
  * mix     : QMIX_Mixer.forward epilogue (q_mix_head.py:81-94) on precomputed hypernet outputs:
  *           hidden = elu(q . |w1_raw|[n,H] + b1) ; q_tot = hidden . |w2_raw| + b2   (n <= 16), and its backward
  *           (abs' = sign, elu' = exp) producing dq, dw1_raw, db1, dw2_raw (db2 = dq_tot).
  * td      : qmix_learner.py:34-35,76-84 masked TD loss; writes dq_tot and stats[2] = {loss_Q, mean(q_tot)}. */
 int xb_qmix_select_fwd(const float *q_all, const float *q_tgt, const float *actions, const float *agent_mask,
-                       const float *filled, int B, int n, int T, int A, int double_q, float *q_eval_taken,
-                       float *q_next_taken, float *filled_sum, double *scratch, void *stream);
+                       const float *filled, const uint8_t *avail, int avail_ld, int B, int n, int T, int A,
+                       int double_q, float *q_eval_taken, float *q_next_taken, float *filled_sum, double *scratch,
+                       void *stream);
 int xb_qmix_select_bwd(const float *d_taken, const float *actions, const float *agent_mask, const float *filled,
                        int B, int n, int T, int A, float *dq_all, void *stream);
 int xb_qmix_mix_fwd(const float *q, const float *w1_raw, const float *b1, const float *w2_raw, const float *b2,

@@ -157,12 +157,18 @@ class QMIXModelOracle(nn.Module):
 class QMIXLearnerOracle:
     def __init__(self, model, agent_keys, learning_rate=7e-4, gamma=0.99, sync_frequency=200, double_q=True,
                  use_grad_clip=False, grad_clip_norm=10.0, end_factor_lr_decay=1.0, total_iters=1,
-                 detach_q_eval=True):
-        """``detach_q_eval=True`` reproduces the reference AS IS: iql_learner.py:57-59 slices ``q_eval`` to
+                 detach_q_eval=True, use_actions_mask=False):
+        """``use_actions_mask=True`` is the INTENDED masking of iql_learner.py:60-81 / value_factorization.py:86-89 for
+        use_rnn (the double-Q arg-max sees unavailable actions at -1e10; target values of unavailable actions at step t+1
+        become -1e10) with the time axis sliced as ``[:, :, 1:]``.  The reference at 4f0b05b slices the AGENT axis there
+        (``[:, 1:]``) and raises a shape error, so this variant cannot be pinned to a live run: "parity unpinned" for the
+        masked branch only - it is anchored on the unmasked branch (which is pinned) plus the two masking statements.
+        ``detach_q_eval=True`` reproduces the reference AS IS: iql_learner.py:57-59 slices ``q_eval`` to
         ``[:, :, :-1]`` INSIDE ``torch.no_grad()``, so with use_rnn=True the sliced tensor carries no graph and the
         agent networks receive no gradient - only the mixer trains (verified against the live reference:
         tests/test_oracle_vs_reference.py).  ``False`` is the evidently intended computation (slice outside no_grad)."""
         self.detach_q_eval = detach_q_eval
+        self.use_actions_mask = use_actions_mask
         self.model, self.agent_keys = model, list(agent_keys)
         # LearnerMAS.build_optimizer (marl_learner.py:64-76): ONE Adam over model.parameters() (targets get no grads)
         self.optimizer = torch.optim.Adam(model.parameters(), lr=learning_rate, eps=1e-5, weight_decay=0.0)
@@ -187,9 +193,20 @@ class QMIXLearnerOracle:
         terminals_tot = terminals.all(dim=1).float() if terminals.dtype == torch.bool else (terminals != 0).all(dim=1).float()
         packed = obs.flatten(0, 1)                                 # [B*n, T+1, obs]
         q_all = self.model.individual_q_networks['shared'](packed).reshape(B, n, T + 1, -1)
+        avail = None
+        if self.use_actions_mask:
+            avail = st(sample['avail_actions'], torch.float32)     # [B, n, T+1, A]
         with torch.no_grad():
-            actions_next = q_all.argmax(dim=-1)[:, :, 1:]
+            if avail is not None:                                  # value_factorization.py:86-89
+                q_det = q_all.clone().detach()
+                q_det[avail == 0] = -1e10
+                actions_next = q_det.argmax(dim=-1)[:, :, 1:]
+            else:
+                actions_next = q_all.argmax(dim=-1)[:, :, 1:]
             q_next = self.model.target_individual_q_networks['shared'](packed).reshape(B, n, T + 1, -1)[:, :, 1:]
+            if avail is not None:                                  # iql_learner.py:75-81, time axis
+                q_next = q_next.clone()
+                q_next[avail[:, :, 1:] == 0] = -1e10
         q_eval = q_all[:, :, :-1]
         if self.detach_q_eval:
             q_eval = q_eval.detach()

@@ -6,9 +6,9 @@
 export XB_EXPERIMENTAL_TC=1
 mkdir -p gpurun_out
 echo "== parity tests (forward default-on, backward / 3 planes / planes gather / tc PPO update behind the env var)"
-timeout 400 python -m pytest tests/test_gpu_tc_conv.py -q -x > gpurun_out/k12_tests.log 2>&1; echo "rc=$?"; tail -15 gpurun_out/k12_tests.log
+timeout 400 python -m pytest tests/test_gpu_tc_conv.py -q > gpurun_out/k12_tests.log 2>&1; echo "rc=$?"; tail -15 gpurun_out/k12_tests.log
 echo "== the same tests with the row-coalesced producer mapping (XB_K12_MAP=1: emulator-verified, never run on hardware)"
-XB_K12_MAP=1 timeout 400 python -m pytest tests/test_gpu_tc_conv.py -q -x > gpurun_out/k12_tests_map1.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/k12_tests_map1.log
+XB_K12_MAP=1 timeout 400 python -m pytest tests/test_gpu_tc_conv.py -q > gpurun_out/k12_tests_map1.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/k12_tests_map1.log
 echo "== per-kernel timings: K12 layers at the PPO minibatch (both producer mappings), K3-P, K10, K11"
 for MAPV in 0 1; do
   XB_K12_MAP=$MAPV timeout 400 python tools/kernel_bench.py --only k12,k3p,k10,k11 --reps 10 > gpurun_out/k12_kernels_map$MAPV.json 2> gpurun_out/k12_kernels_map$MAPV.err; echo "map=$MAPV rc=$?"

@@ -280,15 +280,15 @@ def main():
             geom = tc.linear_geometry(B, 6400)
             x_pl = tc.split_bf16(torch.rand((B, 6400), device=DEV, generator=g), P)
             w_pl = tc.pack_conv_weight(torch.randn((512, 64, 10, 10), device=DEV, generator=g) / 80.0, P)
-            out = torch.empty((B, 512), device=DEV)
+            out_fc = torch.empty((B, 512), device=DEV)
             nt = 256 if P == 2 else 128
 
             def run_fc():
                 for c0 in range(0, 512, nt):
-                    tc.gemm_gather(x_pl, w_pl[:, c0:c0 + nt], geom, relu=True, out_f32=out, out_ld=512, out_c0=c0)
+                    tc.gemm_gather(x_pl, w_pl[:, c0:c0 + nt], geom, relu=True, out_f32=out_fc, out_ld=512, out_c0=c0)
             us = timeit(run_fc, R)
             add(entry(f"K12 forward fc 6400->512 (P={P}, {512 // nt} launches)", f"M={B} N=512 K=6400", us,
-                      x_pl.numel() * 2 + w_pl.numel() * 2 + out.numel() * 4, hbm, 2.0 * B * 512 * 6400, tpk))
+                      x_pl.numel() * 2 + w_pl.numel() * 2 + out_fc.numel() * 4, hbm, 2.0 * B * 512 * 6400, tpk))
     print(json.dumps(out))
 
 

@@ -9,13 +9,19 @@
 // (a) selection:  q_eval_taken[b*T+t, i] = Q[b,i,t,a_{b,i,t}] * mask ;  q_next_taken = Q'[b,i,t+1, argmax/max] * mask
 // =====================================================================================================
 // Layouts: q_all, q_tgt [B, n, T+1, A]; actions, agent_mask [B, n, T] (float32); filled [B, T] (float32).
+// avail (nullable): uint8 [B, n, T+1, avail_ld], non-zero = the action is available at that step.  With it, the double-Q
+// arg-max runs over the eval values with unavailable actions at -1e10 and the target values of unavailable actions are
+// -1e10 before the gather / max - iql_learner.py:60-81 with the time axis sliced ([:, :, 1:], the evidently intended
+// indexing; the reference slices the agent axis and crashes for use_rnn).
 // One thread per (b, i, t).  Also accumulates sum(filled) (needed by the masked loss) deterministically.
 __global__ void __launch_bounds__(256) qmix_select_fwd_kernel(const float *__restrict__ q_all,
                                                               const float *__restrict__ q_tgt,
                                                               const float *__restrict__ actions,
                                                               const float *__restrict__ agent_mask,
-                                                              const float *__restrict__ filled, int B, int n, int T,
-                                                              int A, int double_q, float *__restrict__ q_eval_taken,
+                                                              const float *__restrict__ filled,
+                                                              const uint8_t *__restrict__ avail, int avail_ld, int B,
+                                                              int n, int T, int A, int double_q,
+                                                              float *__restrict__ q_eval_taken,
                                                               float *__restrict__ q_next_taken,
                                                               float *__restrict__ filled_sum,
                                                               double *__restrict__ scratch) {
@@ -31,19 +37,23 @@ __global__ void __launch_bounds__(256) qmix_select_fwd_kernel(const float *__res
         const float *qe1 = qe + A;  // step t+1 of the eval network (double-Q argmax)
         const float *qt1 = q_tgt + (((int64_t)b * n + i) * (T + 1) + t + 1) * A;
         const int a = (int)actions[e];
+        const uint8_t *av1 = avail ? avail + (((int64_t)b * n + i) * (T + 1) + t + 1) * avail_ld : nullptr;
+        const float NEG = -1e10f;
         float nxt;
         if (double_q) {
             int best = 0;
-            float bv = qe1[0];
-            for (int k = 1; k < A; ++k)
-                if (qe1[k] > bv) {  // torch.argmax: first maximal index
-                    bv = qe1[k];
+            float bv = (av1 && !av1[0]) ? NEG : qe1[0];
+            for (int k = 1; k < A; ++k) {
+                const float v = (av1 && !av1[k]) ? NEG : qe1[k];
+                if (v > bv) {  // torch.argmax: first maximal index
+                    bv = v;
                     best = k;
                 }
-            nxt = qt1[best];
+            }
+            nxt = (av1 && !av1[best]) ? NEG : qt1[best];
         } else {
-            nxt = qt1[0];
-            for (int k = 1; k < A; ++k) nxt = fmaxf(nxt, qt1[k]);
+            nxt = (av1 && !av1[0]) ? NEG : qt1[0];
+            for (int k = 1; k < A; ++k) nxt = fmaxf(nxt, (av1 && !av1[k]) ? NEG : qt1[k]);
         }
         const int64_t row = (int64_t)b * T + t;
         q_eval_taken[row * n + i] = qe[a] * m;
@@ -71,18 +81,18 @@ __global__ void __launch_bounds__(256) qmix_select_bwd_kernel(const float *__res
 }
 
 extern "C" int xb_qmix_select_fwd(const float *q_all, const float *q_tgt, const float *actions,
-                                  const float *agent_mask, const float *filled, int B, int n, int T, int A,
-                                  int double_q, float *q_eval_taken, float *q_next_taken, float *filled_sum,
-                                  double *scratch, void *stream) {
+                                  const float *agent_mask, const float *filled, const uint8_t *avail, int avail_ld,
+                                  int B, int n, int T, int A, int double_q, float *q_eval_taken, float *q_next_taken,
+                                  float *filled_sum, double *scratch, void *stream) {
     if (!q_all || !q_tgt || !actions || !agent_mask || !filled || !q_eval_taken || !q_next_taken || !filled_sum ||
         !scratch)
         return XB_EINVAL;
-    if (B <= 0 || n <= 0 || T <= 0 || A <= 0) return XB_EINVAL;
+    if (B <= 0 || n <= 0 || T <= 0 || A <= 0 || (avail && avail_ld < A)) return XB_EINVAL;
     int64_t total = (int64_t)B * n * T, want = (total + 255) / 256;
     int grid = (int)(want < XB_MAX_PARTIALS ? want : XB_MAX_PARTIALS);
-    qmix_select_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(q_all, q_tgt, actions, agent_mask, filled, B, n, T, A,
-                                                                   double_q, q_eval_taken, q_next_taken, filled_sum,
-                                                                   scratch);
+    qmix_select_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(q_all, q_tgt, actions, agent_mask, filled, avail,
+                                                                   avail_ld, B, n, T, A, double_q, q_eval_taken,
+                                                                   q_next_taken, filled_sum, scratch);
     return xb_launch_status();
 }
 

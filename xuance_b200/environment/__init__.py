@@ -1,7 +1,8 @@
 """Environment construction (reference: xuance/environment/__init__.py:12-76 ``make_envs``)."""
 from .envs import REGISTRY_ENV, XuanCeEnvWrapper, CartPoleEnv, SyntheticAtariEnv
+from .ma_envs import SyntheticSMACEnv, XuanCeMultiAgentEnvWrapper
 from .vector_envs import (REGISTRY_VEC_ENV, VecEnv, DummyVecEnv, DummyVecEnv_Atari, SubprocVecEnv, SubprocVecEnv_Atari,
-                          ShmSubprocVecEnv, ShmSubprocVecEnv_Atari)
+                          ShmSubprocVecEnv, ShmSubprocVecEnv_Atari, DummyVecMultiAgentEnv)
 from .tensor_env import TensorEnvWrapper
 
 
@@ -13,8 +14,13 @@ def make_envs(config):
     world = int(os.environ.get("WORLD_SIZE", "1")) if getattr(config, "distributed_training", False) else 1
     rank = int(os.environ.get("RANK", "0")) if world > 1 else 0
     n = config.parallels // world
-    env_cls = REGISTRY_ENV[config.env_id]
     base_seed = getattr(config, "env_seed", 1) + rank * n
+    if getattr(config, "env_name", None) == "StarCraft2":       # SMAC-shaped synthetic multi-agent env (QMIX path)
+        kw = {k: getattr(config, k) for k in ("episode_limit", "p_death", "p_mask") if hasattr(config, k)}
+        fns = [lambda env_seed=None, **_: XuanCeMultiAgentEnvWrapper(SyntheticSMACEnv(seed=env_seed, map_name=config.env_id, **kw))
+               for _ in range(n)]
+        return DummyVecMultiAgentEnv(fns, base_seed)
+    env_cls = REGISTRY_ENV[config.env_id]
 
     def thunk(i):
         return lambda: XuanCeEnvWrapper(env_cls(seed=base_seed + i))

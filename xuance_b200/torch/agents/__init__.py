@@ -10,3 +10,5 @@ try:
     REGISTRY_Agents["SAC"] = SAC_Agent
 except ImportError:
     pass
+from .marl import MARLAgents, OffPolicyMARLAgents, QMIX_Agents
+REGISTRY_Agents["QMIX"] = QMIX_Agents

@@ -26,7 +26,6 @@ class PerDQN_Agent(DQN_Agent):
         self.PER_beta0 = config.PER_beta0
         self.PER_beta = config.PER_beta0
         super().__init__(config, envs, observation_space, action_space, callback)
-        self.delta_beta = (1.0 - self.PER_beta0) / max(1, getattr(config, "running_steps", 1) // max(1, self.n_envs))
 
     def _build_memory(self, auxiliary_info_shape=None):
         self.atari = getattr(self.config, "env_name", None) == "Atari"
@@ -45,10 +44,6 @@ class PerDQN_Agent(DQN_Agent):
         train_info["epsilon-greedy"] = self.e_greedy
         return train_info
 
-    def train(self, train_steps):
-        info = {}
-        for _ in range(train_steps):
-            info = super().train(1)
-            if self.PER_beta < 1.0:
-                self.PER_beta = min(1.0, self.PER_beta + self.delta_beta)
-        return info
+    def _after_update(self, train_steps):
+        """perdqn_agent.py:72 - beta moves only when an update happened, by (1 - beta0) / train_steps."""
+        self.PER_beta = min(1.0, self.PER_beta + (1.0 - self.PER_beta0) / max(1, train_steps))

@@ -76,9 +76,14 @@ class OffPolicyAgent(Agent):
         train_info["noise_scale"] = self.noise_scale
         return train_info
 
+    def _after_update(self, train_steps):
+        """Hook run after every train_epochs call inside ``train`` (PER anneals beta here, perdqn_agent.py:72)."""
+
     def train(self, train_steps):
         train_info = {}
-        obs = self.train_envs.buf_obs
+        # a copy: the vector envs write the next observation into buf_obs in place, which would otherwise alias the
+        # first stored transition's obs to its next_obs (the reference has exactly that aliasing on the first step)
+        obs = np.array(self.train_envs.buf_obs, copy=True)
         for _ in range(train_steps):
             self.obs_rms.update(obs)
             obs = self._process_observation(obs)
@@ -94,6 +99,7 @@ class OffPolicyAgent(Agent):
                 update_info = self.train_epochs(n_epochs=self.n_epochs)
                 self.log_infos(update_info, self.current_step)
                 train_info.update(update_info)
+                self._after_update(train_steps)
                 self.callback.on_train_epochs_end(self.current_step, model=self.model, memory=self.memory,
                                                   current_episode=self.current_episode, train_steps=train_steps,
                                                   update_info=update_info)

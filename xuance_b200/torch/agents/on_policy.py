@@ -78,7 +78,6 @@ class OnPolicyAgent(Agent):
         from ..utils import CapturedStep
         key = int(idx.numel())
         if key not in self._graphs:
-            self.memory._ensure_gae()
             self._graphs[key] = CapturedStep(self._sample_and_update, [idx], self.learner.optimizer.snapshot,
                                              self.learner.optimizer.restore)
         self._graphs[key](idx)
@@ -89,7 +88,10 @@ class OnPolicyAgent(Agent):
         use_graph = getattr(self.config, "use_cuda_graph", False) and hasattr(self.learner, "_device_update")
         if not hasattr(self, "_graphs"):
             self._graphs = {}
-        total = n_epochs * (self.buffer_size // self.batch_size)
+        # pending finish_path segments -> one K2 launch, OUTSIDE any captured region: a graph replay never runs the
+        # buffer's host-side dirty check, so the scan must already have happened for every rollout
+        self.memory._ensure_gae()
+        total = n_epochs * -(-self.buffer_size // self.batch_size)     # a ragged last minibatch counts (ceil)
         done = 0
         for _ in range(n_epochs):
             if self.world_size > 1:

@@ -20,14 +20,16 @@ from .learner import Learner
 
 class _SelectFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q_all, q_tgt, actions, agent_mask, filled, double_q, filled_sum, scratch):
+    def forward(ctx, q_all, q_tgt, actions, agent_mask, filled, double_q, filled_sum, scratch, avail=None):
         B, n, T1, A = q_all.shape
         T = T1 - 1
         q_eval = torch.empty((B * T, n), dtype=torch.float32, device=q_all.device)
         q_next = torch.empty((B * T, n), dtype=torch.float32, device=q_all.device)
+        if avail is not None:
+            assert avail.dtype == torch.uint8 and avail.is_contiguous() and tuple(avail.shape[:3]) == (B, n, T1)
         _lib.call("xb_qmix_select_fwd", _lib.ptr(q_all), _lib.ptr(q_tgt), _lib.ptr(actions), _lib.ptr(agent_mask),
-                  _lib.ptr(filled), B, n, T, A, 1 if double_q else 0, _lib.ptr(q_eval), _lib.ptr(q_next),
-                  _lib.ptr(filled_sum), _lib.ptr(scratch))
+                  _lib.ptr(filled), _lib.ptr(avail), avail.shape[3] if avail is not None else 0, B, n, T, A,
+                  1 if double_q else 0, _lib.ptr(q_eval), _lib.ptr(q_next), _lib.ptr(filled_sum), _lib.ptr(scratch))
         ctx.save_for_backward(actions, agent_mask, filled)
         ctx.dims = (B, n, T, A)
         ctx.mark_non_differentiable(q_next)
@@ -40,7 +42,7 @@ class _SelectFunction(torch.autograd.Function):
         dq_all = torch.zeros((B, n, T + 1, A), dtype=torch.float32, device=d_eval.device)
         _lib.call("xb_qmix_select_bwd", _lib.ptr(d_eval.contiguous()), _lib.ptr(actions), _lib.ptr(agent_mask),
                   _lib.ptr(filled), B, n, T, A, _lib.ptr(dq_all))
-        return dq_all, None, None, None, None, None, None, None
+        return dq_all, None, None, None, None, None, None, None, None
 
 
 class QMIX_Learner(Learner):
@@ -53,6 +55,7 @@ class QMIX_Learner(Learner):
         self.sync_frequency = config.sync_frequency
         self.double_q = getattr(config, "double_q", True)
         self.detach_q_eval = getattr(config, "qmix_rnn_detach_q_eval", False)
+        self.use_actions_mask = getattr(config, "use_actions_mask", False)
         # LearnerMAS.build_optimizer (marl_learner.py:64-76): one Adam(eps=1e-5) + LinearLR over the trainable set
         self.optimizer = FusedAdam(self.model.parameters_model, lr=self.learning_rate, eps=1e-5,
                                    weight_decay=getattr(config, "weight_decay", 0.0),
@@ -81,12 +84,16 @@ class QMIX_Learner(Learner):
     def _stacked(self, sample):
         """[B, n, ...] device tensors from a sample dict (uses the buffer's pre-stacked tensors when present)."""
         f32 = lambda x: torch.as_tensor(x, device=self.device).to(torch.float32).contiguous()
+        u8 = lambda x: torch.as_tensor(x, device=self.device).to(torch.uint8).contiguous()
         if '_stacked' in sample:
             st = sample['_stacked']
-            return {k: f32(st[k]) for k in ('obs', 'actions', 'rewards', 'terminals', 'agent_mask', 'filled', 'state')}
+            out = {k: f32(st[k]) for k in ('obs', 'actions', 'rewards', 'terminals', 'agent_mask', 'filled', 'state')}
+            out['avail'] = u8(st['avail_actions']) if self.use_actions_mask else None
+            return out
         stack = lambda d: torch.stack([torch.as_tensor(d[a], device=self.device) for a in self.agent_keys], dim=1)
         out = {k: f32(stack(sample[k])) for k in ('obs', 'actions', 'rewards', 'terminals', 'agent_mask')}
         out['filled'], out['state'] = f32(sample['filled']), f32(sample['state'])
+        out['avail'] = u8(stack(sample['avail_actions'])) if self.use_actions_mask else None
         return out
 
     def _snapshot(self):
@@ -96,7 +103,7 @@ class QMIX_Learner(Learner):
         self.optimizer.restore(st[0])
         self._filled_sum.copy_(st[1])
 
-    def _device_update(self, obs, actions, rewards, terminals, agent_mask, filled, state):
+    def _device_update(self, obs, actions, rewards, terminals, agent_mask, filled, state, avail=None):
         """qmix_learner.py:24-95 on the device (no host synchronisation, static shapes: CUDA-graph capturable)."""
         B, n, T1 = obs.shape[0], obs.shape[1], obs.shape[2]
         T = T1 - 1
@@ -106,7 +113,7 @@ class QMIX_Learner(Learner):
             q_tgt = self.model.q_values(packed, target=True).reshape(B, n, T + 1, -1).contiguous()
         q_in = q_all.detach() if self.detach_q_eval else q_all
         q_eval_taken, q_next_taken = _SelectFunction.apply(q_in, q_tgt, actions, agent_mask, filled, self.double_q,
-                                                           self._filled_sum, self._scratch)
+                                                           self._filled_sum, self._scratch, avail)
         if self.world_size > 1:
             allreduce_sum_(self._filled_sum)                                # global sum(filled) for the loss
         q_tot_eval = self.model.Q_tot(q_eval_taken, state[:, :-1]).reshape(-1).contiguous()
@@ -128,6 +135,8 @@ class QMIX_Learner(Learner):
         d = self._stacked(sample)
         info = self.callback.on_update_start(self.iterations, model=self.model, batch=d) or {}
         args = [d[k] for k in ('obs', 'actions', 'rewards', 'terminals', 'agent_mask', 'filled', 'state')]
+        if d['avail'] is not None:
+            args.append(d['avail'])
         self.optimizer.prepare()
         if self.use_cuda_graph and self.world_size == 1:
             key = tuple(d['obs'].shape)

@@ -184,6 +184,34 @@ class MixingQNetwork(nn.Module):
         net = (self.target_individual_q_networks if target else self.individual_q_networks)[self.group_keys[0]]
         return net(packed_obs)[0]
 
+    # ---- acting (value_factorization.py:54-96 for one time step): rows are (env, agent) pairs, agent-minor
+    def init_rnn_states(self, n_envs):
+        rep = self.individual_q_networks[self.group_keys[0]].representation.obs_representation
+        return {self.group_keys[0]: rep.init_rnn_states(n_envs * self.n_agents)}
+
+    def init_rnn_states_item(self, i_env, rnn_states):
+        h = rnn_states[self.group_keys[0]]
+        h[:, i_env * self.n_agents:(i_env + 1) * self.n_agents] = 0.0
+        return rnn_states
+
+    @torch.no_grad()
+    def forward(self, observations, avail_actions=None, rnn_states=None, **kwargs):
+        """observations [E*n, 1, obs] (or [E*n, obs]); avail_actions [E*n, A] (non-zero = available) or None;
+        rnn_states {group: [layers, E*n, H]}.  Returns (greedy actions [E*n] int64, q [E*n, A], new rnn_states): the
+        arg-max runs over q with unavailable actions at -1e10 (value_factorization.py:86-91)."""
+        g = self.group_keys[0]
+        obs = torch.as_tensor(observations, dtype=torch.float32, device=self.device)
+        if obs.dim() == 2:
+            obs = obs.unsqueeze(1)
+        h0 = None if rnn_states is None else rnn_states[g]
+        q, rep = self.individual_q_networks[g](obs, rnn_hidden=h0)
+        q = q[:, -1]
+        q_sel = q
+        if avail_actions is not None:
+            av = torch.as_tensor(avail_actions, device=self.device)
+            q_sel = q.masked_fill(av == 0, -1e10)
+        return q_sel.argmax(dim=-1), q, {g: rep.rnn_states}
+
     def Q_tot(self, q_taken, states):
         return self.eval_Qtot(q_taken, states)
 
