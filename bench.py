@@ -290,7 +290,7 @@ def run_own_arm(args):
     prof = _lib.profile["xb_gather_obs"]
     _lib.profile = None
     k3_how = "CUDA events around every K3 launch inside the timed region"
-    if (cfg.use_cuda_graph or not prof) and agent._obs_format() not in (_lib.OBS_PLANES2, _lib.OBS_PLANES3):
+    if (cfg.use_cuda_graph or not prof) and agent._obs_format() not in (_lib.OBS_PLANES2, _lib.OBS_PLANES3, _lib.OBS_PLANE_RAW):
         # graph replays hide per-kernel events: time the same 16 minibatch gathers of one epoch right after the region
         prof = []
         perm_d = torch.from_numpy(np.random.permutation(agent.buffer_size)).to(device)

@@ -226,47 +226,50 @@ int xb_categorical_act(const float *logits, const float *uniforms, const float *
 int xb_rms_update_normalize(const float *x, int N, int64_t D, float *mean, float *var, double count, int update,
                             float *out, float clip_range, float eps, void *stream);
 
-/* ---------------------------------------------------------------- K12 (EXPERIMENTAL): tensor-core layers ------
- * Not on any default path.  Host-verified (tests/test_conv_index.py); on B200 the forward GEMM passes its parity tests
- * (tests/test_gpu_tc_conv.py), the two gradient modes have run but are not yet parity-pinned.  Target: the NatureCNN layers of AC_CNN_Atari / Basic_CNN (rl_models/representations/cnn.py:
- * 45-50, 84-101; layers.py:16-65) that cuDNN runs as CUDA-core fp32 convolutions.
+/* ---------------------------------------------------------------- K12: tensor-core layers (tcgen05 / TMEM) ------
+ * The pixel encoders' convolutions and hidden layer (NatureCNN of AC_CNN_Atari / Basic_CNN: rl_models/representations/cnn.py:
+ * 45-50, 84-101; layers.py:16-65), forward, data gradient and weight gradient, that cuDNN runs as CUDA-core fp32 kernels
+ * (85 % of the fp32 PPO update).  Every float32 operand travels as 1-3 bfloat16 "planes" (x = sum of its planes; plane q =
+ * bf16 of the residual left by the planes before it: 1 plane is exact for integers <= 256 such as raw uint8 pixels, 2
+ * planes are exact to 2^-16, 3 planes to 2^-24); products are accumulated in float32 in TMEM, one accumulator per order of
+ * magnitude (plane-index sum), added smallest first in the epilogue.  planes_a <= planes_b; kept products: index sum <
+ * planes_b.
  * xb_split_bf16       : x (float32[n]) -> planes[0] = bf16(x), planes[1] = bf16(x - planes[0]), [planes[2] = ...]
- * xb_pack_conv_weight : torch [N, C, KH, KW] float32 -> bf16 planes of [N, (kh, kw, c)] (also Linear over a [C,H,W] flatten)
+ * xb_pack_conv_weight : torch [N, C, KH, KW] float32 (* scale) -> bf16 planes of [N, (kh, kw, c)] (also a Linear over a
+ *                       [C,H,W] flatten).  scale = 1/255 folds `observations / 255.0` (cnn.py:98) into the first layer,
+ *                       whose A operand is then the raw uint8 pixel as ONE exact bf16 plane.
  * xb_gemm_gather_tc   : D[m,n] = sum_{t,c} in[b, y*sy+dy[t], x*sx+dx[t], c] * W[n, t*C+c] (+bias, ReLU), m = (b,y,x) over
- *                       [B,OY,OX]; in / W as hi / lo bf16 pairs (NHWC, [N,K]); three tcgen05.mma per product (hi.hi +
- *                       hi.lo + lo.hi, fp32 accumulation in TMEM); result as float32 and / or a hi / lo pair written to
- *                       columns [out_c0, out_c0+N) of row (b*out_H + y*oys+oy0)*out_W + x*oxs+ox0 of a matrix with
- *                       out_ld elements per row (out_ld % 8 == out_c0 % 8 == 0).  C % 8 == 0, (T*C) % 64 == 0,
- *                       N % 32 == 0, N <= 256, T <= 64; dy / dx are HOST arrays (copied into the launch parameters).
- *                       relu_mask (nullable, bf16, addressed like the output): result zeroed where mask <= 0 - the ReLU
- *                       derivative applied to a data gradient, mask = hi plane of the saved activation.
- *                       Forward conv: dy = kh - pad, (sy,sx) = stride; Linear: one tap;
+ *                       [B,OY,OX], n < N; in / W as bf16 planes (NHWC, [N,K]); a work item is (128 sites, n_tile columns),
+ *                       planes_b * n_tile <= 256, n_tile % 32 == 0, N % n_tile == 0; result as float32 and / or
+ *                       planes_out bf16 planes written to columns [out_c0, out_c0+N) of row
+ *                       (b*out_H + y*oys+oy0)*out_W + x*oxs+ox0 of a matrix with out_ld elements per row
+ *                       (out_ld % 8 == out_c0 % 8 == 0).  C % 8 == 0, (T*C) % 64 == 0, T <= 64; dy / dx are HOST arrays
+ *                       (copied into the launch parameters).  relu_mask (nullable, bf16, addressed like the output):
+ *                       result zeroed where mask <= 0 - the ReLU derivative applied to a data gradient, mask = plane 0 of
+ *                       the saved activation.  Forward conv: dy = kh - pad, (sy,sx) = stride; Linear: one tap;
  *                       data gradients: flipped taps over the output gradient, one call per stride phase.
  * xb_wgrad_gather_tc  : weight gradient of the same gathered GEMM: partials[s, (t,c), n] = sum over the sites of split s of
- *                       in[b, y*sy+dy[t], x*sx+dx[t], c] * G[site, n]; G = output gradient [B*OY*OX, N] as a hi / lo pair.
- *                       Both operands are fed MN-major (16-byte units transposed into the core matrices); one CTA work
- *                       item = (128 columns of (t,c), split).  partials: float32 [splits, T*C, N].
- * xb_wgrad_reduce     : dw[N, C, KH, KW] (torch layout) (+)= sum_s partials[s, (kh,kw,c), n], splits added in order. */
+ *                       in[b, y*sy+dy[t], x*sx+dx[t], c] * G[site*g_ld + n]; G = output gradient planes.  Both operands
+ *                       are fed MN-major (16-byte units transposed into the core matrices); one work item =
+ *                       (128 columns of (t,c), n_tile columns, split).  partials: float32 [splits, T*C, N].
+ * xb_wgrad_reduce     : dw[N, C, KH, KW] (torch layout) (+)= scale * sum_s partials[s, (kh,kw,c), n], splits added in order. */
 int xb_split_bf16(const float *x, int64_t n, int planes, void *out /* bf16 [planes, n] */, void *stream);
 /* K3 variant that feeds K12: gathers uint8 rows (sample_batch, memory_tools.py:64-84; idx NULL = rows 0..B-1) and writes
- * dst[q, b, :] = plane q of float32(x)/255.0f for q < planes (bf16 [planes, B, row_bytes]); row_bytes % 16 == 0. */
+ * dst[q, b, :] = plane q of float32(x)/255.0f for q < planes (bf16 [planes, B, row_bytes], planes 2 or 3), or with
+ * planes == 1 the raw pixel value as one exact bf16 plane (the 1/255 lives in the packed weights); row_bytes % 16 == 0. */
 int xb_gather_obs_planes(const uint8_t *src, const int64_t *idx, int64_t B, int64_t row_bytes, int planes, void *dst,
                          void *stream);
-int xb_pack_conv_weight(const float *w, int N, int C, int KH, int KW, int planes, void *out /* bf16 [planes, N, KH*KW*C] */,
-                        void *stream);
-/* Operands are `planes` (2 or 3) bf16 planes, plane q at base + q*plane_stride (elements): x = sum of its planes; plane 0 =
- * bf16(x), each further plane the bf16 of the remaining residual.  2 planes: 3 products per MMA step, operands exact to
- * 2^-16; 3 planes: 6 products, exact to 2^-24 (float32-grade; N <= 128).  out_planes (nullable) receives the result split
- * the same way; relu_mask = plane 0 of a saved activation. */
-int xb_gemm_gather_tc(int planes, const void *in, int64_t in_plane, const void *w, int64_t w_plane, const float *bias,
-                      const void *relu_mask, int B, int IH, int IW, int C, int OY, int OX, int sy, int sx, int T,
-                      const int8_t *dy, const int8_t *dx, int N, int relu, void *out_planes, int64_t out_plane,
-                      float *out_f32, int out_H, int out_W, int oys, int oxs, int oy0, int ox0, int64_t out_ld, int out_c0,
-                      void *stream);
-int xb_wgrad_gather_tc(int planes, const void *in, int64_t in_plane, const void *g, int64_t g_plane, int B, int IH, int IW,
-                       int C, int OY, int OX, int sy, int sx, int T, const int8_t *dy, const int8_t *dx, int N, int splits,
-                       float *partials, void *stream);
-int xb_wgrad_reduce(const float *partials, int splits, int N, int C, int KH, int KW, float *dw, int accumulate,
+int xb_pack_conv_weight(const float *w, int N, int C, int KH, int KW, int planes, float scale,
+                        void *out /* bf16 [planes, N, KH*KW*C] */, void *stream);
+int xb_gemm_gather_tc(int planes_a, int planes_b, const void *in, int64_t in_plane, const void *w, int64_t w_plane,
+                      const float *bias, const void *relu_mask, int B, int IH, int IW, int C, int OY, int OX, int sy, int sx,
+                      int T, const int8_t *dy, const int8_t *dx, int N, int n_tile, int relu, void *out_planes,
+                      int64_t out_plane, int planes_out, float *out_f32, int out_H, int out_W, int oys, int oxs, int oy0,
+                      int ox0, int64_t out_ld, int out_c0, void *stream);
+int xb_wgrad_gather_tc(int planes_a, int planes_b, const void *in, int64_t in_plane, const void *g, int64_t g_plane,
+                       int64_t g_ld, int B, int IH, int IW, int C, int OY, int OX, int sy, int sx, int T, const int8_t *dy,
+                       const int8_t *dx, int N, int n_tile, int splits, float *partials, void *stream);
+int xb_wgrad_reduce(const float *partials, int splits, int N, int C, int KH, int KW, float scale, float *dw, int accumulate,
                     void *stream);
 
 #ifdef __cplusplus

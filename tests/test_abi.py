@@ -102,26 +102,32 @@ def test_every_entry_point_validates_before_touching_the_device():
     assert lib.xb_categorical_act(None, junk, None, 8, 4, junk, None, junk, None, None) == EINVAL
     assert lib.xb_rms_update_normalize(junk, 0, 4, junk, junk, 1e-4, 1, junk, 5.0, 1e-8, None) == EINVAL
     assert lib.xb_rms_update_normalize(junk, 8, 4, junk, junk, 1e-4, 0, None, 5.0, 1e-8, None) == EINVAL  # nothing to do
-    # K12 (experimental tensor-core layers) and its operand preparation
+    # K12 (tensor-core layers) and its operand preparation
     taps = (ctypes.c_int8 * 64)()
-    gg = lambda planes=2, C=32, T=16, N=64, ld=64, c0=0, w=junk: lib.xb_gemm_gather_tc(
-        planes, junk, 1024, w, 1024, None, None, 2, 21, 21, C, 10, 10, 2, 2, T, taps, taps, N, 1, junk, 1024, None, 10, 10,
-        1, 1, 0, 0, ld, c0, None)
-    assert gg(planes=4) == EINVAL                      # 2 or 3 planes
+    gg = lambda pa=2, pb=2, C=32, T=16, N=64, nt=64, ld=64, c0=0, w=junk, po=2: lib.xb_gemm_gather_tc(
+        pa, pb, junk, 1024, w, 1024, None, None, 2, 21, 21, C, 10, 10, 2, 2, T, taps, taps, N, nt, 1, junk, 1024, po, None, 10,
+        10, 1, 1, 0, 0, ld, c0, None)
+    assert gg(pb=4) == EINVAL                          # at most 3 planes
+    assert gg(pa=3, pb=2) == EINVAL                    # planes_a <= planes_b
+    assert gg(po=4) == EINVAL                          # output planes
     assert gg(C=12) == ERANGE                          # channels per tap: multiple of 8 (one 16-byte unit)
     assert gg(T=65) == ERANGE                          # tap table
-    assert gg(N=48) == ERANGE                          # N % 32
-    assert gg(planes=3, N=256) == ERANGE               # three planes: N <= 128 (two pipeline stages must fit)
+    assert gg(N=48, nt=48) == ERANGE                   # column tile % 32
+    assert gg(N=96, nt=64, ld=96) == ERANGE            # N % n_tile
+    assert gg(pa=3, pb=3, N=128, nt=128, ld=128) == ERANGE   # planes_b * n_tile <= 256 (one MMA spans the adjacent planes)
     assert gg(C=8, T=3) == ERANGE                      # K = T*C must be a multiple of the 64-deep stage
     assert gg(ld=32) == EINVAL                         # output row shorter than out_c0 + N
     assert gg(ld=68, c0=4) == EALIGN                   # 16-byte output segments
     assert gg(w=odd) == EALIGN
-    assert lib.xb_wgrad_gather_tc(2, junk, 1024, junk, 1024, 1, 10, 10, 64, 10, 10, 1, 1, 9, taps, taps, 64, 5, junk, None) == EINVAL   # 100 sites cannot feed 5 splits
-    assert lib.xb_wgrad_gather_tc(2, junk, 1024, junk, 1024, 1, 10, 10, 64, 10, 10, 1, 1, 9, taps, taps, 64, 1, None, None) == EINVAL
-    assert lib.xb_wgrad_reduce(junk, 0, 64, 64, 3, 3, junk, 0, None) == EINVAL
+    wg = lambda splits=1, out=junk, g_ld=64: lib.xb_wgrad_gather_tc(2, 2, junk, 1024, junk, 1024, g_ld, 1, 10, 10, 64, 10, 10, 1,
+                                                                  1, 9, taps, taps, 64, 64, splits, out, None)
+    assert wg(splits=5) == EINVAL                      # 100 sites cannot feed 5 splits
+    assert wg(out=None) == EINVAL
+    assert wg(g_ld=32) == EINVAL                       # gradient rows shorter than N
+    assert lib.xb_wgrad_reduce(junk, 0, 64, 64, 3, 3, 1.0, junk, 0, None) == EINVAL
     assert lib.xb_split_bf16(junk, 64, 4, junk, None) == EINVAL
     assert lib.xb_split_bf16(odd, 64, 2, junk, None) == EALIGN
-    assert lib.xb_pack_conv_weight(junk, 32, 4, 8, 8, 1, junk, None) == EINVAL
+    assert lib.xb_pack_conv_weight(junk, 32, 4, 8, 8, 0, 1.0, junk, None) == EINVAL
     assert lib.xb_gather_obs_planes(junk, None, 4, 100, 2, junk, None) == EALIGN                        # row_bytes % 16
     assert lib.xb_gather_obs_planes(junk, None, 4, 28224, 5, junk, None) == EINVAL
     assert lib.xb_gather_obs_planes(junk, None, 0, 28224, 2, junk, None) == 0                           # empty batch

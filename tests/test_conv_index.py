@@ -28,12 +28,12 @@ def emul():
         subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-std=c++17", "-o", so, src], check=True)
     lib = ctypes.CDLL(so)
     P, i, l = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
-    lib.emul_gemm_gather.argtypes = [i, P, l, P, l] + [i] * 9 + [P, P] + [i] * 7 + [l, i, i, i, P]
+    lib.emul_gemm_gather.argtypes = [i, i, P, l, P, l] + [i] * 9 + [P, P] + [i] * 8 + [l, i, i, i, P]
     lib.emul_gemm_gather.restype = i
     lib.emul_pack_weight.argtypes = [P, i, i, i, i, P]
-    lib.emul_wgrad.argtypes = [i, P, l, P, l] + [i] * 9 + [P, P] + [i] * 4 + [P]
+    lib.emul_wgrad.argtypes = [i, i, P, l, P, l, l] + [i] * 9 + [P, P] + [i] * 5 + [P]
     lib.emul_wgrad.restype = i
-    lib.emul_wgrad_reduce.argtypes = [P, i, i, i, i, i, P]
+    lib.emul_wgrad_reduce.argtypes = [P, i, i, i, i, i, ctypes.c_double, P]
     return lib
 
 
@@ -53,16 +53,18 @@ def mapping(request):
     MAP[0] = 0
 
 
-def _run(lib, geom, x_nhwc, w_mat, out, out_ld, out_c0=0, stages=2, planes=2):
-    """x_nhwc: float64 tensor viewed as the geometry's [B, IH, IW, C]; w_mat float64 [N, K]; out float64 [rows, out_ld]."""
-    xp, wp = _split(x_nhwc, planes), _split(w_mat, planes)
+def _run(lib, geom, x_nhwc, w_mat, out, out_ld, out_c0=0, stages=2, planes=2, planes_a=None):
+    """x_nhwc: float64 tensor viewed as the geometry's [B, IH, IW, C]; w_mat float64 [N, K]; out float64 [rows, out_ld].
+    ``planes_a``: planes of the A operand (default ``planes``; 1 = values that one bf16 holds exactly)."""
+    pa = planes if planes_a is None else planes_a
+    xp, wp = _split(x_nhwc, pa), _split(w_mat, planes)
     N, K = w_mat.shape
     assert K == geom.K and xp[0].numel() == geom.B * geom.IH * geom.IW * geom.C
     dy, dx = np.asarray(geom.dy, np.int8), np.asarray(geom.dx, np.int8)
-    rc = lib.emul_gemm_gather(planes, xp.data_ptr(), xp.stride(0), wp.data_ptr(), wp.stride(0), geom.B, geom.IH, geom.IW,
+    rc = lib.emul_gemm_gather(pa, planes, xp.data_ptr(), xp.stride(0), wp.data_ptr(), wp.stride(0), geom.B, geom.IH, geom.IW,
                               geom.C, geom.OY, geom.OX, geom.sy, geom.sx, geom.T, dy.ctypes.data, dx.ctypes.data, N,
-                              geom.out_H, geom.out_W, geom.oys, geom.oxs, geom.oy0, geom.ox0, out_ld, out_c0, stages,
-                              MAP[0], out.data_ptr())
+                              tc.n_tile_for(N, planes), geom.out_H, geom.out_W, geom.oys, geom.oxs, geom.oy0, geom.ox0, out_ld,
+                              out_c0, stages, MAP[0], out.data_ptr())
     assert rc == 0
 
 
@@ -98,8 +100,9 @@ def test_forward_conv_layers(emul, mapping, name, B, H, W, C, N, k, s, planes):
 
 
 def test_linear_layer_with_column_split_and_row_tail(emul, mapping):
-    """Linear(6400 -> 512) over the NHWC-flattened conv3 output: N = 512 runs as two 256-column calls; 130 rows leave a
-    2-row tail tile.  The reference flattens NCHW (cnn.py:92), so the packed weight permutes its columns to (h, w, c)."""
+    """Linear(6400 -> 512) over the NHWC-flattened conv3 output: N = 512 runs as column tiles of 128 (two planes) inside one
+    call and as two 256-column calls; 130 rows leave a 2-row tail tile.  The reference flattens NCHW (cnn.py:92), so the
+    packed weight permutes its columns to (h, w, c)."""
     torch.manual_seed(0)
     Bn, Cc, Hh, Ww, N = 130, 64, 10, 10, 512
     feat = torch.rand(Bn, Cc, Hh, Ww, dtype=torch.float64)
@@ -112,10 +115,27 @@ def test_linear_layer_with_column_split_and_row_tail(emul, mapping):
         _run(emul, g, x_nhwc, packed[c0:c0 + 256].contiguous(), out, N, out_c0=c0, stages=2)
     want = feat.reshape(Bn, -1) @ w.t()
     np.testing.assert_allclose(out.numpy(), want.numpy(), **TOL)
+    out.fill_(float("nan"))
+    _run(emul, g, x_nhwc, packed, out, N, stages=3, planes=3)                     # 8 column tiles of 64, three planes
+    np.testing.assert_allclose(out.numpy(), want.numpy(), rtol=0, atol=2e-6)
+
+
+def test_raw_uint8_plane_first_layer(emul, mapping):
+    """conv1 on ONE exact plane of raw uint8 pixel values against three weight planes carrying the 1/255."""
+    torch.manual_seed(5)
+    B, H, W, C, N, k, s = 2, 84, 84, 4, 32, 8, 4
+    obs = torch.randint(0, 256, (B, H, W, C), dtype=torch.uint8)
+    w = torch.randn(N, C, k, k, dtype=torch.float64) / np.sqrt(C * k * k)
+    g = tc.conv_forward_geometry(B, H, W, C, k, k, s, 2)
+    out = torch.full((g.M, N), float("nan"), dtype=torch.float64)
+    w_scaled = (w.float() * np.float32(1.0 / 255.0)).double()
+    _run(emul, g, obs.double(), _pack(emul, w_scaled), out, N, planes=3, planes_a=1)
+    want = F.conv2d((obs.double() / 255.0).permute(0, 3, 1, 2), w, stride=s, padding=2).permute(0, 2, 3, 1).reshape(g.M, N)
+    np.testing.assert_allclose(out.numpy(), want.numpy(), rtol=0, atol=6e-7)
 
 
 @pytest.mark.parametrize("name,B,H,W,C,N,k,s", [("conv3", 2, 10, 10, 64, 64, 3, 1), ("conv2", 2, 21, 21, 32, 64, 4, 2),
-                                                ("s4", 1, 20, 20, 8, 32, 8, 4)])
+                                                ("s4", 1, 20, 20, 32, 32, 8, 4)])
 def test_data_gradient_phases(emul, mapping, name, B, H, W, C, N, k, s):
     """grad_input of a convolution as one gathered GEMM per stride phase over the output gradient, vs autograd."""
     torch.manual_seed(1)
@@ -152,27 +172,29 @@ def test_weight_gradient(emul, mapping, name, B, H, W, C, N, k, s, splits):
     gp = _split(gy.permute(0, 2, 3, 1).reshape(g.M, N).contiguous(), planes)
     partials = torch.full((splits, g.K, N), float("nan"), dtype=torch.float64)
     dy, dx = np.asarray(g.dy, np.int8), np.asarray(g.dx, np.int8)
-    rc = emul.emul_wgrad(planes, xp.data_ptr(), xp.stride(0), gp.data_ptr(), gp.stride(0), g.B, g.IH, g.IW, g.C, g.OY, g.OX,
-                         g.sy, g.sx, g.T, dy.ctypes.data, dx.ctypes.data, N, splits, 2, MAP[0], partials.data_ptr())
+    rc = emul.emul_wgrad(planes, planes, xp.data_ptr(), xp.stride(0), gp.data_ptr(), gp.stride(0), N, g.B, g.IH, g.IW, g.C, g.OY,
+                         g.OX, g.sy, g.sx, g.T, dy.ctypes.data, dx.ctypes.data, N, tc.n_tile_for(N, planes), splits, 2, MAP[0],
+                         partials.data_ptr())
     assert rc == 0 and not torch.isnan(partials).any()
     dw = torch.full((N, C, k, k), float("nan"), dtype=torch.float64)
-    emul.emul_wgrad_reduce(partials.data_ptr(), splits, N, C, k, k, dw.data_ptr())
+    emul.emul_wgrad_reduce(partials.data_ptr(), splits, N, C, k, k, 1.0, dw.data_ptr())
     np.testing.assert_allclose(dw.numpy(), want.numpy(), **TOL)
 
 
 def test_linear_weight_gradient(emul, mapping):
-    """dW of Linear(6400 -> 256 columns of the 512) : sites = batch rows, one tap, 50 column tiles."""
+    """dW of Linear(6400 -> 128): sites = batch rows, one tap, 50 row tiles x 2 column tiles of 64 of a gradient matrix whose
+    rows are 128 elements apart."""
     torch.manual_seed(3)
-    Bn, K, N = 70, 6400, 64
+    Bn, K, N = 70, 6400, 128
     x = torch.rand(Bn, K, dtype=torch.float64)
     gy = torch.randn(Bn, N, dtype=torch.float64) / 8
     g = tc.linear_geometry(Bn, K)
     xp, gp = _split(x), _split(gy)
     partials = torch.full((2, K, N), float("nan"), dtype=torch.float64)
     dy, dx = np.zeros(1, np.int8), np.zeros(1, np.int8)
-    rc = emul.emul_wgrad(2, xp.data_ptr(), xp.stride(0), gp.data_ptr(), gp.stride(0), g.B, 1, 1, K, 1, 1, 1, 1, 1,
-                         dy.ctypes.data, dx.ctypes.data, N, 2, 2, MAP[0], partials.data_ptr())
-    assert rc == 0
+    rc = emul.emul_wgrad(2, 2, xp.data_ptr(), xp.stride(0), gp.data_ptr(), gp.stride(0), N, g.B, 1, 1, K, 1, 1, 1, 1, 1,
+                         dy.ctypes.data, dx.ctypes.data, N, 64, 2, 2, MAP[0], partials.data_ptr())
+    assert rc == 0 and not torch.isnan(partials).any()
     np.testing.assert_allclose(partials.sum(0).t().numpy(), (gy.t() @ x).numpy(), **TOL)
 
 
@@ -192,14 +214,13 @@ class EmulBackend:
 
     def __init__(self, lib, planes=2):
         self.lib, self.planes = lib, planes
-        self.n_tile = 256 if planes == 2 else 128
 
     def split(self, x):
         return _split(x, self.planes)
 
-    def pack_weight(self, w4d):
+    def pack_weight(self, w4d, scale=1.0):
         N = w4d.shape[0]
-        return _split(w4d.permute(0, 2, 3, 1).reshape(N, -1), self.planes)
+        return _split(w4d.float().permute(0, 2, 3, 1).reshape(N, -1) * np.float32(scale), self.planes)
 
     def empty_planes(self, shape, like):
         return torch.full((self.planes,) + tuple(shape), float("nan"))
@@ -215,15 +236,16 @@ class EmulBackend:
 
     def gemm(self, x_pl, w_pl, geom, bias=None, relu=False, out_f32=None, out_pl=None, out_ld=None, out_c0=0, mask=None):
         P, N = w_pl.shape[0], w_pl.shape[1]
+        PA = x_pl.shape[0]
         out_ld = N if out_ld is None else out_ld
         rows = geom.B * geom.out_H * geom.out_W
         tmp = torch.full((rows, out_ld), float("nan"), dtype=torch.float64)
         x_pl, w_pl = x_pl.contiguous(), w_pl.contiguous()
         dy, dx = np.asarray(geom.dy, np.int8), np.asarray(geom.dx, np.int8)
-        rc = self.lib.emul_gemm_gather(P, x_pl.data_ptr(), x_pl.stride(0), w_pl.data_ptr(), w_pl.stride(0), geom.B, geom.IH,
-                                       geom.IW, geom.C, geom.OY, geom.OX, geom.sy, geom.sx, geom.T, dy.ctypes.data,
-                                       dx.ctypes.data, N, geom.out_H, geom.out_W, geom.oys, geom.oxs, geom.oy0, geom.ox0,
-                                       out_ld, out_c0, 2, MAP[0], tmp.data_ptr())
+        rc = self.lib.emul_gemm_gather(PA, P, x_pl.data_ptr(), x_pl.stride(0), w_pl.data_ptr(), w_pl.stride(0), geom.B,
+                                       geom.IH, geom.IW, geom.C, geom.OY, geom.OX, geom.sy, geom.sx, geom.T, dy.ctypes.data,
+                                       dx.ctypes.data, N, tc.n_tile_for(N, P), geom.out_H, geom.out_W, geom.oys, geom.oxs,
+                                       geom.oy0, geom.ox0, out_ld, out_c0, 2, MAP[0], tmp.data_ptr())
         assert rc == 0
         blk = tmp[:, out_c0:out_c0 + N]
         written = ~torch.isnan(blk[:, 0])
@@ -239,20 +261,21 @@ class EmulBackend:
         if out_f32 is not None:
             out_f32.view(rows, out_ld)[written, out_c0:out_c0 + N] = v
         if out_pl is not None:
-            out_pl.view(P, rows, out_ld)[:, written, out_c0:out_c0 + N] = _split(v, P)
+            Po = out_pl.shape[0]
+            out_pl.view(Po, rows, out_ld)[:, written, out_c0:out_c0 + N] = _split(v, Po)
 
-    def wgrad(self, x_pl, g_pl, geom, N, C, KH, KW):
-        P = g_pl.shape[0]
+    def wgrad(self, x_pl, g_pl, geom, N, C, KH, KW, scale=1.0):
+        P, PA = g_pl.shape[0], x_pl.shape[0]
         splits = 2 if geom.M > 128 else 1
         partials = torch.full((splits, geom.K, N), float("nan"), dtype=torch.float64)
         dy, dx = np.asarray(geom.dy, np.int8), np.asarray(geom.dx, np.int8)
         x_pl, g_pl = x_pl.contiguous(), g_pl.contiguous()
-        rc = self.lib.emul_wgrad(P, x_pl.data_ptr(), x_pl.stride(0), g_pl.data_ptr(), g_pl.stride(0), geom.B, geom.IH,
-                                 geom.IW, geom.C, geom.OY, geom.OX, geom.sy, geom.sx, geom.T, dy.ctypes.data, dx.ctypes.data,
-                                 N, splits, 2, MAP[0], partials.data_ptr())
-        assert rc == 0
+        rc = self.lib.emul_wgrad(PA, P, x_pl.data_ptr(), x_pl.stride(0), g_pl.data_ptr(), g_pl.stride(0), g_pl.stride(1), geom.B,
+                                 geom.IH, geom.IW, geom.C, geom.OY, geom.OX, geom.sy, geom.sx, geom.T, dy.ctypes.data,
+                                 dx.ctypes.data, N, tc.n_tile_for(N, P), splits, 2, MAP[0], partials.data_ptr())
+        assert rc == 0 and not torch.isnan(partials).any()
         dw = torch.full((N, C, KH, KW), float("nan"), dtype=torch.float64)
-        self.lib.emul_wgrad_reduce(partials.data_ptr(), splits, N, C, KH, KW, dw.data_ptr())
+        self.lib.emul_wgrad_reduce(partials.data_ptr(), splits, N, C, KH, KW, float(np.float32(scale)), dw.data_ptr())
         return dw.float()
 
 
@@ -285,7 +308,9 @@ def test_nature_cnn_forward_backward_orchestration(emul, mapping, planes):
     (z_ref * R.double()).sum().backward()
     # K12 path on the emulator
     enc = tc.TensorCoreNatureCNN(convs, fc, (84, 84, 4), backend=EmulBackend(emul, planes))
-    z = tc.tc_encode(enc, _split(x, planes), B)
+    # three planes: the raw uint8 pixels as ONE exact plane (1/255 in the first layer's weights); two planes: x/255 split
+    x_in = _split(obs.float(), 1) if planes == 3 else _split(x, planes)
+    z = tc.tc_encode(enc, x_in, B)
     np.testing.assert_allclose(z.detach().numpy(), z_ref.detach().numpy(), rtol=1e-4, atol=1e-4)
     (z * R).sum().backward()
     for (m, r), name in zip(zip(convs + [fc], ref), ("conv1", "conv2", "conv3", "fc")):

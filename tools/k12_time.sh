@@ -1,8 +1,10 @@
 #!/bin/bash
-# per-layer timings of the K12 kernels (both producer mappings) + the headline bench through the tc encoder
+# K12: parity tests, per-layer timings (both producer mappings), the headline bench through the tc encoder
 mkdir -p gpurun_out
-for MAPV in 0 1; do
-  XB_K12_MAP=$MAPV timeout 300 python tools/kernel_bench.py --only k12 --reps 5 > gpurun_out/k12_kernels_map$MAPV.json 2> gpurun_out/k12_kernels_map$MAPV.err; echo "map=$MAPV rc=$?"
+echo "== parity tests"
+timeout 600 python -m pytest tests/test_gpu_tc_conv.py -q > gpurun_out/k12_tests.log 2>&1; echo "rc=$?"; grep -E "passed|failed|FAILED" gpurun_out/k12_tests.log | tail -30
+for MAPV in 1 0; do
+  XB_K12_MAP=$MAPV timeout 300 python tools/kernel_bench.py --only k12,k3p --reps 5 > gpurun_out/k12_kernels_map$MAPV.json 2> gpurun_out/k12_kernels_map$MAPV.err; echo "map=$MAPV rc=$?"
   python - "$MAPV" <<'PY'
 import json, sys
 try:
@@ -13,7 +15,7 @@ except Exception as e:
     print("no kernel json:", e)
 PY
 done
-for cfgs in "1 3" "1 2" "0 2"; do
+for cfgs in "1 3" "1 2"; do
   set -- $cfgs
   XB_K12_MAP=$1 timeout 300 python bench.py --compute tc --tc-planes $2 --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 0 > gpurun_out/bench_tc_map$1_p$2.json 2> gpurun_out/bench_tc_map$1_p$2.err
   echo "map=$1 planes=$2 rc=$?"; python -c "
@@ -23,5 +25,3 @@ try:
 except Exception as e: print('no json', e)"
   tail -3 gpurun_out/bench_tc_map$1_p$2.err
 done
-echo "== qmix agent tests"
-timeout 600 python -m pytest tests/test_gpu_qmix_agent.py tests/test_gpu_qmix.py -q -x > gpurun_out/qmix_agent_tests.log 2>&1; echo "rc=$?"; tail -15 gpurun_out/qmix_agent_tests.log

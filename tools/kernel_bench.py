@@ -237,33 +237,38 @@ def main():
         Nn, T, rb, B = 256, 128, 28224, 8192
         buf = torch.randint(0, 256, (Nn * T, rb), dtype=torch.uint8, device=DEV, generator=g)
         idx = torch.randperm(Nn * T, device=DEV, generator=g)[:B].contiguous()
-        for P in (2, 3):
-            out = torch.empty((P, B, rb), dtype=torch.bfloat16, device=DEV)
-            us = timeit(lambda: L.call("xb_gather_obs_planes", L.ptr(buf), L.ptr(idx), B, rb, P, L.ptr(out)), R)
+        for P in (1, 2, 3):
+            dst = torch.empty((P, B, rb), dtype=torch.bfloat16, device=DEV)
+            us = timeit(lambda: L.call("xb_gather_obs_planes", L.ptr(buf), L.ptr(idx), B, rb, P, L.ptr(dst)), R)
             add(entry(f"K3-P xb_gather_obs_planes (P={P})", f"{B} rows x {rb} B", us, B * rb * (1 + 2 * P) + 8 * B, hbm))
 
     if want("k12"):
-        # EXPERIMENTAL tensor-core layers at the PPO minibatch (8192 samples): forward, data gradient, weight gradient.
-        # flops = fp32-equivalent 2*M*N*K of the layer (the tensor pipe executes 3x / 6x that in bf16 MMAs)
+        # tensor-core layers at the PPO minibatch (8192 samples): forward, data gradient, weight gradient.
+        # flops = fp32-equivalent 2*M*N*K of the layer (the tensor pipe executes 3x / 6x that in bf16 MMAs; conv1 reads ONE
+        # exact plane of raw pixels, so its factor is 2 / 3)
         from xuance_b200.torch.utils import tc_conv as tc
-        B = 8192
+        B = int(os.environ.get("XB_K12_BATCH", "8192"))
         layers = (("conv1", 84, 84, 4, 32, 8, 4), ("conv2", 21, 21, 32, 64, 4, 2), ("conv3", 10, 10, 64, 64, 3, 1))
-        for P in (2, 3):
+        for P in (3, 2):
             for name, H, W, C, N, k, s in layers:
                 pad = (k - s) // 2
                 geom = tc.conv_forward_geometry(B, H, W, C, k, k, s, pad)
-                x = torch.rand((B, H, W, C), device=DEV, generator=g)
                 w = torch.randn((N, C, k, k), device=DEV, generator=g) / np.sqrt(C * k * k)
-                x_pl, w_pl = tc.split_bf16(x, P), tc.pack_conv_weight(w, P)
+                if name == "conv1":
+                    x_pl = torch.randint(0, 256, (1, B, H, W, C), device=DEV, generator=g).to(torch.bfloat16)
+                    w_pl = tc.pack_conv_weight(w, P, 1.0 / 255.0)
+                else:
+                    x_pl = tc.split_bf16(torch.rand((B, H, W, C), device=DEV, generator=g), P)
+                    w_pl = tc.pack_conv_weight(w, P)
                 out_pl = torch.empty((P, geom.M, N), dtype=torch.bfloat16, device=DEV)
                 fl = 2.0 * geom.M * N * geom.K
                 byts = x_pl.numel() * 2 + w_pl.numel() * 2 + out_pl.numel() * 2
                 us = timeit(lambda: tc.gemm_gather(x_pl, w_pl, geom, relu=True, out_pl=out_pl), R)
-                add(entry(f"K12 forward {name} (P={P})", f"M={geom.M} N={N} K={geom.K}", us, byts, hbm, fl, tpk))
+                add(entry(f"K12 forward {name} (PA={x_pl.shape[0]} PB={P})", f"M={geom.M} N={N} K={geom.K}", us, byts, hbm, fl, tpk))
                 g_pl = tc.split_bf16(torch.randn((geom.M, N), device=DEV, generator=g), P)
                 splits = tc.wgrad_splits(geom.M, geom.K)
                 us = timeit(lambda: tc.wgrad_reduce(tc.wgrad_gather(x_pl, g_pl, geom, splits), N, C, k, k), R)
-                add(entry(f"K12 weight gradient {name} (P={P}, {splits} splits)", f"M={geom.M} N={N} K={geom.K}", us,
+                add(entry(f"K12 weight gradient {name} (PA={x_pl.shape[0]} PB={P}, {splits} splits)", f"M={geom.M} N={N} K={geom.K}", us,
                           x_pl.numel() * 2 + g_pl.numel() * 2, hbm, fl, tpk))
                 if name != "conv1":
                     phases = tc.conv_dgrad_geometries(B, H, W, C, k, k, s, pad, N)
@@ -276,19 +281,29 @@ def main():
                     us = timeit(run_dgrad, R)
                     add(entry(f"K12 data gradient {name} (P={P}, {len(phases)} phases)", f"M={B * H * W} N={C}", us,
                               g_pl.numel() * 2 + dx_pl.numel() * 2, hbm, fl, tpk))
-            # the hidden layer 6400 -> 512
+                del x_pl, w_pl, out_pl, g_pl
+            # the hidden layer 6400 -> 512: forward, data gradient, weight gradient (column tiles inside one launch)
             geom = tc.linear_geometry(B, 6400)
             x_pl = tc.split_bf16(torch.rand((B, 6400), device=DEV, generator=g), P)
-            w_pl = tc.pack_conv_weight(torch.randn((512, 64, 10, 10), device=DEV, generator=g) / 80.0, P)
+            wf = torch.randn((512, 6400), device=DEV, generator=g) / 80.0
+            w_pl = tc.split_bf16(wf, P)
             out_fc = torch.empty((B, 512), device=DEV)
-            nt = 256 if P == 2 else 128
-
-            def run_fc():
-                for c0 in range(0, 512, nt):
-                    tc.gemm_gather(x_pl, w_pl[:, c0:c0 + nt], geom, relu=True, out_f32=out_fc, out_ld=512, out_c0=c0)
-            us = timeit(run_fc, R)
-            add(entry(f"K12 forward fc 6400->512 (P={P}, {512 // nt} launches)", f"M={B} N=512 K=6400", us,
-                      x_pl.numel() * 2 + w_pl.numel() * 2 + out_fc.numel() * 4, hbm, 2.0 * B * 512 * 6400, tpk))
+            fl = 2.0 * B * 512 * 6400
+            us = timeit(lambda: tc.gemm_gather(x_pl, w_pl, geom, relu=True, out_f32=out_fc), R)
+            add(entry(f"K12 forward fc 6400->512 (P={P})", f"M={B} N=512 K=6400", us,
+                      x_pl.numel() * 2 + w_pl.numel() * 2 + out_fc.numel() * 4, hbm, fl, tpk))
+            g_pl = tc.split_bf16(torch.randn((B, 512), device=DEV, generator=g), P)
+            wt_pl = tc.split_bf16(wf.t().contiguous(), P)
+            dx_pl = torch.empty((P, B, 6400), dtype=torch.bfloat16, device=DEV)
+            us = timeit(lambda: tc.gemm_gather(g_pl, wt_pl, tc.linear_geometry(B, 512), out_pl=dx_pl, relu_mask=x_pl[0]), R)
+            add(entry(f"K12 data gradient fc (P={P})", f"M={B} N=6400 K=512", us,
+                      g_pl.numel() * 2 + wt_pl.numel() * 2 + dx_pl.numel() * 2, hbm, fl, tpk))
+            nt = 512 // tc.n_tile_for(512, P)
+            splits = tc.wgrad_splits(B, 6400, nt)
+            us = timeit(lambda: tc.wgrad_reduce(tc.wgrad_gather(x_pl, g_pl, geom, splits), 512, 6400, 1, 1), R)
+            add(entry(f"K12 weight gradient fc (P={P}, {splits} splits)", f"M={B} N=512 K=6400", us,
+                      x_pl.numel() * 2 + g_pl.numel() * 2 + 512 * 6400 * 4, hbm, fl, tpk))
+            del x_pl, w_pl, g_pl, wt_pl, dx_pl
     print(json.dumps(out))
 
 

@@ -13,7 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libxb200.so")
 
 OBS_U8, OBS_F32_NHWC, OBS_F32_NCHW, OBS_BF16_NHWC, OBS_F16_NHWC = 0, 1, 2, 3, 4
-OBS_PLANES2, OBS_PLANES3 = 5, 6   # bf16 plane tensors [P, B, H, W, C] for the experimental K12 layers (xb_gather_obs_planes)
+OBS_PLANES2, OBS_PLANES3, OBS_PLANE_RAW = 5, 6, 7   # bf16 plane tensors [P, B, H, W, C] for the K12 layers (xb_gather_obs_planes);
+#                                                     RAW: one plane holding the uint8 value itself (exact in bf16)
 
 _P = c_void_p
 _SIGNATURES = {
@@ -38,11 +39,12 @@ _SIGNATURES = {
     "xb_soft_update": (c_int, [_P, _P, c_int64, c_float, _P]),
     "xb_split_bf16": (c_int, [_P, c_int64, c_int, _P, _P]),
     "xb_gather_obs_planes": (c_int, [_P, _P, c_int64, c_int64, c_int, _P, _P]),
-    "xb_pack_conv_weight": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
-    "xb_gemm_gather_tc": (c_int, [c_int, _P, c_int64, _P, c_int64, _P, _P] + [c_int] * 9 + [_P, _P, c_int, c_int, _P, c_int64,
-                                  _P] + [c_int] * 6 + [c_int64, c_int, _P]),
-    "xb_wgrad_gather_tc": (c_int, [c_int, _P, c_int64, _P, c_int64] + [c_int] * 9 + [_P, _P, c_int, c_int, _P, _P]),
-    "xb_wgrad_reduce": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P]),
+    "xb_pack_conv_weight": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P]),
+    "xb_gemm_gather_tc": (c_int, [c_int, c_int, _P, c_int64, _P, c_int64, _P, _P] + [c_int] * 9 + [_P, _P, c_int, c_int, c_int,
+                                  _P, c_int64, c_int, _P] + [c_int] * 6 + [c_int64, c_int, _P]),
+    "xb_wgrad_gather_tc": (c_int, [c_int, c_int, _P, c_int64, _P, c_int64, c_int64] + [c_int] * 9 + [_P, _P, c_int, c_int, c_int,
+                                   _P, _P]),
+    "xb_wgrad_reduce": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_float, _P, c_int, _P]),
     "xb_categorical_act": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P]),
     "xb_rms_update_normalize": (c_int, [_P, c_int, c_int64, _P, _P, c_double, c_int, _P, c_float, c_float, _P]),
     "xb_sac_actor_loss": (c_int, [_P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
@@ -113,6 +115,7 @@ def stream():
 
 _KERNELS_PER_CALL = {"xb_gather_scalars": 2}   # calls that launch more than one kernel (second one: normalise)
 profile = None   # optional {abi_name: [(start_event, end_event), ...]} filled when set (bench.py roofline timing)
+nvtx = os.environ.get("XB_NVTX", "0") == "1"   # NVTX range per ABI call (nsys / ncu --nvtx timelines); off by default
 
 
 def call(name, *args):
@@ -120,6 +123,13 @@ def call(name, *args):
     global launch_count
     fn = getattr(load(), name)
     launch_count += _KERNELS_PER_CALL.get(name, 1)
+    if nvtx:
+        torch.cuda.nvtx.range_push(name)
+        try:
+            check(fn(*args, stream()), name)
+        finally:
+            torch.cuda.nvtx.range_pop()
+        return
     if profile is not None and name in profile:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -38,7 +38,7 @@ class PreparedObs:
 
     def __init__(self, tensor, fmt, hwc):
         self.tensor, self.fmt, self.hwc = tensor, fmt, hwc
-        self._n = tensor.shape[1] if fmt in (_lib.OBS_PLANES2, _lib.OBS_PLANES3) else tensor.shape[0]
+        self._n = tensor.shape[1] if fmt in (_lib.OBS_PLANES2, _lib.OBS_PLANES3, _lib.OBS_PLANE_RAW) else tensor.shape[0]
         self.shape = (self._n,) + tuple(hwc)
 
     def __len__(self):
@@ -366,9 +366,15 @@ class DummyOnPolicyBuffer(Buffer):
     def finish_paths(self, vals, mask=None):
         """Batched form: ``finish_path(vals[i], i)`` for every env (or those with mask[i])."""
         vals = vals.detach().float().cpu().numpy() if isinstance(vals, torch.Tensor) else np.asarray(vals, np.float32)
-        for i in range(self.n_envs):
-            if mask is None or mask[i]:
-                self.finish_path(vals[i], i)
+        end = self.n_size if self.full else self.ptr
+        sel = np.ones(self.n_envs, bool) if mask is None else np.asarray(mask, bool).copy()
+        env = np.flatnonzero(sel & (self.start_ids < end))        # paths with at least one stored step
+        if env.size:
+            self._seg_end_h.numpy()[env, end - 1] = 1
+            self._boot_h.numpy()[env, end - 1] = vals.reshape(-1)[env].astype(np.float32)
+            self._covered_h.numpy()[env] = end
+            self._gae_dirty = True
+        self.start_ids[np.flatnonzero(sel)] = self.ptr
 
     def _ensure_gae(self):
         if not self._gae_dirty:
@@ -438,8 +444,8 @@ class DummyOnPolicyBuffer(Buffer):
         idx_t = self._index_tensor(indexes)
         H, W, C = self._obs_shape
         B = idx_t.numel()
-        if fmt in (_lib.OBS_PLANES2, _lib.OBS_PLANES3):        # experimental K12 input: bf16 planes of u8/255
-            P = 2 if fmt == _lib.OBS_PLANES2 else 3
+        if fmt in (_lib.OBS_PLANES2, _lib.OBS_PLANES3, _lib.OBS_PLANE_RAW):   # K12 input: bf16 planes of u8/255, or the raw
+            P = {_lib.OBS_PLANES2: 2, _lib.OBS_PLANES3: 3, _lib.OBS_PLANE_RAW: 1}[fmt]    # pixel value as one exact plane
             out = torch.empty((P, B, H, W, C), dtype=torch.bfloat16, device=self.device)
             _lib.call("xb_gather_obs_planes", _lib.ptr(self._obs), _lib.ptr(idx_t), B, H * W * C, P, _lib.ptr(out))
             return self._assemble(PreparedObs(out, fmt, (H, W, C)), idx_t, self._gather_fields(idx_t))
@@ -626,10 +632,9 @@ class PerOffPolicyBuffer(DummyOffPolicyBuffer):
         if self._u_evt[i] is not None:
             self._u_evt[i].synchronize()
         host = self._u_host[i].numpy()
-        if uniforms is None:
-            for e in range(N):
-                for j in range(k):
-                    host[e, j] = random.random()
+        if uniforms is None:             # N*k draws of random.random() in the reference's (env-major) order
+            _rnd = random.random
+            host.reshape(-1)[:] = [_rnd() for _ in range(N * k)]
         else:
             host[...] = np.asarray(uniforms, dtype=np.float64).reshape(N, k)
         u = self._u_host[i].to(self.device, non_blocking=True)

@@ -110,10 +110,10 @@ XB_HD void xb_stage_fwd(const XbConvGeom &g, int row, bool live, int b, int y, i
 
 // weight-gradient GEMM: the chunk holds 64 consecutive sites starting at chunk_site0 (sites >= site_end are zero);
 // thread = (site pp = row & 63, half uh = row >> 6 of the tile's 16 column units); MN-major operands;
-// the second operand is the output gradient G[site, n]
+// the second operand is the output gradient G[site, g_c0 + n] of a matrix with g_ld elements per site (g.N = tile width)
 template <class EmitA, class EmitG>
-XB_HD void xb_stage_wgrad(const XbConvGeom &g, int row, int64_t mt, int64_t chunk_site0, int64_t site_end, EmitA &&emit_a,
-                          EmitG &&emit_g) {
+XB_HD void xb_stage_wgrad(const XbConvGeom &g, int row, int64_t mt, int64_t chunk_site0, int64_t site_end, int64_t g_ld,
+                          int g_c0, EmitA &&emit_a, EmitG &&emit_g) {
     const int K = g.T * g.C;
     const int pp = row & (XB_CONV_KC - 1), uh = row >> 6;
     const int64_t site = chunk_site0 + pp;
@@ -127,7 +127,7 @@ XB_HD void xb_stage_wgrad(const XbConvGeom &g, int row, int64_t mt, int64_t chun
         emit_a(xb_canon_off_mn(u * 8, pp, XB_CONV_KC), off);
     }
     for (int j = uh; j < g.N / 8; j += 2)
-        emit_g(xb_canon_off_mn(j * 8, pp, XB_CONV_KC), in_run ? site * g.N + j * 8 : (int64_t)-1);
+        emit_g(xb_canon_off_mn(j * 8, pp, XB_CONV_KC), in_run ? site * g_ld + g_c0 + j * 8 : (int64_t)-1);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -162,8 +162,8 @@ XB_HD void xb_stage_fwd_v2(const XbConvGeom &g, int t, const int (*sites)[3], in
 
 // weight gradient: thread t owns sites 16w + 8*si + (l & 7), si < 2, of the chunk and the column units 4*quad + (l >> 3)
 template <class EmitA, class EmitG>
-XB_HD void xb_stage_wgrad_v2(const XbConvGeom &g, int t, int64_t mt, int64_t chunk_site0, int64_t site_end, EmitA &&emit_a,
-                             EmitG &&emit_g) {
+XB_HD void xb_stage_wgrad_v2(const XbConvGeom &g, int t, int64_t mt, int64_t chunk_site0, int64_t site_end, int64_t g_ld,
+                             int g_c0, EmitA &&emit_a, EmitG &&emit_g) {
     const int K = g.T * g.C;
     const int w = t >> 5, l = t & 31, rs = l & 7, uo = l >> 3;
     for (int si = 0; si < 2; ++si) {
@@ -179,7 +179,7 @@ XB_HD void xb_stage_wgrad_v2(const XbConvGeom &g, int t, int64_t mt, int64_t chu
             emit_a(xb_canon_off_mn(u * 8, pp, XB_CONV_KC), off);
         }
         for (int j = uo; j < (g.N >> 3); j += 4)
-            emit_g(xb_canon_off_mn(j * 8, pp, XB_CONV_KC), in_run ? site * g.N + j * 8 : (int64_t)-1);
+            emit_g(xb_canon_off_mn(j * 8, pp, XB_CONV_KC), in_run ? site * g_ld + g_c0 + j * 8 : (int64_t)-1);
     }
 }
 

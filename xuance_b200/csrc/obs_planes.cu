@@ -17,7 +17,9 @@ __global__ void __launch_bounds__(OP_THREADS) gather_obs_planes_kernel(const uin
     __shared__ uint16_t lut[P][256];
     const int tid = threadIdx.x;
     {
-        float r = __fdiv_rn((float)(tid & 255), 255.0f);          // the float32 value the reference network sees
+        // P >= 2: the float32 value the reference network sees, x / 255.  P == 1: the pixel value itself, which a bf16 holds
+        // exactly (8 significant bits) - the first layer's packed weights then carry the 1/255 (xb_pack_conv_weight scale)
+        float r = P == 1 ? (float)(tid & 255) : __fdiv_rn((float)(tid & 255), 255.0f);
 #pragma unroll
         for (int q = 0; q < P; ++q) {
             const __nv_bfloat16 h = __float2bfloat16_rn(r);
@@ -74,7 +76,7 @@ __global__ void __launch_bounds__(OP_THREADS) gather_obs_planes_kernel(const uin
 
 extern "C" int xb_gather_obs_planes(const uint8_t *src, const int64_t *idx, int64_t B, int64_t row_bytes, int planes,
                                     void *dst, void *stream) {
-    if (!src || !dst || B < 0 || row_bytes <= 0 || (planes != 2 && planes != 3)) return XB_EINVAL;
+    if (!src || !dst || B < 0 || row_bytes <= 0 || planes < 1 || planes > 3) return XB_EINVAL;
     if (B == 0) return XB_OK;
     if (row_bytes % 16 != 0 || !xb_aligned(src, 16) || !xb_aligned(dst, 16)) return XB_EALIGN;
     if (row_bytes * OP_STAGES > 200 * 1024) return XB_ERANGE;
@@ -82,7 +84,14 @@ extern "C" int xb_gather_obs_planes(const uint8_t *src, const int64_t *idx, int6
     int64_t ctas = (int64_t)xb_sm_count() * 2;
     if (ctas > B) ctas = B;
     cudaStream_t s = (cudaStream_t)stream;
-    if (planes == 2) {
+    if (planes == 1) {
+        static bool set1 = false;
+        if (!set1) {
+            cudaFuncSetAttribute(gather_obs_planes_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            set1 = true;
+        }
+        gather_obs_planes_kernel<1><<<(int)ctas, OP_THREADS, smem, s>>>(src, idx, B, (int)row_bytes, (uint16_t *)dst);
+    } else if (planes == 2) {
         static bool set2 = false;
         if (!set2) {
             cudaFuncSetAttribute(gather_obs_planes_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

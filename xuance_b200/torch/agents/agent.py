@@ -177,7 +177,7 @@ class Agent(ABC):
                   device=self.device)
         rep = REGISTRY_Representation[representation_key](**kw)
         if hasattr(rep, "set_compute"):
-            rep.tc_planes = getattr(config, "tc_planes", 2)       # only read by the experimental compute="tc"
+            rep.tc_planes = getattr(config, "tc_planes", 3)       # planes per float32 operand of compute="tc" (3 = exact to 2^-24)
             rep.set_compute(getattr(config, "compute", "fp32"))
         return rep
 

@@ -93,13 +93,14 @@ class OnPolicyAgent(Agent):
         self.memory._ensure_gae()
         total = n_epochs * -(-self.buffer_size // self.batch_size)     # a ragged last minibatch counts (ceil)
         done = 0
-        for _ in range(n_epochs):
+        indexes = np.arange(self.buffer_size)      # shuffled IN PLACE every epoch, as the reference does (on_policy.py:196-199):
+        for _ in range(n_epochs):                  # epoch e's order is the composition of e shuffles, same RNG stream
             if self.world_size > 1:
                 batches = stratified_minibatches(self.buffer_size, self.buffer_size // self.batch_size, self._shard_rng)
                 perm = np.concatenate(batches)
             else:
-                perm = np.arange(self.buffer_size)
-                np.random.shuffle(perm)
+                np.random.shuffle(indexes)
+                perm = indexes
             perm_d = torch.from_numpy(perm).to(self.device, non_blocking=True)   # one H2D per epoch
             for start in range(0, self.buffer_size, self.batch_size):
                 idx = perm_d[start:start + self.batch_size]

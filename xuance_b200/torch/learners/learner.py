@@ -98,10 +98,91 @@ class Learner(ABC):
                     o.load_state_dict(s)
             elif self.optimizer is not None:
                 self.optimizer.load_state_dict(opt)
-        if 'rng_state' in ckpt:
-            torch.set_rng_state(ckpt['rng_state'].cpu())
+        self._restore_rng(ckpt)
+        self._safe_scheduler_step()
         print(f"Successfully load model from '{model_path}'.")
         return model_path
+
+    @staticmethod
+    def _restore_rng(ckpt):
+        """drl_learner.py:146-152 / 172-178: CPU generator and every visible device's CUDA generator."""
+        if ckpt.get('rng_state') is not None:
+            torch.set_rng_state(ckpt['rng_state'].cpu())
+        cuda_states = ckpt.get('cuda_rng_state')
+        if isinstance(cuda_states, (list, tuple)) and torch.cuda.is_available():
+            for i, state in enumerate(cuda_states[:torch.cuda.device_count()]):
+                torch.cuda.set_rng_state(state.cpu(), device=i)
+
+    # ---------------------------------------------------------------- snapshots (drl_learner.py:34-44, 159-189)
+    # The reference keeps ONE rolling file, <model_dir>/DDP_Snapshot/snapshot.pt, written by rank 0 and loaded by every rank
+    # when a distributed learner is constructed, so an interrupted torchrun job resumes with policy, optimiser and RNG state.
+    @property
+    def snapshot_path(self):
+        return os.path.join(os.getcwd(), self.model_dir, "DDP_Snapshot")
+
+    def save_snapshot(self):
+        if self.rank != 0:
+            return None
+        os.makedirs(self.snapshot_path, exist_ok=True)
+        path = os.path.join(self.snapshot_path, "snapshot.pt")
+        torch.save({"policy": self.model.state_dict(), "optimizer": self._opt_state(), "iterations": self.iterations,
+                    "rng_state": torch.get_rng_state(), "cuda_rng_state": torch.cuda.get_rng_state_all()}, path)
+        return path
+
+    def load_snapshot(self, snapshot_path=None):
+        """Accepts the snapshot directory or the file; also reads the reference's older {'MODEL_STATE': ...} layout."""
+        path = self.snapshot_path if snapshot_path is None else snapshot_path
+        if os.path.isdir(path):
+            path = os.path.join(path, "snapshot.pt")
+        snap = torch.load(path, map_location=self.device, weights_only=False)
+        if "MODEL_STATE" in snap:
+            self.model.load_state_dict(snap["MODEL_STATE"])
+            return path
+        self.model.load_state_dict(snap["policy"])
+        opt = snap.get("optimizer")
+        if opt is not None and self.optimizer is not None:
+            if isinstance(self.optimizer, dict):
+                for k, v in self.optimizer.items():
+                    v.load_state_dict(opt[k])
+            elif isinstance(self.optimizer, list):
+                for o, st in zip(self.optimizer, opt):
+                    o.load_state_dict(st)
+            else:
+                self.optimizer.load_state_dict(opt)
+        self._restore_rng(snap)
+        its = int(snap.get("iterations", 0))
+        if its:                                    # resume the LinearLR schedule where the interrupted run stopped
+            self.iterations = its
+            self._fast_forward_scheduler(its)
+        return path
+
+    def _schedulers(self):
+        sch = self.scheduler
+        if sch is None:
+            return []
+        return list(sch.values()) if isinstance(sch, dict) else (list(sch) if isinstance(sch, list) else [sch])
+
+    def _fast_forward_scheduler(self, current_iters):
+        for sch in self._schedulers():
+            sch.last_epoch = int(current_iters)
+            if hasattr(sch, "_get_closed_form_lr"):             # LinearLR: lr(t) in closed form (its step() is a recurrence)
+                lrs = sch._get_closed_form_lr()
+                for group, lr in zip(sch.optimizer.param_groups, lrs):
+                    group["lr"] = lr
+                sch._last_lr = list(lrs)
+
+    def _safe_scheduler_step(self):
+        """drl_learner.py:191-210: a run restarted with ``config.rt_epoch`` (evaluation epochs already done) moves the
+        learning-rate schedule to the matching iteration."""
+        if not hasattr(self.config, "rt_epoch") or not self._schedulers():
+            return
+        try:
+            train_steps = self.config.running_steps // self.config.parallels
+            eval_interval = self.config.eval_interval // self.config.parallels
+            num_epoch = int(train_steps / eval_interval)
+            self._fast_forward_scheduler(int(self.total_iters * self.config.rt_epoch / num_epoch))
+        except Exception as e:                     # the reference swallows this too (prints and carries on)
+            print(f"scheduler fast-forward skipped: {e}")
 
     @abstractmethod
     def update(self, *args):

@@ -63,12 +63,12 @@ class _PixelEncoder(nn.Module):
     def preferred_obs_format(self):
         """K3 output format this encoder consumes without any further copy."""
         if self.compute == "tc":
-            return _lib.OBS_PLANES2 if self._tc.be.planes == 2 else _lib.OBS_PLANES3
+            return _lib.OBS_PLANE_RAW      # one exact bf16 plane of the uint8 pixels; the 1/255 lives in conv1's packed weights
         return {"fp32": _lib.OBS_F32_NCHW, "fp32_cl": _lib.OBS_F32_NHWC, "tf32": _lib.OBS_F32_NHWC,
                 "bf16": _lib.OBS_BF16_NHWC}[self.compute]
 
-    # ---- EXPERIMENTAL "tc" mode: the conv stack + hidden layer as K12 launches (split-bf16 tcgen05 GEMMs with fp32-level
-    # accuracy, utils/tc_conv.py).  Forward parity-tested on B200, backward not yet pinned; see DESIGN.md section 9.
+    # ---- "tc" mode: the conv stack + hidden layer as K12 launches (split-bf16 tcgen05 GEMMs, float32 accumulation in TMEM,
+    # utils/tc_conv.py): forward, data gradients and weight gradients; pinned against float64 in tests/test_gpu_tc_conv.py.
     def _build_tc(self):
         from ..utils.tc_conv import TensorCoreNatureCNN, CudaBackend
         mods = list(self.model)
@@ -85,18 +85,21 @@ class _PixelEncoder(nn.Module):
                                       "(AC_CNN_Atari with one hidden layer) or by AdaptiveMaxPool2d(1,1), Flatten (Basic_CNN)")
         C, H, W = self.input_shape
         self._tc = TensorCoreNatureCNN(convs, rest[1] if hidden else None, (H, W, C),
-                                       backend=CudaBackend(planes=getattr(self, "tc_planes", 2)))
+                                       backend=CudaBackend(planes=getattr(self, "tc_planes", 3)))
         self._tc_pooled = pooled
 
     def _run_tc(self, observations):
         from ..utils import tc_conv
         P = self._tc.be.planes
-        if isinstance(observations, PreparedObs) and observations.fmt in (_lib.OBS_PLANES2, _lib.OBS_PLANES3):
+        if isinstance(observations, np.ndarray) and observations.dtype == np.uint8:
+            observations = torch.from_numpy(observations).to(self.device)
+        if isinstance(observations, PreparedObs) and observations.fmt in (_lib.OBS_PLANES2, _lib.OBS_PLANES3, _lib.OBS_PLANE_RAW):
             planes = observations.tensor                                   # K3-P already produced [P, B, H, W, C]
-        elif isinstance(observations, torch.Tensor) and observations.is_cuda and observations.dtype == torch.uint8:
-            obs = observations.contiguous()
-            planes = torch.empty((P,) + tuple(obs.shape), dtype=torch.bfloat16, device=obs.device)
-            _lib.call("xb_gather_obs_planes", _lib.ptr(obs), None, obs.shape[0], obs[0].numel(), P, _lib.ptr(planes))
+        elif isinstance(observations, torch.Tensor) and observations.is_cuda and observations.dtype == torch.uint8 \
+                and observations[0].numel() % 16 == 0:
+            obs = observations.contiguous()                                # raw pixels -> one exact plane
+            planes = torch.empty((1,) + tuple(obs.shape), dtype=torch.bfloat16, device=obs.device)
+            _lib.call("xb_gather_obs_planes", _lib.ptr(obs), None, obs.shape[0], obs[0].numel(), 1, _lib.ptr(planes))
         else:
             x = self._as_input_f32_nhwc(observations)
             planes = tc_conv.split_bf16(x, P)

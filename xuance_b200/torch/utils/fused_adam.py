@@ -100,10 +100,25 @@ class FusedAdam(torch.optim.Optimizer):
         if "initial_lr" in groups[0]:
             self.param_groups[0]["initial_lr"] = groups[0]["initial_lr"]
         st = state_dict.get("state", {})
+        # the saved ids enumerate the param group position by position (torch.optim.Optimizer.state_dict); the bucket holds
+        # only the trainable, de-duplicated parameters, so map position -> parameter object -> bucket slot
+        group_params = self.param_groups[0]["params"]
+        saved_ids = groups[0]["params"]
+        if len(saved_ids) != len(group_params):
+            raise ValueError("optimizer checkpoint has %d parameters, this optimizer %d" % (len(saved_ids), len(group_params)))
+        slot = {id(p): i for i, p in enumerate(self.bucket.params)}
         ms, vs = self.bucket.views(self.exp_avg), self.bucket.views(self.exp_avg_sq)
-        for i, pid in enumerate(groups[0]["params"]):
-            if pid in st:
-                ms[i].copy_(st[pid]["exp_avg"])
-                vs[i].copy_(st[pid]["exp_avg_sq"])
-                self.step_count = int(float(st[pid]["step"]))
+        for pos, pid in enumerate(saved_ids):
+            if pid not in st:
+                continue
+            i = slot.get(id(group_params[pos]))
+            if i is None:                     # frozen / duplicate parameter: no moments on this side
+                continue
+            m, v = st[pid]["exp_avg"], st[pid]["exp_avg_sq"]
+            if tuple(m.shape) != tuple(ms[i].shape):
+                raise ValueError("optimizer checkpoint: moment of parameter %d has shape %s, expected %s"
+                                 % (pos, tuple(m.shape), tuple(ms[i].shape)))
+            ms[i].copy_(m)
+            vs[i].copy_(v)
+            self.step_count = int(float(st[pid]["step"]))
         self._step_t.fill_(float(self.step_count))

@@ -1,11 +1,11 @@
-"""EXPERIMENTAL host side of K12 (``xb_gemm_gather_tc``, include/xb200.h): geometry builders that express the NatureCNN
-layers (xuance/torch/rl_models/representations/cnn.py:45-50, 84-101; modules/layers.py:16-65) and their data gradients
-as the gathered-operand GEMM of ``xuance_b200/csrc/conv_index.h``, plus thin launch wrappers.
+"""Host side of K12 (``xb_gemm_gather_tc`` / ``xb_wgrad_gather_tc``, include/xb200.h): geometry builders that express the
+NatureCNN layers (xuance/torch/rl_models/representations/cnn.py:45-50, 84-101; modules/layers.py:16-65), their data
+gradients and weight gradients as the gathered-operand GEMM of ``xuance_b200/csrc/conv_index.h``, thin launch wrappers, and
+``TensorCoreNatureCNN`` - the forward / backward orchestration behind ``compute="tc"`` of the pixel encoders.
 
-Nothing on a default path imports this module.  The geometry and the kernel's index arithmetic are verified on the host
-(tests/test_conv_index.py emulates the shared-memory staging and the descriptor reads and compares with
-``torch.nn.functional.conv2d`` / autograd); on B200 the forward GEMM passes tests/test_gpu_tc_conv.py, the gradient modes
-have run end to end but their per-layer parity tests are still gated.
+The geometry and the kernel's index arithmetic are verified on the host (tests/test_conv_index.py emulates the
+shared-memory staging, the descriptor reads and the per-plane MMA issue and compares with ``torch.nn.functional.conv2d`` /
+autograd); tests/test_gpu_tc_conv.py pins every mode against float64 on B200.
 """
 from dataclasses import dataclass, field
 from typing import List
@@ -131,10 +131,11 @@ def dgrad_weight_matrix(w, taps):
 
 
 # ------------------------------------------------------------------------------------------------ device wrappers
-# Operands are "plane tensors": bfloat16 [P, ...] with x = planes.sum(0) - P = 2 (hi, lo; exact to 2^-16, three products
-# per MMA step) or P = 3 (hi, mid, lo; exact to 2^-24, six products: float32-grade results, including which side of
-# zero a ReLU input falls on - with P = 2 an activation within ~1e-5 of zero can take the other side than the float32
-# network does and shift the upstream gradients by O(1/batch)).
+# Operands are "plane tensors": bfloat16 [P, ...] with x = planes.sum(0); plane q = bf16 of the residual the planes before
+# it leave.  P = 1 is exact for raw uint8 pixels (integers <= 256), P = 2 is exact to 2^-16, P = 3 to 2^-24.  A K12 launch
+# multiplies an A operand of PA planes with a B operand of PB >= PA planes and keeps the products whose plane indices sum
+# to < PB, each order of magnitude in its own float32 accumulator (added smallest first in the epilogue - the tensor core
+# truncates when it adds into an accumulator).
 def split_bf16(x, planes=2):
     """float32 CUDA tensor -> bfloat16 [planes, *x.shape]."""
     x = x.contiguous()
@@ -143,13 +144,24 @@ def split_bf16(x, planes=2):
     return out
 
 
-def pack_conv_weight(w, planes=2):
-    """[N, C, KH, KW] float32 CUDA -> bfloat16 [planes, N, KH*KW*C] in (kh, kw, c) column order."""
+def pack_conv_weight(w, planes=2, scale=1.0):
+    """[N, C, KH, KW] float32 CUDA -> bfloat16 [planes, N, KH*KW*C] in (kh, kw, c) column order, times ``scale``."""
     w = w.contiguous()
     N, C, KH, KW = w.shape
     out = torch.empty((planes, N, KH * KW * C), dtype=torch.bfloat16, device=w.device)
-    _lib.call("xb_pack_conv_weight", _lib.ptr(w), N, C, KH, KW, planes, _lib.ptr(out))
+    _lib.call("xb_pack_conv_weight", _lib.ptr(w), N, C, KH, KW, planes, float(scale), _lib.ptr(out))
     return out
+
+
+def n_tile_for(N, planes_b):
+    """Columns per work item: the largest multiple of 32 that divides N with planes_b * n_tile <= 256 (one tcgen05.mma
+    spans the planes_b adjacent weight planes of a tile)."""
+    t = (256 // planes_b) // 32 * 32
+    while t >= 32:
+        if N % t == 0:
+            return t
+        t -= 32
+    raise ValueError("N = %d has no column tile that is a multiple of 32" % N)
 
 
 def _plane_arg(t):
@@ -158,51 +170,70 @@ def _plane_arg(t):
     return _lib.ptr(t[0]), t.stride(0)
 
 
-def gemm_gather(x_pl, w_pl, geom, bias=None, relu=False, out_f32=None, out_pl=None, out_ld=None, out_c0=0, relu_mask=None):
-    """One K12 launch.  ``x_pl`` [P, B, IH, IW, C] (any shape with that element order), ``w_pl`` [P, N, K] (row slices
-    allowed); outputs are caller-allocated: ``out_f32`` [rows, out_ld] and / or ``out_pl`` [P, rows, out_ld]."""
-    P, N, K = w_pl.shape
-    assert K == geom.K and x_pl.shape[0] == P, (K, geom.K, x_pl.shape[0], P)
+_TAPS = {}
+
+
+def _taps(geom):
+    """int8 host arrays of the tap offsets (kept alive per geometry: the ABI copies them at launch time)."""
+    key = (tuple(geom.dy), tuple(geom.dx))
+    if key not in _TAPS:
+        _TAPS[key] = (torch.tensor(geom.dy, dtype=torch.int8), torch.tensor(geom.dx, dtype=torch.int8))
+    return _TAPS[key]
+
+
+def gemm_gather(x_pl, w_pl, geom, bias=None, relu=False, out_f32=None, out_pl=None, out_ld=None, out_c0=0, relu_mask=None,
+                n_tile=None):
+    """One K12 launch.  ``x_pl`` [PA, B, IH, IW, C] (any shape with that element order), ``w_pl`` [PB, N, K]; outputs are
+    caller-allocated: ``out_f32`` [rows, out_ld] and / or ``out_pl`` [P_out, rows, out_ld]."""
+    PB, N, K = w_pl.shape
+    PA = x_pl.shape[0]
+    assert K == geom.K and PA <= PB, (K, geom.K, PA, PB)
     out_ld = N if out_ld is None else out_ld
-    dy = torch.tensor(geom.dy, dtype=torch.int8)
-    dx = torch.tensor(geom.dx, dtype=torch.int8)
+    n_tile = n_tile_for(N, PB) if n_tile is None else n_tile
+    dy, dx = _taps(geom)
     xp, xs = _plane_arg(x_pl)
     wp, ws = _plane_arg(w_pl)
     op, os_ = _plane_arg(out_pl) if out_pl is not None else (None, 0)
-    _lib.call("xb_gemm_gather_tc", P, xp, xs, wp, ws, _lib.ptr(bias) if bias is not None else None,
+    _lib.call("xb_gemm_gather_tc", PA, PB, xp, xs, wp, ws, _lib.ptr(bias) if bias is not None else None,
               _lib.ptr(relu_mask) if relu_mask is not None else None, geom.B, geom.IH, geom.IW, geom.C, geom.OY, geom.OX,
-              geom.sy, geom.sx, geom.T, dy.data_ptr(), dx.data_ptr(), N, 1 if relu else 0, op, os_,
-              _lib.ptr(out_f32) if out_f32 is not None else None, geom.out_H, geom.out_W, geom.oys, geom.oxs, geom.oy0,
-              geom.ox0, out_ld, out_c0)
+              geom.sy, geom.sx, geom.T, dy.data_ptr(), dx.data_ptr(), N, n_tile, 1 if relu else 0, op, os_,
+              out_pl.shape[0] if out_pl is not None else 0, _lib.ptr(out_f32) if out_f32 is not None else None, geom.out_H,
+              geom.out_W, geom.oys, geom.oxs, geom.oy0, geom.ox0, out_ld, out_c0)
     return out_f32, out_pl
 
 
-def wgrad_gather(x_pl, g_pl, geom, splits):
+def wgrad_gather(x_pl, g_pl, geom, splits, n_tile=None):
     """Partial weight gradients [splits, K, N] (float32) of the gathered GEMM ``geom`` for the output gradient planes
-    ``g_pl`` [P, sites, N]."""
-    P, _, N = g_pl.shape
+    ``g_pl`` [PB, sites, N]."""
+    PB, _, N = g_pl.shape
+    PA = x_pl.shape[0]
+    assert PA <= PB and g_pl.stride(2) == 1
+    n_tile = n_tile_for(N, PB) if n_tile is None else n_tile
     partials = torch.empty((splits, geom.K, N), dtype=torch.float32, device=g_pl.device)
-    dy = torch.tensor(geom.dy, dtype=torch.int8)
-    dx = torch.tensor(geom.dx, dtype=torch.int8)
+    dy, dx = _taps(geom)
     xp, xs = _plane_arg(x_pl)
-    gp, gs = _plane_arg(g_pl)
-    _lib.call("xb_wgrad_gather_tc", P, xp, xs, gp, gs, geom.B, geom.IH, geom.IW, geom.C, geom.OY, geom.OX, geom.sy, geom.sx,
-              geom.T, dy.data_ptr(), dx.data_ptr(), N, splits, _lib.ptr(partials))
+    _lib.call("xb_wgrad_gather_tc", PA, PB, xp, xs, _lib.ptr(g_pl), g_pl.stride(0), g_pl.stride(1), geom.B, geom.IH, geom.IW,
+              geom.C, geom.OY, geom.OX, geom.sy, geom.sx, geom.T, dy.data_ptr(), dx.data_ptr(), N, n_tile, splits,
+              _lib.ptr(partials))
     return partials
 
 
-def wgrad_reduce(partials, N, C, KH, KW, out=None, accumulate=False):
-    """[splits, (kh,kw,c), N] partials -> torch-layout weight gradient [N, C, KH, KW]."""
+def wgrad_reduce(partials, N, C, KH, KW, out=None, accumulate=False, scale=1.0):
+    """[splits, (kh,kw,c), N] partials -> torch-layout weight gradient [N, C, KH, KW] (times ``scale``)."""
     out = torch.empty((N, C, KH, KW), dtype=torch.float32, device=partials.device) if out is None else out
-    _lib.call("xb_wgrad_reduce", _lib.ptr(partials), partials.shape[0], N, C, KH, KW, _lib.ptr(out), 1 if accumulate else 0)
+    _lib.call("xb_wgrad_reduce", _lib.ptr(partials), partials.shape[0], N, C, KH, KW, float(scale), _lib.ptr(out),
+              1 if accumulate else 0)
     return out
 
 
-def wgrad_splits(M, K, sm_count=148):
-    """Split count for the weight gradient: about two work items per SM, at least 8 chunks of 64 sites per split, and the
-    rule of ``xb_wgrad_sites_per_split`` (no empty split)."""
-    m_tiles = -(-K // 128)
+def wgrad_splits(M, K, n_tiles=1, sm_count=148):
+    """Split count for the weight gradient: about two work items per SM, at least 8 chunks of 64 sites per split, at most
+    4096 sites per split (the tensor core truncates on every addition into the accumulator: a chain of n K-steps carries a
+    bias of up to n * 2^-24 relative, so long reductions are cut and the pieces added in float32 by xb_wgrad_reduce), and
+    the rule of ``xb_wgrad_sites_per_split`` (no empty split)."""
+    m_tiles = -(-K // 128) * n_tiles
     s = max(1, min((2 * sm_count) // m_tiles, M // (8 * KC)))
+    s = max(s, -(-M // 4096))
     while s > 1:
         per = -(-(-(-M // s)) // KC) * KC
         if (s - 1) * per < M:
@@ -215,15 +246,14 @@ class CudaBackend:
     """The product backend of ``TensorCoreNatureCNN``: every method is one or a few C-ABI launches (K12).  The host test
     substitutes an emulated backend with the same methods (tests/test_conv_index.py) to check the orchestration."""
 
-    def __init__(self, planes=2):
+    def __init__(self, planes=3):
         self.planes = planes
-        self.n_tile = 256 if planes == 2 else 128        # output columns per launch (shared-memory stage size)
 
     def split(self, x):
         return split_bf16(x, self.planes)
 
-    def pack_weight(self, w4d):
-        return pack_conv_weight(w4d, self.planes)
+    def pack_weight(self, w4d, scale=1.0):
+        return pack_conv_weight(w4d, self.planes, scale)
 
     def empty_planes(self, shape, like):
         return torch.empty((self.planes,) + tuple(shape), dtype=torch.bfloat16, device=like.device)
@@ -235,9 +265,10 @@ class CudaBackend:
         gemm_gather(x_pl, w_pl, geom, bias=bias, relu=relu, out_f32=out_f32, out_pl=out_pl, out_ld=out_ld, out_c0=out_c0,
                     relu_mask=mask)
 
-    def wgrad(self, x_pl, g_pl, geom, N, C, KH, KW):
-        splits = wgrad_splits(geom.M, geom.K)
-        return wgrad_reduce(wgrad_gather(x_pl, g_pl, geom, splits), N, C, KH, KW)
+    def wgrad(self, x_pl, g_pl, geom, N, C, KH, KW, scale=1.0):
+        nt = N // n_tile_for(N, g_pl.shape[0])
+        splits = wgrad_splits(geom.M, geom.K, nt)
+        return wgrad_reduce(wgrad_gather(x_pl, g_pl, geom, splits), N, C, KH, KW, scale=scale)
 
     def colsum(self, g_pl):
         # bias gradient: reduce the bf16 planes straight into float32 (no float32 copy of the [P, sites, N] tensor)
@@ -251,6 +282,10 @@ class TensorCoreNatureCNN:
     """The convolution stack + hidden layer of AC_CNN_Atari / Basic_CNN's conv part (cnn.py:45-50, 84-101) as K12 launches,
     forward AND backward, for one batch size.  Activations live as bf16 plane tensors (NHWC) between layers; the ReLU
     derivative is applied inside the data-gradient GEMM's epilogue from plane 0 of the saved activation.
+
+    The input is either ``planes`` planes of the normalised observation x/255, or ONE plane holding the raw uint8 pixel
+    values (exact in bf16): then the first layer's packed weights and its weight gradient carry the 1/255, the layer's A
+    operand costs a third of the traffic and a third of the tensor work, and the minibatch gather writes one plane.
 
     ``convs``: nn.Conv2d modules (padding (k - s)//2 as layers.py:46 builds them), each followed by ReLU;
     ``fc``: nn.Linear over the NCHW-flattened last feature map, followed by ReLU."""
@@ -292,20 +327,18 @@ class TensorCoreNatureCNN:
     # ---- forward: returns float32 [sites of the last layer, features]; keeps what backward needs
     def forward(self, x_pl, B):
         be, plan = self.be, self._plan(B)
+        raw = x_pl.shape[0] == 1 and be.planes > 1          # one exact plane of uint8 values: 1/255 goes into the weights
         saved, cur, out_f32 = [], x_pl, None
         for li, L in enumerate(plan):
             mod = self.convs[li] if L["kind"] == "conv" else self.fc
             N, g = L["N"], L["fwd"]
             w4 = (mod.weight if L["kind"] == "conv" else mod.weight.reshape(N, L["C"], L["KH"], L["KW"])).detach()
-            w_pl = be.pack_weight(w4)
-            bias = mod.bias.detach()
+            scale = 1.0 / 255.0 if (raw and li == 0) else 1.0
+            w_pl = be.pack_weight(w4, scale)
             out_pl = be.empty_planes((g.M, N), cur)
             out_f32 = be.empty_f32((g.M, N), cur) if li == len(plan) - 1 else None
-            for c0 in range(0, N, be.n_tile):
-                n1 = min(N, c0 + be.n_tile)
-                be.gemm(cur, w_pl[:, c0:n1], g, bias=bias[c0:n1], relu=True, out_f32=out_f32, out_pl=out_pl, out_ld=N,
-                        out_c0=c0)
-            saved.append(dict(x=cur, y=out_pl, w4=w4))
+            be.gemm(cur, w_pl, g, bias=mod.bias.detach(), relu=True, out_f32=out_f32, out_pl=out_pl, out_ld=N)
+            saved.append(dict(x=cur, y=out_pl, w4=w4, scale=scale))
             cur = out_pl
         self._saved = (B, saved)
         return out_f32
@@ -317,18 +350,12 @@ class TensorCoreNatureCNN:
         plan = self._plan(B)
         grads = [None] * (2 * len(plan))
         y_last = saved[-1]["y"]
-        g_pl = be.split(dz * (be.to_float(y_last) > 0).to(dz.dtype))            # ReLU derivative of the last layer
+        g_pl = be.split(dz * (y_last[0] > 0).to(dz.dtype))            # ReLU derivative of the last layer (plane 0 > 0)
         for li in range(len(plan) - 1, -1, -1):
             L, sv = plan[li], saved[li]
             N, C, KH, KW = L["N"], L["C"], L["KH"], L["KW"]
             # -- weight and bias gradients (the weight gradient gathers exactly like the forward)
-            if N <= be.n_tile:
-                dw = be.wgrad(sv["x"], g_pl, L["fwd"], N, C, KH, KW)
-            else:
-                dw = be.empty_f32((N, C, KH, KW), dz)
-                for c0 in range(0, N, be.n_tile):
-                    n1 = min(N, c0 + be.n_tile)
-                    dw[c0:n1] = be.wgrad(sv["x"], g_pl[:, :, c0:n1].contiguous(), L["fwd"], n1 - c0, C, KH, KW)
+            dw = be.wgrad(sv["x"], g_pl, L["fwd"], N, C, KH, KW, sv["scale"])
             grads[2 * li] = dw if L["kind"] == "conv" else dw.reshape(N, C * KH * KW)
             grads[2 * li + 1] = be.colsum(g_pl)
             if li == 0:
@@ -343,9 +370,7 @@ class TensorCoreNatureCNN:
             else:
                 K = C * KH * KW
                 w_pl = be.split(sv["w4"].permute(0, 2, 3, 1).reshape(N, K).t().contiguous())   # [P, K (h,w,c), N]
-                for c0 in range(0, K, be.n_tile):
-                    n1 = min(K, c0 + be.n_tile)
-                    be.gemm(g_pl, w_pl[:, c0:n1], L["dgrad"], out_pl=out_pl, out_ld=K, out_c0=c0, mask=prev_y[0])
+                be.gemm(g_pl, w_pl, L["dgrad"], out_pl=out_pl, out_ld=K, mask=prev_y[0])
             g_pl = out_pl
         return grads
 
