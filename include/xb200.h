@@ -83,6 +83,9 @@ int xb_gather_obs(const uint8_t *src, const int64_t *idx, int64_t B, int H, int 
 int64_t xb_scratch_doubles(void);
 int xb_gather_scalars(const float *fields, int64_t slots, const int64_t *idx, int64_t B, int F,
                       float *out, int adv_field, float *stats_out, double *scratch, void *stream);
+/* adv[b] <- (adv[b] - stats[0]) / (stats[1] + 1e-8) with GIVEN statistics: the second half of memory_tools.py:281-282 for a
+ * minibatch that is sharded over ranks (its global mean / population std are all-reduced once per epoch). */
+int xb_adv_normalize(float *adv, int64_t B, const float *stats, void *stream);
 
 /* ---------------------------------------------------------------- K4: fused PPO-Clip loss fwd+bwd ----
  * Replaces ppo_learner.py:46-60 plus the autograd backward of those lines down to (logits, value):

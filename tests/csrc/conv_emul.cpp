@@ -18,13 +18,16 @@ inline float &at(std::vector<float> &smem, uint32_t byte_off) { return smem[byte
 extern "C" int emul_gemm_gather(int PA, int PB, const float *in, int64_t in_plane, const float *w, int64_t w_plane, int B,
                                 int IH, int IW, int C, int OY, int OX, int sy, int sx, int T, const int8_t *dy,
                                 const int8_t *dx, int N_total, int N, int out_H, int out_W, int oys, int oxs, int oy0, int ox0,
-                                int64_t out_ld, int out_c0, int stages, int map, double *out) {
+                                int64_t out_ld, int out_c0, int stages, double *out) {
     if (PA < 1 || PA > PB || PB > 3 || N_total % N || PB * N > 256) return -2;
     XbConvGeom g;
     g.B = B, g.IH = IH, g.IW = IW, g.C = C, g.OY = OY, g.OX = OX, g.sy = sy, g.sx = sx, g.T = T, g.N = N;
     for (int t = 0; t < XB_CONV_MAX_TAPS; ++t) g.dy[t] = t < T ? dy[t] : 0, g.dx[t] = t < T ? dx[t] : 0;
+    xb_geom_finish(g);
     const int KC = XB_CONV_KC, TM = XB_CONV_TILE_M, K = T * C;
-    if (K % KC || C % 8 || N % 8) return -1;
+    if (K % KC || C % 8 || N % 8 || K > 8 * XB_CONV_MAX_UNITS) return -1;
+    std::vector<XbUnit> tab(K / 8);
+    for (int i = 0; i < K / 8; ++i) tab[i] = xb_unit(g, i);
     const int n_chunks = K / KC;
     const uint32_t a_plane = xb_conv_a_plane_bytes(), ws_plane = xb_conv_w_plane_bytes(N);
     const uint32_t stage_bytes = PA * a_plane + PB * ws_plane;
@@ -42,12 +45,10 @@ extern "C" int emul_gemm_gather(int PA, int PB, const float *in, int64_t in_plan
         for (int kc = 0; kc < n_chunks; ++kc, ++it) {
             const uint32_t base = (it % stages) * stage_bytes;
             for (uint32_t i = 0; i < stage_bytes / 2; ++i) smem[base / 2 + i] = nan;     // poison the stage
-            // ---- producer (conv_tc.cu, warps 5-8): thread = row; the staging routine is the kernel's own
-            for (int row = 0; row < TM; ++row) {
-                const int64_t m = tile * TM + row;
-                const bool live = m < M;
-                int b = 0, y = 0, x = 0;
-                if (live) xb_conv_site(g, m, b, y, x);
+            // ---- producers (conv_tc.cu, warps 5-12): 256 threads, the staging routine and the tap table are the kernel's own
+            for (int pt = 0; pt < XB_CONV_PRODUCERS; ++pt) {
+                XbSite sites[4];
+                for (int gi = 0; gi < 4; ++gi) sites[gi] = xb_site(g, tile * TM + xb_fwd_row(pt, gi), M);
                 auto emit_a = [&](uint32_t dst, int64_t src) {
                     for (int q = 0; q < PA; ++q)
                         for (int j = 0; j < 8; ++j)
@@ -58,17 +59,7 @@ extern "C" int emul_gemm_gather(int PA, int PB, const float *in, int64_t in_plan
                         for (int j = 0; j < 8; ++j)
                             at(smem, base + PA * a_plane + q * ws_plane + dst + 2 * j) = src >= 0 ? w[q * w_plane + w_off + src + j] : 0.f;
                 };
-                if (map == 0) {
-                    xb_stage_fwd(g, row, live, b, y, x, kc, emit_a, emit_w);
-                } else {                                        // conv_tc.cu, MAP = 1: the thread feeds four rows
-                    int sites4[4][3];
-                    for (int gi = 0; gi < 4; ++gi) {
-                        const int64_t mm = tile * TM + xb_v2_row(row, gi);
-                        sites4[gi][0] = -1, sites4[gi][1] = 0, sites4[gi][2] = 0;
-                        if (mm < M) xb_conv_site(g, mm, sites4[gi][0], sites4[gi][1], sites4[gi][2]);
-                    }
-                    xb_stage_fwd_v2(g, row, sites4, kc, emit_a, emit_w);
-                }
+                xb_stage_fwd(g, tab.data(), pt, sites, kc, emit_a, emit_w);
             }
             // ---- tensor core (conv_tc.cu MMA warp): per K step of 16 ONE instruction per A plane pa, whose B operand is the
             // first (PB - pa) weight planes read as ONE matrix of (PB - pa) * N rows starting at the first plane (the planes
@@ -121,12 +112,16 @@ extern "C" void emul_pack_weight(const float *w, int N, int C, int KH, int KW, f
 // (mn, k) at start + (mn/8)*SBO + (k/8)*LBO + (k%8)*16 + (mn%8)*2
 extern "C" int emul_wgrad(int PA, int PB, const float *in, int64_t in_plane, const float *gr, int64_t g_plane, int64_t g_ld,
                           int B, int IH, int IW, int C, int OY, int OX, int sy, int sx, int T, const int8_t *dy,
-                          const int8_t *dx, int N_total, int N, int splits, int stages, int map, double *partials) {
+                          const int8_t *dx, int N_total, int N, int splits, int stages, double *partials) {
     if (PA < 1 || PA > PB || PB > 3 || N_total % N || PB * N > 256) return -2;
     XbConvGeom g;
     g.B = B, g.IH = IH, g.IW = IW, g.C = C, g.OY = OY, g.OX = OX, g.sy = sy, g.sx = sx, g.T = T, g.N = N;
     for (int t = 0; t < XB_CONV_MAX_TAPS; ++t) g.dy[t] = t < T ? dy[t] : 0, g.dx[t] = t < T ? dx[t] : 0;
+    xb_geom_finish(g);
     const int KC = XB_CONV_KC, TM = XB_CONV_TILE_M, K = T * C;
+    if (K > 8 * XB_CONV_MAX_UNITS) return -1;
+    std::vector<XbUnit> tab(K / 8);
+    for (int i = 0; i < K / 8; ++i) tab[i] = xb_unit(g, i);
     const int64_t M = (int64_t)B * OY * OX;
     const int64_t per = xb_wgrad_sites_per_split(M, splits);
     if (per == 0 || C % 8 || N % 8) return -1;
@@ -149,7 +144,7 @@ extern "C" int emul_wgrad(int PA, int PB, const float *in, int64_t in_plane, con
         for (int kc = 0; kc < n_chunks; ++kc, ++it) {
             const uint32_t base = (it % stages) * stage_bytes;
             for (uint32_t i = 0; i < stage_bytes / 2; ++i) smem[base / 2 + i] = nan;
-            for (int row = 0; row < TM; ++row) {
+            for (int pt = 0; pt < XB_CONV_PRODUCERS; ++pt) {
                 auto emit_a = [&](uint32_t dst, int64_t src) {
                     for (int q = 0; q < PA; ++q)
                         for (int j = 0; j < 8; ++j)
@@ -160,8 +155,7 @@ extern "C" int emul_wgrad(int PA, int PB, const float *in, int64_t in_plane, con
                         for (int j = 0; j < 8; ++j)
                             at(smem, base + PA * a_plane + q * ws_plane + dst + 2 * j) = src >= 0 ? gr[q * g_plane + src + j] : 0.f;
                 };
-                if (map == 0) xb_stage_wgrad(g, row, mt, s0 + (int64_t)kc * KC, site_end, g_ld, nt * N, emit_a, emit_g);
-                else xb_stage_wgrad_v2(g, row, mt, s0 + (int64_t)kc * KC, site_end, g_ld, nt * N, emit_a, emit_g);
+                xb_stage_wgrad(g, tab.data(), pt, mt, s0 + (int64_t)kc * KC, site_end, M, g_ld, nt * N, emit_a, emit_g);
             }
             const uint32_t LBO = 128, SBO = (KC / 8) * 128;
             const uint32_t w_addr = base + PA * a_plane;
@@ -206,4 +200,13 @@ extern "C" void emul_wgrad_reduce(const double *partials, int splits, int N, int
         for (int sp = 0; sp < splits; ++sp) s += partials[((int64_t)sp * K + k) * N + n];
         dw[xb_pack_weight_src(i, C, KH, KW)] = s * scale;
     }
+}
+
+// xb_div (multiply-high division by a launch-time constant): mismatches against n / d over [lo, hi) plus the top of the range
+extern "C" int64_t emul_div_check(uint32_t d, uint32_t lo, uint32_t hi) {
+    const XbDiv v = xb_div_make(d);
+    int64_t bad = 0;
+    for (uint32_t n = lo; n < hi; ++n) bad += xb_div(n, v) != n / d;
+    for (uint32_t n = 0x7fffffffu - 4096; n <= 0x7fffffffu - 1; ++n) bad += xb_div(n, v) != n / d;
+    return bad;
 }

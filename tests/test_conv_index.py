@@ -28,10 +28,10 @@ def emul():
         subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-std=c++17", "-o", so, src], check=True)
     lib = ctypes.CDLL(so)
     P, i, l = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
-    lib.emul_gemm_gather.argtypes = [i, i, P, l, P, l] + [i] * 9 + [P, P] + [i] * 8 + [l, i, i, i, P]
+    lib.emul_gemm_gather.argtypes = [i, i, P, l, P, l] + [i] * 9 + [P, P] + [i] * 8 + [l, i, i, P]
     lib.emul_gemm_gather.restype = i
     lib.emul_pack_weight.argtypes = [P, i, i, i, i, P]
-    lib.emul_wgrad.argtypes = [i, i, P, l, P, l, l] + [i] * 9 + [P, P] + [i] * 5 + [P]
+    lib.emul_wgrad.argtypes = [i, i, P, l, P, l, l] + [i] * 9 + [P, P] + [i] * 4 + [P]
     lib.emul_wgrad.restype = i
     lib.emul_wgrad_reduce.argtypes = [P, i, i, i, i, i, ctypes.c_double, P]
     return lib
@@ -41,16 +41,6 @@ def _split(x, planes=2):
     """float -> float32 [planes, ...] of bf16-representable values (oracle/tc_numerics.py: what xb_split_bf16 and the
     kernel epilogues produce)."""
     return split_planes(x, planes)
-
-
-MAP = [0]      # producer mapping the emulator stages with (conv_tc.cu's MAP template parameter); set by the `mapping` fixture
-
-
-@pytest.fixture(params=[0, 1], ids=["map0", "map1"])
-def mapping(request):
-    MAP[0] = request.param
-    yield request.param
-    MAP[0] = 0
 
 
 def _run(lib, geom, x_nhwc, w_mat, out, out_ld, out_c0=0, stages=2, planes=2, planes_a=None):
@@ -64,7 +54,7 @@ def _run(lib, geom, x_nhwc, w_mat, out, out_ld, out_c0=0, stages=2, planes=2, pl
     rc = lib.emul_gemm_gather(pa, planes, xp.data_ptr(), xp.stride(0), wp.data_ptr(), wp.stride(0), geom.B, geom.IH, geom.IW,
                               geom.C, geom.OY, geom.OX, geom.sy, geom.sx, geom.T, dy.ctypes.data, dx.ctypes.data, N,
                               tc.n_tile_for(N, planes), geom.out_H, geom.out_W, geom.oys, geom.oxs, geom.oy0, geom.ox0, out_ld,
-                              out_c0, stages, MAP[0], out.data_ptr())
+                              out_c0, stages, out.data_ptr())
     assert rc == 0
 
 
@@ -84,7 +74,7 @@ TOL = dict(rtol=0, atol=4e-5)     # |x - hi - lo| <= 2^-17 |x| per operand; sums
 @pytest.mark.parametrize("planes", [2, 3])
 @pytest.mark.parametrize("name,B,H,W,C,N,k,s", [("conv1", 2, 84, 84, 4, 32, 8, 4), ("conv2", 2, 21, 21, 32, 64, 4, 2),
                                                 ("conv3", 3, 10, 10, 64, 64, 3, 1), ("odd", 1, 13, 9, 8, 32, 4, 2)])
-def test_forward_conv_layers(emul, mapping, name, B, H, W, C, N, k, s, planes):
+def test_forward_conv_layers(emul, name, B, H, W, C, N, k, s, planes):
     """The three NatureCNN convolutions with the reference's padding rule (k - s)//2 (layers.py:46), NHWC input."""
     torch.manual_seed(len(name))
     pad = (k - s) // 2
@@ -99,7 +89,7 @@ def test_forward_conv_layers(emul, mapping, name, B, H, W, C, N, k, s, planes):
     np.testing.assert_allclose(out.numpy(), want.numpy(), rtol=0, atol=4e-5 if planes == 2 else 6e-7)
 
 
-def test_linear_layer_with_column_split_and_row_tail(emul, mapping):
+def test_linear_layer_with_column_split_and_row_tail(emul):
     """Linear(6400 -> 512) over the NHWC-flattened conv3 output: N = 512 runs as column tiles of 128 (two planes) inside one
     call and as two 256-column calls; 130 rows leave a 2-row tail tile.  The reference flattens NCHW (cnn.py:92), so the
     packed weight permutes its columns to (h, w, c)."""
@@ -120,7 +110,7 @@ def test_linear_layer_with_column_split_and_row_tail(emul, mapping):
     np.testing.assert_allclose(out.numpy(), want.numpy(), rtol=0, atol=2e-6)
 
 
-def test_raw_uint8_plane_first_layer(emul, mapping):
+def test_raw_uint8_plane_first_layer(emul):
     """conv1 on ONE exact plane of raw uint8 pixel values against three weight planes carrying the 1/255."""
     torch.manual_seed(5)
     B, H, W, C, N, k, s = 2, 84, 84, 4, 32, 8, 4
@@ -136,7 +126,7 @@ def test_raw_uint8_plane_first_layer(emul, mapping):
 
 @pytest.mark.parametrize("name,B,H,W,C,N,k,s", [("conv3", 2, 10, 10, 64, 64, 3, 1), ("conv2", 2, 21, 21, 32, 64, 4, 2),
                                                 ("s4", 1, 20, 20, 32, 32, 8, 4)])
-def test_data_gradient_phases(emul, mapping, name, B, H, W, C, N, k, s):
+def test_data_gradient_phases(emul, name, B, H, W, C, N, k, s):
     """grad_input of a convolution as one gathered GEMM per stride phase over the output gradient, vs autograd."""
     torch.manual_seed(1)
     pad = (k - s) // 2
@@ -156,7 +146,7 @@ def test_data_gradient_phases(emul, mapping, name, B, H, W, C, N, k, s):
 
 @pytest.mark.parametrize("name,B,H,W,C,N,k,s,splits", [("conv1", 2, 84, 84, 4, 32, 8, 4, 3), ("conv2", 4, 21, 21, 32, 64, 4, 2, 3),
                                                        ("conv3", 3, 10, 10, 64, 64, 3, 1, 2), ("conv3_1split", 1, 10, 10, 64, 64, 3, 1, 1)])
-def test_weight_gradient(emul, mapping, name, B, H, W, C, N, k, s, splits):
+def test_weight_gradient(emul, name, B, H, W, C, N, k, s, splits):
     """grad_weight as the MN-major gathered GEMM (split over sites, then reduced into torch's [N, C, KH, KW]) vs autograd.
     conv3 has K = 576 = 4.5 column tiles (a half-empty tile); conv1 runs on the pixel-folded view."""
     torch.manual_seed(2)
@@ -173,7 +163,7 @@ def test_weight_gradient(emul, mapping, name, B, H, W, C, N, k, s, splits):
     partials = torch.full((splits, g.K, N), float("nan"), dtype=torch.float64)
     dy, dx = np.asarray(g.dy, np.int8), np.asarray(g.dx, np.int8)
     rc = emul.emul_wgrad(planes, planes, xp.data_ptr(), xp.stride(0), gp.data_ptr(), gp.stride(0), N, g.B, g.IH, g.IW, g.C, g.OY,
-                         g.OX, g.sy, g.sx, g.T, dy.ctypes.data, dx.ctypes.data, N, tc.n_tile_for(N, planes), splits, 2, MAP[0],
+                         g.OX, g.sy, g.sx, g.T, dy.ctypes.data, dx.ctypes.data, N, tc.n_tile_for(N, planes), splits, 2,
                          partials.data_ptr())
     assert rc == 0 and not torch.isnan(partials).any()
     dw = torch.full((N, C, k, k), float("nan"), dtype=torch.float64)
@@ -181,7 +171,7 @@ def test_weight_gradient(emul, mapping, name, B, H, W, C, N, k, s, splits):
     np.testing.assert_allclose(dw.numpy(), want.numpy(), **TOL)
 
 
-def test_linear_weight_gradient(emul, mapping):
+def test_linear_weight_gradient(emul):
     """dW of Linear(6400 -> 128): sites = batch rows, one tap, 50 row tiles x 2 column tiles of 64 of a gradient matrix whose
     rows are 128 elements apart."""
     torch.manual_seed(3)
@@ -193,9 +183,18 @@ def test_linear_weight_gradient(emul, mapping):
     partials = torch.full((2, K, N), float("nan"), dtype=torch.float64)
     dy, dx = np.zeros(1, np.int8), np.zeros(1, np.int8)
     rc = emul.emul_wgrad(2, 2, xp.data_ptr(), xp.stride(0), gp.data_ptr(), gp.stride(0), N, g.B, 1, 1, K, 1, 1, 1, 1, 1,
-                         dy.ctypes.data, dx.ctypes.data, N, 64, 2, 2, MAP[0], partials.data_ptr())
+                         dy.ctypes.data, dx.ctypes.data, N, 64, 2, 2, partials.data_ptr())
     assert rc == 0 and not torch.isnan(partials).any()
     np.testing.assert_allclose(partials.sum(0).t().numpy(), (gy.t() @ x).numpy(), **TOL)
+
+
+def test_fast_division_is_exact(emul):
+    """xb_div: every divisor the layers use (sites per image, grid width) and awkward ones, over ranges of n < 2^31."""
+    emul.emul_div_check.restype = ctypes.c_int64
+    emul.emul_div_check.argtypes = [ctypes.c_uint32] * 3
+    for d in (1, 2, 3, 7, 10, 21, 100, 441, 484, 144, 6400, 12345, 65537, 1 << 20, (1 << 31) - 1):
+        assert emul.emul_div_check(d, 0, 200000) == 0, d
+        assert emul.emul_div_check(d, 3612672 - 1000, 3612672 + 1000) == 0, d
 
 
 def test_wgrad_split_rule():
@@ -245,7 +244,7 @@ class EmulBackend:
         rc = self.lib.emul_gemm_gather(PA, P, x_pl.data_ptr(), x_pl.stride(0), w_pl.data_ptr(), w_pl.stride(0), geom.B,
                                        geom.IH, geom.IW, geom.C, geom.OY, geom.OX, geom.sy, geom.sx, geom.T, dy.ctypes.data,
                                        dx.ctypes.data, N, tc.n_tile_for(N, P), geom.out_H, geom.out_W, geom.oys, geom.oxs,
-                                       geom.oy0, geom.ox0, out_ld, out_c0, 2, MAP[0], tmp.data_ptr())
+                                       geom.oy0, geom.ox0, out_ld, out_c0, 2, tmp.data_ptr())
         assert rc == 0
         blk = tmp[:, out_c0:out_c0 + N]
         written = ~torch.isnan(blk[:, 0])
@@ -272,7 +271,7 @@ class EmulBackend:
         x_pl, g_pl = x_pl.contiguous(), g_pl.contiguous()
         rc = self.lib.emul_wgrad(PA, P, x_pl.data_ptr(), x_pl.stride(0), g_pl.data_ptr(), g_pl.stride(0), g_pl.stride(1), geom.B,
                                  geom.IH, geom.IW, geom.C, geom.OY, geom.OX, geom.sy, geom.sx, geom.T, dy.ctypes.data,
-                                 dx.ctypes.data, N, tc.n_tile_for(N, P), splits, 2, MAP[0], partials.data_ptr())
+                                 dx.ctypes.data, N, tc.n_tile_for(N, P), splits, 2, partials.data_ptr())
         assert rc == 0 and not torch.isnan(partials).any()
         dw = torch.full((N, C, KH, KW), float("nan"), dtype=torch.float64)
         self.lib.emul_wgrad_reduce(partials.data_ptr(), splits, N, C, KH, KW, float(np.float32(scale)), dw.data_ptr())
@@ -280,7 +279,7 @@ class EmulBackend:
 
 
 @pytest.mark.parametrize("planes", [2, 3])
-def test_nature_cnn_forward_backward_orchestration(emul, mapping, planes):
+def test_nature_cnn_forward_backward_orchestration(emul, planes):
     """The whole encoder (3 convs + Linear, cnn.py:84-101) forward and backward through TensorCoreNatureCNN with the
     emulated backend vs torch autograd in float64: layer chaining, NHWC <-> NCHW-flatten weight permutation, ReLU masks in
     the data-gradient epilogues, stride-phase data gradients, column-split Linear (320 = 256 + 64 outputs)."""

@@ -27,6 +27,7 @@ _SIGNATURES = {
     "xb_gather_obs": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P, c_int, _P]),
     "xb_scratch_doubles": (c_int64, []),
     "xb_gather_scalars": (c_int, [_P, c_int64, _P, c_int64, c_int, _P, c_int, _P, _P, _P]),
+    "xb_adv_normalize": (c_int, [_P, c_int64, _P, _P]),
     "xb_ppo_loss_fwd_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int64, c_float, c_float, c_float,
                                     c_int, _P, _P, _P, _P, _P]),
     "xb_per_insert": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_float, _P]),

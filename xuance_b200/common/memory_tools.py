@@ -391,7 +391,22 @@ class DummyOnPolicyBuffer(Buffer):
         self._gae_dirty = False
 
     # -------- K3
-    def _gather_fields(self, idx_t):
+    def global_adv_stats(self, perm_d, n_minibatch):
+        """Sharded runs: (mean, population std) of the advantages of every GLOBAL minibatch of one epoch, float32
+        [n_minibatch, 2] on the device, from ONE all-reduce per epoch (3 doubles per minibatch) instead of one per
+        minibatch.  ``perm_d``: this rank's slot permutation of the epoch, minibatch m = its m-th equal slice."""
+        import torch.distributed as dist
+        self._ensure_gae()
+        a = self.advantages.reshape(-1)[perm_d].reshape(n_minibatch, -1).double()
+        mom = torch.stack([a.sum(1), (a * a).sum(1), torch.full((n_minibatch,), float(a.shape[1]), dtype=torch.float64,
+                                                               device=self.device)])
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(mom)
+        mean = mom[0] / mom[2]
+        std = (mom[1] / mom[2] - mean * mean).clamp_min(0).sqrt()
+        return torch.stack([mean, std], dim=1).float().contiguous()
+
+    def _gather_fields(self, idx_t, adv_stats=None):
         B = idx_t.numel()
         g0 = self._gather_first
         F = len(self._names) - g0
@@ -401,7 +416,9 @@ class DummyOnPolicyBuffer(Buffer):
         sharded = adv_field >= 0 and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         _lib.call("xb_gather_scalars", _lib.ptr(self._fields[g0]), self.n_envs * self.n_size, _lib.ptr(idx_t), B, F,
                   _lib.ptr(out), -1 if sharded else adv_field, _lib.ptr(self._stats), _lib.ptr(self._scratch))
-        if sharded:
+        if sharded and adv_stats is not None:      # global statistics of this minibatch, all-reduced once per epoch
+            _lib.call("xb_adv_normalize", _lib.ptr(out[adv_field]), B, _lib.ptr(adv_stats))
+        elif sharded:
             # this rank holds B of the B*world rows of the global minibatch: normalise with the GLOBAL mean / population
             # std (memory_tools.py:281-282 applied to the whole minibatch) - one 3-double all-reduce
             a = out[adv_field].double()
@@ -425,21 +442,21 @@ class DummyOnPolicyBuffer(Buffer):
             "advantages": row("advantages"),
         }
 
-    def sample(self, indexes):
+    def sample(self, indexes, adv_stats=None):
         """reference :267-287.  ``indexes`` are flat slots (env*T+step, as np.arange(buffer_size) shuffled by
         the agent); returns CUDA tensors with the reference's keys, shapes and dtypes."""
         assert self.full, "Not enough transitions for on-policy buffer to random sample"
         self._ensure_gae()
         idx_t = self._index_tensor(indexes)
         obs = self._gather_rows(self._obs, idx_t)
-        return self._assemble(obs, idx_t, self._gather_fields(idx_t))
+        return self._assemble(obs, idx_t, self._gather_fields(idx_t, adv_stats))
 
-    def sample_prepared(self, indexes, fmt):
+    def sample_prepared(self, indexes, fmt, adv_stats=None):
         """Fast path used by train_epochs: the observation gather also converts u8 -> float in the layout the
         network wants (K3 fused), skipping the u8 intermediate.  Only for uint8 image buffers."""
         assert self.full, "Not enough transitions for on-policy buffer to random sample"
         if self.obs_dtype != torch.uint8 or len(self._obs_shape) != 3 or fmt == _lib.OBS_U8:
-            return self.sample(indexes)
+            return self.sample(indexes, adv_stats)
         self._ensure_gae()
         idx_t = self._index_tensor(indexes)
         H, W, C = self._obs_shape
@@ -448,13 +465,13 @@ class DummyOnPolicyBuffer(Buffer):
             P = {_lib.OBS_PLANES2: 2, _lib.OBS_PLANES3: 3, _lib.OBS_PLANE_RAW: 1}[fmt]    # pixel value as one exact plane
             out = torch.empty((P, B, H, W, C), dtype=torch.bfloat16, device=self.device)
             _lib.call("xb_gather_obs_planes", _lib.ptr(self._obs), _lib.ptr(idx_t), B, H * W * C, P, _lib.ptr(out))
-            return self._assemble(PreparedObs(out, fmt, (H, W, C)), idx_t, self._gather_fields(idx_t))
+            return self._assemble(PreparedObs(out, fmt, (H, W, C)), idx_t, self._gather_fields(idx_t, adv_stats))
         dt = {_lib.OBS_F32_NHWC: torch.float32, _lib.OBS_F32_NCHW: torch.float32,
               _lib.OBS_BF16_NHWC: torch.bfloat16, _lib.OBS_F16_NHWC: torch.float16}[fmt]
         shape = (B, C, H, W) if fmt == _lib.OBS_F32_NCHW else (B, H, W, C)
         out = torch.empty(shape, dtype=dt, device=self.device)
         _lib.call("xb_gather_obs", _lib.ptr(self._obs), _lib.ptr(idx_t), B, H, W, C, _lib.ptr(out), fmt)
-        return self._assemble(PreparedObs(out, fmt, (H, W, C)), idx_t, self._gather_fields(idx_t))
+        return self._assemble(PreparedObs(out, fmt, (H, W, C)), idx_t, self._gather_fields(idx_t, adv_stats))
 
 
 class DummyOnPolicyBuffer_Atari(DummyOnPolicyBuffer):

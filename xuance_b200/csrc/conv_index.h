@@ -27,14 +27,45 @@
 #define XB_CONV_KC 64           // K elements per pipeline stage (8 core matrices, 128 B per operand row)
 #define XB_CONV_TILE_M 128      // rows per CTA tile = TMEM lanes
 
+#define XB_CONV_MAX_UNITS 1024  // 16-byte K units per GEMM row the tap table holds: K = T * C <= 8192
+#define XB_CONV_PRODUCERS 256   // producer threads per CTA (8 warps)
+
+// division by a launch-time constant d >= 1 for 0 <= n < 2^31:  n / d == umulhi(n, mul) >> shift   (mul == 0: d == 1)
+struct XbDiv {
+    uint32_t mul, shift;
+};
+inline XbDiv xb_div_make(uint32_t d) {
+    XbDiv v = {0u, 0u};
+    if (d > 1) {
+        uint32_t lg = 0;
+        while ((1ull << lg) < d) ++lg;                       // ceil(log2 d)
+        const uint32_t p = 31 + lg;
+        v.mul = (uint32_t)(((1ull << p) + d - 1) / d);
+        v.shift = p - 32;
+    }
+    return v;
+}
+XB_HD uint32_t xb_div(uint32_t n, const XbDiv &v) {
+#if defined(__CUDA_ARCH__)
+    return v.mul ? (__umulhi(n, v.mul) >> v.shift) : n;
+#else
+    return v.mul ? (uint32_t)(((uint64_t)n * v.mul) >> 32) >> v.shift : n;
+#endif
+}
+
 struct XbConvGeom {
-    int B, IH, IW, C;           // input tensor [B, IH, IW, C] (bf16 hi / lo planes), C % 8 == 0
+    int B, IH, IW, C;           // input tensor [B, IH, IW, C] (bf16 planes), C % 8 == 0
     int OY, OX;                 // output grid per image
     int sy, sx;                 // input step per output step
     int T;                      // taps; K = T * C, K % XB_CONV_KC == 0
-    int N;                      // output channels (GEMM N), N % 16 == 0, N <= 256
+    int N;                      // GEMM columns of one work item (the tile width), N % 32 == 0
+    XbDiv div_img, div_ox;      // divisions by OY*OX and OX (xb_geom_finish)
     int8_t dy[XB_CONV_MAX_TAPS], dx[XB_CONV_MAX_TAPS];
 };
+inline void xb_geom_finish(XbConvGeom &g) {
+    g.div_img = xb_div_make((uint32_t)(g.OY * g.OX));
+    g.div_ox = xb_div_make((uint32_t)g.OX);
+}
 
 // byte offset of element (r, k) of a [rows x KP] bf16 operand in the K-major no-swizzle canonical layout
 // (8-row x 16-byte core matrices; K-adjacent cores 128 B apart; 8-row groups KP/8*128 B apart)
@@ -50,24 +81,13 @@ XB_HD uint32_t xb_canon_off_mn(int mn, int k, int KP) {
     return (uint32_t)((mn >> 3) * (KP >> 3) * 128 + (k >> 3) * 128 + (k & 7) * 16 + (mn & 7) * 2);
 }
 
-// site m -> (b, y, x)
+// site m -> (b, y, x); m < 2^31
 XB_HD void xb_conv_site(const XbConvGeom &g, int64_t m, int &b, int &y, int &x) {
     const int per_img = g.OY * g.OX;
-    b = (int)(m / per_img);
-    const int rem = (int)(m - (int64_t)b * per_img);
-    y = rem / g.OX;
+    b = (int)xb_div((uint32_t)m, g.div_img);
+    const int rem = (int)((uint32_t)m - (uint32_t)b * (uint32_t)per_img);
+    y = (int)xb_div((uint32_t)rem, g.div_ox);
     x = rem - y * g.OX;
-}
-
-// element offset (in bf16 elements, into the NHWC input) of the 8-channel unit starting at GEMM column k0 (k0 % 8 == 0)
-// for site (b, y, x); returns -1 when the tap falls outside the image (the unit is zero-filled)
-XB_HD int64_t xb_conv_unit_src(const XbConvGeom &g, int b, int y, int x, int k0) {
-    const int t = k0 / g.C;
-    const int c = k0 - t * g.C;
-    const int iy = y * g.sy + g.dy[t];
-    const int ix = x * g.sx + g.dx[t];
-    if (iy < 0 || iy >= g.IH || ix < 0 || ix >= g.IW) return -1;
-    return (((int64_t)b * g.IH + iy) * g.IW + ix) * g.C + c;
 }
 
 // packed weight [N, (kh, kw, c)] element i  <-  torch weight [N, C, KH, KW] element xb_pack_weight_src(i, ...)
@@ -89,98 +109,94 @@ XB_HD int64_t xb_wgrad_sites_per_split(int64_t M, int splits) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// What ONE producer thread (`row` in [0,128)) stages for one K chunk.  emit_a / emit_w receive (byte offset of the 16-byte
-// unit inside the stage's hi plane of that operand, element offset of its 8 source values or -1 for a zero unit).
-// The kernel turns each call into two cp.async (hi and lo plane); the host test writes an emulated shared memory.
+// Staging: what ONE of the 256 producer threads copies for one K chunk.  emit_a / emit_w receive (byte offset of the
+// 16-byte unit inside plane 0 of that operand in the stage, element offset of its 8 source values or -1 for a zero unit);
+// the kernel turns each call into one cp.async per plane, the host test writes an emulated shared memory.
+//
+// Everything that does not depend on the row is tabulated once per launch (XbUnit per 16-byte K unit: tap offsets and the
+// element offset relative to the site's un-shifted pixel) and everything that does not depend on the chunk once per tile
+// (XbSite per row): a unit then costs two adds, two unsigned compares and a select.  (The first version recomputed
+// tap = k / C and the site by integer division for every unit; with ONE producer warp per scheduler those dependent
+// instruction chains, not the loads, set the pace: ~4.5k cycles per chunk on B200 whatever the byte count.)
+//
+// Mapping (row-coalesced): in the canonical no-swizzle layouts the shared-memory bank of a 16-byte unit depends only on
+// (row & 7) [K-major] / (site & 7) [MN-major], so a warp instruction is conflict-free as soon as its 32 lanes hold each of
+// the 8 residues four times, which leaves the other lane bits free to walk along MEMORY-contiguous units: lane ->
+// (residue = lane & 7, unit = lane >> 3), i.e. 8 rows x 4 consecutive units = 8 x 64 contiguous bytes per instruction
+// (whole 32-byte sectors; a thread-per-row mapping uses half of every sector it fetches).
+// Thread pt in [0,256): team = pt >> 7 takes K units team*4 .. team*4+3 of the chunk (forward) / the sites with
+// (site >> 3) & 1 == team (weight gradient); w = (pt >> 5) & 3, rs = pt & 7, uo = (pt >> 3) & 3.
 // ---------------------------------------------------------------------------------------------------------------------
-// forward / data-gradient GEMM: thread = site (b, y, x) (live = inside the problem); K-major operands
+struct XbUnit {
+    int32_t off;                // (dy * IW + dx) * C + c: element offset relative to pixel (y*sy, x*sx) channel 0
+    int16_t dy, dx;
+};
+XB_HD XbUnit xb_unit(const XbConvGeom &g, int ku) {
+    const int k0 = ku * 8, t = k0 / g.C, c = k0 - t * g.C;
+    XbUnit e;
+    e.dy = g.dy[t], e.dx = g.dx[t];
+    e.off = ((int)e.dy * g.IW + (int)e.dx) * g.C + c;
+    return e;
+}
+
+struct XbSite {
+    int64_t base;               // element offset of pixel (y*sy, x*sx), channel 0, of image b
+    int32_t iy0, ix0;           // y*sy, x*sx; a row outside the problem has iy0 far below zero (every unit reads as zero)
+};
+XB_HD XbSite xb_site(const XbConvGeom &g, int64_t m, int64_t M) {
+    XbSite s;
+    s.base = 0, s.iy0 = -(1 << 24), s.ix0 = 0;
+    if (m < M) {
+        int b, y, x;
+        xb_conv_site(g, m, b, y, x);
+        s.iy0 = y * g.sy, s.ix0 = x * g.sx;
+        s.base = (((int64_t)b * g.IH + s.iy0) * g.IW + s.ix0) * g.C;
+    }
+    return s;
+}
+XB_HD int64_t xb_unit_src(const XbConvGeom &g, const XbSite &s, const XbUnit &e) {
+    const int iy = s.iy0 + e.dy, ix = s.ix0 + e.dx;
+    return ((unsigned)iy < (unsigned)g.IH && (unsigned)ix < (unsigned)g.IW) ? s.base + e.off : (int64_t)-1;
+}
+
+// rows a producer thread feeds in the forward mapping: 32*w + 8*gi + rs, gi < 4 (both teams own the same rows)
+XB_HD int xb_fwd_row(int pt, int gi) { return 32 * ((pt >> 5) & 3) + 8 * gi + (pt & 7); }
+
+// forward / data-gradient GEMM (K-major operands): the thread's 4 rows x 1 K unit of A, and its share of the weight tile
 template <class EmitA, class EmitW>
-XB_HD void xb_stage_fwd(const XbConvGeom &g, int row, bool live, int b, int y, int x, int kc, EmitA &&emit_a,
+XB_HD void xb_stage_fwd(const XbConvGeom &g, const XbUnit *tab, int pt, const XbSite *sites, int kc, EmitA &&emit_a,
                         EmitW &&emit_w) {
     const int K = g.T * g.C;
-    for (int u = 0; u < XB_CONV_KC / 8; ++u) {
-        const int64_t off = live ? xb_conv_unit_src(g, b, y, x, kc * XB_CONV_KC + u * 8) : -1;
-        emit_a(xb_canon_off(row, u * 8, XB_CONV_KC), off);
-    }
-    for (int idx = row; idx < g.N * (XB_CONV_KC / 8); idx += XB_CONV_TILE_M) {
-        const int n = idx >> 3, u = idx & 7;
+    const int team = pt >> 7, w = (pt >> 5) & 3, rs = pt & 7, uo = (pt >> 3) & 3;
+    const int u = team * 4 + uo;
+    const XbUnit e = tab[kc * (XB_CONV_KC / 8) + u];
+    for (int gi = 0; gi < 4; ++gi)
+        emit_a(xb_canon_off(32 * w + 8 * gi + rs, u * 8, XB_CONV_KC), xb_unit_src(g, sites[gi], e));
+    for (int j = w; j < (g.N >> 3); j += 4) {               // 8-row groups of the weight tile, dealt to the warps
+        const int n = j * 8 + rs;
         emit_w(xb_canon_off(n, u * 8, XB_CONV_KC), (int64_t)n * K + kc * XB_CONV_KC + u * 8);
     }
 }
 
-// weight-gradient GEMM: the chunk holds 64 consecutive sites starting at chunk_site0 (sites >= site_end are zero);
-// thread = (site pp = row & 63, half uh = row >> 6 of the tile's 16 column units); MN-major operands;
-// the second operand is the output gradient G[site, g_c0 + n] of a matrix with g_ld elements per site (g.N = tile width)
+// weight-gradient GEMM (MN-major operands): the chunk holds 64 consecutive sites starting at chunk_site0 (sites >=
+// site_end are zero); the thread owns site pp = 16*w + 8*team + rs and the column units 4*quad + uo, quad < 4, of the
+// tile's 128 (t, c) columns; the second operand is the output gradient G[site*g_ld + g_c0 + n]
 template <class EmitA, class EmitG>
-XB_HD void xb_stage_wgrad(const XbConvGeom &g, int row, int64_t mt, int64_t chunk_site0, int64_t site_end, int64_t g_ld,
-                          int g_c0, EmitA &&emit_a, EmitG &&emit_g) {
+XB_HD void xb_stage_wgrad(const XbConvGeom &g, const XbUnit *tab, int pt, int64_t mt, int64_t chunk_site0, int64_t site_end,
+                          int64_t M, int64_t g_ld, int g_c0, EmitA &&emit_a, EmitG &&emit_g) {
     const int K = g.T * g.C;
-    const int pp = row & (XB_CONV_KC - 1), uh = row >> 6;
+    const int team = pt >> 7, w = (pt >> 5) & 3, rs = pt & 7, uo = (pt >> 3) & 3;
+    const int pp = 16 * w + 8 * team + rs;
     const int64_t site = chunk_site0 + pp;
     const bool in_run = site < site_end;
-    int b = 0, y = 0, x = 0;
-    if (in_run) xb_conv_site(g, site, b, y, x);
-    for (int j = 0; j < 8; ++j) {
-        const int u = uh * 8 + j;
-        const int64_t kcol = mt * XB_CONV_TILE_M + u * 8;
-        const int64_t off = (in_run && kcol < K) ? xb_conv_unit_src(g, b, y, x, (int)kcol) : -1;
-        emit_a(xb_canon_off_mn(u * 8, pp, XB_CONV_KC), off);
+    const XbSite s = xb_site(g, in_run ? site : M, M);
+    for (int quad = 0; quad < 4; ++quad) {
+        const int u = quad * 4 + uo;
+        const int64_t ku = mt * (XB_CONV_TILE_M / 8) + u;
+        emit_a(xb_canon_off_mn(u * 8, pp, XB_CONV_KC), ku * 8 < K ? xb_unit_src(g, s, tab[ku]) : (int64_t)-1);
     }
-    for (int j = uh; j < g.N / 8; j += 2)
+    for (int j = uo; j < (g.N >> 3); j += 4)
         emit_g(xb_canon_off_mn(j * 8, pp, XB_CONV_KC), in_run ? site * g_ld + g_c0 + j * 8 : (int64_t)-1);
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Row-coalesced producer mapping (MAP = 1; same shared-memory image, different division of the units among the 128
-// producer threads).  In the canonical no-swizzle layouts the shared-memory bank of a 16-byte unit depends only on
-// (row & 7) [K-major] / (site & 7) [MN-major], so a warp instruction is conflict-free as soon as its 32 lanes hold each of
-// the 8 residues four times - which leaves the other lane bits free to walk along MEMORY-contiguous units: lane ->
-// (residue = lane & 7, unit offset = lane >> 3), i.e. 8 rows x 4 consecutive units = 8 x 64 contiguous bytes per
-// instruction instead of 32 scattered 16-byte pieces (half of every 32-byte sector wasted).
-// ---------------------------------------------------------------------------------------------------------------------
-// forward: producer thread t = (warp w, lane l) owns rows 32w + 8*gi + (l & 7), gi < 4, and units (l >> 3) and 4 + (l >> 3)
-XB_HD int xb_v2_row(int t, int gi) { return 32 * (t >> 5) + 8 * gi + (t & 7); }
-
-// sites: the thread's four sites as {b, y, x} (b < 0: row outside the problem)
-template <class EmitA, class EmitW>
-XB_HD void xb_stage_fwd_v2(const XbConvGeom &g, int t, const int (*sites)[3], int kc, EmitA &&emit_a, EmitW &&emit_w) {
-    const int K = g.T * g.C;
-    const int w = t >> 5, l = t & 31, rs = l & 7, uo = l >> 3;
-    for (int half = 0; half < 2; ++half) {
-        const int u = half * 4 + uo, k0 = kc * XB_CONV_KC + u * 8;
-        for (int gi = 0; gi < 4; ++gi) {
-            const int *s = sites[gi];
-            const int64_t off = s[0] >= 0 ? xb_conv_unit_src(g, s[0], s[1], s[2], k0) : -1;
-            emit_a(xb_canon_off(32 * w + 8 * gi + rs, u * 8, XB_CONV_KC), off);
-        }
-    }
-    for (int q = w; q < (g.N >> 3) * 2; q += 4) {            // (8-row group, half) pairs of the weight tile, dealt to the warps
-        const int n = (q >> 1) * 8 + rs, u = (q & 1) * 4 + uo;
-        emit_w(xb_canon_off(n, u * 8, XB_CONV_KC), (int64_t)n * K + kc * XB_CONV_KC + u * 8);
-    }
-}
-
-// weight gradient: thread t owns sites 16w + 8*si + (l & 7), si < 2, of the chunk and the column units 4*quad + (l >> 3)
-template <class EmitA, class EmitG>
-XB_HD void xb_stage_wgrad_v2(const XbConvGeom &g, int t, int64_t mt, int64_t chunk_site0, int64_t site_end, int64_t g_ld,
-                             int g_c0, EmitA &&emit_a, EmitG &&emit_g) {
-    const int K = g.T * g.C;
-    const int w = t >> 5, l = t & 31, rs = l & 7, uo = l >> 3;
-    for (int si = 0; si < 2; ++si) {
-        const int pp = 16 * w + 8 * si + rs;
-        const int64_t site = chunk_site0 + pp;
-        const bool in_run = site < site_end;
-        int b = 0, y = 0, x = 0;
-        if (in_run) xb_conv_site(g, site, b, y, x);
-        for (int quad = 0; quad < 4; ++quad) {
-            const int u = quad * 4 + uo;
-            const int64_t kcol = mt * XB_CONV_TILE_M + u * 8;
-            const int64_t off = (in_run && kcol < K) ? xb_conv_unit_src(g, b, y, x, (int)kcol) : -1;
-            emit_a(xb_canon_off_mn(u * 8, pp, XB_CONV_KC), off);
-        }
-        for (int j = uo; j < (g.N >> 3); j += 4)
-            emit_g(xb_canon_off_mn(j * 8, pp, XB_CONV_KC), in_run ? site * g_ld + g_c0 + j * 8 : (int64_t)-1);
-    }
 }
 
 // shared-memory bytes of one pipeline stage: the P planes of A (hi | [mid |] lo) followed by the P planes of W.

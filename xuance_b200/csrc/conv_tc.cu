@@ -1,25 +1,27 @@
-// K12 (EXPERIMENTAL; nothing on the default path calls it.  Status after round 1: the forward GEMM passed on B200 -
-// tests/test_gpu_tc_conv.py, profiles/r01_k12_bringup_forward.log; the data-gradient and weight-gradient modes ran on
-// hardware inside the whole-encoder backward and agreed with cuDNN fp32 to ~4e-3 of max|grad|, per-layer parity pending):
-// gathered-operand GEMM on the 5th-generation tensor cores for the NatureCNN layers (cnn.py:45-50, 84-101) - the 85 %
-// of the fp32 PPO step that cuDNN's CUDA-core fp32 convolutions take.
+// K12: gathered-operand GEMM on the 5th-generation tensor cores (tcgen05.mma, TMEM accumulators) for the NatureCNN layers
+// (cnn.py:45-50, 84-101) - forward, data gradient and weight gradient of the three convolutions and the hidden layer, the
+// 85 % of the fp32 PPO step that cuDNN's CUDA-core fp32 convolutions take.
 //
 //   D[m, n] = sum_{t, c} in[b, y*sy + dy[t], x*sx + dx[t], c] * W[n, t*C + c]  (+ bias[n], ReLU)      conv_index.h
 //
-// Numerics as K9-TC: every fp32 operand travels as x = hi + lo (two bf16 tensors) and each product is the three MMAs
-// hi.hi + hi.lo + lo.hi accumulated in fp32 in TMEM (~1e-5 relative, i.e. inside the fp32 parity tolerance).
+// Numerics: every fp32 operand travels as 1-3 bf16 planes (x = sum of its planes); the kept plane products are accumulated
+// in fp32 in TMEM, one accumulator per order of magnitude, and added smallest first in the epilogue (see the kernel).
 //
-// Structure (one CTA per SM, persistent over 128-row tiles, 9 warps):
-//   warps 5-8  producers : thread = tile row.  Per K chunk of 64 the row's 8 units (16 B = 8 channels of one tap) and
-//                          this thread's share of the weight rows are fetched with 16-byte cp.async straight into the
-//                          K-major no-swizzle canonical layout (zero-fill for padding taps / tail rows); a chunk is
-//                          published (wait_group -> fence.proxy.async -> mbarrier arrive) one chunk behind the issue
-//                          point so that a group is always in flight.
-//   warp 4     MMA       : lane 0 waits full[stage], issues 3 x 4 tcgen05.mma (M 128, N, K 16) and commits onto
-//                          empty[stage]; after the last chunk commits onto acc_full[a].  Two accumulators in TMEM.
-//   warps 0-3  epilogue  : thread = row = TMEM lane.  tcgen05.ld 32 columns at a time, bias + ReLU, then the row is
-//                          written as fp32 and / or as the hi / lo bf16 pair the next layer consumes.
+// Structure (one CTA per SM, persistent over work items = (128-row tile, column tile), 13 warps):
+//   warps 5-12 producers : 256 threads, row-coalesced mapping (conv_index.h): per K chunk of 64 each thread issues its
+//                          16-byte cp.async units straight into the K-major (MN-major for the weight gradient) no-swizzle
+//                          canonical layout (zero-fill for padding taps / tail rows) and hands the stage's full barrier an
+//                          ASYNCHRONOUS arrival (cp.async.mbarrier.arrive.noinc) - no producer ever waits for a load, so
+//                          all `stages` chunks are in flight.
+//   warp 4     MMA       : lane 0 waits full[stage], issues PA tcgen05.mma per K step of 16 (A plane pa x the first PB - pa
+//                          weight planes, which sit adjacent in the stage and are ONE operand of (PB - pa) * N rows) and
+//                          commits onto empty[stage]; after the last chunk commits onto acc_full[a].  Two accumulator sets.
+//   warps 0-3  epilogue  : thread = row = TMEM lane.  tcgen05.ld 32 columns at a time from each accumulator group, added
+//                          smallest first, bias + ReLU / ReLU-derivative mask, then the row is written as fp32 and / or as
+//                          the bf16 planes the next layer consumes.
 #include <cstdlib>
+
+#include <cuda.h>      // CUtensorMap + the cuTensorMapEncodeTiled prototype (resolved at run time through the runtime API)
 
 #include "tc_common.cuh"
 #include "conv_index.h"
@@ -28,12 +30,18 @@ namespace {
 using namespace xbtc;
 
 constexpr int KC = XB_CONV_KC, TILE_M = XB_CONV_TILE_M;
-constexpr int EPI_WARPS = 4, PROD_WARPS = 4;
+constexpr int EPI_WARPS = 4, PROD_WARPS = XB_CONV_PRODUCERS / 32;
 constexpr int MMA_WARP = EPI_WARPS;
 constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;
 constexpr int MAX_STAGES = 6;
 
 struct ConvParams {
+    // TMA descriptors of the operands that are plain matrices (bf16 planes as the outermost dimension): the B operand
+    // (packed weights [N_total, K] forward, output gradient [sites, g_ld] in the weight gradient) and, for a Linear layer,
+    // the A operand.  Gathered A operands (convolutions) keep the cp.async path.
+    alignas(64) CUtensorMap tm_a;
+    alignas(64) CUtensorMap tm_b;
+    int a_tma, b_tma;
     XbConvGeom g;                          // g.N = columns per work item (the tile width N)
     const __nv_bfloat16 *in[3];            // A planes: [B, IH, IW, C]
     const __nv_bfloat16 *w[3];             // B planes.  forward: weight [N_total, K].  weight gradient: output gradient [P, w_ld]
@@ -56,10 +64,33 @@ struct ConvParams {
     int64_t sites_per_split;
 };
 
+// 16-byte cp.async with zero-fill.  CA = through L1 (sector sharing between the lanes of a request and reuse of the
+// overlapping windows of the raw-pixel first layer: 1080 -> 774 us on B200); otherwise L2 only (better for the wider layers).
+template <bool CA>
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+    if (CA) asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+    else asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// TMA: one 3-D tile {c0 .. c0+box0, c1 .. c1+box1, all planes} -> shared memory, completion bytes on an mbarrier
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+// shared-memory matrix descriptor of a 128-byte-swizzled operand (the layout TMA writes with CU_TENSOR_MAP_SWIZZLE_128B):
+// K-major:  rows of 64 elements = 128 B, 8-row groups 1024 B apart (SBO), leading offset unused (16 B);
+// MN-major: rows of 64 MN elements = 128 B per K index, 8-K groups 1024 B apart (SBO), 64-element MN blocks LBO apart
+// (cute/atom/mma_traits_sm100.hpp: K  B128 ((8,n),2):((8,SBO),1);  MN B128 ((8,n),(8,k)):((1,LBO),(8,SBO)), 16-byte units)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;                                   // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                                   // layout type SWIZZLE_128B
+    return d;
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
@@ -86,15 +117,14 @@ __device__ __forceinline__ uint32_t make_idesc_mn(int M, int N) { return make_id
 // in the canonical layouts they ARE one operand of PB*N rows: ONE tcgen05.mma per A plane multiplies it with the first
 // (PB - pa) B planes and lands in the accumulator columns of groups pa .. PB-1 - every A plane is read from shared memory
 // once per K step instead of once per product (shared-memory operand reads, not the tensor pipe, bound N <= 64 tiles).
-// MAP: how the 16-byte units of a stage are dealt to the producer threads (conv_index.h): 0 = thread per row,
-// 1 = row-coalesced (8 rows x 4 memory-contiguous units per warp instruction).
-template <bool WGRAD, int PA, int PB, int MAP>
+template <bool WGRAD, int PA, int PB>
 __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
     static_assert(PA >= 1 && PA <= PB && PB <= 3, "plane counts");
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_slot;
     __shared__ float s_bias[256];
+    __shared__ XbUnit s_units[XB_CONV_MAX_UNITS];     // per 16-byte K unit: tap offsets + element offset (conv_index.h)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const XbConvGeom &g = p.g;
@@ -117,7 +147,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(&full_bar[s], PROD_WARPS * 32);       // one asynchronous arrival per producer thread
+            // one asynchronous arrival per producer thread (+ the expect_tx arrival of the thread that issues the TMA copies)
+            mbar_init(&full_bar[s], PROD_WARPS * 32 + ((p.a_tma || p.b_tma) ? 1 : 0));
             mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -131,15 +162,17 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                      "r"(tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
+    for (int i = tid; i < K / 8; i += THREADS) s_units[i] = xb_unit(g, i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     const uint32_t smem_base = smem_u32(smem);
+    if ((p.a_tma || p.b_tma) && (smem_base & 1023u)) __trap();     // the 128-byte swizzle pattern repeats every 1024 B
 
     if (warp > MMA_WARP) {
-        // ------------------------------------------------------------------ producers
-        const int row = tid - (MMA_WARP + 1) * 32;    // 0..127
+        // ------------------------------------------------------------------ producers (256 threads)
+        const int pt = tid - (MMA_WARP + 1) * 32;
         uint32_t it = 0;
         for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
             const int n_chunks = chunks_of(w);
@@ -147,19 +180,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
             const int64_t rem = WGRAD ? w - sp * mn_tiles : w;
             const int64_t mt = rem / p.n_tiles;
             const int nt = (int)(rem - mt * p.n_tiles);
-            // forward: this thread's site, fixed for the tile
-            const int64_t m = mt * TILE_M + row;
-            const bool live = !WGRAD && m < p.M;
-            int b = 0, y = 0, x = 0;
-            if (live) xb_conv_site(g, m, b, y, x);
-            int sites4[4][3];                                  // MAP = 1, forward: the four rows this thread feeds
-            if (MAP == 1 && !WGRAD) {
+            XbSite sites[4];                                   // forward: the four rows this thread feeds, fixed for the tile
+            if (!WGRAD) {
 #pragma unroll
-                for (int gi = 0; gi < 4; ++gi) {
-                    const int64_t mm = mt * TILE_M + xb_v2_row(row, gi);
-                    sites4[gi][0] = -1, sites4[gi][1] = 0, sites4[gi][2] = 0;
-                    if (mm < p.M) xb_conv_site(g, mm, sites4[gi][0], sites4[gi][1], sites4[gi][2]);
-                }
+                for (int gi = 0; gi < 4; ++gi) sites[gi] = xb_site(g, mt * TILE_M + xb_fwd_row(pt, gi), p.M);
             }
             const int64_t w_off = WGRAD ? 0 : (int64_t)nt * N * K;        // forward: first weight row of this n tile
             const int64_t site_end = WGRAD ? ((sp + 1) * p.sites_per_split < p.M ? (sp + 1) * p.sites_per_split : p.M) : 0;
@@ -169,28 +193,42 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                 const uint32_t base = smem_base + (uint32_t)stage * stage_bytes;
                 const uint32_t wbase = base + PA * a_plane;
                 auto emit_a = [&](uint32_t dst_off, int64_t src) {       // src < 0: the 16 bytes are zero-filled
+                    if (p.a_tma) return;
                     const uint32_t nbytes = src >= 0 ? 16u : 0u;
                     const int64_t o = src >= 0 ? src : 0;
 #pragma unroll
-                    for (int q = 0; q < PA; ++q) cp_async16(base + q * a_plane + dst_off, p.in[q] + o, nbytes);
+                    for (int q = 0; q < PA; ++q) cp_async16<PA == 1>(base + q * a_plane + dst_off, p.in[q] + o, nbytes);
                 };
                 auto emit_w = [&](uint32_t dst_off, int64_t src) {
+                    if (p.b_tma) return;
                     const uint32_t nbytes = src >= 0 ? 16u : 0u;
                     const int64_t o = src >= 0 ? src + w_off : 0;
 #pragma unroll
-                    for (int q = 0; q < PB; ++q) cp_async16(wbase + q * w_plane + dst_off, p.w[q] + o, nbytes);
+                    for (int q = 0; q < PB; ++q) cp_async16<false>(wbase + q * w_plane + dst_off, p.w[q] + o, nbytes);
                 };
-                if (MAP == 0) {
-                    if (!WGRAD) xb_stage_fwd(g, row, live, b, y, x, kc, emit_a, emit_w);
-                    else xb_stage_wgrad(g, row, mt, sp * p.sites_per_split + (int64_t)kc * KC, site_end, p.w_ld, nt * N, emit_a, emit_w);
-                } else {
-                    if (!WGRAD) xb_stage_fwd_v2(g, row, sites4, kc, emit_a, emit_w);
-                    else xb_stage_wgrad_v2(g, row, mt, sp * p.sites_per_split + (int64_t)kc * KC, site_end, p.w_ld, nt * N, emit_a, emit_w);
+                const int64_t site0 = sp * p.sites_per_split + (int64_t)kc * KC;     // weight gradient: first site of the chunk
+                if (pt == 0 && (p.a_tma || p.b_tma)) {
+                    // plain-matrix operands: one elected thread arms the barrier with the byte count and issues the tile
+                    // copies; every plane of an operand travels in ONE box (planes are the outermost tensor dimension)
+                    const uint32_t bytes = (p.a_tma ? PA * a_plane : 0u) + (p.b_tma ? PB * w_plane : 0u);
+                    mbar_expect_tx(&full_bar[stage], bytes);
+                    if (p.b_tma) {
+                        if (!WGRAD) tma_load_3d(wbase, &p.tm_b, kc * KC, nt * N, 0, &full_bar[stage]);          // W[n, k] rows
+                        else tma_load_3d(wbase, &p.tm_b, nt * N, (int)site0, 0, &full_bar[stage]);               // G[site, n] rows
+                    }
+                    if (p.a_tma) {
+                        if (!WGRAD) {
+                            tma_load_3d(base, &p.tm_a, kc * KC, (int)(mt * TILE_M), 0, &full_bar[stage]);        // A[row, k]
+                        } else {                                    // A[site, kcol]: two blocks of 64 columns
+                            tma_load_3d(base, &p.tm_a, (int)(mt * TILE_M), (int)site0, 0, &full_bar[stage]);
+                            tma_load_3d(base + PA * (a_plane / 2), &p.tm_a, (int)(mt * TILE_M) + 64, (int)site0, 0, &full_bar[stage]);
+                        }
+                    }
                 }
+                if (!WGRAD) xb_stage_fwd(g, s_units, pt, sites, kc, emit_a, emit_w);
+                else xb_stage_wgrad(g, s_units, pt, mt, site0, site_end, p.M, p.w_ld, nt * N, emit_a, emit_w);
                 // asynchronous publication: the barrier receives this thread's arrival when the copies issued above have
                 // landed - the producer never waits for its own loads, so up to `stages` chunks of loads are in flight
-                // (the round-1 wait_group -> fence -> arrive sequence exposed the full load latency once per chunk:
-                // ~100 cycles per KB staged, measured on B200, whatever the mapping)
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full_bar[stage])) : "memory");
                 ++it;
             }
@@ -215,14 +253,26 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                     const uint32_t w_addr = base + PA * a_plane;
 #pragma unroll
                     for (int ks = 0; ks < KC / 16; ++ks) {
+                        // B operand: the first (PB - pa) planes, adjacent in the stage, are ONE operand of (PB - pa) * N rows.
+                        //  cp.async : no-swizzle canonical layout (conv_index.h), K step = two core matrices = 256 B
+                        //  TMA      : 128-byte swizzle.  K-major: rows of 128 B, K step = 32 B inside the row.
+                        //             MN-major (weight gradient, N = 64): one 64-column block per plane, blocks w_plane apart,
+                        //             K step = 16 sites = 2048 B
+                        const uint64_t b_desc = !p.b_tma ? make_desc(w_addr + ks * 256, KC)
+                                                : (!WGRAD ? make_desc_sw128(w_addr + ks * 32, 16, 1024)
+                                                          : make_desc_sw128(w_addr + ks * 2048, w_plane, 1024));
 #pragma unroll
                         for (int pa = 0; pa < PA; ++pa) {
-                            // A plane pa x B planes 0 .. PB-1-pa (one operand of (PB-pa)*N rows) -> accumulator groups pa .. PB-1.
+                            // A plane pa x B planes 0 .. PB-1-pa -> accumulator groups pa .. PB-1.
                             // pa = 0 covers every group, so its first instruction of a work item (acc = 0) initialises them all.
                             const int nb = PB - pa;
                             const uint32_t idesc = WGRAD ? make_idesc_mn(TILE_M, nb * N) : make_idesc(TILE_M, nb * N);
-                            mma_bf16(d_tmem + (uint32_t)(pa * N), make_desc(base + pa * a_plane + ks * 256, KC),
-                                     make_desc(w_addr + ks * 256, KC), idesc, pa == 0 ? acc : 1u);
+                            // A operand by TMA (Linear layers).  K-major: [128 rows][128 B] per plane.  MN-major: two blocks of
+                            // 64 columns, each [planes][64 sites][128 B]: plane stride a_plane/2, block stride PA*a_plane/2
+                            const uint64_t a_desc = !p.a_tma ? make_desc(base + pa * a_plane + ks * 256, KC)
+                                                    : (!WGRAD ? make_desc_sw128(base + pa * a_plane + ks * 32, 16, 1024)
+                                                              : make_desc_sw128(base + pa * (a_plane / 2) + ks * 2048, PA * (a_plane / 2), 1024));
+                            mma_bf16(d_tmem + (uint32_t)(pa * N), a_desc, b_desc, idesc, pa == 0 ? acc : 1u);
                         }
                         acc = 1;
                     }
@@ -399,6 +449,49 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float *__restric
     }
 }
 
+// ---------------------------------------------------------------- TMA descriptors (host)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+        cudaGetLastError();
+    }
+    return fn;
+}
+// XB_K12_TMA=0 keeps every operand on the cp.async path (the one the host emulator models)
+bool tma_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("XB_K12_TMA");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+// bf16 tensor [planes][rows][cols] (cols contiguous, row_stride / plane_stride in elements), tiles {64 cols, box_rows, planes},
+// 128-byte swizzle, zero fill outside [rows, cols]
+bool make_tmap(CUtensorMap *tm, const void *base, int64_t cols, int64_t rows, int planes, int64_t row_stride,
+               int64_t plane_stride, int box_rows) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    if (((uintptr_t)base & 15) || (row_stride * 2) % 16 || (plane_stride * 2) % 16 || box_rows > 256) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)row_stride * 2, (cuuint64_t)(planes > 1 ? plane_stride : row_stride * rows) * 2};
+    const cuuint32_t box[3] = {64, (cuuint32_t)box_rows, (cuuint32_t)planes};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int fill_params(ConvParams &p, int pa, int pb, const void *in, int64_t in_plane, const void *w, int64_t w_plane, int B,
                 int IH, int IW, int C, int OY, int OX, int sy, int sx, int T, const int8_t *dy, const int8_t *dx, int N,
                 int n_tile) {
@@ -408,9 +501,11 @@ int fill_params(ConvParams &p, int pa, int pb, const void *in, int64_t in_plane,
         return XB_EINVAL;
     // one tcgen05.mma spans pb * n_tile columns (<= 256, a multiple of 16); two accumulators of pb * n_tile columns in TMEM
     if (T > XB_CONV_MAX_TAPS || n_tile % 32 != 0 || N % n_tile != 0 || pb * n_tile > 256 || C % 8 != 0) return XB_ERANGE;
+    if ((int64_t)T * C > 8 * XB_CONV_MAX_UNITS || (int64_t)B * OY * OX >= (int64_t)1 << 31) return XB_ERANGE;   // tap table, 32-bit sites
     if (!xb_aligned(in, 16) || !xb_aligned(w, 16) || in_plane % 8 != 0 || w_plane % 8 != 0) return XB_EALIGN;
     p.g.B = B, p.g.IH = IH, p.g.IW = IW, p.g.C = C, p.g.OY = OY, p.g.OX = OX, p.g.sy = sy, p.g.sx = sx, p.g.T = T, p.g.N = n_tile;
     for (int t = 0; t < XB_CONV_MAX_TAPS; ++t) p.g.dy[t] = t < T ? dy[t] : 0, p.g.dx[t] = t < T ? dx[t] : 0;
+    xb_geom_finish(p.g);
     const __nv_bfloat16 *ib = (const __nv_bfloat16 *)in, *wb = (const __nv_bfloat16 *)w;
     for (int q = 0; q < 3; ++q) p.in[q] = q < pa ? ib + q * in_plane : nullptr, p.w[q] = q < pb ? wb + q * w_plane : nullptr;
     p.M = (int64_t)B * OY * OX;
@@ -420,32 +515,21 @@ int fill_params(ConvParams &p, int pa, int pb, const void *in, int64_t in_plane,
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) return XB_ERANGE;
     p.stages = stages;
+    p.a_tma = p.b_tma = 0;
     return XB_OK;
 }
 
-template <bool WGRAD, int PA, int PB, int MAP>
-int launch_map(const ConvParams &p, int64_t work, void *stream) {
+template <bool WGRAD, int PA, int PB>
+int launch_pp(const ConvParams &p, int64_t work, void *stream) {
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(conv_tc_kernel<WGRAD, PA, PB, MAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel<WGRAD, PA, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr = true;
     }
     const int grid = (int)(work < xb_sm_count() ? work : xb_sm_count());
     const size_t smem = (size_t)p.stages * (PA * xb_conv_a_plane_bytes() + PB * xb_conv_w_plane_bytes(p.g.N));
-    conv_tc_kernel<WGRAD, PA, PB, MAP><<<grid, THREADS, smem, (cudaStream_t)stream>>>(p);
+    conv_tc_kernel<WGRAD, PA, PB><<<grid, THREADS, smem, (cudaStream_t)stream>>>(p);
     return xb_launch_status();
-}
-
-// XB_K12_MAP=0 selects the thread-per-row producer mapping; default 1 = row-coalesced (8 rows x 64 contiguous bytes per warp
-// instruction: a quarter of the L1 wavefronts of mapping 0, measured on B200 - DESIGN.md section 3)
-template <bool WGRAD, int PA, int PB>
-int launch_pp(const ConvParams &p, int64_t work, void *stream) {
-    static int map = -1;
-    if (map < 0) {
-        const char *e = getenv("XB_K12_MAP");
-        map = (e && e[0] == '0') ? 0 : 1;
-    }
-    return map == 1 ? launch_map<WGRAD, PA, PB, 1>(p, work, stream) : launch_map<WGRAD, PA, PB, 0>(p, work, stream);
 }
 
 template <bool WGRAD>
@@ -514,6 +598,14 @@ extern "C" int xb_gemm_gather_tc(int planes_a, int planes_b, const void *in, int
     p.out_H = out_H, p.out_W = out_W, p.oys = oys, p.oxs = oxs, p.oy0 = oy0, p.ox0 = ox0;
     p.out_ld = out_ld, p.out_c0 = out_c0;
     p.splits = 1, p.sites_per_split = 0, p.w_ld = 0;
+    if (tma_enabled()) {
+        const int64_t K = (int64_t)T * C;
+        // weights [planes_b][N][K]: tiles of {64 k, n_tile rows, all planes}
+        p.b_tma = make_tmap(&p.tm_b, w, K, N, planes_b, K, w_plane, n_tile) ? 1 : 0;
+        // a Linear layer's input [planes_a][B][C] is a plain matrix too: tiles of {64 k, 128 rows, all planes}
+        if (T == 1 && IH == 1 && IW == 1 && OY == 1 && OX == 1)
+            p.a_tma = make_tmap(&p.tm_a, in, C, B, planes_a, C, in_plane, TILE_M) ? 1 : 0;
+    }
     const int64_t tiles = (p.M + TILE_M - 1) / TILE_M * p.n_tiles;
     return launch<false>(planes_a, planes_b, p, tiles, stream);
 }
@@ -535,6 +627,13 @@ extern "C" int xb_wgrad_gather_tc(int planes_a, int planes_b, const void *in, in
     const int64_t per = xb_wgrad_sites_per_split(p.M, splits);
     if (per == 0) return XB_EINVAL;     // too many splits for this many sites
     p.splits = splits, p.sites_per_split = per;
+    if (tma_enabled()) {
+        // output gradient [planes_b][sites][g_ld]: tiles of {64 columns, 64 sites, all planes} (one 64-column block per plane)
+        if (n_tile == 64) p.b_tma = make_tmap(&p.tm_b, g, N, p.M, planes_b, g_ld, g_plane, KC) ? 1 : 0;
+        // a Linear layer's input [planes_a][sites][C]: tiles of {64 columns, 64 sites, all planes}, two per 128-column tile
+        if (T == 1 && IH == 1 && IW == 1 && OY == 1 && OX == 1)
+            p.a_tma = make_tmap(&p.tm_a, in, C, B, planes_a, C, in_plane, KC) ? 1 : 0;
+    }
     const int64_t K = (int64_t)T * C, work = (K + TILE_M - 1) / TILE_M * p.n_tiles * splits;
     return launch<true>(planes_a, planes_b, p, work, stream);
 }

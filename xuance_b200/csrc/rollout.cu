@@ -495,6 +495,16 @@ __global__ void __launch_bounds__(256) adv_normalize_kernel(float *__restrict__ 
 
 extern "C" int64_t xb_scratch_doubles(void) { return XB_SCRATCH_DOUBLES; }
 
+// normalise with GIVEN statistics (sharded minibatches: the global mean / std of the minibatch come from one all-reduce
+// per epoch, memory_tools.global_adv_stats)
+extern "C" int xb_adv_normalize(float *adv, int64_t B, const float *stats, void *stream) {
+    if (!adv || !stats || B <= 0) return XB_EINVAL;
+    int64_t want = (B + 255) / 256;
+    int grid = (int)(want < XB_MAX_PARTIALS ? want : XB_MAX_PARTIALS);
+    adv_normalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(adv, B, stats);
+    return xb_launch_status();
+}
+
 extern "C" int xb_gather_scalars(const float *fields, int64_t slots, const int64_t *idx, int64_t B, int F, float *out,
                                  int adv_field, float *stats_out, double *scratch, void *stream) {
     if (!fields || !out || B <= 0 || F <= 0 || slots <= 0 || adv_field >= F) return XB_EINVAL;

@@ -63,24 +63,26 @@ class OnPolicyAgent(Agent):
             return rep.preferred_obs_format()
         return _lib.OBS_U8
 
-    def _sample_and_update(self, idx):
-        """Device half of one minibatch: K3 gathers (+ adv-norm) -> network -> K4 -> backward -> [all-reduce] -> K7."""
-        s = self.memory.sample_prepared(idx, self._obs_format()) if getattr(self.config, "fused_sample", True) \
-            else self.memory.sample(idx)
+    def _sample_and_update(self, idx, adv_stats=None):
+        """Device half of one minibatch: K3 gathers (+ adv-norm) -> network -> K4 -> backward -> [all-reduce] -> K7.
+        ``adv_stats`` (sharded runs): the minibatch's global advantage mean / std, all-reduced once per epoch."""
+        s = self.memory.sample_prepared(idx, self._obs_format(), adv_stats) if getattr(self.config, "fused_sample", True) \
+            else self.memory.sample(idx, adv_stats)
         lrn = self.learner
         old_logp = s['aux_batch'].get('old_logp') if lrn.loss_kind == 0 else None
         lrn._device_update(s['obs'], s['actions'], s['returns'], s[lrn.adv_key], old_logp)
 
-    def _graphed_minibatch(self, idx):
+    def _graphed_minibatch(self, idx, adv_stats=None):
         """One CUDA-graph replay per minibatch (config.use_cuda_graph): the host only uploads 16 bytes of Adam
         hyper-parameters and the minibatch's slot indices.  Matters once the per-GPU minibatch is small (8 GPUs: 1024
         rows per rank) and Python launch overhead would otherwise bound the step."""
         from ..utils import CapturedStep
         key = int(idx.numel())
+        args = [idx] if adv_stats is None else [idx, adv_stats]
         if key not in self._graphs:
-            self._graphs[key] = CapturedStep(self._sample_and_update, [idx], self.learner.optimizer.snapshot,
+            self._graphs[key] = CapturedStep(self._sample_and_update, args, self.learner.optimizer.snapshot,
                                              self.learner.optimizer.restore)
-        self._graphs[key](idx)
+        self._graphs[key](*args)
 
     def train_epochs(self, n_epochs=1):
         """on_policy.py:182-205."""
@@ -102,18 +104,23 @@ class OnPolicyAgent(Agent):
                 np.random.shuffle(indexes)
                 perm = indexes
             perm_d = torch.from_numpy(perm).to(self.device, non_blocking=True)   # one H2D per epoch
-            for start in range(0, self.buffer_size, self.batch_size):
+            adv_all = None
+            if self.world_size > 1 and getattr(self.memory, "use_advnorm", False):
+                # ONE small all-reduce per epoch yields the global advantage statistics of all its minibatches
+                adv_all = self.memory.global_adv_stats(perm_d, self.buffer_size // self.batch_size)
+            for mb, start in enumerate(range(0, self.buffer_size, self.batch_size)):
                 idx = perm_d[start:start + self.batch_size]
+                stats = adv_all[mb] if adv_all is not None else None
                 done += 1
                 if use_graph:
                     self.learner.host_pre_step()
-                    self._graphed_minibatch(idx)
+                    self._graphed_minibatch(idx, stats)
                     self.learner.host_post_step()
                     if done == total:
                         train_info = self.learner.materialize_info()
                 else:
-                    samples = self.memory.sample_prepared(idx, self._obs_format()) \
-                        if getattr(self.config, "fused_sample", True) else self.memory.sample(idx)
+                    samples = self.memory.sample_prepared(idx, self._obs_format(), stats) \
+                        if getattr(self.config, "fused_sample", True) else self.memory.sample(idx, stats)
                     train_info = self.learner.update(sync=(done == total), **samples)
         return train_info
 

@@ -25,7 +25,7 @@ class PPO_Learner(Learner):
                                                            total_iters=self._lr_total_iters())
         self.vf_coef, self.ent_coef = getattr(config, "vf_coef", 0.0), config.ent_coef
         self.clip_range = getattr(config, "clip_range", 0.0)
-        self._stats = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self._stats = self.optimizer.bucket.tail[:8]      # the logged sums travel in the gradient bucket's tail
         self._scratch = _lib.scratch(self.device)
 
     def _lr_total_iters(self):
@@ -60,8 +60,7 @@ class PPO_Learner(Learner):
         self.optimizer.zero_grad()
         torch.autograd.backward([logits_c, v_c], [dlogits, dvalue])
         if self.world_size > 1:
-            allreduce_sum_(self.optimizer.bucket.grad)   # the one data-path collective
-            allreduce_sum_(self._stats)
+            allreduce_sum_(self.optimizer.bucket.grad_all)   # the ONE collective of an update: gradient + logged statistics
         self.optimizer.launch(max_norm=self.grad_clip_norm if self.use_grad_clip else None)
 
     def host_pre_step(self):

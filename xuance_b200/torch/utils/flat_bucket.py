@@ -22,6 +22,8 @@ def cudnn_rnn_front(module):
 
 
 class FlatBucket:
+    TAIL = 32   # float32 slots after the last gradient: per-update statistics ride in the SAME all-reduce as the gradient
+
     def __init__(self, params, front=()):
         """``front``: parameters to lay out first (see ``cudnn_rnn_front``); ``self.params`` keeps the caller's order."""
         seen, plist = set(), []
@@ -47,7 +49,9 @@ class FlatBucket:
             off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
         self.numel = off
         self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad_all = torch.zeros(off + self.TAIL, dtype=torch.float32, device=dev)   # what a sharded learner all-reduces
+        self.grad = self.grad_all[:off]
+        self.tail = self.grad_all[off:]
         for p, o in zip(plist, self.offsets):
             v = self._view(self.flat, p, o)
             v.copy_(p.data)
