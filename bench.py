@@ -35,14 +35,25 @@ WORKLOAD = ("PPO-Clip train_epochs(4) = 16 x (sample 8192 + update) over a resid
 
 # ------------------------------------------------------------------------------------------------ helpers
 def measured_peaks():
+    """(HBM GB/s, sustained dense bf16 TFLOP/s, source)."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
             d = json.load(open(p))
-            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", 1400.0)), "measured (MEASURED_PEAKS.json)"
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of that kernel at the
+    bench shape (profiles/r02_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep); None when not captured."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    try:
+        return json.load(open(p)).get(kernel_key, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -201,6 +212,59 @@ def run_reference_arm(args):
 _T0 = time.time()
 
 
+def parity_vs_single(agent, world):
+    """Hardware evidence that G ranks compute the 1-GPU update: one global minibatch (every rank contributes batch_size of
+    its own rollout rows) is applied (1) sharded - K4 scaled by 1/B_total, ONE sum all-reduce of gradient + statistics, K7 -
+    and (2) by every rank alone on the all-gathered 8192 rows; the two parameter vectors are compared.  State is restored."""
+    import torch
+    import torch.distributed as dist
+    lrn, mem = agent.learner, agent.memory
+    snap, its, sched = lrn.optimizer.snapshot(), lrn.iterations, lrn.scheduler.state_dict()
+    B = agent.batch_size
+    idx = torch.arange(B, device=mem.device, dtype=torch.int64) * (agent.buffer_size // B)
+    stats = mem.global_adv_stats(idx, 1)[0]
+    s = mem.sample(idx, stats)
+    local = [s["obs"], s["actions"].float().contiguous(), s["returns"].contiguous(), s["advantages"].contiguous(),
+             s["aux_batch"]["old_logp"].contiguous()]
+    lrn.optimizer.prepare()
+    lrn._device_update(*local)
+    torch.cuda.synchronize()
+    p_dist = lrn.optimizer.bucket.flat.clone()
+    lrn.optimizer.restore(snap)
+
+    def gather(x):
+        parts = [torch.empty_like(x) for _ in range(world)]
+        dist.all_gather(parts, x.contiguous())
+        return torch.cat(parts)
+    full = [gather(x) for x in local]
+    ws, lrn.world_size = lrn.world_size, 1
+    lrn.optimizer.prepare()
+    lrn._device_update(*full)
+    lrn.world_size = ws
+    torch.cuda.synchronize()
+    p_single = lrn.optimizer.bucket.flat.clone()
+    lrn.optimizer.restore(snap)
+    lrn.iterations = its
+    lrn.scheduler.load_state_dict(sched)
+    d = torch.stack([(p_dist - p_single).abs().max(), (p_single - snap[0]).abs().max()]).double()
+    dist.all_reduce(d, op=dist.ReduceOp.MAX)
+    # time the one collective of an update in isolation (gradient bucket + statistics tail)
+    buf = lrn.optimizer.bucket.grad_all
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        dist.all_reduce(buf)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(10):
+        dist.all_reduce(buf)
+    b.record()
+    torch.cuda.synchronize()
+    lrn.optimizer.bucket.grad_all.zero_()
+    return {"max_abs_param_diff": float(d[0]), "max_abs_param_step": float(d[1]), "global_rows": B * world,
+            "what": "same global minibatch, sharded over %d ranks vs every rank alone on the gathered rows; one Adam step" % world,
+            "allreduce_ms": a.elapsed_time(b) / 10.0, "allreduce_bytes": buf.numel() * 4}
+
+
 def _log(msg):
     if os.environ.get("XB_BENCH_VERBOSE", "1") != "0":
         sys.stderr.write("[bench %6.1fs rank %s] %s\n" % (time.time() - _T0, os.environ.get("RANK", "0"), msg))
@@ -229,7 +293,7 @@ def run_own_arm(args):
     n_local = N_ENVS // world
     cfg = ppo_namespace(device, n_local, world > 1, args.compute)
     cfg.tc_planes = args.tc_planes
-    cfg.use_cuda_graph = bool(args.graph) if args.graph >= 0 else world > 1
+    cfg.use_cuda_graph = bool(args.graph) if args.graph >= 0 else True     # same execution mode at every N
     obs_space, act_space = Box(0, 255, OBS_SHAPE, np.uint8), Discrete(N_ACTIONS)
     agent = PPO_Agent(cfg, envs=None, observation_space=obs_space, action_space=act_space)  # buffer: n_local envs
     assert agent.n_envs == n_local
@@ -275,7 +339,6 @@ def run_own_arm(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    _lib.profile = {"xb_gather_obs": []}
     launches0 = _lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -287,27 +350,6 @@ def run_own_arm(args):
     elapsed_ms = e0.elapsed_time(e1)
     _log("timed region done: %.1f ms/step" % (elapsed_ms / args.steps))
     launches = _lib.launch_count - launches0
-    prof = _lib.profile["xb_gather_obs"]
-    _lib.profile = None
-    k3_how = "CUDA events around every K3 launch inside the timed region"
-    if (cfg.use_cuda_graph or not prof) and agent._obs_format() not in (_lib.OBS_PLANES2, _lib.OBS_PLANES3, _lib.OBS_PLANE_RAW):
-        # graph replays hide per-kernel events: time the same 16 minibatch gathers of one epoch right after the region
-        prof = []
-        perm_d = torch.from_numpy(np.random.permutation(agent.buffer_size)).to(device)
-        fmt = agent._obs_format()
-        for start in range(0, agent.buffer_size, agent.batch_size):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            idx = perm_d[start:start + agent.batch_size]
-            out = torch.empty((agent.batch_size, int(np.prod(OBS_SHAPE))), dtype=torch.float32 if fmt != _lib.OBS_BF16_NHWC
-                              else torch.bfloat16, device=device)
-            a.record()
-            _lib.call("xb_gather_obs", _lib.ptr(mem._obs), _lib.ptr(idx), agent.batch_size, *OBS_SHAPE, _lib.ptr(out), fmt)
-            b.record()
-            prof.append((a, b))
-            del out
-        torch.cuda.synchronize()
-        k3_how = "CUDA events around 4 x n_minibatch K3 launches issued right after the timed region (graph replay hides per-kernel events)"
-    k3_ms = float(np.mean([a.elapsed_time(b) for a, b in prof])) if prof else None
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
     if world > 1:
@@ -351,23 +393,84 @@ def run_own_arm(args):
                "d2h_bytes_per_step": 32 * world, "steps": args.e2e_steps,
                "what": "128 x memory.store(pinned host arrays) + finish_path + train_epochs(4) + info dict read"}
 
-    # ---- roofline of the dominant kernel written here (K3 fused gather + u8->float)
-    peak, peak_src = measured_peaks()
-    B_local = (N_ENVS * T // N_MINIBATCH) // world
-    obs_bytes = int(np.prod(OBS_SHAPE))
-    out_w = {"fp32": 4, "fp32_cl": 4, "tf32": 4, "bf16": 2, "tc": 4}[args.compute]
-    alg_bytes = B_local * obs_bytes * (1 + out_w) + 8 * B_local
-    roofline = None
-    if k3_ms:
+    parity = parity_vs_single(agent, world) if world > 1 else None
+    if parity:
+        _log("parity vs 1 GPU: max |dp| = %.3g (step %.3g), all-reduce %.3f ms" % (
+            parity["max_abs_param_diff"], parity["max_abs_param_step"], parity["allreduce_ms"]))
+
+    # ---- roofline of the dominant kernels: CUDA events around every launch of ONE epoch (n_minibatch updates) replayed
+    # eagerly right after the timed region (graph replays hide per-kernel events); same buffers, same shapes, same stream
+    hbm_peak, tc_peak, peak_src = measured_peaks()
+    roofline, kernel_ms = None, {}
+    names = ["xb_gemm_gather_tc", "xb_wgrad_gather_tc", "xb_gather_obs_planes", "xb_gather_obs", "xb_ppo_loss_fwd_bwd",
+             "xb_adam_step", "xb_grad_sumsq", "xb_gather_scalars"]
+    from xuance_b200.torch.utils import tc_conv
+    saved_graph = agent.config.use_cuda_graph
+    agent.config.use_cuda_graph = False
+    snap = agent.learner.optimizer.snapshot()
+    its, sched_state = agent.learner.iterations, agent.learner.scheduler.state_dict()
+    agent.train_epochs(1)                                   # warm the eager path (cuDNN / cuBLAS handles, allocator)
+    barrier()
+    _lib.profile = {n: [] for n in names}
+    tc_conv.flop_log = []
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    agent.train_epochs(1)
+    p1.record()
+    torch.cuda.synchronize()
+    prof, flog = _lib.profile, tc_conv.flop_log
+    _lib.profile, tc_conv.flop_log = None, None
+    agent.learner.optimizer.restore(snap)
+    agent.learner.iterations = its
+    agent.learner.scheduler.load_state_dict(sched_state)
+    agent.config.use_cuda_graph = saved_graph
+    eager_epoch_ms = p0.elapsed_time(p1)
+    for n in names:
+        if prof[n]:
+            kernel_ms[n] = float(sum(a.elapsed_time(b) for a, b in prof[n]))
+    if flog:
+        # pair the FLOP log with the events in launch order (each ABI name keeps its own ordered list)
+        it_f = {"xb_gemm_gather_tc": iter(prof["xb_gemm_gather_tc"]), "xb_wgrad_gather_tc": iter(prof["xb_wgrad_gather_tc"])}
+        per_layer, tot_fl, tot_eq, tot_ms = {}, 0.0, 0.0, 0.0
+        for nm, tag, fl, eq in flog:
+            a, b = next(it_f[nm])
+            ms = a.elapsed_time(b)
+            d = per_layer.setdefault(nm.replace("xb_", "").replace("_tc", "") + " " + tag, [0.0, 0.0, 0.0, 0])
+            d[0] += ms; d[1] += fl; d[2] += eq; d[3] += 1
+            tot_fl += fl; tot_eq += eq; tot_ms += ms
+        n_upd = max(1, N_MINIBATCH)
+        top = max(per_layer.items(), key=lambda kv: kv[1][0])
+        ach = tot_fl / (tot_ms * 1e-3) / 1e12
+        roofline = {"kernel": "conv_tc_kernel (K12: tcgen05 gathered-operand GEMM; %d launches per update: forward, data and "
+                              "weight gradients of conv1-3 + the 6400->512 layer)" % (len(flog) // n_upd),
+                    "bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak,
+                    "traffic": ncu_traffic("conv_tc_kernel:" + top[0]),
+                    "peak_source": peak_src + ", bf16_tflops_sustained",
+                    "algorithmic_flops_per_update": tot_fl / n_upd,
+                    "what": "executed bf16 tensor FLOPs = 2*M*N*K x kept plane products (6 for 3x3 planes, 3 for the raw-pixel "
+                            "first layer) / summed CUDA-event time of the K12 launches",
+                    "fp32_equivalent_tflops": tot_eq / (tot_ms * 1e-3) / 1e12,
+                    "avg_update_ms": tot_ms / n_upd, "launches_timed": len(flog),
+                    "timed": "CUDA events around every K12 launch of one eager epoch run right after the timed region",
+                    "share_of_step": (tot_ms * N_EPOCHS) / (elapsed_ms / args.steps),
+                    "slowest_layer": {"layer": top[0], "ms_per_update": top[1][0] / n_upd,
+                                      "tflops_executed": top[1][1] / (top[1][0] * 1e-3) / 1e12},
+                    "per_layer_ms_per_update": {k: round(v[0] / n_upd, 4) for k, v in sorted(per_layer.items(), key=lambda kv: -kv[1][0])}}
+    elif kernel_ms.get("xb_gather_obs"):
+        B_local = (N_ENVS * T // N_MINIBATCH) // world
+        obs_bytes = int(np.prod(OBS_SHAPE))
+        out_w = {"fp32": 4, "fp32_cl": 4, "tf32": 4, "bf16": 2}.get(args.compute, 4)
+        alg_bytes = B_local * obs_bytes * (1 + out_w) + 8 * B_local
+        k3_ms = kernel_ms["xb_gather_obs"] / len(prof["xb_gather_obs"])
         ach = alg_bytes / (k3_ms * 1e-3) / 1e9
         roofline = {"kernel": "gather_obs_kernel (K3: minibatch gather + u8->float)", "bound": "hbm",
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of
-                    # this kernel at this shape (profiles/r01_k3_gather_obs_f32nchw_raw.csv: 231.8 MB + 867.4 MB)
-                    "traffic": 1.0992e9 if (args.compute == "fp32" and B_local == 8192) else None,
+                    "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                    "traffic": ncu_traffic("gather_obs_kernel:%s:%d" % (args.compute, B_local)),
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                    "avg_launch_ms": k3_ms, "launches_timed": len(prof), "timed": k3_how,
+                    "avg_launch_ms": k3_ms, "launches_timed": len(prof["xb_gather_obs"]),
+                    "timed": "CUDA events around every K3 launch of one eager epoch run right after the timed region",
                     "share_of_step": (k3_ms * N_EPOCHS * N_MINIBATCH) / (elapsed_ms / args.steps)}
+    phases = {"eager_epoch_ms": eager_epoch_ms, "own_kernels_ms_per_epoch": {k: round(v, 3) for k, v in kernel_ms.items()}}
 
     if rank != 0:
         return
@@ -384,10 +487,13 @@ def run_own_arm(args):
                        "parallelism": "dp%d (envs sharded, 1 NCCL grad all-reduce/update)" % world,
                        "compute": {"fp32": "fp32, TF32 disabled (reference arithmetic)", "fp32_cl": "fp32, TF32 disabled, channels-last convolutions", "tf32": "fp32 storage, TF32 convs/matmuls",
                                    "bf16": "bf16 autocast convs, fp32 master weights",
-                                   "tc": "EXPERIMENTAL: split-bf16 (hi+lo) tcgen05 layers, fp32 accumulation, fp32-level accuracy"}[args.compute],
+                                   "tc": "tcgen05 layers (K12): every fp32 operand as %d bf16 planes (exact to 2^-%d), raw uint8 pixels as "
+                                         "one exact plane, fp32 accumulation in TMEM per product order; heads / loss / Adam fp32"
+                                         % (args.tc_planes, 8 * args.tc_planes)}[args.compute],
                        "l2": "inputs (925 MB uint8 rollout / G) exceed the 126 MB L2; no explicit flush",
                        "cuda_graph": bool(cfg.use_cuda_graph)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "phases": phases, "parity_vs_1gpu": parity,
             "last_info": {k: (float(v) if not isinstance(v, dict) else v) for k, v in info.items()}}
     print(json.dumps(line))
 
@@ -398,13 +504,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="xuance_b200", choices=["xuance_b200", "reference"])
-    ap.add_argument("--compute", default="fp32", choices=["fp32", "fp32_cl", "tf32", "bf16", "tc"],
-                    help="'tc' = EXPERIMENTAL split-bf16 tcgen05 layers (K12); not a default, see DESIGN.md section 9")
+    ap.add_argument("--compute", default="tc", choices=["fp32", "fp32_cl", "tf32", "bf16", "tc"],
+                    help="'tc' (default) = the K12 tcgen05 layers, float32-grade split-bf16 arithmetic; 'fp32' = cuDNN / cuBLAS "
+                         "CUDA-core fp32 (round 1's headline); 'tf32' / 'bf16' = reduced-precision library paths, for context")
     ap.add_argument("--tc-planes", type=int, default=3, choices=[2, 3],
                     help="with --compute tc: bf16 planes per operand (3 = float32-grade, 2 = ~1e-5 forward error)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", type=int, default=-1, help="CUDA-graph the minibatch update: 1/0; default: on when --gpus > 1")
+    ap.add_argument("--graph", type=int, default=-1, help="CUDA-graph the minibatch update: 1/0; default: on (every N)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":
         args.warmup = 3

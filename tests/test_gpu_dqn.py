@@ -85,3 +85,43 @@ def test_dqn_learner_matches_oracle(per, double_q, graph):
     so, sp = om.state_dict(), model.state_dict()
     for k in so:
         np.testing.assert_allclose(sp[k].cpu().numpy(), so[k].numpy(), rtol=1e-3, atol=1e-4, err_msg=k)
+
+
+def test_dueling_dqn_update_matches_autograd():
+    """DuelDQN (q_head.py:42-80, dueldqn_learner.py): the dueling network through the K6 TD path vs the same update written
+    with torch autograd + torch.optim.Adam on a float32 copy of the network."""
+    import copy
+    from xuance_b200.common import Discrete, Box, BaseCallback
+    from xuance_b200.torch.rl_models import Basic_MLP, DuelingDeepQNetwork
+    from xuance_b200.torch.learners import DuelDQN_Learner
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(4)
+    A, B, D = 6, 128, 17
+    rep = Basic_MLP((D,), [64], None, nn.init.orthogonal_, nn.ReLU, "cuda:0")
+    model = DuelingDeepQNetwork(rep, [64], Discrete(A), None, nn.init.orthogonal_, nn.ReLU, "cuda:0").to("cuda:0")
+    assert model.eval_Q_head.v_model[0].out_features == 32 and model.eval_Q_head.a_model[-1].out_features == A
+    ref = copy.deepcopy(model)
+    lrn = DuelDQN_Learner(_cfg(), model, BaseCallback())
+    opt = torch.optim.Adam(list(ref.representation.parameters()) + list(ref.eval_Q_head.parameters()), 1e-4, eps=1e-5)
+    sch = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1.0, end_factor=0.5, total_iters=lrn.total_iters)
+    rng = np.random.default_rng(5)
+    for it in range(4):
+        s = {"obs": rng.normal(size=(B, D)).astype(np.float32), "actions": rng.integers(0, A, size=B).astype(np.float32),
+             "obs_next": rng.normal(size=(B, D)).astype(np.float32), "rewards": rng.normal(size=B).astype(np.float32),
+             "terminals": (rng.random(B) < 0.2).astype(np.float32)}
+        t = {k: torch.from_numpy(v).cuda() for k, v in s.items()}
+        info = lrn.update(**t)
+        q = ref(t["obs"]).values
+        pred = q.gather(-1, t["actions"].long().unsqueeze(-1)).squeeze(-1)
+        with torch.no_grad():
+            y = t["rewards"] + 0.99 * (1 - t["terminals"]) * ref.target(t["obs_next"]).values.max(-1).values
+        loss = nn.functional.mse_loss(pred, y)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        sch.step()
+        if (it + 1) % 2 == 0:
+            ref.copy_target()
+        np.testing.assert_allclose(info["Qloss"], loss.item(), rtol=2e-4, atol=1e-6)
+    for (k, p), (_, q) in zip(model.state_dict().items(), ref.state_dict().items()):
+        np.testing.assert_allclose(p.cpu().numpy(), q.cpu().numpy(), rtol=1e-3, atol=1e-5, err_msg=k)

@@ -25,12 +25,12 @@ def _product_model(n, obs_dim, A, S, device="cuda:0"):
     return keys, grouping, MixingQNetwork(grouping, q, QMIX_Mixer(S, 32, 32, n, device), use_rnn=True, device=device).to(device)
 
 
-def _buffers(keys, obs_dim, A, S, n_envs, C, Be, T):
+def _buffers(keys, obs_dim, A, S, n_envs, C, Be, T, device="cuda:0"):
     from xuance_b200.common import MARL_OffPolicyBuffer_RNN, Box, Discrete
     prod = MARL_OffPolicyBuffer_RNN(agent_keys=keys, state_space=Box(-1, 1, (S,)),
                                     obs_space={k: Box(-1, 1, (obs_dim,)) for k in keys},
                                     act_space={k: Discrete(A) for k in keys}, n_envs=n_envs, buffer_size=C,
-                                    batch_size=Be, max_episode_steps=T, device="cuda:0")
+                                    batch_size=Be, max_episode_steps=T, device=device)
     return prod, EpisodeReplayOracle(keys, obs_dim, S, n_envs, C, Be, T)
 
 

@@ -125,3 +125,19 @@ def test_qmix_learns_through_the_agent_registry():
     # episode score = sum over <=20 steps of the fraction of living agents that hit their cue
     assert after > before + 4.0 and after > 8.0, (before, after)
     agent.finish()
+
+
+def test_vdn_agent_trains_through_the_registry():
+    """REGISTRY_Agents["VDN"]: the sum mixer (no parameters) through the same rollout / replay / learner path."""
+    from xuance_b200.environment import make_envs
+    from xuance_b200.torch.agents import REGISTRY_Agents
+    from xuance_b200.torch.rl_models import VDN_mixer
+    cfg = _qmix_config(agent="VDN", learner="VDN_Learner", running_steps=20000, decay_step_greedy=6000)
+    agent = REGISTRY_Agents["VDN"](cfg, make_envs(cfg))
+    assert isinstance(agent.model.eval_Qtot, VDN_mixer) and not list(agent.model.eval_Qtot.parameters())
+    before = float(np.mean(agent.test(16, make_envs(cfg))))
+    info = agent.train(cfg.running_steps // cfg.parallels)
+    assert np.isfinite(info["loss_Q"])
+    after = float(np.mean(agent.test(32, make_envs(cfg))))
+    assert after > before + 2.0, (before, after)
+    agent.finish()

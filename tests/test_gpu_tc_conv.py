@@ -190,6 +190,65 @@ def test_linear_layer_all_modes(planes, atol):
     np.testing.assert_allclose(dw.cpu().numpy(), (gy.double().t() @ x.double()).cpu().numpy(), rtol=0, atol=atol)
 
 
+@pytest.mark.parametrize("planes,atol", [(2, 5e-5), (3, 3e-6)])
+def test_box_convolutions_forward_and_data_gradient(planes, atol):
+    """conv2 / conv3 forward and their data gradients with the A operand fetched by TMA boxes from padded-row activations
+    (xb_gemm_box_tc): every geometry BoxNatureCNN builds, against float64 convolutions / autograd."""
+    import torch.nn as nn
+    from xuance_b200.torch.utils import tc_conv as tc
+    torch.manual_seed(11)
+    B = 5
+    convs = [nn.Conv2d(4, 32, 8, 4, padding=2), nn.Conv2d(32, 64, 4, 2, padding=1), nn.Conv2d(64, 64, 3, 1, padding=1)]
+    enc = tc.BoxNatureCNN([c.to(DEV) for c in convs], None, (84, 84, 4), backend=tc.CudaBackend(planes))
+    P = enc._plan(B)
+    hp1, hp2, off1 = P["hp1"], P["hp2"], P["off1"]
+    a1 = torch.rand(B, 21, 21, 32, device=DEV)                               # conv2's input (conv1's activation)
+    act1 = torch.zeros(planes, B, hp1, 21, 32, dtype=torch.bfloat16, device=DEV)
+    act1[:, :, off1:off1 + 21] = tc.split_bf16(a1, planes)
+    act1 = act1.view(planes, B * hp1, 21, 32)
+    w2, b2 = convs[1].weight.detach(), convs[1].bias.detach()
+    out2 = torch.zeros(planes, B * hp2, 10, 64, dtype=torch.bfloat16, device=DEV)
+    tc.gemm_box(act1, tc.pack_conv_weight(w2, planes), P["fwd2"], bias=b2, relu=True, out_pl=out2, out_ld=64)
+    want2 = F.relu(F.conv2d(a1.permute(0, 3, 1, 2).double(), w2.double(), b2.double(), stride=2, padding=1)).permute(0, 2, 3, 1)
+    got2 = out2.float().sum(0).view(B, hp2, 10, 64)
+    np.testing.assert_allclose(got2[:, 1:11].cpu().numpy(), want2.cpu().numpy(), rtol=0, atol=atol)
+    assert float(got2[:, 0].abs().max()) == 0.0 and float(got2[:, 11].abs().max()) == 0.0      # padding rows never written
+    # conv3 forward from the padded act2 into the plain matrix
+    w3, b3 = convs[2].weight.detach(), convs[2].bias.detach()
+    a2 = got2[:, 1:11].contiguous()
+    out3 = torch.full((B * 100, 64), float("nan"), device=DEV)
+    tc.gemm_box(out2, tc.pack_conv_weight(w3, planes), P["fwd3"], bias=b3, relu=True, out_f32=out3, out_ld=64)
+    want3 = F.relu(F.conv2d(a2.permute(0, 3, 1, 2).double(), w3.double(), b3.double(), stride=1, padding=1)).permute(0, 2, 3, 1)
+    np.testing.assert_allclose(out3.view(B, 10, 10, 64).cpu().numpy(), want3.cpu().numpy(), rtol=0, atol=atol)
+    # conv3 data gradient (mask = act2 plane 0) into act2's padded layout
+    g3 = torch.randn(B, 10, 10, 64, device=DEV)
+    g3p = torch.zeros(planes, B, hp2, 10, 64, dtype=torch.bfloat16, device=DEV)
+    g3p[:, :, 1:11] = tc.split_bf16(g3, planes)
+    g3p = g3p.view(planes, B * hp2, 10, 64)
+    x2 = a2.double().permute(0, 3, 1, 2).requires_grad_(True)
+    y3 = F.conv2d(x2, w3.double(), stride=1, padding=1)
+    (dx2,) = torch.autograd.grad(y3, x2, g3.double().permute(0, 3, 1, 2))
+    want = dx2.permute(0, 2, 3, 1) * (out2[0].float().view(B, hp2, 10, 64)[:, 1:11] > 0)
+    d2 = torch.zeros(planes, B * hp2, 10, 64, dtype=torch.bfloat16, device=DEV)
+    tc.gemm_box(g3p, tc.split_bf16(tc.dgrad_weight_matrix(w3, P["taps3"]), planes), P["dg3"], out_pl=d2, out_ld=64, relu_mask=out2[0])
+    np.testing.assert_allclose(d2.float().sum(0).view(B, hp2, 10, 64)[:, 1:11].cpu().numpy(), want.cpu().numpy(), rtol=0, atol=atol * 4)
+    # conv2 data gradient: four stride phases into act1's padded layout (mask = act1 plane 0)
+    g2 = torch.randn(B, 10, 10, 64, device=DEV)
+    g2p = torch.zeros(planes, B, hp2, 10, 64, dtype=torch.bfloat16, device=DEV)
+    g2p[:, :, 1:11] = tc.split_bf16(g2, planes)
+    g2p = g2p.view(planes, B * hp2, 10, 64)
+    x1 = a1.double().permute(0, 3, 1, 2).requires_grad_(True)
+    y2 = F.conv2d(x1, w2.double(), stride=2, padding=1)
+    (dx1,) = torch.autograd.grad(y2, x1, g2.double().permute(0, 3, 1, 2))
+    mask1 = act1[0].float().view(B, hp1, 21, 32)[:, off1:off1 + 21] > 0
+    d1 = torch.zeros(planes, B * hp1, 21, 32, dtype=torch.bfloat16, device=DEV)
+    for bg, taps in P["dg2"]:
+        tc.gemm_box(g2p, tc.split_bf16(tc.dgrad_weight_matrix(w2, taps), planes), bg, out_pl=d1, out_ld=32, relu_mask=act1[0])
+    got1 = d1.float().sum(0).view(B, hp1, 21, 32)
+    np.testing.assert_allclose(got1[:, off1:off1 + 21].cpu().numpy(), (dx1.permute(0, 2, 3, 1) * mask1).cpu().numpy(), rtol=0, atol=atol * 4)
+    assert float(got1[:, :off1].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("planes,fwd_tol,grad_tol", [(2, 1e-4, 2e-2), (3, 2e-5, 2e-3)])
 def test_encoder_matches_cudnn_fp32(planes, fwd_tol, grad_tol):
     """Whole encoder forward + backward vs the cuDNN fp32 path.  Per-layer gradients with a given mask are pinned above; here

@@ -3,7 +3,13 @@
 DQN+PER (2^20-transition HBM replay, B=512), SAC (1M replay, B=1024) and QMIX (5 agents x 72-d, T=60, 32 episodes)
 on one B200, next to the oracle port of the reference's torch-CPU path on the host.  Prints one JSON object.
 
-    python tools/algo_bench.py [--iters 200] [--cpu-iters 5] [--no-cpu]
+    python tools/algo_bench.py [--iters 200] [--cpu-iters 5] [--no-cpu] [--graph]
+    torchrun --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 tools/algo_bench.py --no-cpu --graph    (G GPUs)
+
+Multi-GPU (BASELINE configs 3 and 5 are multi-GPU configurations): one process per GPU; the replay is sharded (envs / episodes
+per rank), every update takes batch/G rows from every rank, the gradient bucket (+ logged statistics) is all-reduced once per
+update inside the captured graph; the time of an update is the max over ranks (barrier + synchronize on both sides) and the
+global batch is fixed (strong scaling).
 """
 import argparse
 import json
@@ -19,18 +25,28 @@ import torch.nn as nn
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-DEV = "cuda:0"
+RANK, WORLD, LOCAL = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+DEV = "cuda:%d" % LOCAL
 
 
 def timed(fn, iters, warm=10):
+    import torch.distributed as dist
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
+    if WORLD > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     for _ in range(iters):
         fn()
+    e1.record()
     torch.cuda.synchronize()
-    return (time.perf_counter() - t0) / iters
+    t = torch.tensor([e0.elapsed_time(e1) / 1e3 / iters], dtype=torch.float64, device=DEV)
+    if WORLD > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
 
 
 def cpu_timed(fn, iters):
@@ -45,9 +61,9 @@ def bench_perdqn(args):
     from xuance_b200.common import PerOffPolicyBuffer, Box, Discrete, BaseCallback
     from xuance_b200.torch.rl_models import Basic_CNN, DeepQNetwork
     from xuance_b200.torch.learners import PerDQN_Learner
-    N, S, B, A = 16, 65536, 512, 4
+    N, S, B, A = 16 // WORLD, 65536, 512 // WORLD, 4          # this rank's envs and its share of the 512-row batch
     buf = PerOffPolicyBuffer(Box(0, 255, (84, 84, 4), np.uint8), Discrete(A), None, N, N * S, B, alpha=0.5, device=DEV)
-    g = torch.Generator(device=DEV).manual_seed(0)
+    g = torch.Generator(device=DEV).manual_seed(RANK)
     for t in range(64):   # real stores through K1 + K5 insert, then the rest of the ring is declared filled
         o = torch.randint(0, 256, (N, 84, 84, 4), dtype=torch.uint8, device=DEV, generator=g)
         buf.store(o, torch.randint(0, A, (N,), device=DEV), torch.randn(N, device=DEV), torch.zeros(N, device=DEV), o)
@@ -62,9 +78,12 @@ def bench_perdqn(args):
         lvl //= 2
     rep = Basic_CNN(input_shape=(84, 84, 4), kernels=[8, 4, 3], strides=[4, 2, 1], filters=[32, 64, 64], activation=nn.ReLU, device=DEV)
     model = DeepQNetwork(rep, [512], Discrete(A), None, None, nn.ReLU, DEV).to(DEV)
-    cfg = Namespace(distributed_training=False, episode_length=1000, use_grad_clip=False, grad_clip_norm=0.5, device=DEV,
-                    model_dir="/tmp/x", running_steps=10**7, parallels=N, learning_rate=1e-4, gamma=0.99, sync_frequency=500,
-                    start_training=0, training_frequency=1)
+    cfg = Namespace(distributed_training=WORLD > 1, episode_length=1000, use_grad_clip=False, grad_clip_norm=0.5, device=DEV,
+                    model_dir="/tmp/x", running_steps=10**7, parallels=N * WORLD, learning_rate=1e-4, gamma=0.99,
+                    sync_frequency=500, start_training=0, training_frequency=1, compute=args.compute, tc_planes=3)
+    if args.compute != "fp32":
+        rep.tc_planes = 3
+        rep.set_compute(args.compute)
     cfg.use_cuda_graph = args.graph
     lrn = PerDQN_Learner(cfg, model, BaseCallback())
 
@@ -74,8 +93,8 @@ def bench_perdqn(args):
         buf.update_priorities(s["step_choices"], td)
 
     dt = timed(step, args.iters)
-    out = {"config": "DQN+PER, 2^20-transition uint8 HBM replay (59 GB), 16 envs, B=512", "gpu_updates_per_s": 1 / dt,
-           "gpu_transitions_per_s": B / dt, "gpu_ms_per_update": dt * 1e3}
+    out = {"config": "DQN+PER, 2^20-transition uint8 HBM replay (59 GB), 16 envs, B=512 (global), encoder compute=%s" % args.compute,
+           "gpu_updates_per_s": 1 / dt, "gpu_transitions_per_s": B * WORLD / dt, "gpu_ms_per_update": dt * 1e3}
     if not args.no_cpu:
         from oracle.replay import PerReplayOracle
         from oracle.nets import DeepQNetworkOracle
@@ -104,7 +123,7 @@ def bench_sac(args):
     from xuance_b200.common import DummyOffPolicyBuffer, Box, BaseCallback
     from xuance_b200.torch.rl_models import Basic_Identical, SAC_GaussianActor, TwinActionValueCritic, SoftActorCritic
     from xuance_b200.torch.learners import REGISTRY_Learners
-    N, S, B, od, ad = 4, 250000, 1024, 17, 6
+    N, S, B, od, ad = 4, 250000 // WORLD, 1024 // WORLD, 17, 6
     aspace = Box(-1, 1, (ad,), np.float32)
     buf = DummyOffPolicyBuffer(Box(-10, 10, (od,), np.float32), aspace, None, N, N * S, B, device=DEV)
     buf._obs.normal_(), buf._next_obs.normal_(), buf._act_rows.uniform_(-1, 1), buf._fields.normal_()
@@ -112,15 +131,15 @@ def bench_sac(args):
     rep = Basic_Identical((od,), device=DEV)
     model = SoftActorCritic(SAC_GaussianActor(rep, [256, 256], aspace, None, None, nn.LeakyReLU, nn.Tanh, DEV),
                             TwinActionValueCritic(deepcopy(rep), aspace, [256, 256], None, None, nn.LeakyReLU, DEV)).to(DEV)
-    cfg = Namespace(distributed_training=False, episode_length=1000, use_grad_clip=False, grad_clip_norm=0.5, device=DEV,
+    cfg = Namespace(distributed_training=WORLD > 1, episode_length=1000, use_grad_clip=False, grad_clip_norm=0.5, device=DEV,
                     model_dir="/tmp/x", running_steps=10**6, parallels=N, start_training=0, training_frequency=1,
                     learning_rate_actor=1e-3, learning_rate_critic=1e-3, tau=0.005, gamma=0.99, alpha=0.2,
                     use_automatic_entropy_tuning=True)
     cfg.use_cuda_graph = args.graph
     lrn = REGISTRY_Learners["SAC_Learner"](cfg, model, BaseCallback())
     dt = timed(lambda: lrn.update(sync=False, **buf.sample()), args.iters)
-    out = {"config": "SAC, 17-d obs / 6-d act, 1M replay, B=1024, MLP 256-256", "gpu_updates_per_s": 1 / dt,
-           "gpu_transitions_per_s": B / dt, "gpu_ms_per_update": dt * 1e3}
+    out = {"config": "SAC, 17-d obs / 6-d act, 1M replay, B=1024 (global), MLP 256-256", "gpu_updates_per_s": 1 / dt,
+           "gpu_transitions_per_s": B * WORLD / dt, "gpu_ms_per_update": dt * 1e3}
     if not args.no_cpu:
         from oracle.replay import UniformReplayOracle
         from oracle.sac import SACModelOracle, SACLearnerOracle
@@ -139,23 +158,24 @@ def bench_qmix(args, Be=32):
     from xuance_b200.common import BaseCallback
     from xuance_b200.torch.learners import REGISTRY_Learners
     n, od, A, S, T = 5, 72, 12, 98, 60
-    keys, grouping, model = _product_model(n, od, A, S)
+    Be_global, Be = Be, Be // WORLD                              # this rank's share of the episodes of an update
+    keys, grouping, model = _product_model(n, od, A, S, device=DEV)
     n_envs, C = 8, max(256, 2 * Be)
-    prod, ob = _buffers(keys, od, A, S, n_envs, C, Be, T)
-    for ev in qmix_episode_stream(np.random.default_rng(0), keys, n_envs, T, od, A, S, C // n_envs):
+    prod, ob = _buffers(keys, od, A, S, n_envs, C, Be, T, device=DEV)
+    for ev in qmix_episode_stream(np.random.default_rng(RANK), keys, n_envs, T, od, A, S, C // n_envs):
         if ev[0] == 'store':
             prod.store(**ev[1]), ob.store(**ev[1])
         else:
             prod.finish_path(ev[1], **ev[2]), ob.finish_path(ev[1], **ev[2])
-    cfg = Namespace(distributed_training=False, episode_length=T, use_grad_clip=False, grad_clip_norm=10.0, device=DEV,
+    cfg = Namespace(distributed_training=WORLD > 1, episode_length=T, use_grad_clip=False, grad_clip_norm=10.0, device=DEV,
                     model_dir="/tmp/x", running_steps=10**7, parallels=n_envs, use_parameter_sharing=True, use_rnn=True,
                     use_actions_mask=False, learning_rate=7e-4, sync_frequency=200, double_q=True, n_epochs=1,
                     start_training=0, gamma=0.99)
     cfg.use_cuda_graph = args.graph
     lrn = REGISTRY_Learners["QMIX_Learner"](cfg, grouping, model, BaseCallback())
     dt = timed(lambda: lrn.update(prod.sample(), sync=False), args.iters)
-    out = {"config": f"QMIX, 5 agents x 72-d, S=98, A=12, T=60, {Be} episodes/update, GRU 64 + mixer 32/32",
-           "gpu_updates_per_s": 1 / dt, "gpu_agent_steps_per_s": Be * T * n / dt, "gpu_ms_per_update": dt * 1e3}
+    out = {"config": f"QMIX, 5 agents x 72-d, S=98, A=12, T=60, {Be_global} episodes/update (global), GRU 64 + mixer 32/32",
+           "gpu_updates_per_s": 1 / dt, "gpu_agent_steps_per_s": Be_global * T * n / dt, "gpu_ms_per_update": dt * 1e3}
     if not args.no_cpu:
         from oracle.qmix import QMIXModelOracle, QMIXLearnerOracle
         ol = QMIXLearnerOracle(QMIXModelOracle(n, od, A, S), keys, detach_q_eval=False)
@@ -171,7 +191,14 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--only", default="")
     ap.add_argument("--graph", action="store_true", help="capture the learners' device update in a CUDA graph")
+    ap.add_argument("--compute", default="fp32", choices=["fp32", "tc"], help="pixel encoder of the PER-DQN network")
     args = ap.parse_args()
+    torch.cuda.set_device(LOCAL)
+    torch.manual_seed(0)          # identical initial weights on every rank
+    if WORLD > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(DEV))
+        args.no_cpu = True
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.benchmark = True
@@ -185,7 +212,11 @@ def main():
         res["qmix"] = bench_qmix(args)
         res["qmix_4096"] = bench_qmix(Namespace(**{**vars(args), "iters": 20, "no_cpu": True}), Be=1024)
     res["cuda_graph"] = bool(args.graph)
-    print(json.dumps(res))
+    res["n_gpus"] = WORLD
+    if RANK == 0:
+        print(json.dumps(res))
+    if WORLD > 1:
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":

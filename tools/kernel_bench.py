@@ -304,6 +304,33 @@ def main():
             add(entry(f"K12 weight gradient fc (P={P}, {splits} splits)", f"M={B} N=512 K=6400", us,
                       x_pl.numel() * 2 + g_pl.numel() * 2 + 512 * 6400 * 4, hbm, fl, tpk))
             del x_pl, w_pl, g_pl, wt_pl, dx_pl
+    if want("k12box"):
+        # the convolutions after the first with padded-row activations + TMA boxes (BoxNatureCNN's geometries), 3 planes
+        import torch.nn as nn
+        from xuance_b200.torch.utils import tc_conv as tc
+        B, Pn = int(os.environ.get("XB_K12_BATCH", "8192")), 3
+        convs = [nn.Conv2d(4, 32, 8, 4, padding=2).to(DEV), nn.Conv2d(32, 64, 4, 2, padding=1).to(DEV), nn.Conv2d(64, 64, 3, 1, padding=1).to(DEV)]
+        enc = tc.BoxNatureCNN(convs, None, (84, 84, 4), backend=tc.CudaBackend(Pn))
+        P = enc._plan(B)
+        rnd = lambda *sh: torch.randn(sh, device=DEV, generator=g).to(torch.bfloat16)
+        act1, act2 = rnd(Pn, B * P["hp1"], 21, 32), rnd(Pn, B * P["hp2"], 10, 64)
+        g3, d2, d1 = rnd(Pn, B * P["hp2"], 10, 64), torch.zeros(Pn, B * P["hp2"], 10, 64, dtype=torch.bfloat16, device=DEV), torch.zeros(Pn, B * P["hp1"], 21, 32, dtype=torch.bfloat16, device=DEV)
+        w2, w3 = tc.pack_conv_weight(convs[1].weight.detach(), Pn), tc.pack_conv_weight(convs[2].weight.detach(), Pn)
+        out3 = torch.empty(Pn, B * 100, 64, dtype=torch.bfloat16, device=DEV)
+        us = timeit(lambda: tc.gemm_box(act1, w2, P["fwd2"], relu=True, out_pl=d2, out_ld=64), R)
+        add(entry("K12-box forward conv2 (P=3)", f"M={B * 100} N=64 K=512", us, act1.numel() * 2 + d2.numel() * 2, hbm, 2.0 * B * 100 * 64 * 512, tpk))
+        us = timeit(lambda: tc.gemm_box(act2, w3, P["fwd3"], relu=True, out_pl=out3, out_ld=64), R)
+        add(entry("K12-box forward conv3 (P=3)", f"M={B * 100} N=64 K=576", us, act2.numel() * 2 + out3.numel() * 2, hbm, 2.0 * B * 100 * 64 * 576, tpk))
+        wd3 = tc.split_bf16(tc.dgrad_weight_matrix(convs[2].weight.detach(), P["taps3"]), Pn)
+        us = timeit(lambda: tc.gemm_box(g3, wd3, P["dg3"], out_pl=d2, out_ld=64, relu_mask=act2[0]), R)
+        add(entry("K12-box data gradient conv3 (P=3)", f"M={B * 100} N=64 K=576", us, g3.numel() * 2 + d2.numel() * 2, hbm, 2.0 * B * 100 * 64 * 576, tpk))
+        wds = [tc.split_bf16(tc.dgrad_weight_matrix(convs[1].weight.detach(), taps), Pn) for _, taps in P["dg2"]]
+
+        def run_dg2():
+            for (bg, _), wd in zip(P["dg2"], wds):
+                tc.gemm_box(g3, wd, bg, out_pl=d1, out_ld=32, relu_mask=act1[0])
+        us = timeit(run_dg2, R)
+        add(entry("K12-box data gradient conv2 (P=3, 4 phases)", f"M={B * 441} N=32 K=256", us, 4 * g3.numel() * 2 + d1.numel() * 2, hbm, 2.0 * B * 100 * 64 * 512, tpk))
     print(json.dumps(out))
 
 

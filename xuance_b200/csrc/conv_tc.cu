@@ -42,6 +42,14 @@ struct ConvParams {
     alignas(64) CUtensorMap tm_a;
     alignas(64) CUtensorMap tm_b;
     int a_tma, b_tma;
+    // a_box: the A operand of a convolution fetched by TMA as ONE 4-D box per plane and chunk from an activation tensor
+    // stored with padded rows, {channels, pixels, merged image-rows, planes}: a tile is box_h consecutive grid rows of box_w
+    // sites; chunk kc reads the box at (box_c0[kc], box_w0[kc], tile_row0 * box_rs + box_r[kc]).  Output rows are decoded as
+    // (merged row R = tile * box_h + r / box_w, x = r % box_w), image b = R / box_hp, y = R % box_hp, valid if
+    // box_y0 <= y <= box_y1 (rows outside are the padding / garbage rows of the padded layout and are never written).
+    int a_box, box_w, box_h, box_hp, box_y0, box_y1, box_rs, box_chunks;
+    XbDiv box_div_w, box_div_hp;
+    int16_t box_c0[16], box_w0[16], box_r[16];
     XbConvGeom g;                          // g.N = columns per work item (the tile width N)
     const __nv_bfloat16 *in[3];            // A planes: [B, IH, IW, C]
     const __nv_bfloat16 *w[3];             // B planes.  forward: weight [N_total, K].  weight gradient: output gradient [P, w_ld]
@@ -76,6 +84,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm,
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
         ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
         : "memory");
 }
 // shared-memory matrix descriptor of a 128-byte-swizzled operand (the layout TMA writes with CU_TENSOR_MAP_SWIZZLE_128B):
@@ -131,12 +145,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
     const int N = g.N, K = g.T * g.C, S = p.stages;
     const uint32_t a_plane = xb_conv_a_plane_bytes(), w_plane = xb_conv_w_plane_bytes(N);
     const uint32_t stage_bytes = PA * a_plane + PB * w_plane;
-    const int64_t m_tiles = WGRAD ? (K + TILE_M - 1) / TILE_M : (p.M + TILE_M - 1) / TILE_M;
+    const int box_rows = p.box_w * p.box_h;                  // a_box: rows of a tile that hold sites (<= 128)
+    const int64_t m_tiles = WGRAD ? (K + TILE_M - 1) / TILE_M
+                                  : (p.a_box ? ((int64_t)g.B * p.box_hp + p.box_h - 1) / p.box_h : (p.M + TILE_M - 1) / TILE_M);
     const int64_t mn_tiles = m_tiles * p.n_tiles;
     const int64_t n_work = WGRAD ? mn_tiles * p.splits : mn_tiles;
     // chunks of one work item
     auto chunks_of = [&](int64_t w) -> int {
-        if (!WGRAD) return K / KC;
+        if (!WGRAD) return p.a_box ? p.box_chunks : K / KC;
         const int64_t sp = w / mn_tiles, s0 = sp * p.sites_per_split;
         const int64_t cnt = (p.M - s0) < p.sites_per_split ? (p.M - s0) : p.sites_per_split;
         return (int)((cnt + KC - 1) / KC);
@@ -162,7 +178,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                      "r"(tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    for (int i = tid; i < K / 8; i += THREADS) s_units[i] = xb_unit(g, i);
+    if (!p.a_box)
+        for (int i = tid; i < K / 8; i += THREADS) s_units[i] = xb_unit(g, i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -181,7 +198,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
             const int64_t mt = rem / p.n_tiles;
             const int nt = (int)(rem - mt * p.n_tiles);
             XbSite sites[4];                                   // forward: the four rows this thread feeds, fixed for the tile
-            if (!WGRAD) {
+            if (!WGRAD && !p.a_tma) {
 #pragma unroll
                 for (int gi = 0; gi < 4; ++gi) sites[gi] = xb_site(g, mt * TILE_M + xb_fwd_row(pt, gi), p.M);
             }
@@ -210,13 +227,18 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                 if (pt == 0 && (p.a_tma || p.b_tma)) {
                     // plain-matrix operands: one elected thread arms the barrier with the byte count and issues the tile
                     // copies; every plane of an operand travels in ONE box (planes are the outermost tensor dimension)
-                    const uint32_t bytes = (p.a_tma ? PA * a_plane : 0u) + (p.b_tma ? PB * w_plane : 0u);
+                    const uint32_t bytes = (p.a_tma ? PA * (p.a_box ? (uint32_t)box_rows * 128u : a_plane) : 0u) + (p.b_tma ? PB * w_plane : 0u);
                     mbar_expect_tx(&full_bar[stage], bytes);
                     if (p.b_tma) {
                         if (!WGRAD) tma_load_3d(wbase, &p.tm_b, kc * KC, nt * N, 0, &full_bar[stage]);          // W[n, k] rows
                         else tma_load_3d(wbase, &p.tm_b, nt * N, (int)site0, 0, &full_bar[stage]);               // G[site, n] rows
                     }
-                    if (p.a_tma) {
+                    if (p.a_box) {                          // one box per plane: {64 B or 128 B of channels, pixels, grid rows}
+#pragma unroll
+                        for (int q = 0; q < PA; ++q)
+                            tma_load_4d(base + q * a_plane, &p.tm_a, p.box_c0[kc], p.box_w0[kc],
+                                        (int)(mt * p.box_h) * p.box_rs + p.box_r[kc], q, &full_bar[stage]);
+                    } else if (p.a_tma) {
                         if (!WGRAD) {
                             tma_load_3d(base, &p.tm_a, kc * KC, (int)(mt * TILE_M), 0, &full_bar[stage]);        // A[row, k]
                         } else {                                    // A[site, kcol]: two blocks of 64 columns
@@ -296,7 +318,15 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
             const int nt = (int)(rem - mt * p.n_tiles);
             bool live;
             int64_t orow = 0;
-            if (!WGRAD) {
+            if (!WGRAD && p.a_box) {
+                const int gr = (int)xb_div((uint32_t)tid, p.box_div_w), x = tid - gr * p.box_w;
+                const int64_t R = mt * p.box_h + gr;                       // merged (image, padded row) index
+                const int b = (int)xb_div((uint32_t)R, p.box_div_hp), y = (int)(R - (int64_t)b * p.box_hp);
+                live = tid < box_rows && b < g.B && y >= p.box_y0 && y <= p.box_y1;
+                if (live)
+                    orow = (((int64_t)b * p.out_H + ((y - p.box_y0) * p.oys + p.oy0)) * p.out_W + (x * p.oxs + p.ox0)) * p.out_ld +
+                           p.out_c0 + (int64_t)nt * N;
+            } else if (!WGRAD) {
                 const int64_t m = mt * TILE_M + tid;
                 live = m < p.M;
                 if (live) {
@@ -305,14 +335,16 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                     orow = (((int64_t)b * p.out_H + (y * p.oys + p.oy0)) * p.out_W + (x * p.oxs + p.ox0)) * p.out_ld + p.out_c0 +
                            (int64_t)nt * N;
                 }
-                // the bias slice of this n tile (only the epilogue warps read / write s_bias; named barrier 1, 128 threads)
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int i = tid; i < N; i += EPI_WARPS * 32) s_bias[i] = p.bias ? p.bias[nt * N + i] : 0.f;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
             } else {
                 const int64_t kcol = mt * TILE_M + tid;
                 live = kcol < K;
                 orow = ((sp * K + kcol) * p.n_tiles + nt) * (int64_t)N;       // partials [splits, K, N_total]
+            }
+            if (!WGRAD) {
+                // the bias slice of this n tile (only the epilogue warps read / write s_bias; named barrier 1, 128 threads)
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int i = tid; i < N; i += EPI_WARPS * 32) s_bias[i] = p.bias ? p.bias[nt * N + i] : 0.f;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
             }
             mbar_wait(&acc_full[a], (tcount >> 1) & 1u);
             tc_fence_after();
@@ -492,6 +524,23 @@ bool make_tmap(CUtensorMap *tm, const void *base, int64_t cols, int64_t rows, in
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// bf16 activation tensor [planes][rows][pixels][channels] (padded-row layout, rows = images x padded rows per image merged),
+// boxes of {box_c channels, box_px pixels, box_h rows taken every row_step-th row, one plane}, 128-byte swizzle
+bool make_tmap_box(CUtensorMap *tm, const void *base, int C, int W, int64_t rows, int planes, int64_t plane_stride, int box_c,
+                   int box_px, int box_h, int row_step) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    if (((uintptr_t)base & 15) || (C * 2) % 16 || (plane_stride * 2) % 16) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)rows, (cuuint64_t)planes};
+    const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)(planes > 1 ? plane_stride : rows * W * C) * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_px, (cuuint32_t)((box_h - 1) * row_step + 1), 1};
+    const cuuint32_t estr[4] = {1, 1, (cuuint32_t)row_step, 1};
+    if (box[2] > 256 || box[1] > 256) return false;
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int fill_params(ConvParams &p, int pa, int pb, const void *in, int64_t in_plane, const void *w, int64_t w_plane, int B,
                 int IH, int IW, int C, int OY, int OX, int sy, int sx, int T, const int8_t *dy, const int8_t *dx, int N,
                 int n_tile) {
@@ -515,7 +564,8 @@ int fill_params(ConvParams &p, int pa, int pb, const void *in, int64_t in_plane,
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) return XB_ERANGE;
     p.stages = stages;
-    p.a_tma = p.b_tma = 0;
+    p.a_tma = p.b_tma = p.a_box = 0;
+    p.box_w = p.box_h = p.box_hp = 1, p.box_y0 = p.box_y1 = 0, p.box_rs = 1, p.box_chunks = 0;
     return XB_OK;
 }
 
@@ -607,6 +657,53 @@ extern "C" int xb_gemm_gather_tc(int planes_a, int planes_b, const void *in, int
             p.a_tma = make_tmap(&p.tm_a, in, C, B, planes_a, C, in_plane, TILE_M) ? 1 : 0;
     }
     const int64_t tiles = (p.M + TILE_M - 1) / TILE_M * p.n_tiles;
+    return launch<false>(planes_a, planes_b, p, tiles, stream);
+}
+
+// The same GEMM with the A operand of a convolution fetched by TMA boxes from a padded-row activation tensor (see ConvParams
+// a_box); needs a driver that resolves cuTensorMapEncodeTiled (returns XB_EINVAL otherwise - there is no silent fallback).
+extern "C" int xb_gemm_box_tc(int planes_a, int planes_b, const void *in, int64_t in_plane, int C, int W, int64_t in_rows,
+                              int box_c, int box_px, int box_h, int row_step, int n_chunks, const int16_t *c0,
+                              const int16_t *w0, const int16_t *r0, const void *w, int64_t w_plane, const float *bias,
+                              const void *relu_mask, int B, int hp, int y0, int y1, int N, int n_tile, int relu,
+                              void *out_planes, int64_t out_plane, int planes_out, float *out_f32, int out_H, int out_W,
+                              int oys, int oxs, int oy0, int ox0, int64_t out_ld, int out_c0, void *stream) {
+    if (!c0 || !w0 || !r0 || n_chunks <= 0 || n_chunks > 16) return XB_EINVAL;
+    if ((box_c != 32 && box_c != 64) || box_px <= 0 || box_h <= 0 || row_step <= 0 || (box_px * box_c) % 64 != 0) return XB_EINVAL;
+    const int box_w = box_px * box_c / 64;                  // sites (GEMM rows) per grid row
+    if (box_w * box_h > TILE_M || hp <= 0 || y0 < 0 || y1 < y0 || y1 >= hp || B <= 0) return XB_ERANGE;
+    ConvParams p;
+    // geometry fields that the generic checks read: one "tap" of 64 channels per chunk
+    int8_t zero[XB_CONV_MAX_TAPS] = {0};
+    const int rc = fill_params(p, planes_a, planes_b, in, in_plane, w, w_plane, B, 1, 1, 64, 1, 1, 1, 1, n_chunks, zero, zero, N,
+                               n_tile);
+    if (rc != XB_OK) return rc;
+    if (!out_planes && !out_f32) return XB_EINVAL;
+    if (out_planes && (planes_out < 1 || planes_out > 3)) return XB_EINVAL;
+    if (out_ld % 8 != 0 || out_c0 % 8 != 0 || out_plane % 8 != 0) return XB_EALIGN;
+    if ((out_planes && !xb_aligned(out_planes, 16)) || (out_f32 && !xb_aligned(out_f32, 16)) ||
+        (relu_mask && !xb_aligned(relu_mask, 16)))
+        return XB_EALIGN;
+    if (!tma_enabled()) return XB_EINVAL;
+    const int64_t K = (int64_t)n_chunks * KC;
+    if (!make_tmap_box(&p.tm_a, in, C, W, in_rows, planes_a, in_plane, box_c, box_px, box_h, row_step)) return XB_EINVAL;
+    if (!make_tmap(&p.tm_b, w, K, N, planes_b, K, w_plane, n_tile)) return XB_EINVAL;
+    p.a_tma = p.b_tma = p.a_box = 1;
+    p.box_w = box_w, p.box_h = box_h, p.box_hp = hp, p.box_y0 = y0, p.box_y1 = y1, p.box_rs = row_step, p.box_chunks = n_chunks;
+    p.box_div_w = xb_div_make((uint32_t)box_w), p.box_div_hp = xb_div_make((uint32_t)hp);
+    for (int i = 0; i < 16; ++i) p.box_c0[i] = i < n_chunks ? c0[i] : 0, p.box_w0[i] = i < n_chunks ? w0[i] : 0, p.box_r[i] = i < n_chunks ? r0[i] : 0;
+    p.bias = bias;
+    p.mask = (const __nv_bfloat16 *)relu_mask;
+    __nv_bfloat16 *ob = (__nv_bfloat16 *)out_planes;
+    p.p_out = ob ? planes_out : 0;
+    for (int q = 0; q < 3; ++q) p.out[q] = (ob && q < planes_out) ? ob + q * out_plane : nullptr;
+    p.out_f32 = out_f32;
+    p.relu = relu;
+    p.out_H = out_H, p.out_W = out_W, p.oys = oys, p.oxs = oxs, p.oy0 = oy0, p.ox0 = ox0;
+    p.out_ld = out_ld, p.out_c0 = out_c0;
+    p.splits = 1, p.sites_per_split = 0, p.w_ld = 0;
+    p.M = (int64_t)B * hp * box_w;
+    const int64_t tiles = ((int64_t)B * hp + box_h - 1) / box_h * p.n_tiles;
     return launch<false>(planes_a, planes_b, p, tiles, stream);
 }
 

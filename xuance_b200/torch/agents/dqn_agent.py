@@ -3,7 +3,7 @@ perdqn_agent.py:17-109 (beta annealing, priorities fed back after every update).
 import torch
 
 from ...common import PerOffPolicyBuffer
-from ..rl_models import DeepQNetwork
+from ..rl_models import DeepQNetwork, DuelingDeepQNetwork
 from .off_policy import OffPolicyAgent
 
 
@@ -19,6 +19,16 @@ class DQN_Agent(OffPolicyAgent):
         return DeepQNetwork(representation=rep, hidden_size=self.config.q_hidden_size, action_space=self.action_space,
                             normalizer=self.normalize_fn, initializer=self.initializer, activation=self.activation,
                             device=self.device).to(self.device)
+
+
+class DuelDQN_Agent(DQN_Agent):
+    """dueldqn_agent.py:10-45: DQN_Agent with the dueling network."""
+
+    def _build_model(self):
+        rep = self._build_representation(self.config.representation, self.observation_space, self.config)
+        return DuelingDeepQNetwork(representation=rep, hidden_size=self.config.q_hidden_size, action_space=self.action_space,
+                                   normalizer=self.normalize_fn, initializer=self.initializer, activation=self.activation,
+                                   device=self.device).to(self.device)
 
 
 class PerDQN_Agent(DQN_Agent):

@@ -22,7 +22,7 @@ import torch.nn as nn
 
 from ...common import AgentGrouping, BaseCallback, MARL_OffPolicyBuffer_RNN, space2shape
 from ..rl_models import (REGISTRY_Representation, ActivationFunctions, AgentFeatureEncoder, DiscreteActionValueCritic,
-                         QMIX_Mixer, MixingQNetwork)
+                         QMIX_Mixer, VDN_mixer, MixingQNetwork)
 from .agent import set_seed, set_device, InitializeFunctions, NormalizeFunctions
 from ..utils import init_distributed_mode
 
@@ -382,6 +382,10 @@ class QMIX_Agents(OffPolicyMARLAgents):
         self.memory = self._build_memory()
         self.learner = self._build_learner(self.config, self.agent_grouping, self.model, self.callback)
 
+    def _build_mixer(self):
+        return QMIX_Mixer(dim_state=self.state_space.shape[0], dim_hidden=self.config.hidden_dim_mixing_net,
+                          dim_hypernet_hidden=self.config.hidden_dim_hyper_net, n_agents=self.n_agents, device=self.device)
+
     def _build_model(self):
         q_networks = nn.ModuleDict()
         for group_key, group_agents in self.groups.items():
@@ -391,8 +395,14 @@ class QMIX_Agents(OffPolicyMARLAgents):
                 representation=enc, action_space=self.action_space[ref], critic_hidden_size=self.config.q_hidden_size,
                 normalizer=self.normalize_fn, initializer=self.initializer, activation=self.activation,
                 device=self.device)
-        mixer = QMIX_Mixer(dim_state=self.state_space.shape[0], dim_hidden=self.config.hidden_dim_mixing_net,
-                           dim_hypernet_hidden=self.config.hidden_dim_hyper_net, n_agents=self.n_agents,
-                           device=self.device)
+        mixer = self._build_mixer()
         return MixingQNetwork(grouping=self.agent_grouping, q_networks=q_networks, mixer=mixer, use_rnn=self.use_rnn,
                               device=self.device).to(self.device)
+
+
+class VDN_Agents(QMIX_Agents):
+    """vdn_agents.py: value decomposition with the parameter-free sum mixer; same rollout loop, buffer and learner update
+    (the reference's VDN_Learner differs from QMIX_Learner only in not passing the global state to the mixer)."""
+
+    def _build_mixer(self):
+        return VDN_mixer()

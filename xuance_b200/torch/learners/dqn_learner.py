@@ -26,7 +26,7 @@ class DQN_Learner(Learner):
         self.gamma = config.gamma
         self.sync_frequency = config.sync_frequency
         self.n_actions = self.model.n_actions
-        self._stats = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self._stats = self.optimizer.bucket.tail[:4]       # logged sums ride in the gradient all-reduce (bucket tail)
         self._scratch = _lib.scratch(self.device)
         self.use_cuda_graph = getattr(config, "use_cuda_graph", False)
         self._graphs = {}
@@ -57,8 +57,7 @@ class DQN_Learner(Learner):
         self.optimizer.zero_grad()
         torch.autograd.backward([evalQ], [dq])
         if self.world_size > 1:
-            allreduce_sum_(self.optimizer.bucket.grad)
-            allreduce_sum_(self._stats)
+            allreduce_sum_(self.optimizer.bucket.grad_all)   # the one collective: gradient + logged statistics
         self.optimizer.launch(max_norm=self.grad_clip_norm if self.use_grad_clip else None)
         return td.abs()
 
@@ -70,7 +69,7 @@ class DQN_Learner(Learner):
         info = self.callback.on_update_start(self.iterations, model=self.model, obs=obs, act=act, next_obs=nxt,
                                              rew=rew, termination=ter) or {}
         self.optimizer.prepare()
-        if self.use_cuda_graph and self.world_size == 1:
+        if self.use_cuda_graph:        # NCCL captures into the graph as in the PPO path
             key = (tuple(obs.shape), obs.dtype)
             if key not in self._graphs:
                 self._graphs[key] = CapturedStep(self._device_update, [obs, nxt, act, rew, ter], self._snapshot,
@@ -102,3 +101,8 @@ class PerDQN_Learner(DQN_Learner):
 class DDQN_Learner(DQN_Learner):
     """Double DQN - mirror of xuance/torch/learners/qlearning_family/ddqn_learner.py:13-80."""
     double_q = True
+
+
+class DuelDQN_Learner(DQN_Learner):
+    """Dueling DQN - mirror of xuance/torch/learners/qlearning_family/dueldqn_learner.py:12-80: the TD arithmetic is the DQN
+    learner's (max over the target network's Q); the dueling decomposition lives in the network head."""

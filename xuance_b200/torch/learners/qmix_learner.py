@@ -65,7 +65,7 @@ class QMIX_Learner(Learner):
                                                            total_iters=self.total_iters)
         dev = self.device
         self._filled_sum = torch.zeros(1, dtype=torch.float32, device=dev)
-        self._stats = torch.zeros(2, dtype=torch.float32, device=dev)
+        self._stats = self.optimizer.bucket.tail[:2]       # logged sums ride in the gradient all-reduce (bucket tail)
         self._scratch = _lib.scratch(dev)
         self.use_cuda_graph = getattr(config, "use_cuda_graph", False)
         self._graphs = {}
@@ -126,7 +126,7 @@ class QMIX_Learner(Learner):
         self.optimizer.zero_grad()
         torch.autograd.backward([q_tot_eval], [dq_tot])
         if self.world_size > 1:
-            allreduce_sum_(self.optimizer.bucket.grad)
+            allreduce_sum_(self.optimizer.bucket.grad_all)   # gradient + logged statistics in one collective
         self.optimizer.launch(max_norm=self.grad_clip_norm if self.use_grad_clip else None)
         return None
 
@@ -138,7 +138,7 @@ class QMIX_Learner(Learner):
         if d['avail'] is not None:
             args.append(d['avail'])
         self.optimizer.prepare()
-        if self.use_cuda_graph and self.world_size == 1:
+        if self.use_cuda_graph:        # the two collectives (sum(filled), gradient bucket) capture into the graph
             key = tuple(d['obs'].shape)
             if key not in self._graphs:
                 self._graphs[key] = CapturedStep(self._device_update, args, self._snapshot, self._restore)

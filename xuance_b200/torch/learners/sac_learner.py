@@ -41,8 +41,11 @@ class SAC_Learner(Learner):
         self.use_cuda_graph = getattr(config, "use_cuda_graph", False)
         self._graphs = {}
         dev = self.device
-        self._stats_a = torch.zeros(4, dtype=torch.float32, device=dev)
-        self._stats_c = torch.zeros(2, dtype=torch.float32, device=dev)
+        # the logged sums (and mean(log_pi), which the temperature step needs globally) ride in the tails of the two gradient
+        # buckets: TWO collectives per update.  They cannot be one: the reference steps the actor before it evaluates the
+        # critic target (sac_learner.py:53-72), so the critic gradient does not exist when the actor's must be reduced.
+        self._stats_a = self.optimizer['actor'].bucket.tail[:4]
+        self._stats_c = self.optimizer['critic'].bucket.tail[:2]
         self._scratch = _lib.scratch(dev)
         self._alpha_loss = torch.zeros(1, dtype=torch.float32, device=dev)
 
@@ -81,7 +84,7 @@ class SAC_Learner(Learner):
         self.optimizer['actor'].zero_grad()
         torch.autograd.backward([log_pi, q1, q2], [dlp, dq1, dq2], inputs=self.optimizer['actor'].bucket.params)
         if self.world_size > 1:
-            allreduce_sum_(self.optimizer['actor'].bucket.grad)
+            allreduce_sum_(self.optimizer['actor'].bucket.grad_all)
         self.optimizer['actor'].launch(max_norm=clip)
 
         # ---- critic step (:62-72)
@@ -97,14 +100,12 @@ class SAC_Learner(Learner):
         self.optimizer['critic'].zero_grad()
         torch.autograd.backward([aq1, aq2], [dq1, dq2])
         if self.world_size > 1:
-            allreduce_sum_(self.optimizer['critic'].bucket.grad)
+            allreduce_sum_(self.optimizer['critic'].bucket.grad_all)
         self.optimizer['critic'].launch(max_norm=clip)
 
         # ---- temperature step (:74-82): d/dlog_alpha of -mean(log_alpha*(log_pi+H_target)) = -(mean(log_pi)+H_target)
         if self.use_automatic_entropy_tuning:
-            mean_lp = self._stats_a[2:3]
-            if self.world_size > 1:
-                mean_lp = allreduce_sum_(mean_lp.clone())
+            mean_lp = self._stats_a[2:3]          # already the global mean: summed with the actor gradient
             g = -(mean_lp + self.target_entropy)
             self._alpha_loss.copy_(self.log_alpha.detach() * g)
             self.alpha_optimizer.zero_grad()
@@ -129,7 +130,7 @@ class SAC_Learner(Learner):
             o.prepare()
         if self.use_automatic_entropy_tuning:
             self.alpha_optimizer.prepare()
-        graphed = self.use_cuda_graph and self.world_size == 1 and (noise_pi is None) == (noise_next is None)
+        graphed = self.use_cuda_graph and (noise_pi is None) == (noise_next is None)
         if graphed:
             args = [obs, act, nxt, rew, ter] + ([] if noise_pi is None else [noise_pi, noise_next])
             key = (tuple(obs.shape), len(args))

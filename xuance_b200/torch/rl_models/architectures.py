@@ -8,7 +8,7 @@ import torch
 import torch.nn as nn
 
 from ...common.spaces import is_discrete
-from .heads import QValueHead, SAC_GaussianActorHead, GaussianActorHead, ValueHead
+from .heads import DuelingQValueHead, QValueHead, SAC_GaussianActorHead, GaussianActorHead, ValueHead
 from .outputs import ModelOutput, StochasticActorOutput, TwinCriticOutput
 
 
@@ -100,6 +100,11 @@ class DeepQNetwork(nn.Module):
             tp.data.copy_(ep)
         for ep, tp in zip(self.eval_Q_head.parameters(), self.target_Q_head.parameters()):
             tp.data.copy_(ep)
+
+
+class DuelingDeepQNetwork(DeepQNetwork):
+    """deep_q_network.py:102-103."""
+    q_head_cls = DuelingQValueHead
 
 
 class GaussianActor(nn.Module):

@@ -101,3 +101,27 @@ class QValueHead(nn.Module):
         if avail_actions is not None:
             q_values[avail_actions == 0] = -1e10
         return q_values
+
+
+class DuelingQValueHead(nn.Module):
+    """q_head.py:42-80: Q = V + (A - mean(A)); both streams use hidden sizes h // 2.  (The reference hands the NORMALISER
+    where the last layers' initialiser belongs, so those two layers keep torch's default initialisation - kept.)"""
+
+    def __init__(self, feature_dim, hidden_size, n_actions, normalizer=None, initializer=None, activation=None,
+                 device=None, **kwargs):
+        super().__init__()
+        self.feature_dim, self.n_actions = feature_dim, n_actions
+        half = [h // 2 for h in hidden_size]
+        v_layers, shape = _stack(feature_dim, half, normalizer, activation, initializer, device)
+        v_layers.extend(mlp_block(shape[0], 1, None, None, None, device)[0])
+        self.v_model = nn.Sequential(*v_layers)
+        a_layers, shape = _stack(feature_dim, half, normalizer, activation, initializer, device)
+        a_layers.extend(mlp_block(shape[0], n_actions, None, None, None, device)[0])
+        self.a_model = nn.Sequential(*a_layers)
+
+    def forward(self, features, avail_actions=None, **kwargs):
+        values, advantages = self.v_model(features), self.a_model(features)
+        q_values = values + (advantages - advantages.mean(dim=-1).unsqueeze(dim=-1))
+        if avail_actions is not None:
+            q_values[avail_actions == 0] = -1e10
+        return q_values

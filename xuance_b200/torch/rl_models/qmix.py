@@ -160,6 +160,16 @@ class QMIX_Mixer(nn.Module):
         return _MixFunction.apply(q, w1, b1, w2, b2, self.n_agents, self.dim_hidden).view(-1, 1)
 
 
+class VDN_mixer(nn.Module):
+    """q_mix_head.py VDN_mixer: Q_tot = sum_i Q_i (no parameters, the global state is ignored)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+
+    def forward(self, values_n, states=None):
+        return values_n.reshape(values_n.shape[0] if values_n.dim() == 2 else -1, -1).sum(dim=-1, keepdim=True)
+
+
 class MixingQNetwork(nn.Module):
     """value_factorization.py:17-174 for one shared group: eval/target agent networks + eval/target mixers."""
 

@@ -70,7 +70,8 @@ class _PixelEncoder(nn.Module):
     # ---- "tc" mode: the conv stack + hidden layer as K12 launches (split-bf16 tcgen05 GEMMs, float32 accumulation in TMEM,
     # utils/tc_conv.py): forward, data gradients and weight gradients; pinned against float64 in tests/test_gpu_tc_conv.py.
     def _build_tc(self):
-        from ..utils.tc_conv import TensorCoreNatureCNN, CudaBackend
+        import os
+        from ..utils.tc_conv import TensorCoreNatureCNN, BoxNatureCNN, CudaBackend
         mods = list(self.model)
         convs, fc, i = [], None, 0
         while i + 1 < len(mods) and isinstance(mods[i], nn.Conv2d) and isinstance(mods[i + 1], nn.ReLU):
@@ -84,8 +85,13 @@ class _PixelEncoder(nn.Module):
             raise NotImplementedError("compute='tc' covers Conv2d+ReLU stacks followed by Flatten, Linear, ReLU "
                                       "(AC_CNN_Atari with one hidden layer) or by AdaptiveMaxPool2d(1,1), Flatten (Basic_CNN)")
         C, H, W = self.input_shape
-        self._tc = TensorCoreNatureCNN(convs, rest[1] if hidden else None, (H, W, C),
-                                       backend=CudaBackend(planes=getattr(self, "tc_planes", 3)))
+        # padded-row activations + TMA boxes for the convolutions after the first when the stack has the NatureCNN shape
+        # (XB_K12_BOX=0 / XB_K12_TMA=0 keep the gathered cp.async path for every convolution)
+        cls = TensorCoreNatureCNN
+        probe = BoxNatureCNN(convs, rest[1] if hidden else None, (H, W, C))
+        if probe._box_ok() and os.environ.get("XB_K12_BOX", "1") != "0" and os.environ.get("XB_K12_TMA", "1") != "0":
+            cls = BoxNatureCNN
+        self._tc = cls(convs, rest[1] if hidden else None, (H, W, C), backend=CudaBackend(planes=getattr(self, "tc_planes", 3)))
         self._tc_pooled = pooled
 
     def _run_tc(self, observations):

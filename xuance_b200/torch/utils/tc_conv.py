@@ -171,6 +171,18 @@ def _plane_arg(t):
 
 
 _TAPS = {}
+flop_log = None      # bench.py: when a list, every K12 launch appends (abi name, layer tag, executed bf16 FLOPs, fp32-equivalent FLOPs)
+
+
+def _products(pa, pb):
+    """Plane products one launch executes: A plane i meets the first pb - i B planes."""
+    return sum(pb - i for i in range(pa))
+
+
+def _log_flops(name, rows, cols, depth, pa, pb):
+    if flop_log is not None:
+        eq = 2.0 * rows * cols * depth
+        flop_log.append((name, "M=%d N=%d K=%d PA=%d PB=%d" % (rows, cols, depth, pa, pb), eq * _products(pa, pb), eq))
 
 
 def _taps(geom):
@@ -194,6 +206,7 @@ def gemm_gather(x_pl, w_pl, geom, bias=None, relu=False, out_f32=None, out_pl=No
     xp, xs = _plane_arg(x_pl)
     wp, ws = _plane_arg(w_pl)
     op, os_ = _plane_arg(out_pl) if out_pl is not None else (None, 0)
+    _log_flops("xb_gemm_gather_tc", geom.M, N, K, PA, PB)
     _lib.call("xb_gemm_gather_tc", PA, PB, xp, xs, wp, ws, _lib.ptr(bias) if bias is not None else None,
               _lib.ptr(relu_mask) if relu_mask is not None else None, geom.B, geom.IH, geom.IW, geom.C, geom.OY, geom.OX,
               geom.sy, geom.sx, geom.T, dy.data_ptr(), dx.data_ptr(), N, n_tile, 1 if relu else 0, op, os_,
@@ -212,6 +225,7 @@ def wgrad_gather(x_pl, g_pl, geom, splits, n_tile=None):
     partials = torch.empty((splits, geom.K, N), dtype=torch.float32, device=g_pl.device)
     dy, dx = _taps(geom)
     xp, xs = _plane_arg(x_pl)
+    _log_flops("xb_wgrad_gather_tc", geom.K, N, geom.M, PA, PB)
     _lib.call("xb_wgrad_gather_tc", PA, PB, xp, xs, _lib.ptr(g_pl), g_pl.stride(0), g_pl.stride(1), geom.B, geom.IH, geom.IW,
               geom.C, geom.OY, geom.OX, geom.sy, geom.sx, geom.T, dy.data_ptr(), dx.data_ptr(), N, n_tile, splits,
               _lib.ptr(partials))
@@ -373,6 +387,246 @@ class TensorCoreNatureCNN:
                 be.gemm(g_pl, w_pl, L["dgrad"], out_pl=out_pl, out_ld=K, mask=prev_y[0])
             g_pl = out_pl
         return grads
+
+
+# ------------------------------------------------------------------------------------------------ padded-row layouts + TMA boxes
+@dataclass
+class BoxGeometry:
+    """One ``xb_gemm_box_tc`` call (include/xb200.h): a convolution over an activation stored with padded rows
+    [planes][B*hp_in][W][C]; see ConvParams.a_box in conv_tc.cu."""
+    B: int
+    C: int
+    W: int
+    hp_in: int
+    box_c: int
+    box_px: int
+    box_h: int
+    row_step: int
+    chunks: List[tuple]          # (c0, w0, r0) per 64-deep K chunk
+    hp_out: int
+    y0: int
+    y1: int
+    out_H: int
+    out_W: int
+    oys: int = 1
+    oxs: int = 1
+    oy0: int = 0
+    ox0: int = 0
+
+    @property
+    def sites_per_row(self):
+        return self.box_px * self.box_c // 64
+
+    @property
+    def K(self):
+        return 64 * len(self.chunks)
+
+    @property
+    def M(self):                  # rows the kernel computes (padded grid)
+        return self.B * self.hp_out * self.sites_per_row
+
+
+_BOXTAB = {}
+
+
+def gemm_box(x_pl, w_pl, bg, bias=None, relu=False, out_f32=None, out_pl=None, out_ld=None, out_c0=0, relu_mask=None,
+             n_tile=None):
+    """One K12 launch with the A operand fetched by TMA boxes (``x_pl`` [PA, B*hp_in, W, C], padded rows)."""
+    PB, N, K = w_pl.shape
+    PA = x_pl.shape[0]
+    assert K == bg.K and PA <= PB and tuple(x_pl.shape[1:]) == (bg.B * bg.hp_in, bg.W, bg.C), (x_pl.shape, bg)
+    out_ld = N if out_ld is None else out_ld
+    n_tile = n_tile_for(N, PB) if n_tile is None else n_tile
+    key = tuple(bg.chunks)
+    if key not in _BOXTAB:
+        _BOXTAB[key] = tuple(torch.tensor([c[i] for c in bg.chunks], dtype=torch.int16) for i in range(3))
+    c0, w0, r0 = _BOXTAB[key]
+    xp, xs = _plane_arg(x_pl)
+    wp, ws = _plane_arg(w_pl)
+    op, os_ = _plane_arg(out_pl) if out_pl is not None else (None, 0)
+    _log_flops("xb_gemm_box_tc", bg.M, N, K, PA, PB)
+    _lib.call("xb_gemm_box_tc", PA, PB, xp, xs, bg.C, bg.W, bg.B * bg.hp_in, bg.box_c, bg.box_px, bg.box_h, bg.row_step,
+              len(bg.chunks), c0.data_ptr(), w0.data_ptr(), r0.data_ptr(), wp, ws,
+              _lib.ptr(bias) if bias is not None else None, _lib.ptr(relu_mask) if relu_mask is not None else None,
+              bg.B, bg.hp_out, bg.y0, bg.y1, N, n_tile, 1 if relu else 0, op, os_,
+              out_pl.shape[0] if out_pl is not None else 0, _lib.ptr(out_f32) if out_f32 is not None else None,
+              bg.out_H, bg.out_W, bg.oys, bg.oxs, bg.oy0, bg.ox0, out_ld, out_c0)
+
+
+class BoxNatureCNN(TensorCoreNatureCNN):
+    """``TensorCoreNatureCNN`` with the activations between the convolutions kept in PADDED-ROW layouts so that the A
+    operands of every convolution after the first (forward and data gradient) are plain TMA boxes instead of 16-byte
+    cp.async gathers - on B200 a CTA's cp.async stream tops out near 13 B/clk (L1 miss tracking), a quarter of what the
+    tensor pipe needs for these 64-column layers.
+
+    Layout of an activation with H real rows: [P, B, hp, W, C], real row i at row i + off, every other row zero (written once
+    at allocation and never again).  A layer with stride s reads input row s*y' + r0[kh] for its output (padded) row y', which
+    requires hp_in = s * hp_out; garbage rows of the padded output grid are computed and dropped.  Supported after the
+    first convolution: (C_in = 32, s = 2) and (C_in = 64, s = 1) - the NatureCNN / Basic_CNN stacks; the first
+    convolution (raw uint8 plane, 4 channels) and all weight gradients keep the gathered path, with the padded tensors
+    described to it as ordinary geometries."""
+
+    HP = {0: None}
+
+    def _box_ok(self):
+        cs = self.convs
+        if len(cs) != 3:
+            return False
+        c1, c2, c3 = cs
+        return (c2.in_channels == 32 and c2.stride[0] == 2 and c2.kernel_size[0] % 2 == 0 and c3.in_channels == 64
+                and c3.stride[0] == 1 and c2.out_channels == 64 and c3.out_channels == 64 and c1.out_channels == 32)
+
+    def _plan(self, B):
+        if B in self._plans:
+            return self._plans[B]
+        assert self._box_ok(), "BoxNatureCNN: unsupported convolution stack"
+        H, W, C = self.in_hwc
+        c1, c2, c3 = self.convs
+        k1, s1, p1 = c1.kernel_size[0], c1.stride[0], c1.padding[0]
+        k2, s2, p2 = c2.kernel_size[0], c2.stride[0], c2.padding[0]
+        k3, s3, p3 = c3.kernel_size[0], c3.stride[0], c3.padding[0]
+        H1, W1 = conv_out(H, k1, s1, p1), conv_out(W, k1, s1, p1)          # 21 x 21
+        H2, W2 = conv_out(H1, k2, s2, p2), conv_out(W1, k2, s2, p2)        # 10 x 10
+        H3, W3 = conv_out(H2, k3, s3, p3), conv_out(W2, k3, s3, p3)        # 10 x 10
+        assert H3 == H2 and W3 == W2 and W2 * 2 <= 256
+        # padded grids: conv3's sites and conv2's sites share hp2 rows per image (valid rows 1 .. H2); conv2 reads act1 with
+        # row step 2, so act1 has hp1 = 2 * hp2 rows per image
+        hp2 = H2 + 2
+        hp1 = 2 * hp2
+        off1 = p2 + 2 * 1                                                    # real row i of act1 at padded row i + off1
+        assert off1 + H1 <= hp1
+        P = dict(B=B, H=H, W=W, C=C, H1=H1, W1=W1, H2=H2, W2=W2, hp1=hp1, hp2=hp2, off1=off1,
+                 N1=c1.out_channels, N2=c2.out_channels, N3=c3.out_channels)
+        # ---- conv1 forward (gathered, raw plane) writing into act1's padded layout
+        g1 = conv_forward_geometry(B, H, W, C, k1, k1, s1, p1)
+        g1.out_H, g1.oy0 = hp1, off1
+        P["fwd1"] = g1
+        # conv1 weight gradient: the sites are ALL rows of the padded act1 grid (zero gradient rows contribute nothing)
+        w1 = conv_forward_geometry(B, H, W, C, k1, k1, s1, p1)
+        w1.OY = hp1
+        w1.dy = [d - s1 * off1 for d in w1.dy]
+        w1.out_H = hp1
+        P["wg1"] = w1.check()
+        # ---- conv2 forward (box): chunk = (kh, pair of kw) x 32 channels
+        ch2 = [(0, kw - p2, kh) for kh in range(k2) for kw in range(0, k2, 2)]
+        P["fwd2"] = BoxGeometry(B=B, C=32, W=W1, hp_in=hp1, box_c=32, box_px=2 * W2, box_h=hp2, row_step=2, chunks=ch2,
+                                hp_out=hp2, y0=1, y1=H2, out_H=hp2, out_W=W2, oy0=1)
+        P["wg2"] = GatherGeometry(B=B, IH=hp1, IW=W1, C=32, OY=hp2, OX=W2, sy=2, sx=2,
+                                  dy=[kh for kh in range(k2) for _ in range(k2)], dx=[kw - p2 for _ in range(k2) for kw in range(k2)],
+                                  out_H=hp2, out_W=W2).check()
+        # ---- conv3 forward (box): chunk = one tap x 64 channels; result goes to the PLAIN [B, H3*W3*64] matrix the Linear reads
+        taps3 = [(kh, kw) for kh in range(k3) for kw in range(k3)]
+        P["taps3"] = taps3
+        P["fwd3"] = BoxGeometry(B=B, C=64, W=W2, hp_in=hp2, box_c=64, box_px=W2, box_h=hp2, row_step=1,
+                                chunks=[(0, kw - p3, kh - p3 + 1 - 1) for kh, kw in taps3], hp_out=hp2, y0=1, y1=H2,
+                                out_H=H3, out_W=W3, oy0=0)
+        P["wg3"] = GatherGeometry(B=B, IH=hp2, IW=W2, C=64, OY=hp2, OX=W2, sy=1, sx=1, dy=[kh - p3 for kh, _ in taps3],
+                                  dx=[kw - p3 for _, kw in taps3], out_H=hp2, out_W=W2).check()
+        # ---- conv3 data gradient (box over the padded output gradient): flipped taps, written into act2's layout
+        P["dg3"] = BoxGeometry(B=B, C=64, W=W2, hp_in=hp2, box_c=64, box_px=W2, box_h=hp2, row_step=1,
+                               chunks=[(0, p3 - kw, p3 - kh) for kh, kw in taps3], hp_out=hp2, y0=1, y1=H2,
+                               out_H=hp2, out_W=W2, oy0=1)
+        # ---- conv2 data gradient: one box GEMM per stride phase over g2 (padded, real row i at i + 1), into act1's layout
+        dg2 = []
+        for py in range(2):
+            for px in range(2):
+                ny, nx = (H1 - py + 1) // 2, (W1 - px + 1) // 2
+                taps = [(kh, kw) for kh in range(k2) if (py + p2 - kh) % 2 == 0 for kw in range(k2) if (px + p2 - kw) % 2 == 0]
+                chunks = [(0, (px + p2 - kw) // 2, (py + p2 - kh) // 2 + 1) for kh, kw in taps]
+                bh = min(hp2, 128 // nx)
+                dg2.append((BoxGeometry(B=B, C=64, W=W2, hp_in=hp2, box_c=64, box_px=nx, box_h=bh, row_step=1, chunks=chunks,
+                                        hp_out=hp2, y0=0, y1=ny - 1, out_H=hp1, out_W=W1, oys=2, oxs=2, oy0=py + off1, ox0=px),
+                            taps))
+        P["dg2"] = dg2
+        if self.fc is not None:
+            N, K = self.fc.weight.shape
+            assert K == H3 * W3 * c3.out_channels
+            P["fc"] = dict(N=N, K=K, fwd=linear_geometry(B, K), dgrad=linear_geometry(B, N), C=c3.out_channels, KH=H3, KW=W3)
+        self._plans[B] = P
+        return P
+
+    def _buffers(self, B, like):
+        key = ("buf", B)
+        if key not in self._plans:
+            P, be = self._plan(B), self.be
+            z = lambda *shape: torch.zeros((be.planes,) + shape, dtype=torch.bfloat16, device=like.device)
+            self._plans[key] = dict(act1=z(B * P["hp1"], P["W1"], P["N1"]), act2=z(B * P["hp2"], P["W2"], P["N2"]),
+                                    g3=z(B * P["hp2"], P["W2"], P["N3"]), g2=z(B * P["hp2"], P["W2"], P["N2"]),
+                                    g1=z(B * P["hp1"], P["W1"], P["N1"]))
+        return self._plans[key]
+
+    def forward(self, x_pl, B):
+        be, P = self.be, self._plan(B)
+        buf = self._buffers(B, x_pl)
+        c1, c2, c3 = self.convs
+        raw = x_pl.shape[0] == 1 and be.planes > 1
+        scale = 1.0 / 255.0 if raw else 1.0
+        w1 = be.pack_weight(c1.weight.detach(), scale)
+        gemm_gather(x_pl, w1, P["fwd1"], bias=c1.bias.detach(), relu=True, out_pl=buf["act1"], out_ld=P["N1"])
+        w2 = be.pack_weight(c2.weight.detach())
+        gemm_box(buf["act1"], w2, P["fwd2"], bias=c2.bias.detach(), relu=True, out_pl=buf["act2"], out_ld=P["N2"])
+        w3 = be.pack_weight(c3.weight.detach())
+        n3 = P["H2"] * P["W2"]
+        act3 = be.empty_planes((B * n3, P["N3"]), x_pl)
+        last_conv = self.fc is None
+        out3 = be.empty_f32((B * n3, P["N3"]), x_pl) if last_conv else None
+        gemm_box(buf["act2"], w3, P["fwd3"], bias=c3.bias.detach(), relu=True, out_pl=act3, out_f32=out3, out_ld=P["N3"])
+        saved = dict(x=x_pl, act3=act3, scale=scale)
+        if last_conv:
+            self._saved = (B, saved)
+            return out3
+        F_ = P["fc"]
+        w4 = self.fc.weight.detach().reshape(F_["N"], F_["C"], F_["KH"], F_["KW"])
+        wfc = be.pack_weight(w4)
+        y = be.empty_planes((B, F_["N"]), x_pl)
+        out = be.empty_f32((B, F_["N"]), x_pl)
+        gemm_gather(act3.view(be.planes, B, F_["K"]), wfc, F_["fwd"], bias=self.fc.bias.detach(), relu=True, out_f32=out, out_pl=y)
+        saved.update(y=y, w4=w4)
+        self._saved = (B, saved)
+        return out
+
+    def backward(self, dz):
+        be = self.be
+        B, sv = self._saved
+        P, buf = self._plan(B), self._buffers(B, dz)
+        c1, c2, c3 = self.convs
+        n3 = P["H2"] * P["W2"]
+        grads = []
+        act3 = sv["act3"]
+        if self.fc is not None:
+            F_ = P["fc"]
+            g4 = be.split(dz * (sv["y"][0] > 0).to(dz.dtype))
+            x3 = act3.view(be.planes, B, F_["K"])
+            dwfc = be.wgrad(x3, g4, F_["fwd"], F_["N"], F_["C"], F_["KH"], F_["KW"])
+            gfc = [dwfc.reshape(F_["N"], F_["K"]), be.colsum(g4)]
+            wt = be.split(sv["w4"].permute(0, 2, 3, 1).reshape(F_["N"], F_["K"]).t().contiguous())      # [P, K (h,w,c), N]
+            g3p = be.empty_planes((B, F_["K"]), dz)
+            gemm_gather(g4, wt, F_["dgrad"], out_pl=g3p, relu_mask=x3[0])
+            g3p = g3p.view(be.planes, B, P["H2"], P["W2"] * P["N3"])
+        else:
+            gfc = []
+            g3p = be.split(dz * (act3[0] > 0).to(dz.dtype)).view(be.planes, B, P["H2"], P["W2"] * P["N3"])
+        # conv3's output gradient in the padded site space (rows 1 .. H2 of hp2)
+        buf["g3"].view(be.planes, B, P["hp2"], P["W2"] * P["N3"])[:, :, 1:1 + P["H2"]].copy_(g3p)
+        g3 = buf["g3"]
+        G3 = g3.view(be.planes, -1, P["N3"])
+        k3 = c3.kernel_size[0]
+        dw3 = be.wgrad(buf["act2"], G3, P["wg3"], P["N3"], P["N2"], k3, k3)
+        db3 = be.colsum(G3)
+        wd3 = be.split(dgrad_weight_matrix(c3.weight.detach(), P["taps3"]))
+        gemm_box(g3, wd3, P["dg3"], out_pl=buf["g2"], out_ld=P["N2"], relu_mask=buf["act2"][0])
+        G2 = buf["g2"].view(be.planes, -1, P["N2"])
+        k2 = c2.kernel_size[0]
+        dw2 = be.wgrad(buf["act1"], G2, P["wg2"], P["N2"], P["N1"], k2, k2)
+        db2 = be.colsum(G2)
+        for bg, taps in P["dg2"]:
+            wd = be.split(dgrad_weight_matrix(c2.weight.detach(), taps))
+            gemm_box(buf["g2"], wd, bg, out_pl=buf["g1"], out_ld=P["N1"], relu_mask=buf["act1"][0])
+        G1 = buf["g1"].view(be.planes, -1, P["N1"])
+        k1 = c1.kernel_size[0]
+        dw1 = be.wgrad(sv["x"], G1, P["wg1"], P["N1"], self.in_hwc[2], k1, k1, sv["scale"])
+        db1 = be.colsum(G1)
+        return [dw1, db1, dw2, db2, dw3, db3] + gfc
 
 
 class _TCEncoderFn(torch.autograd.Function):
