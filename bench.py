@@ -402,7 +402,8 @@ def run_own_arm(args):
     # eagerly right after the timed region (graph replays hide per-kernel events); same buffers, same shapes, same stream
     hbm_peak, tc_peak, peak_src = measured_peaks()
     roofline, kernel_ms = None, {}
-    names = ["xb_gemm_gather_tc", "xb_wgrad_gather_tc", "xb_gather_obs_planes", "xb_gather_obs", "xb_ppo_loss_fwd_bwd",
+    names = ["xb_gemm_gather_tc", "xb_gemm_box_tc", "xb_wgrad_gather_tc", "xb_wgrad_box_tc", "xb_wgrad_reduce", "xb_split_bf16",
+             "xb_pack_conv_weight", "xb_gather_obs_planes", "xb_gather_obs", "xb_ppo_loss_fwd_bwd",
              "xb_adam_step", "xb_grad_sumsq", "xb_gather_scalars"]
     from xuance_b200.torch.utils import tc_conv
     saved_graph = agent.config.use_cuda_graph
@@ -430,7 +431,7 @@ def run_own_arm(args):
             kernel_ms[n] = float(sum(a.elapsed_time(b) for a, b in prof[n]))
     if flog:
         # pair the FLOP log with the events in launch order (each ABI name keeps its own ordered list)
-        it_f = {"xb_gemm_gather_tc": iter(prof["xb_gemm_gather_tc"]), "xb_wgrad_gather_tc": iter(prof["xb_wgrad_gather_tc"])}
+        it_f = {n: iter(prof[n]) for n in ("xb_gemm_gather_tc", "xb_gemm_box_tc", "xb_wgrad_gather_tc", "xb_wgrad_box_tc")}
         per_layer, tot_fl, tot_eq, tot_ms = {}, 0.0, 0.0, 0.0
         for nm, tag, fl, eq in flog:
             a, b = next(it_f[nm])

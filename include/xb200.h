@@ -271,16 +271,31 @@ int xb_gemm_gather_tc(int planes_a, int planes_b, const void *in, int64_t in_pla
                       int ox0, int64_t out_ld, int out_c0, void *stream);
 /* xb_gemm_gather_tc for a convolution whose input is stored in a PADDED-ROW layout [planes][B * hp_in][W][C] (hp_in rows per
  * image of which the first / last are zero padding), with the A operand fetched by TMA: a work item is box_h consecutive
- * grid rows x (box_px * box_c / 64) sites (<= 128 GEMM rows); chunk i (64 K values = box_c channels of 64 / box_c adjacent
- * pixels) is ONE box per plane at channel c0[i], pixel w0[i] (negative = left padding, zero-filled by the TMA unit), row
- * tile_row0 * row_step + r0[i].  Output sites are indexed over a padded grid too: hp rows per image, rows y0..y1 valid (the
+ * grid rows x box_px sites (<= 128 GEMM rows); chunk i (64 K values = box_c = 64 channels of one pixel; a 32-channel tensor
+ * is passed as its 64-channel pixel-pair view) is ONE box per plane at channel c0[i], pixel w0[i] (negative = left padding,
+ * zero-filled by the TMA unit), rows tile_row0 * row_step + r0[i] + k * row_step, k < box_h (the tensor is described to the
+ * TMA unit as {channel, pixel, row mod row_step, row / row_step, plane}; in_rows must be a multiple of row_step).
+ * relu_mask rows are the output's, in a tensor mask_W pixels wide with the pixel index shifted by mask_x0 (mask_W = 0: laid
+ * out exactly like the output).  Output sites are indexed over a padded grid too: hp rows per image, rows y0..y1 valid (the
  * others are never written: the caller keeps them zero), row y lands at ((b*out_H + (y-y0)*oys + oy0)*out_W + x*oxs + ox0).
  * W is [planes_b][N][n_chunks*64] in chunk order.  Everything else as xb_gemm_gather_tc. */
 int xb_gemm_box_tc(int planes_a, int planes_b, const void *in, int64_t in_plane, int C, int W, int64_t in_rows, int box_c,
                    int box_px, int box_h, int row_step, int n_chunks, const int16_t *c0, const int16_t *w0, const int16_t *r0,
-                   const void *w, int64_t w_plane, const float *bias, const void *relu_mask, int B, int hp, int y0, int y1, int N,
-                   int n_tile, int relu, void *out_planes, int64_t out_plane, int planes_out, float *out_f32, int out_H,
-                   int out_W, int oys, int oxs, int oy0, int ox0, int64_t out_ld, int out_c0, void *stream);
+                   const void *w, int64_t w_plane, const float *bias, const void *relu_mask, int mask_W, int mask_x0, int B,
+                   int hp, int y0, int y1, int N, int n_tile, int relu, void *out_planes, int64_t out_plane, int planes_out,
+                   float *out_f32, int out_H, int out_W, int oys, int oxs, int oy0, int ox0, int64_t out_ld, int out_c0,
+                   void *stream);
+/* Weight gradient of the same convolution with both operands fetched by TMA boxes: `in` as for xb_gemm_box_tc, `g` the
+ * output gradient in the padded site layout [planes_b][g_rows][box_px*box_c/64 sites][N]; a chunk of the reduction is box_h
+ * grid rows (box_w * box_h <= 64 sites), N % 64 == 0; partials: float32 [splits, n_chunks*64, N] (reduce with xb_wgrad_reduce). */
+int xb_wgrad_box_tc(int planes_a, int planes_b, const void *in, int64_t in_plane, int C, int W, int64_t in_rows, int box_c,
+                    int box_px, int box_h, int row_step, int n_chunks, const int16_t *c0, const int16_t *w0, const int16_t *r0,
+                    const void *g, int64_t g_plane, int64_t g_rows, int N, int splits, float *partials, void *stream);
+/* Test hook: the raw shared-memory image (first out_bytes, 0xEE = untouched) after ONE TMA box load of the 4-D tensor map the
+ * box mode builds - lets the tests pin the layout (pixel packing, row step, 128-byte swizzle, zero fill) byte for byte. */
+int xb_debug_tma_box(const void *in, int64_t in_plane, int planes, int C, int W, int64_t rows, int box_c, int box_px, int box_h,
+                     int row_step, int c0, int c1, int c2, int c3, uint32_t expect_bytes, void *out, uint32_t out_bytes,
+                     void *stream);
 int xb_wgrad_gather_tc(int planes_a, int planes_b, const void *in, int64_t in_plane, const void *g, int64_t g_plane,
                        int64_t g_ld, int B, int IH, int IW, int C, int OY, int OX, int sy, int sx, int T, const int8_t *dy,
                        const int8_t *dx, int N, int n_tile, int splits, float *partials, void *stream);

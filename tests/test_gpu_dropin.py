@@ -47,7 +47,7 @@ def test_reference_loop_over_xb200_classes_equals_product_agent(fused):
             info = reference_train_epochs(agent, n_epochs)
         else:
             agent = SimpleNamespace(buffer_size=N * T, batch_size=N * T // n_mb, memory=memory, learner=learner, model=model,
-                                    world_size=1, config=SimpleNamespace(use_cuda_graph=False, fused_sample=fused))
+                                    world_size=1, device=DEV, config=SimpleNamespace(use_cuda_graph=False, fused_sample=fused))
             agent._obs_format = lambda: OnPolicyAgent._obs_format(agent)
             info = OnPolicyAgent.train_epochs(agent, n_epochs)
         results.append((info, {k: v.detach().clone() for k, v in model.state_dict().items()}))

@@ -203,12 +203,15 @@ def test_box_convolutions_forward_and_data_gradient(planes, atol):
     P = enc._plan(B)
     hp1, hp2, off1 = P["hp1"], P["hp2"], P["off1"]
     a1 = torch.rand(B, 21, 21, 32, device=DEV)                               # conv2's input (conv1's activation)
-    act1 = torch.zeros(planes, B, hp1, 21, 32, dtype=torch.bfloat16, device=DEV)
-    act1[:, :, off1:off1 + 21] = tc.split_bf16(a1, planes)
-    act1 = act1.view(planes, B * hp1, 21, 32)
+    W1p, xo1 = P["W1p"], P["xo1"]                                            # one zero pixel on the left: pixel pairs are 128 B
+    assert (W1p, xo1) == (22, 1)
+    act1 = torch.zeros(planes, B, hp1, W1p, 32, dtype=torch.bfloat16, device=DEV)
+    act1[:, :, off1:off1 + 21, xo1:xo1 + 21] = tc.split_bf16(a1, planes)
+    act1 = act1.view(planes, B * hp1, W1p, 32)
+    act1_pairs = act1.view(planes, B * hp1, W1p // 2, 64)
     w2, b2 = convs[1].weight.detach(), convs[1].bias.detach()
     out2 = torch.zeros(planes, B * hp2, 10, 64, dtype=torch.bfloat16, device=DEV)
-    tc.gemm_box(act1, tc.pack_conv_weight(w2, planes), P["fwd2"], bias=b2, relu=True, out_pl=out2, out_ld=64)
+    tc.gemm_box(act1_pairs, tc.pack_conv_weight(w2, planes), P["fwd2"], bias=b2, relu=True, out_pl=out2, out_ld=64)
     want2 = F.relu(F.conv2d(a1.permute(0, 3, 1, 2).double(), w2.double(), b2.double(), stride=2, padding=1)).permute(0, 2, 3, 1)
     got2 = out2.float().sum(0).view(B, hp2, 10, 64)
     np.testing.assert_allclose(got2[:, 1:11].cpu().numpy(), want2.cpu().numpy(), rtol=0, atol=atol)
@@ -240,13 +243,23 @@ def test_box_convolutions_forward_and_data_gradient(planes, atol):
     x1 = a1.double().permute(0, 3, 1, 2).requires_grad_(True)
     y2 = F.conv2d(x1, w2.double(), stride=2, padding=1)
     (dx1,) = torch.autograd.grad(y2, x1, g2.double().permute(0, 3, 1, 2))
-    mask1 = act1[0].float().view(B, hp1, 21, 32)[:, off1:off1 + 21] > 0
+    mask1 = act1[0].float().view(B, hp1, W1p, 32)[:, off1:off1 + 21, xo1:xo1 + 21] > 0
     d1 = torch.zeros(planes, B * hp1, 21, 32, dtype=torch.bfloat16, device=DEV)
     for bg, taps in P["dg2"]:
         tc.gemm_box(g2p, tc.split_bf16(tc.dgrad_weight_matrix(w2, taps), planes), bg, out_pl=d1, out_ld=32, relu_mask=act1[0])
     got1 = d1.float().sum(0).view(B, hp1, 21, 32)
     np.testing.assert_allclose(got1[:, off1:off1 + 21].cpu().numpy(), (dx1.permute(0, 2, 3, 1) * mask1).cpu().numpy(), rtol=0, atol=atol * 4)
     assert float(got1[:, :off1].abs().max()) == 0.0
+    # weight gradients of conv3 and conv2 with both operands as TMA boxes (reduction chunks of 6 grid rows = 60 sites)
+    for w, x_pad, g_pad, bg, xin, gout, stride, cin in ((w3, out2, g3p, P["fwd3"], a2, g3, 1, 64), (w2, act1_pairs, g2p, P["fwd2"], a1, g2, 2, 32)):
+        wd = w.double().requires_grad_(True)
+        y = F.conv2d(xin.double().permute(0, 3, 1, 2), wd, stride=stride, padding=1)
+        (want_w,) = torch.autograd.grad(y, wd, gout.double().permute(0, 3, 1, 2))
+        k = w.shape[-1]
+        for splits in (1, 3):
+            dw = tc.wgrad_reduce(tc.wgrad_box(x_pad, g_pad.view(planes, B * hp2, 10, 64), bg, 6, splits), 64, cin, k, k)
+            np.testing.assert_allclose(dw.cpu().numpy(), want_w.cpu().numpy(), rtol=0, atol=atol * 8 * max(1.0, float(want_w.abs().max())),
+                                       err_msg="cin=%d splits=%d" % (cin, splits))
 
 
 @pytest.mark.parametrize("planes,fwd_tol,grad_tol", [(2, 1e-4, 2e-2), (3, 2e-5, 2e-3)])

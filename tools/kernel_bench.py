@@ -313,11 +313,12 @@ def main():
         enc = tc.BoxNatureCNN(convs, None, (84, 84, 4), backend=tc.CudaBackend(Pn))
         P = enc._plan(B)
         rnd = lambda *sh: torch.randn(sh, device=DEV, generator=g).to(torch.bfloat16)
-        act1, act2 = rnd(Pn, B * P["hp1"], 21, 32), rnd(Pn, B * P["hp2"], 10, 64)
+        act1, act2 = rnd(Pn, B * P["hp1"], P["W1p"], 32), rnd(Pn, B * P["hp2"], 10, 64)
+        act1_pairs = act1.view(Pn, B * P["hp1"], P["W1p"] // 2, 64)
         g3, d2, d1 = rnd(Pn, B * P["hp2"], 10, 64), torch.zeros(Pn, B * P["hp2"], 10, 64, dtype=torch.bfloat16, device=DEV), torch.zeros(Pn, B * P["hp1"], 21, 32, dtype=torch.bfloat16, device=DEV)
         w2, w3 = tc.pack_conv_weight(convs[1].weight.detach(), Pn), tc.pack_conv_weight(convs[2].weight.detach(), Pn)
         out3 = torch.empty(Pn, B * 100, 64, dtype=torch.bfloat16, device=DEV)
-        us = timeit(lambda: tc.gemm_box(act1, w2, P["fwd2"], relu=True, out_pl=d2, out_ld=64), R)
+        us = timeit(lambda: tc.gemm_box(act1_pairs, w2, P["fwd2"], relu=True, out_pl=d2, out_ld=64), R)
         add(entry("K12-box forward conv2 (P=3)", f"M={B * 100} N=64 K=512", us, act1.numel() * 2 + d2.numel() * 2, hbm, 2.0 * B * 100 * 64 * 512, tpk))
         us = timeit(lambda: tc.gemm_box(act2, w3, P["fwd3"], relu=True, out_pl=out3, out_ld=64), R)
         add(entry("K12-box forward conv3 (P=3)", f"M={B * 100} N=64 K=576", us, act2.numel() * 2 + out3.numel() * 2, hbm, 2.0 * B * 100 * 64 * 576, tpk))
@@ -331,6 +332,11 @@ def main():
                 tc.gemm_box(g3, wd, bg, out_pl=d1, out_ld=32, relu_mask=act1[0])
         us = timeit(run_dg2, R)
         add(entry("K12-box data gradient conv2 (P=3, 4 phases)", f"M={B * 441} N=32 K=256", us, 4 * g3.numel() * 2 + d1.numel() * 2, hbm, 2.0 * B * 100 * 64 * 512, tpk))
+        for nm, xp_, bgk, K in (("conv2", act1_pairs, "fwd2", 512), ("conv3", act2, "fwd3", 576)):
+            sp = tc.wgrad_box_splits(B * P["hp2"], 6, K, 64)
+            us = timeit(lambda: tc.wgrad_box(xp_, g3, P[bgk], 6, sp), R)
+            add(entry("K12-box weight gradient %s (P=3, %d splits)" % (nm, sp), f"M={B * 100} N=64 K={K}", us,
+                      xp_.numel() * 2 + g3.numel() * 2, hbm, 2.0 * B * 100 * 64 * K, tpk))
     print(json.dumps(out))
 
 

@@ -54,6 +54,7 @@ struct ConvParams {
     const __nv_bfloat16 *in[3];            // A planes: [B, IH, IW, C]
     const __nv_bfloat16 *w[3];             // B planes.  forward: weight [N_total, K].  weight gradient: output gradient [P, w_ld]
     const float *bias;                     // [N_total] or null (forward)
+    int mask_W, mask_x0;                   // box mode: the mask tensor's row width / pixel offset (its rows as the output's)
     const __nv_bfloat16 *mask;             // forward, nullable: result elements are zeroed where mask <= 0; same
                                            // addressing as the output (the ReLU derivative of a saved activation's hi plane)
     __nv_bfloat16 *out[3];                 // forward: p_out result planes (nullable)
@@ -86,10 +87,17 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm,
         ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
         : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, uint64_t *bar) {
+// one box of a padded-row activation tensor viewed as {channels, pixels, row phase (row mod S), row / S, plane}: row `r` of
+// the tensor is (phase r mod S, index r / S), so a convolution of stride S reads CONSECUTIVE indices of ONE phase - no
+// traversal stride is needed (measured: a 64-byte inner box under the 128-byte swizzle pads every pixel to a 128-byte
+// row, so 32-channel tensors are described as 64-channel pixel pairs instead, see BoxNatureCNN)
+__device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap *tm, int c, int w, int row, int S, int plane,
+                                             uint64_t *bar) {
+    const int idx = S == 1 ? row : (row >= 0 ? row / S : -((-row + S - 1) / S));      // floor(row / S)
+    const int ph = row - idx * S;
     asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+        ::"r"(dst), "l"(tm), "r"(c), "r"(w), "r"(ph), "r"(idx), "r"(plane), "r"(smem_u32(bar))
         : "memory");
 }
 // shared-memory matrix descriptor of a 128-byte-swizzled operand (the layout TMA writes with CU_TENSOR_MAP_SWIZZLE_128B):
@@ -155,7 +163,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
         if (!WGRAD) return p.a_box ? p.box_chunks : K / KC;
         const int64_t sp = w / mn_tiles, s0 = sp * p.sites_per_split;
         const int64_t cnt = (p.M - s0) < p.sites_per_split ? (p.M - s0) : p.sites_per_split;
-        return (int)((cnt + KC - 1) / KC);
+        // a_box: the reduction runs over merged grid rows (p.M of them), box_h rows = box_h * box_w <= 64 sites per chunk
+        return p.a_box ? (int)((cnt + p.box_h - 1) / p.box_h) : (int)((cnt + KC - 1) / KC);
     };
     const uint32_t acc_cols = (uint32_t)(PB * N);           // one accumulator = PB groups of N columns
     uint32_t tmem_cols = 32;
@@ -180,6 +189,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
     }
     if (!p.a_box)
         for (int i = tid; i < K / 8; i += THREADS) s_units[i] = xb_unit(g, i);
+    if (WGRAD && p.a_box) {
+        // a chunk holds box_h * box_w <= 64 sites: the rows of each 64-site block that no box ever writes must read as zero
+        const uint32_t total = (uint32_t)S * stage_bytes;
+        for (uint32_t i = tid * 16u; i < total; i += THREADS * 16u) *reinterpret_cast<uint4 *>(smem + i) = make_uint4(0, 0, 0, 0);
+        fence_proxy_async();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -227,17 +242,36 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                 if (pt == 0 && (p.a_tma || p.b_tma)) {
                     // plain-matrix operands: one elected thread arms the barrier with the byte count and issues the tile
                     // copies; every plane of an operand travels in ONE box (planes are the outermost tensor dimension)
-                    const uint32_t bytes = (p.a_tma ? PA * (p.a_box ? (uint32_t)box_rows * 128u : a_plane) : 0u) + (p.b_tma ? PB * w_plane : 0u);
+                    uint32_t bytes = (p.a_tma ? PA * (p.a_box ? (uint32_t)box_rows * 128u : a_plane) : 0u) + (p.b_tma ? PB * w_plane : 0u);
+                    if (p.a_box && WGRAD) {                 // blocks of this tile that exist (1 or 2) + the G box, box_rows sites each
+                        const int nblk = ((int)mt * 2 + 1 < p.box_chunks) ? 2 : 1;
+                        bytes = (uint32_t)(nblk * PA + PB) * (uint32_t)box_rows * 128u;
+                    }
                     mbar_expect_tx(&full_bar[stage], bytes);
-                    if (p.b_tma) {
+                    if (p.b_tma && !(p.a_box && WGRAD)) {
                         if (!WGRAD) tma_load_3d(wbase, &p.tm_b, kc * KC, nt * N, 0, &full_bar[stage]);          // W[n, k] rows
                         else tma_load_3d(wbase, &p.tm_b, nt * N, (int)site0, 0, &full_bar[stage]);               // G[site, n] rows
                     }
-                    if (p.a_box) {                          // one box per plane: {64 B or 128 B of channels, pixels, grid rows}
+                    if (p.a_box && WGRAD) {
+                        // weight gradient over padded-row tensors: the chunk is box_h grid rows of the site grid; the two
+                        // 64-column blocks of the tile are the forward's K chunks 2*mt and 2*mt+1 (same box tables); G is a
+                        // box of the padded output-gradient tensor.  (bytes: see the expect_tx above)
+                        const int row0 = (int)(sp * p.sites_per_split) + kc * p.box_h;
+                        for (int j = 0; j < 2; ++j) {
+                            const int ci = (int)mt * 2 + j;
+                            if (ci >= p.box_chunks) break;
+#pragma unroll
+                            for (int q = 0; q < PA; ++q)
+                                tma_load_box(base + j * PA * (a_plane / 2) + q * (a_plane / 2), &p.tm_a, p.box_c0[ci], p.box_w0[ci],
+                                             row0 * p.box_rs + p.box_r[ci], p.box_rs, q, &full_bar[stage]);
+                        }
+#pragma unroll
+                        for (int q = 0; q < PB; ++q) tma_load_box(wbase + q * w_plane, &p.tm_b, nt * N, 0, row0, 1, q, &full_bar[stage]);
+                    } else if (p.a_box) {                   // one box per plane: {64 B or 128 B of channels, pixels, grid rows}
 #pragma unroll
                         for (int q = 0; q < PA; ++q)
-                            tma_load_4d(base + q * a_plane, &p.tm_a, p.box_c0[kc], p.box_w0[kc],
-                                        (int)(mt * p.box_h) * p.box_rs + p.box_r[kc], q, &full_bar[stage]);
+                            tma_load_box(base + q * a_plane, &p.tm_a, p.box_c0[kc], p.box_w0[kc],
+                                         (int)(mt * p.box_h) * p.box_rs + p.box_r[kc], p.box_rs, q, &full_bar[stage]);
                     } else if (p.a_tma) {
                         if (!WGRAD) {
                             tma_load_3d(base, &p.tm_a, kc * KC, (int)(mt * TILE_M), 0, &full_bar[stage]);        // A[row, k]
@@ -317,15 +351,18 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
             const int64_t mt = rem / p.n_tiles;
             const int nt = (int)(rem - mt * p.n_tiles);
             bool live;
-            int64_t orow = 0;
+            int64_t orow = 0, mrow = 0;                                   // element offsets of the output row / of its mask row
             if (!WGRAD && p.a_box) {
                 const int gr = (int)xb_div((uint32_t)tid, p.box_div_w), x = tid - gr * p.box_w;
                 const int64_t R = mt * p.box_h + gr;                       // merged (image, padded row) index
                 const int b = (int)xb_div((uint32_t)R, p.box_div_hp), y = (int)(R - (int64_t)b * p.box_hp);
                 live = tid < box_rows && b < g.B && y >= p.box_y0 && y <= p.box_y1;
-                if (live)
-                    orow = (((int64_t)b * p.out_H + ((y - p.box_y0) * p.oys + p.oy0)) * p.out_W + (x * p.oxs + p.ox0)) * p.out_ld +
-                           p.out_c0 + (int64_t)nt * N;
+                if (live) {
+                    const int64_t orw = (int64_t)b * p.out_H + ((y - p.box_y0) * p.oys + p.oy0);
+                    const int ox = x * p.oxs + p.ox0;
+                    orow = (orw * p.out_W + ox) * p.out_ld + p.out_c0 + (int64_t)nt * N;
+                    mrow = (orw * p.mask_W + ox + p.mask_x0) * p.out_ld + p.out_c0 + (int64_t)nt * N;
+                }
             } else if (!WGRAD) {
                 const int64_t m = mt * TILE_M + tid;
                 live = m < p.M;
@@ -334,6 +371,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                     xb_conv_site(g, m, b, y, x);
                     orow = (((int64_t)b * p.out_H + (y * p.oys + p.oy0)) * p.out_W + (x * p.oxs + p.ox0)) * p.out_ld + p.out_c0 +
                            (int64_t)nt * N;
+                    mrow = orow;
                 }
             } else {
                 const int64_t kcol = mt * TILE_M + tid;
@@ -366,7 +404,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                     }
                 }
                 if (!WGRAD && p.mask && live) {
-                    const uint4 *mk = reinterpret_cast<const uint4 *>(p.mask + orow + c0);
+                    const uint4 *mk = reinterpret_cast<const uint4 *>(p.mask + mrow + c0);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const uint4 q = mk[j];
@@ -525,18 +563,21 @@ bool make_tmap(CUtensorMap *tm, const void *base, int64_t cols, int64_t rows, in
 }
 
 // bf16 activation tensor [planes][rows][pixels][channels] (padded-row layout, rows = images x padded rows per image merged),
-// boxes of {box_c channels, box_px pixels, box_h rows taken every row_step-th row, one plane}, 128-byte swizzle
+// boxes of {64 channels, box_px pixels, box_h rows of ONE row phase, one plane}, 128-byte swizzle
 bool make_tmap_box(CUtensorMap *tm, const void *base, int C, int W, int64_t rows, int planes, int64_t plane_stride, int box_c,
                    int box_px, int box_h, int row_step) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return false;
-    if (((uintptr_t)base & 15) || (C * 2) % 16 || (plane_stride * 2) % 16) return false;
-    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)rows, (cuuint64_t)planes};
-    const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)(planes > 1 ? plane_stride : rows * W * C) * 2};
-    const cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_px, (cuuint32_t)((box_h - 1) * row_step + 1), 1};
-    const cuuint32_t estr[4] = {1, 1, (cuuint32_t)row_step, 1};
-    if (box[2] > 256 || box[1] > 256) return false;
-    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
+    if (((uintptr_t)base & 15) || (C * 2) % 16 || (plane_stride * 2) % 16 || rows % row_step != 0) return false;
+    if (box_c * 2 != 128 || box_px > 256 || box_h > 256) return false;     // 128-byte inner box: one shared-memory row per pixel
+    const cuuint64_t S = (cuuint64_t)row_step;
+    // {channels, pixels, row phase, row / S, plane}
+    const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, S, (cuuint64_t)rows / S, (cuuint64_t)planes};
+    const cuuint64_t row_b = (cuuint64_t)W * C * 2;
+    const cuuint64_t strides[4] = {(cuuint64_t)C * 2, row_b, S * row_b, (cuuint64_t)(planes > 1 ? plane_stride : rows * W * C) * 2};
+    const cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)box_px, 1, (cuuint32_t)box_h, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(base), dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -665,12 +706,13 @@ extern "C" int xb_gemm_gather_tc(int planes_a, int planes_b, const void *in, int
 extern "C" int xb_gemm_box_tc(int planes_a, int planes_b, const void *in, int64_t in_plane, int C, int W, int64_t in_rows,
                               int box_c, int box_px, int box_h, int row_step, int n_chunks, const int16_t *c0,
                               const int16_t *w0, const int16_t *r0, const void *w, int64_t w_plane, const float *bias,
-                              const void *relu_mask, int B, int hp, int y0, int y1, int N, int n_tile, int relu,
+                              const void *relu_mask, int mask_W, int mask_x0, int B, int hp, int y0, int y1, int N, int n_tile,
+                              int relu,
                               void *out_planes, int64_t out_plane, int planes_out, float *out_f32, int out_H, int out_W,
                               int oys, int oxs, int oy0, int ox0, int64_t out_ld, int out_c0, void *stream) {
     if (!c0 || !w0 || !r0 || n_chunks <= 0 || n_chunks > 16) return XB_EINVAL;
-    if ((box_c != 32 && box_c != 64) || box_px <= 0 || box_h <= 0 || row_step <= 0 || (box_px * box_c) % 64 != 0) return XB_EINVAL;
-    const int box_w = box_px * box_c / 64;                  // sites (GEMM rows) per grid row
+    if (box_c != 64 || box_px <= 0 || box_h <= 0 || row_step <= 0 || row_step > 8) return XB_EINVAL;
+    const int box_w = box_px;                               // sites (GEMM rows) per grid row: one 64-channel pixel each
     if (box_w * box_h > TILE_M || hp <= 0 || y0 < 0 || y1 < y0 || y1 >= hp || B <= 0) return XB_ERANGE;
     ConvParams p;
     // geometry fields that the generic checks read: one "tap" of 64 channels per chunk
@@ -689,6 +731,7 @@ extern "C" int xb_gemm_box_tc(int planes_a, int planes_b, const void *in, int64_
     if (!make_tmap_box(&p.tm_a, in, C, W, in_rows, planes_a, in_plane, box_c, box_px, box_h, row_step)) return XB_EINVAL;
     if (!make_tmap(&p.tm_b, w, K, N, planes_b, K, w_plane, n_tile)) return XB_EINVAL;
     p.a_tma = p.b_tma = p.a_box = 1;
+    p.mask_W = mask_W > 0 ? mask_W : out_W, p.mask_x0 = mask_W > 0 ? mask_x0 : 0;
     p.box_w = box_w, p.box_h = box_h, p.box_hp = hp, p.box_y0 = y0, p.box_y1 = y1, p.box_rs = row_step, p.box_chunks = n_chunks;
     p.box_div_w = xb_div_make((uint32_t)box_w), p.box_div_hp = xb_div_make((uint32_t)hp);
     for (int i = 0; i < 16; ++i) p.box_c0[i] = i < n_chunks ? c0[i] : 0, p.box_w0[i] = i < n_chunks ? w0[i] : 0, p.box_r[i] = i < n_chunks ? r0[i] : 0;
@@ -733,6 +776,79 @@ extern "C" int xb_wgrad_gather_tc(int planes_a, int planes_b, const void *in, in
     }
     const int64_t K = (int64_t)T * C, work = (K + TILE_M - 1) / TILE_M * p.n_tiles * splits;
     return launch<true>(planes_a, planes_b, p, work, stream);
+}
+
+// Weight gradient of a convolution over padded-row tensors with BOTH operands fetched by TMA boxes (see ConvParams a_box and
+// the producer): partials[s, (chunk, 64 k), n] summed over the grid rows of split s.
+extern "C" int xb_wgrad_box_tc(int planes_a, int planes_b, const void *in, int64_t in_plane, int C, int W, int64_t in_rows,
+                               int box_c, int box_px, int box_h, int row_step, int n_chunks, const int16_t *c0,
+                               const int16_t *w0, const int16_t *r0, const void *g, int64_t g_plane, int64_t g_rows, int N,
+                               int splits, float *partials, void *stream) {
+    if (!c0 || !w0 || !r0 || n_chunks <= 0 || n_chunks > 16 || !partials || splits <= 0) return XB_EINVAL;
+    if (box_c != 64 || box_px <= 0 || box_h <= 0 || row_step <= 0 || row_step > 8) return XB_EINVAL;
+    const int box_w = box_px;
+    if (box_w * box_h > KC || N % 64 != 0 || g_rows <= 0) return XB_ERANGE;
+    if (!xb_aligned(partials, 16)) return XB_EALIGN;
+    ConvParams p;
+    int8_t zero[XB_CONV_MAX_TAPS] = {0};
+    const int rc = fill_params(p, planes_a, planes_b, in, in_plane, g, g_plane, 1, 1, 1, 64, 1, 1, 1, 1, n_chunks, zero, zero, N, 64);
+    if (rc != XB_OK) return rc;
+    if (!tma_enabled()) return XB_EINVAL;
+    if (!make_tmap_box(&p.tm_a, in, C, W, in_rows, planes_a, in_plane, box_c, box_px, box_h, row_step)) return XB_EINVAL;
+    if (!make_tmap_box(&p.tm_b, g, N, box_w, g_rows, planes_b, g_plane, 64, box_w, box_h, 1)) return XB_EINVAL;
+    p.a_tma = p.b_tma = p.a_box = 1;
+    p.box_w = box_w, p.box_h = box_h, p.box_hp = 1, p.box_y0 = 0, p.box_y1 = 0, p.box_rs = row_step, p.box_chunks = n_chunks;
+    p.box_div_w = xb_div_make((uint32_t)box_w), p.box_div_hp = xb_div_make(1u);
+    for (int i = 0; i < 16; ++i) p.box_c0[i] = i < n_chunks ? c0[i] : 0, p.box_w0[i] = i < n_chunks ? w0[i] : 0, p.box_r[i] = i < n_chunks ? r0[i] : 0;
+    p.bias = nullptr, p.mask = nullptr, p.out_f32 = partials, p.p_out = 0;
+    for (int q = 0; q < 3; ++q) p.out[q] = nullptr;
+    p.relu = 0;
+    p.out_H = p.out_W = p.oys = p.oxs = 1, p.oy0 = p.ox0 = 0, p.out_ld = N, p.out_c0 = 0;
+    p.w_ld = N;
+    // the reduction runs over the g_rows merged grid rows, cut into `splits` runs that are multiples of box_h rows
+    int64_t per = (g_rows + splits - 1) / splits;
+    per = (per + box_h - 1) / box_h * box_h;
+    if ((int64_t)(splits - 1) * per >= g_rows) return XB_EINVAL;
+    p.M = g_rows;
+    p.splits = splits, p.sites_per_split = per;
+    const int64_t K = (int64_t)n_chunks * KC, work = (K + TILE_M - 1) / TILE_M * p.n_tiles * splits;
+    return launch<true>(planes_a, planes_b, p, work, stream);
+}
+
+// ---------------------------------------------------------------- diagnostic: raw shared-memory image of one TMA box
+namespace {
+__global__ void tma_probe_kernel(const __grid_constant__ CUtensorMap tm, int c0, int c1, int c2, int c3, int rs, uint32_t bytes,
+                                 uint8_t *out, uint32_t out_bytes) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    for (uint32_t i = threadIdx.x; i < out_bytes; i += blockDim.x) smem[i] = 0xEE;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, bytes);
+        tma_load_box(smem_u32(smem), &tm, c0, c1, c2, rs, c3, &bar);
+    }
+    mbar_wait(&bar, 0);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < out_bytes; i += blockDim.x) out[i] = smem[i];
+}
+}  // namespace
+
+// test hook: loads ONE box of the 4-D map make_tmap_box would build and returns the first out_bytes of shared memory (0xEE =
+// never written), so that the layout assumptions of the box mode can be checked byte for byte (tests/test_gpu_tc_conv.py)
+extern "C" int xb_debug_tma_box(const void *in, int64_t in_plane, int planes, int C, int W, int64_t rows, int box_c, int box_px,
+                                int box_h, int row_step, int c0, int c1, int c2, int c3, uint32_t expect_bytes, void *out,
+                                uint32_t out_bytes, void *stream) {
+    CUtensorMap tm;
+    if (!make_tmap_box(&tm, in, C, W, rows, planes, in_plane, box_c, box_px, box_h, row_step)) return XB_EINVAL;
+    if (out_bytes > 64 * 1024) return XB_ERANGE;
+    cudaFuncSetAttribute(tma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    tma_probe_kernel<<<1, 256, 64 * 1024, (cudaStream_t)stream>>>(tm, c0, c1, c2, c3, row_step, expect_bytes, (uint8_t *)out, out_bytes);
+    return xb_launch_status();
 }
 
 extern "C" int xb_wgrad_reduce(const float *partials, int splits, int N, int C, int KH, int KW, float scale, float *dw,

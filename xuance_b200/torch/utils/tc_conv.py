@@ -412,10 +412,12 @@ class BoxGeometry:
     oxs: int = 1
     oy0: int = 0
     ox0: int = 0
+    mask_W: int = 0              # ReLU mask tensor: pixels per row / pixel offset when it is not laid out like the output
+    mask_x0: int = 0
 
     @property
     def sites_per_row(self):
-        return self.box_px * self.box_c // 64
+        return self.box_px
 
     @property
     def K(self):
@@ -427,6 +429,8 @@ class BoxGeometry:
 
 
 _BOXTAB = {}
+import os as _os
+BOX_WGRAD = _os.environ.get("XB_K12_BOX_WGRAD", "1") != "0"     # conv2 / conv3 weight gradients through TMA boxes too
 
 
 def gemm_box(x_pl, w_pl, bg, bias=None, relu=False, out_f32=None, out_pl=None, out_ld=None, out_c0=0, relu_mask=None,
@@ -448,9 +452,42 @@ def gemm_box(x_pl, w_pl, bg, bias=None, relu=False, out_f32=None, out_pl=None, o
     _lib.call("xb_gemm_box_tc", PA, PB, xp, xs, bg.C, bg.W, bg.B * bg.hp_in, bg.box_c, bg.box_px, bg.box_h, bg.row_step,
               len(bg.chunks), c0.data_ptr(), w0.data_ptr(), r0.data_ptr(), wp, ws,
               _lib.ptr(bias) if bias is not None else None, _lib.ptr(relu_mask) if relu_mask is not None else None,
-              bg.B, bg.hp_out, bg.y0, bg.y1, N, n_tile, 1 if relu else 0, op, os_,
+              bg.mask_W, bg.mask_x0, bg.B, bg.hp_out, bg.y0, bg.y1, N, n_tile, 1 if relu else 0, op, os_,
               out_pl.shape[0] if out_pl is not None else 0, _lib.ptr(out_f32) if out_f32 is not None else None,
               bg.out_H, bg.out_W, bg.oys, bg.oxs, bg.oy0, bg.ox0, out_ld, out_c0)
+
+
+def wgrad_box(x_pl, g_pl, bg, box_h, splits):
+    """Partial weight gradients [splits, K, N] of the convolution ``bg`` (its forward BoxGeometry) with both operands fetched
+    by TMA boxes: ``x_pl`` [PA, B*hp_in, W, C] padded input, ``g_pl`` [PB, B*hp_out, sites_per_row, N] padded output gradient;
+    a reduction chunk is ``box_h`` grid rows."""
+    PB, g_rows, spr, N = g_pl.shape
+    PA = x_pl.shape[0]
+    assert spr == bg.sites_per_row and g_rows == bg.B * bg.hp_out and PA <= PB
+    key = tuple(bg.chunks)
+    if key not in _BOXTAB:
+        _BOXTAB[key] = tuple(torch.tensor([c[i] for c in bg.chunks], dtype=torch.int16) for i in range(3))
+    c0, w0, r0 = _BOXTAB[key]
+    partials = torch.empty((splits, bg.K, N), dtype=torch.float32, device=g_pl.device)
+    xp, xs = _plane_arg(x_pl)
+    _log_flops("xb_wgrad_box_tc", bg.K, N, g_rows * spr, PA, PB)
+    _lib.call("xb_wgrad_box_tc", PA, PB, xp, xs, bg.C, bg.W, bg.B * bg.hp_in, bg.box_c, bg.box_px, box_h, bg.row_step,
+              len(bg.chunks), c0.data_ptr(), w0.data_ptr(), r0.data_ptr(), _lib.ptr(g_pl), g_pl.stride(0), g_rows, N, splits,
+              _lib.ptr(partials))
+    return partials
+
+
+def wgrad_box_splits(g_rows, box_h, K, N, sm_count=148):
+    """Splits for the box weight gradient: about two work items per SM, chains of at most 4096 sites (truncating adds)."""
+    tiles = -(-K // 128) * (N // 64)
+    s = max(1, (2 * sm_count) // tiles, -(-g_rows * 10 // 4096))
+    s = min(s, max(1, g_rows // (4 * box_h)))
+    while s > 1:
+        per = -(-(-(-g_rows // s)) // box_h) * box_h
+        if (s - 1) * per < g_rows:
+            break
+        s -= 1
+    return s
 
 
 class BoxNatureCNN(TensorCoreNatureCNN):
@@ -461,10 +498,14 @@ class BoxNatureCNN(TensorCoreNatureCNN):
 
     Layout of an activation with H real rows: [P, B, hp, W, C], real row i at row i + off, every other row zero (written once
     at allocation and never again).  A layer with stride s reads input row s*y' + r0[kh] for its output (padded) row y', which
-    requires hp_in = s * hp_out; garbage rows of the padded output grid are computed and dropped.  Supported after the
-    first convolution: (C_in = 32, s = 2) and (C_in = 64, s = 1) - the NatureCNN / Basic_CNN stacks; the first
-    convolution (raw uint8 plane, 4 channels) and all weight gradients keep the gathered path, with the padded tensors
-    described to it as ordinary geometries."""
+    requires hp_in = s * hp_out; garbage rows of the padded output grid are computed and dropped.  A TMA box must have a
+    128-byte inner extent (measured with tools/tma_probe.py: a 64-byte inner box under the 128-byte swizzle still takes one
+    128-byte shared-memory row per pixel), so the 32-channel activation of the first convolution is stored W1p = W1 + 1
+    pixels wide with ONE zero pixel on the left and read as 64-channel PIXEL PAIRS: the taps (kh, kw0), (kh, kw0 + 1) of the
+    stride-2 convolution are pair x + kw0 / 2 for output pixel x.  Supported after the first convolution: (C_in = 32, s = 2,
+    odd padding, even kernel) and (C_in = 64, s = 1) - the NatureCNN / Basic_CNN stacks; the first convolution (raw uint8
+    plane, 4 channels) and its weight gradient keep the gathered path, with the padded tensors described to it as ordinary
+    geometries."""
 
     HP = {0: None}
 
@@ -473,7 +514,8 @@ class BoxNatureCNN(TensorCoreNatureCNN):
         if len(cs) != 3:
             return False
         c1, c2, c3 = cs
-        return (c2.in_channels == 32 and c2.stride[0] == 2 and c2.kernel_size[0] % 2 == 0 and c3.in_channels == 64
+        return (c2.in_channels == 32 and c2.stride[0] == 2 and c2.kernel_size[0] % 2 == 0 and c2.padding[0] % 2 == 1
+                and c3.in_channels == 64
                 and c3.stride[0] == 1 and c2.out_channels == 64 and c3.out_channels == 64 and c1.out_channels == 32)
 
     def _plan(self, B):
@@ -495,11 +537,15 @@ class BoxNatureCNN(TensorCoreNatureCNN):
         hp1 = 2 * hp2
         off1 = p2 + 2 * 1                                                    # real row i of act1 at padded row i + off1
         assert off1 + H1 <= hp1
-        P = dict(B=B, H=H, W=W, C=C, H1=H1, W1=W1, H2=H2, W2=W2, hp1=hp1, hp2=hp2, off1=off1,
+        # act1 pixel i at column i + xo1 of W1p (even) columns: column 2x + kw0 - p2 + xo1 of tap kw0 (even) is even
+        xo1 = p2 % 2
+        W1p = -(-max(W1 + xo1, 2 * (W2 - 1) + k2 - p2 + xo1) // 2) * 2
+        P = dict(B=B, H=H, W=W, C=C, H1=H1, W1=W1, H2=H2, W2=W2, hp1=hp1, hp2=hp2, off1=off1, W1p=W1p, xo1=xo1,
                  N1=c1.out_channels, N2=c2.out_channels, N3=c3.out_channels)
         # ---- conv1 forward (gathered, raw plane) writing into act1's padded layout
         g1 = conv_forward_geometry(B, H, W, C, k1, k1, s1, p1)
         g1.out_H, g1.oy0 = hp1, off1
+        g1.out_W, g1.ox0 = W1p, xo1
         P["fwd1"] = g1
         # conv1 weight gradient: the sites are ALL rows of the padded act1 grid (zero gradient rows contribute nothing)
         w1 = conv_forward_geometry(B, H, W, C, k1, k1, s1, p1)
@@ -507,13 +553,13 @@ class BoxNatureCNN(TensorCoreNatureCNN):
         w1.dy = [d - s1 * off1 for d in w1.dy]
         w1.out_H = hp1
         P["wg1"] = w1.check()
-        # ---- conv2 forward (box): chunk = (kh, pair of kw) x 32 channels
-        ch2 = [(0, kw - p2, kh) for kh in range(k2) for kw in range(0, k2, 2)]
-        P["fwd2"] = BoxGeometry(B=B, C=32, W=W1, hp_in=hp1, box_c=32, box_px=2 * W2, box_h=hp2, row_step=2, chunks=ch2,
+        # ---- conv2 forward (box over act1's pixel-pair view [B*hp1, W1p/2, 64]): chunk = (kh, kw0 and kw0 + 1) x 32 channels
+        ch2 = [(0, (kw - p2 + xo1) // 2, kh) for kh in range(k2) for kw in range(0, k2, 2)]
+        P["fwd2"] = BoxGeometry(B=B, C=64, W=W1p // 2, hp_in=hp1, box_c=64, box_px=W2, box_h=hp2, row_step=2, chunks=ch2,
                                 hp_out=hp2, y0=1, y1=H2, out_H=hp2, out_W=W2, oy0=1)
-        P["wg2"] = GatherGeometry(B=B, IH=hp1, IW=W1, C=32, OY=hp2, OX=W2, sy=2, sx=2,
-                                  dy=[kh for kh in range(k2) for _ in range(k2)], dx=[kw - p2 for _ in range(k2) for kw in range(k2)],
-                                  out_H=hp2, out_W=W2).check()
+        P["wg2"] = GatherGeometry(B=B, IH=hp1, IW=W1p, C=32, OY=hp2, OX=W2, sy=2, sx=2,
+                                  dy=[kh for kh in range(k2) for _ in range(k2)],
+                                  dx=[kw - p2 + xo1 for _ in range(k2) for kw in range(k2)], out_H=hp2, out_W=W2).check()
         # ---- conv3 forward (box): chunk = one tap x 64 channels; result goes to the PLAIN [B, H3*W3*64] matrix the Linear reads
         taps3 = [(kh, kw) for kh in range(k3) for kw in range(k3)]
         P["taps3"] = taps3
@@ -535,7 +581,8 @@ class BoxNatureCNN(TensorCoreNatureCNN):
                 chunks = [(0, (px + p2 - kw) // 2, (py + p2 - kh) // 2 + 1) for kh, kw in taps]
                 bh = min(hp2, 128 // nx)
                 dg2.append((BoxGeometry(B=B, C=64, W=W2, hp_in=hp2, box_c=64, box_px=nx, box_h=bh, row_step=1, chunks=chunks,
-                                        hp_out=hp2, y0=0, y1=ny - 1, out_H=hp1, out_W=W1, oys=2, oxs=2, oy0=py + off1, ox0=px),
+                                        hp_out=hp2, y0=0, y1=ny - 1, out_H=hp1, out_W=W1, oys=2, oxs=2, oy0=py + off1, ox0=px,
+                                        mask_W=W1p, mask_x0=xo1),
                             taps))
         P["dg2"] = dg2
         if self.fc is not None:
@@ -550,9 +597,11 @@ class BoxNatureCNN(TensorCoreNatureCNN):
         if key not in self._plans:
             P, be = self._plan(B), self.be
             z = lambda *shape: torch.zeros((be.planes,) + shape, dtype=torch.bfloat16, device=like.device)
-            self._plans[key] = dict(act1=z(B * P["hp1"], P["W1"], P["N1"]), act2=z(B * P["hp2"], P["W2"], P["N2"]),
+            pairs = lambda t: t.view(be.planes, B * P["hp1"], P["W1p"] // 2, 2 * P["N1"])
+            self._plans[key] = dict(act1=z(B * P["hp1"], P["W1p"], P["N1"]), act2=z(B * P["hp2"], P["W2"], P["N2"]),
                                     g3=z(B * P["hp2"], P["W2"], P["N3"]), g2=z(B * P["hp2"], P["W2"], P["N2"]),
                                     g1=z(B * P["hp1"], P["W1"], P["N1"]))
+            self._plans[key]["act1_pairs"] = pairs(self._plans[key]["act1"])
         return self._plans[key]
 
     def forward(self, x_pl, B):
@@ -564,7 +613,7 @@ class BoxNatureCNN(TensorCoreNatureCNN):
         w1 = be.pack_weight(c1.weight.detach(), scale)
         gemm_gather(x_pl, w1, P["fwd1"], bias=c1.bias.detach(), relu=True, out_pl=buf["act1"], out_ld=P["N1"])
         w2 = be.pack_weight(c2.weight.detach())
-        gemm_box(buf["act1"], w2, P["fwd2"], bias=c2.bias.detach(), relu=True, out_pl=buf["act2"], out_ld=P["N2"])
+        gemm_box(buf["act1_pairs"], w2, P["fwd2"], bias=c2.bias.detach(), relu=True, out_pl=buf["act2"], out_ld=P["N2"])
         w3 = be.pack_weight(c3.weight.detach())
         n3 = P["H2"] * P["W2"]
         act3 = be.empty_planes((B * n3, P["N3"]), x_pl)
@@ -611,13 +660,21 @@ class BoxNatureCNN(TensorCoreNatureCNN):
         g3 = buf["g3"]
         G3 = g3.view(be.planes, -1, P["N3"])
         k3 = c3.kernel_size[0]
-        dw3 = be.wgrad(buf["act2"], G3, P["wg3"], P["N3"], P["N2"], k3, k3)
+        if BOX_WGRAD:
+            sp3 = wgrad_box_splits(B * P["hp2"], 6, P["fwd3"].K, P["N3"])
+            dw3 = wgrad_reduce(wgrad_box(buf["act2"], g3, P["fwd3"], 6, sp3), P["N3"], P["N2"], k3, k3)
+        else:
+            dw3 = be.wgrad(buf["act2"], G3, P["wg3"], P["N3"], P["N2"], k3, k3)
         db3 = be.colsum(G3)
         wd3 = be.split(dgrad_weight_matrix(c3.weight.detach(), P["taps3"]))
         gemm_box(g3, wd3, P["dg3"], out_pl=buf["g2"], out_ld=P["N2"], relu_mask=buf["act2"][0])
         G2 = buf["g2"].view(be.planes, -1, P["N2"])
         k2 = c2.kernel_size[0]
-        dw2 = be.wgrad(buf["act1"], G2, P["wg2"], P["N2"], P["N1"], k2, k2)
+        if BOX_WGRAD:
+            sp2 = wgrad_box_splits(B * P["hp2"], 6, P["fwd2"].K, P["N2"])
+            dw2 = wgrad_reduce(wgrad_box(buf["act1_pairs"], buf["g2"], P["fwd2"], 6, sp2), P["N2"], P["N1"], k2, k2)
+        else:
+            dw2 = be.wgrad(buf["act1"], G2, P["wg2"], P["N2"], P["N1"], k2, k2)
         db2 = be.colsum(G2)
         for bg, taps in P["dg2"]:
             wd = be.split(dgrad_weight_matrix(c2.weight.detach(), taps))
