@@ -404,7 +404,7 @@ def run_own_arm(args):
     roofline, kernel_ms = None, {}
     names = ["xb_gemm_gather_tc", "xb_gemm_box_tc", "xb_wgrad_gather_tc", "xb_wgrad_box_tc", "xb_wgrad_reduce", "xb_split_bf16",
              "xb_pack_conv_weight", "xb_gather_obs_planes", "xb_gather_obs", "xb_ppo_loss_fwd_bwd",
-             "xb_adam_step", "xb_grad_sumsq", "xb_gather_scalars"]
+             "xb_adam_step", "xb_grad_sumsq", "xb_gather_scalars", "nccl_all_reduce"]
     from xuance_b200.torch.utils import tc_conv
     saved_graph = agent.config.use_cuda_graph
     agent.config.use_cuda_graph = False

@@ -247,15 +247,20 @@ int xb_rms_update_normalize(const float *x, int N, int64_t D, float *mean, float
  *                       planes_out bf16 planes written to columns [out_c0, out_c0+N) of row
  *                       (b*out_H + y*oys+oy0)*out_W + x*oxs+ox0 of a matrix with out_ld elements per row
  *                       (out_ld % 8 == out_c0 % 8 == 0).  C % 8 == 0, (T*C) % 64 == 0, T <= 64; dy / dx are HOST arrays
- *                       (copied into the launch parameters).  relu_mask (nullable, bf16, addressed like the output):
- *                       result zeroed where mask <= 0 - the ReLU derivative applied to a data gradient, mask = plane 0 of
- *                       the saved activation.  Forward conv: dy = kh - pad, (sy,sx) = stride; Linear: one tap;
+ *                       (copied into the launch parameters).  relu_mask (nullable, bf16, the output's pixel index in a
+ *                       matrix of mask_ld elements per pixel from column mask_c0; mask_ld = 0: addressed exactly like
+ *                       the output): result zeroed where mask <= 0 - the ReLU derivative applied to a data gradient,
+ *                       mask = plane 0 of the saved activation.  colsum (nullable, float32 [ceil(M/128)][N]): row i =
+ *                       column sums of the result rows of M tile i (after bias / ReLU / mask; deterministic) - the
+ *                       partials of the bias gradient of the layer whose output gradient this call produces
+ *                       (finish with xb_wgrad_reduce(colsum, tiles, N, 1, 1, 1, 1.0, db)).  Forward conv: dy = kh - pad, (sy,sx) = stride; Linear: one tap;
  *                       data gradients: flipped taps over the output gradient, one call per stride phase.
  * xb_wgrad_gather_tc  : weight gradient of the same gathered GEMM: partials[s, (t,c), n] = sum over the sites of split s of
  *                       in[b, y*sy+dy[t], x*sx+dx[t], c] * G[site*g_ld + n]; G = output gradient planes.  Both operands
  *                       are fed MN-major (16-byte units transposed into the core matrices); one work item =
  *                       (128 columns of (t,c), n_tile columns, split).  partials: float32 [splits, T*C, N].
- * xb_wgrad_reduce     : dw[N, C, KH, KW] (torch layout) (+)= scale * sum_s partials[s, (kh,kw,c), n], splits added in order. */
+ * xb_wgrad_reduce     : dw[N, C, KH, KW] (torch layout) (+)= scale * sum_s partials[s, (kh,kw,c), n], splits added in a fixed
+ *                       order; `partials` is scratch: with more than 256 splits groups of rows are folded in place first. */
 int xb_split_bf16(const float *x, int64_t n, int planes, void *out /* bf16 [planes, n] */, void *stream);
 /* K3 variant that feeds K12: gathers uint8 rows (sample_batch, memory_tools.py:64-84; idx NULL = rows 0..B-1) and writes
  * dst[q, b, :] = plane q of float32(x)/255.0f for q < planes (bf16 [planes, B, row_bytes], planes 2 or 3), or with
@@ -265,10 +270,10 @@ int xb_gather_obs_planes(const uint8_t *src, const int64_t *idx, int64_t B, int6
 int xb_pack_conv_weight(const float *w, int N, int C, int KH, int KW, int planes, float scale,
                         void *out /* bf16 [planes, N, KH*KW*C] */, void *stream);
 int xb_gemm_gather_tc(int planes_a, int planes_b, const void *in, int64_t in_plane, const void *w, int64_t w_plane,
-                      const float *bias, const void *relu_mask, int B, int IH, int IW, int C, int OY, int OX, int sy, int sx,
-                      int T, const int8_t *dy, const int8_t *dx, int N, int n_tile, int relu, void *out_planes,
-                      int64_t out_plane, int planes_out, float *out_f32, int out_H, int out_W, int oys, int oxs, int oy0,
-                      int ox0, int64_t out_ld, int out_c0, void *stream);
+                      const float *bias, const void *relu_mask, int64_t mask_ld, int mask_c0, int B, int IH, int IW, int C,
+                      int OY, int OX, int sy, int sx, int T, const int8_t *dy, const int8_t *dx, int N, int n_tile, int relu,
+                      void *out_planes, int64_t out_plane, int planes_out, float *out_f32, int out_H, int out_W, int oys,
+                      int oxs, int oy0, int ox0, int64_t out_ld, int out_c0, float *colsum, void *stream);
 /* xb_gemm_gather_tc for a convolution whose input is stored in a PADDED-ROW layout [planes][B * hp_in][W][C] (hp_in rows per
  * image of which the first / last are zero padding), with the A operand fetched by TMA: a work item is box_h consecutive
  * grid rows x box_px sites (<= 128 GEMM rows); chunk i (64 K values = box_c = 64 channels of one pixel; a 32-channel tensor
@@ -284,7 +289,7 @@ int xb_gemm_box_tc(int planes_a, int planes_b, const void *in, int64_t in_plane,
                    const void *w, int64_t w_plane, const float *bias, const void *relu_mask, int mask_W, int mask_x0, int B,
                    int hp, int y0, int y1, int N, int n_tile, int relu, void *out_planes, int64_t out_plane, int planes_out,
                    float *out_f32, int out_H, int out_W, int oys, int oxs, int oy0, int ox0, int64_t out_ld, int out_c0,
-                   void *stream);
+                   float *colsum, void *stream);
 /* Weight gradient of the same convolution with both operands fetched by TMA boxes: `in` as for xb_gemm_box_tc, `g` the
  * output gradient in the padded site layout [planes_b][g_rows][box_px*box_c/64 sites][N]; a chunk of the reduction is box_h
  * grid rows (box_w * box_h <= 64 sites), N % 64 == 0; partials: float32 [splits, n_chunks*64, N] (reduce with xb_wgrad_reduce). */
@@ -299,7 +304,7 @@ int xb_debug_tma_box(const void *in, int64_t in_plane, int planes, int C, int W,
 int xb_wgrad_gather_tc(int planes_a, int planes_b, const void *in, int64_t in_plane, const void *g, int64_t g_plane,
                        int64_t g_ld, int B, int IH, int IW, int C, int OY, int OX, int sy, int sx, int T, const int8_t *dy,
                        const int8_t *dx, int N, int n_tile, int splits, float *partials, void *stream);
-int xb_wgrad_reduce(const float *partials, int splits, int N, int C, int KH, int KW, float scale, float *dw, int accumulate,
+int xb_wgrad_reduce(float *partials, int splits, int N, int C, int KH, int KW, float scale, float *dw, int accumulate,
                     void *stream);
 
 #ifdef __cplusplus

@@ -105,8 +105,8 @@ def test_every_entry_point_validates_before_touching_the_device():
     # K12 (tensor-core layers) and its operand preparation
     taps = (ctypes.c_int8 * 64)()
     gg = lambda pa=2, pb=2, C=32, T=16, N=64, nt=64, ld=64, c0=0, w=junk, po=2: lib.xb_gemm_gather_tc(
-        pa, pb, junk, 1024, w, 1024, None, None, 2, 21, 21, C, 10, 10, 2, 2, T, taps, taps, N, nt, 1, junk, 1024, po, None, 10,
-        10, 1, 1, 0, 0, ld, c0, None)
+        pa, pb, junk, 1024, w, 1024, None, None, 0, 0, 2, 21, 21, C, 10, 10, 2, 2, T, taps, taps, N, nt, 1, junk, 1024, po, None, 10,
+        10, 1, 1, 0, 0, ld, c0, None, None)
     assert gg(pb=4) == EINVAL                          # at most 3 planes
     assert gg(pa=3, pb=2) == EINVAL                    # planes_a <= planes_b
     assert gg(po=4) == EINVAL                          # output planes

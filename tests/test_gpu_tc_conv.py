@@ -233,8 +233,12 @@ def test_box_convolutions_forward_and_data_gradient(planes, atol):
     (dx2,) = torch.autograd.grad(y3, x2, g3.double().permute(0, 3, 1, 2))
     want = dx2.permute(0, 2, 3, 1) * (out2[0].float().view(B, hp2, 10, 64)[:, 1:11] > 0)
     d2 = torch.zeros(planes, B * hp2, 10, 64, dtype=torch.bfloat16, device=DEV)
-    tc.gemm_box(g3p, tc.split_bf16(tc.dgrad_weight_matrix(w3, P["taps3"]), planes), P["dg3"], out_pl=d2, out_ld=64, relu_mask=out2[0])
+    cs2 = torch.full((P["dg3"].m_tiles, 64), float("nan"), device=DEV)
+    tc.gemm_box(g3p, tc.split_bf16(tc.dgrad_weight_matrix(w3, P["taps3"]), planes), P["dg3"], out_pl=d2, out_ld=64, relu_mask=out2[0],
+                colsum=cs2)
     np.testing.assert_allclose(d2.float().sum(0).view(B, hp2, 10, 64)[:, 1:11].cpu().numpy(), want.cpu().numpy(), rtol=0, atol=atol * 4)
+    # fused bias-gradient partials: column sums of exactly the rows written (padding / garbage rows contribute nothing)
+    np.testing.assert_allclose(tc.bias_grad(cs2, 64).cpu().numpy(), want.sum((0, 1, 2)).cpu().numpy(), rtol=0, atol=atol * 400)
     # conv2 data gradient: four stride phases into act1's padded layout (mask = act1 plane 0)
     g2 = torch.randn(B, 10, 10, 64, device=DEV)
     g2p = torch.zeros(planes, B, hp2, 10, 64, dtype=torch.bfloat16, device=DEV)
@@ -245,9 +249,15 @@ def test_box_convolutions_forward_and_data_gradient(planes, atol):
     (dx1,) = torch.autograd.grad(y2, x1, g2.double().permute(0, 3, 1, 2))
     mask1 = act1[0].float().view(B, hp1, W1p, 32)[:, off1:off1 + 21, xo1:xo1 + 21] > 0
     d1 = torch.zeros(planes, B * hp1, 21, 32, dtype=torch.bfloat16, device=DEV)
+    cs1 = torch.full((sum(bg.m_tiles for bg, _ in P["dg2"]), 32), float("nan"), device=DEV)
+    row = 0
     for bg, taps in P["dg2"]:
-        tc.gemm_box(g2p, tc.split_bf16(tc.dgrad_weight_matrix(w2, taps), planes), bg, out_pl=d1, out_ld=32, relu_mask=act1[0])
+        tc.gemm_box(g2p, tc.split_bf16(tc.dgrad_weight_matrix(w2, taps), planes), bg, out_pl=d1, out_ld=32, relu_mask=act1[0],
+                    colsum=cs1[row:row + bg.m_tiles])
+        row += bg.m_tiles
     got1 = d1.float().sum(0).view(B, hp1, 21, 32)
+    np.testing.assert_allclose(tc.bias_grad(cs1, 32).cpu().numpy(), (dx1.permute(0, 2, 3, 1) * mask1).sum((0, 1, 2)).cpu().numpy(),
+                               rtol=0, atol=atol * 2000)
     np.testing.assert_allclose(got1[:, off1:off1 + 21].cpu().numpy(), (dx1.permute(0, 2, 3, 1) * mask1).cpu().numpy(), rtol=0, atol=atol * 4)
     assert float(got1[:, :off1].abs().max()) == 0.0
     # weight gradients of conv3 and conv2 with both operands as TMA boxes (reduction chunks of 6 grid rows = 60 sites)
@@ -260,6 +270,35 @@ def test_box_convolutions_forward_and_data_gradient(planes, atol):
             dw = tc.wgrad_reduce(tc.wgrad_box(x_pad, g_pad.view(planes, B * hp2, 10, 64), bg, 6, splits), 64, cin, k, k)
             np.testing.assert_allclose(dw.cpu().numpy(), want_w.cpu().numpy(), rtol=0, atol=atol * 8 * max(1.0, float(want_w.abs().max())),
                                        err_msg="cin=%d splits=%d" % (cin, splits))
+        # the same gradients through the gathered kernel over the padded tensors (BoxNatureCNN's default for conv2)
+        geo = P["wg3"] if cin == 64 else P["wg2"]
+        x_plain = x_pad if cin == 64 else act1
+        dw = enc.be.wgrad(x_plain, g_pad.view(planes, -1, 64), geo, 64, cin, k, k)
+        np.testing.assert_allclose(dw.cpu().numpy(), want_w.cpu().numpy(), rtol=0, atol=atol * 8 * max(1.0, float(want_w.abs().max())),
+                                   err_msg="gathered over padded rows, cin=%d" % cin)
+
+
+@pytest.mark.parametrize("planes,atol", [(2, 5e-5), (3, 3e-6)])
+def test_linear_data_gradient_into_padded_rows_with_mask_and_colsum(planes, atol):
+    """The Linear layer's data gradient written at a column offset of wider rows (conv3's padded output-gradient tensor), with
+    the ReLU mask read from a plain matrix (mask_ld / mask_c0) and the fused column sums (bias-gradient partials)."""
+    from xuance_b200.torch.utils import tc_conv as tc
+    torch.manual_seed(5)
+    B, N_in, N_out, ld, c0 = 300, 128, 640, 768, 64
+    g = torch.randn(B, N_in, device=DEV)
+    w = torch.randn(N_in, N_out, device=DEV) / 8          # [K, N] of the data-gradient GEMM
+    act = torch.randn(B, N_out, device=DEV)
+    mask_pl = tc.split_bf16(act, planes)
+    out = torch.zeros(planes, B, ld, dtype=torch.bfloat16, device=DEV)
+    cs = torch.full((-(-B // 128), N_out), float("nan"), device=DEV)
+    tc.gemm_gather(tc.split_bf16(g, planes), tc.split_bf16(w.t().contiguous(), planes), tc.linear_geometry(B, N_in), out_pl=out,
+                   out_ld=ld, out_c0=c0, relu_mask=mask_pl[0], mask_ld=N_out, mask_c0=0, colsum=cs)
+    want = (g.double() @ w.double()) * (mask_pl[0].float() > 0)
+    got = out.float().sum(0)
+    np.testing.assert_allclose(got[:, c0:c0 + N_out].cpu().numpy(), want.cpu().numpy(), rtol=0, atol=atol * 8)
+    assert float(got[:, :c0].abs().max()) == 0.0 and float(got[:, c0 + N_out:].abs().max()) == 0.0
+    np.testing.assert_allclose(cs.sum(0).cpu().numpy(), want.sum(0).cpu().numpy(), rtol=0, atol=atol * 800)
+    np.testing.assert_allclose(tc.bias_grad(cs, 64).cpu().numpy(), want.view(B, 10, 64).sum((0, 1)).cpu().numpy(), rtol=0, atol=atol * 8000)
 
 
 @pytest.mark.parametrize("planes,fwd_tol,grad_tol", [(2, 1e-4, 2e-2), (3, 2e-5, 2e-3)])

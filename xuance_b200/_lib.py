@@ -41,11 +41,11 @@ _SIGNATURES = {
     "xb_split_bf16": (c_int, [_P, c_int64, c_int, _P, _P]),
     "xb_gather_obs_planes": (c_int, [_P, _P, c_int64, c_int64, c_int, _P, _P]),
     "xb_pack_conv_weight": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P]),
-    "xb_gemm_gather_tc": (c_int, [c_int, c_int, _P, c_int64, _P, c_int64, _P, _P] + [c_int] * 9 + [_P, _P, c_int, c_int, c_int,
-                                  _P, c_int64, c_int, _P] + [c_int] * 6 + [c_int64, c_int, _P]),
+    "xb_gemm_gather_tc": (c_int, [c_int, c_int, _P, c_int64, _P, c_int64, _P, _P, c_int64, c_int] + [c_int] * 9
+                          + [_P, _P, c_int, c_int, c_int, _P, c_int64, c_int, _P] + [c_int] * 6 + [c_int64, c_int, _P, _P]),
     "xb_gemm_box_tc": (c_int, [c_int, c_int, _P, c_int64, c_int, c_int, c_int64, c_int, c_int, c_int, c_int, c_int, _P, _P, _P,
                                _P, c_int64, _P, _P] + [c_int] * 9 + [_P, c_int64, c_int, _P]
-                       + [c_int] * 6 + [c_int64, c_int, _P]),
+                       + [c_int] * 6 + [c_int64, c_int, _P, _P]),
     "xb_debug_tma_box": (c_int, [_P, c_int64] + [c_int] * 12 + [ctypes.c_uint32, _P, ctypes.c_uint32, _P]),
     "xb_wgrad_box_tc": (c_int, [c_int, c_int, _P, c_int64, c_int, c_int, c_int64, c_int, c_int, c_int, c_int, c_int, _P, _P, _P,
                                 _P, c_int64, c_int64, c_int, c_int, _P, _P]),
@@ -114,6 +114,15 @@ def ptr(t):
     if not t.is_cuda:
         raise RuntimeError("xb200: expected a CUDA tensor, got a %s tensor (no CPU fallback)" % t.device)
     return t.data_ptr()
+
+
+def use_device(device):
+    """Make ``device`` the process's current CUDA device: ``call`` launches on the CURRENT device's current stream, so every
+    owner of device memory (agents, buffers, learners) selects its device once at construction (one process drives one GPU)."""
+    device = torch.device(device)
+    if device.type == "cuda" and torch.cuda.is_available():
+        torch.cuda.set_device(device if device.index is not None else torch.device("cuda", torch.cuda.current_device()))
+    return device
 
 
 def stream():

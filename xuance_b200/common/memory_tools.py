@@ -60,6 +60,7 @@ class Buffer(ABC):
             raise RuntimeError("xuance_b200 buffers are device-resident: device must be a CUDA device, got %s "
                                "(there is no CPU fallback)" % (self.device,))
         _lib.load()
+        _lib.use_device(self.device)
 
     @property
     def full(self):

@@ -42,6 +42,7 @@ class MARL_OffPolicyBuffer_RNN:
         if self.device.type != "cuda":
             raise RuntimeError("xuance_b200 buffers are device-resident: device must be CUDA (no CPU fallback)")
         _lib.load()
+        _lib.use_device(self.device)
         self._obs_dim = int(np.prod(self.obs_shape[k0]))
         self._state_dim = int(np.prod(space2shape(state_space))) if self.store_global_state else 0
         self._n_act = int(self.avail_actions_shape[k0][0]) if self.use_actions_mask else 0

@@ -55,6 +55,10 @@ struct ConvParams {
     const __nv_bfloat16 *w[3];             // B planes.  forward: weight [N_total, K].  weight gradient: output gradient [P, w_ld]
     const float *bias;                     // [N_total] or null (forward)
     int mask_W, mask_x0;                   // box mode: the mask tensor's row width / pixel offset (its rows as the output's)
+    int64_t mask_ld;                       // the mask tensor's channels per pixel and first channel (as out_ld / out_c0)
+    int mask_c0;
+    float *colsum;                         // forward, nullable: [work items of M][N total] column sums of the rows this
+                                           // item wrote (after bias / ReLU / mask) - the next layer's bias-gradient partials
     const __nv_bfloat16 *mask;             // forward, nullable: result elements are zeroed where mask <= 0; same
                                            // addressing as the output (the ReLU derivative of a saved activation's hi plane)
     __nv_bfloat16 *out[3];                 // forward: p_out result planes (nullable)
@@ -146,6 +150,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_slot;
     __shared__ float s_bias[256];
+    __shared__ float s_colsum[4][256];                // per epilogue warp: column sums of its 32 rows (ConvParams.colsum)
     __shared__ XbUnit s_units[XB_CONV_MAX_UNITS];     // per 16-byte K unit: tap offsets + element offset (conv_index.h)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -361,7 +366,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                     const int64_t orw = (int64_t)b * p.out_H + ((y - p.box_y0) * p.oys + p.oy0);
                     const int ox = x * p.oxs + p.ox0;
                     orow = (orw * p.out_W + ox) * p.out_ld + p.out_c0 + (int64_t)nt * N;
-                    mrow = (orw * p.mask_W + ox + p.mask_x0) * p.out_ld + p.out_c0 + (int64_t)nt * N;
+                    mrow = (orw * p.mask_W + ox + p.mask_x0) * p.mask_ld + p.mask_c0 + (int64_t)nt * N;
                 }
             } else if (!WGRAD) {
                 const int64_t m = mt * TILE_M + tid;
@@ -369,9 +374,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                 if (live) {
                     int b, y, x;
                     xb_conv_site(g, m, b, y, x);
-                    orow = (((int64_t)b * p.out_H + (y * p.oys + p.oy0)) * p.out_W + (x * p.oxs + p.ox0)) * p.out_ld + p.out_c0 +
-                           (int64_t)nt * N;
-                    mrow = orow;
+                    const int64_t opix = ((int64_t)b * p.out_H + (y * p.oys + p.oy0)) * p.out_W + (x * p.oxs + p.ox0);
+                    orow = opix * p.out_ld + p.out_c0 + (int64_t)nt * N;
+                    mrow = opix * p.mask_ld + p.mask_c0 + (int64_t)nt * N;
                 }
             } else {
                 const int64_t kcol = mt * TILE_M + tid;
@@ -439,10 +444,35 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                         }
                     }
                 }
+                if (!WGRAD && p.colsum) {
+                    // column sums over this warp's 32 rows by a transposing butterfly: after the step with offset `off` a lane
+                    // keeps the half of its columns selected by that bit of its index, so lane j ends with column c0 + j
+                    if (!live) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                    }
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool upper = (lane & off) != 0;
+#pragma unroll
+                        for (int i = 0; i < off; ++i) {
+                            const float send = upper ? v[i] : v[i + off];
+                            const float keep = upper ? v[i + off] : v[i];
+                            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
+                    }
+                    s_colsum[tid >> 5][c0 + lane] = v[0];
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[a]);
+            if (!WGRAD && p.colsum) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int i = tid; i < N; i += EPI_WARPS * 32)            // fixed order: deterministic
+                    p.colsum[(mt * p.n_tiles + nt) * (int64_t)N + i] =
+                        ((s_colsum[0][i] + s_colsum[1][i]) + s_colsum[2][i]) + s_colsum[3][i];
+            }
             ++tcount;
         }
     }
@@ -454,17 +484,44 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
     }
 }
 
-// weight-gradient finish: sum the split partials [splits, K, N] in split order and scatter to torch's [N, C, KH, KW]
-// (column k = (kh, kw, c) of the packed layout -> xb_pack_weight_src); accumulate != 0 adds to dw (autograd .grad)
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restrict__ ws, int splits, int N, int C, int KH,
-                                                           int KW, float scale, float *__restrict__ dw, int accumulate) {
+// weight-gradient finish: sum the split partials [splits, K, N] in a fixed order and scatter to torch's [N, C, KH, KW]
+// (column k = (kh, kw, c) of the packed layout -> xb_pack_weight_src); accumulate != 0 adds to dw (autograd .grad).
+// A block owns E = 256 / lanes consecutive (k, n) elements - coalesced rows of the partial matrices - and `lanes` threads
+// per element walk the splits interleaved.  Many splits (bias-gradient partials: one row per M tile) are first folded in
+// place, group g of `group` consecutive splits into its first row (blockIdx.y = g), then the group rows are summed.
+__device__ __forceinline__ float reduce_splits(const float *__restrict__ ws, int64_t total, int64_t j, int first, int last, int step,
+                                               int lanes, int E, float *part) {
+    const int e = threadIdx.x % E, l = threadIdx.x / E;
+    float s = 0.f;
+    if (j < total)
+        for (int sp = first + l * step; sp < last; sp += lanes * step) s += ws[(int64_t)sp * total + j];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (l == 0)
+        for (int q = 1; q < lanes; ++q) s += part[e + q * E];
+    return s;
+}
+
+__global__ void __launch_bounds__(256) wgrad_fold_kernel(float *__restrict__ ws, int splits, int group, int lanes, int64_t total) {
+    __shared__ float part[256];
+    const int E = 256 / lanes;
+    const int64_t j = (int64_t)blockIdx.x * E + threadIdx.x % E;
+    const int first = blockIdx.y * group, last = min(first + group, splits);
+    const float s = reduce_splits(ws, total, j, first, last, 1, lanes, E, part);
+    if (threadIdx.x < E && j < total) ws[(int64_t)first * total + j] = s;     // read only by this thread before
+}
+
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restrict__ ws, int splits, int step, int lanes, int N, int C,
+                                                           int KH, int KW, float scale, float *__restrict__ dw, int accumulate) {
+    __shared__ float part[256];
     const int64_t K = (int64_t)C * KH * KW, total = (int64_t)N * K;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t n = i / K, k = i - n * K;              // i indexes the PACKED layout [N, (kh, kw, c)]
-        float s = 0.f;
-        for (int sp = 0; sp < splits; ++sp) s += ws[((int64_t)sp * K + k) * N + n];
+    const int E = 256 / lanes;
+    const int64_t j = (int64_t)blockIdx.x * E + threadIdx.x % E;
+    float s = reduce_splits(ws, total, j, 0, splits, step, lanes, E, part);
+    if (threadIdx.x < E && j < total) {
         s = __fmul_rn(s, scale);
-        const int64_t dst = xb_pack_weight_src(i, C, KH, KW);
+        const int64_t k = j / N, n = j - k * N;
+        const int64_t dst = xb_pack_weight_src(n * K + k, C, KH, KW);     // packed index [N, (kh, kw, c)] -> [N, C, KH, KW]
         dw[dst] = accumulate ? dw[dst] + s : s;
     }
 }
@@ -662,10 +719,11 @@ extern "C" int xb_pack_conv_weight(const float *w, int N, int C, int KH, int KW,
 }
 
 extern "C" int xb_gemm_gather_tc(int planes_a, int planes_b, const void *in, int64_t in_plane, const void *w, int64_t w_plane,
-                                 const float *bias, const void *relu_mask, int B, int IH, int IW, int C, int OY, int OX,
-                                 int sy, int sx, int T, const int8_t *dy, const int8_t *dx, int N, int n_tile, int relu,
-                                 void *out_planes, int64_t out_plane, int planes_out, float *out_f32, int out_H, int out_W,
-                                 int oys, int oxs, int oy0, int ox0, int64_t out_ld, int out_c0, void *stream) {
+                                 const float *bias, const void *relu_mask, int64_t mask_ld, int mask_c0, int B, int IH, int IW,
+                                 int C, int OY, int OX, int sy, int sx, int T, const int8_t *dy, const int8_t *dx, int N,
+                                 int n_tile, int relu, void *out_planes, int64_t out_plane, int planes_out, float *out_f32,
+                                 int out_H, int out_W, int oys, int oxs, int oy0, int ox0, int64_t out_ld, int out_c0,
+                                 float *colsum, void *stream) {
     ConvParams p;
     const int rc = fill_params(p, planes_a, planes_b, in, in_plane, w, w_plane, B, IH, IW, C, OY, OX, sy, sx, T, dy, dx, N, n_tile);
     if (rc != XB_OK) return rc;
@@ -679,8 +737,12 @@ extern "C" int xb_gemm_gather_tc(int planes_a, int planes_b, const void *in, int
     if ((out_planes && !xb_aligned(out_planes, 16)) || (out_f32 && !xb_aligned(out_f32, 16)) ||
         (relu_mask && !xb_aligned(relu_mask, 16)))
         return XB_EALIGN;
+    if (mask_ld != 0 && (mask_ld % 8 != 0 || mask_c0 % 8 != 0 || mask_c0 < 0 || mask_ld < (int64_t)mask_c0 + N)) return XB_EALIGN;
     p.bias = bias;
     p.mask = (const __nv_bfloat16 *)relu_mask;
+    p.mask_W = out_W, p.mask_x0 = 0;
+    p.mask_ld = mask_ld != 0 ? mask_ld : out_ld, p.mask_c0 = mask_ld != 0 ? mask_c0 : out_c0;
+    p.colsum = colsum;
     __nv_bfloat16 *ob = (__nv_bfloat16 *)out_planes;
     p.p_out = ob ? planes_out : 0;
     for (int q = 0; q < 3; ++q) p.out[q] = (ob && q < planes_out) ? ob + q * out_plane : nullptr;
@@ -709,7 +771,7 @@ extern "C" int xb_gemm_box_tc(int planes_a, int planes_b, const void *in, int64_
                               const void *relu_mask, int mask_W, int mask_x0, int B, int hp, int y0, int y1, int N, int n_tile,
                               int relu,
                               void *out_planes, int64_t out_plane, int planes_out, float *out_f32, int out_H, int out_W,
-                              int oys, int oxs, int oy0, int ox0, int64_t out_ld, int out_c0, void *stream) {
+                              int oys, int oxs, int oy0, int ox0, int64_t out_ld, int out_c0, float *colsum, void *stream) {
     if (!c0 || !w0 || !r0 || n_chunks <= 0 || n_chunks > 16) return XB_EINVAL;
     if (box_c != 64 || box_px <= 0 || box_h <= 0 || row_step <= 0 || row_step > 8) return XB_EINVAL;
     const int box_w = box_px;                               // sites (GEMM rows) per grid row: one 64-channel pixel each
@@ -732,6 +794,8 @@ extern "C" int xb_gemm_box_tc(int planes_a, int planes_b, const void *in, int64_
     if (!make_tmap(&p.tm_b, w, K, N, planes_b, K, w_plane, n_tile)) return XB_EINVAL;
     p.a_tma = p.b_tma = p.a_box = 1;
     p.mask_W = mask_W > 0 ? mask_W : out_W, p.mask_x0 = mask_W > 0 ? mask_x0 : 0;
+    p.mask_ld = out_ld, p.mask_c0 = out_c0;
+    p.colsum = colsum;
     p.box_w = box_w, p.box_h = box_h, p.box_hp = hp, p.box_y0 = y0, p.box_y1 = y1, p.box_rs = row_step, p.box_chunks = n_chunks;
     p.box_div_w = xb_div_make((uint32_t)box_w), p.box_div_hp = xb_div_make((uint32_t)hp);
     for (int i = 0; i < 16; ++i) p.box_c0[i] = i < n_chunks ? c0[i] : 0, p.box_w0[i] = i < n_chunks ? w0[i] : 0, p.box_r[i] = i < n_chunks ? r0[i] : 0;
@@ -759,7 +823,7 @@ extern "C" int xb_wgrad_gather_tc(int planes_a, int planes_b, const void *in, in
     if (rc != XB_OK) return rc;
     if (!partials || splits <= 0 || g_ld < N) return XB_EINVAL;
     if (!xb_aligned(partials, 16) || g_ld % 8 != 0) return XB_EALIGN;
-    p.bias = nullptr, p.mask = nullptr, p.out_f32 = partials, p.p_out = 0;
+    p.bias = nullptr, p.mask = nullptr, p.colsum = nullptr, p.out_f32 = partials, p.p_out = 0;
     for (int q = 0; q < 3; ++q) p.out[q] = nullptr;
     p.relu = 0;
     p.out_H = p.out_W = p.oys = p.oxs = 1, p.oy0 = p.ox0 = 0, p.out_ld = N, p.out_c0 = 0;
@@ -800,7 +864,7 @@ extern "C" int xb_wgrad_box_tc(int planes_a, int planes_b, const void *in, int64
     p.box_w = box_w, p.box_h = box_h, p.box_hp = 1, p.box_y0 = 0, p.box_y1 = 0, p.box_rs = row_step, p.box_chunks = n_chunks;
     p.box_div_w = xb_div_make((uint32_t)box_w), p.box_div_hp = xb_div_make(1u);
     for (int i = 0; i < 16; ++i) p.box_c0[i] = i < n_chunks ? c0[i] : 0, p.box_w0[i] = i < n_chunks ? w0[i] : 0, p.box_r[i] = i < n_chunks ? r0[i] : 0;
-    p.bias = nullptr, p.mask = nullptr, p.out_f32 = partials, p.p_out = 0;
+    p.bias = nullptr, p.mask = nullptr, p.colsum = nullptr, p.out_f32 = partials, p.p_out = 0;
     for (int q = 0; q < 3; ++q) p.out[q] = nullptr;
     p.relu = 0;
     p.out_H = p.out_W = p.oys = p.oxs = 1, p.oy0 = p.ox0 = 0, p.out_ld = N, p.out_c0 = 0;
@@ -851,12 +915,28 @@ extern "C" int xb_debug_tma_box(const void *in, int64_t in_plane, int planes, in
     return xb_launch_status();
 }
 
-extern "C" int xb_wgrad_reduce(const float *partials, int splits, int N, int C, int KH, int KW, float scale, float *dw,
-                               int accumulate, void *stream) {
+extern "C" int xb_wgrad_reduce(float *partials, int splits, int N, int C, int KH, int KW, float scale, float *dw, int accumulate,
+                               void *stream) {
     if (!partials || !dw || splits <= 0 || N <= 0 || C <= 0 || KH <= 0 || KW <= 0) return XB_EINVAL;
     const int64_t total = (int64_t)N * C * KH * KW;
-    int64_t want = (total + 255) / 256;
-    const int grid = (int)(want < (int64_t)xb_sm_count() * 8 ? want : (int64_t)xb_sm_count() * 8);
-    wgrad_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(partials, splits, N, C, KH, KW, scale, dw, accumulate);
+    auto lanes_for = [&](int n_splits, int64_t groups) {
+        int lanes = 1;
+        while (lanes < 8 && lanes * 2 <= n_splits && total / (256 / lanes) * groups < (int64_t)xb_sm_count() * 16) lanes *= 2;
+        return lanes;
+    };
+    int step = 1;
+    if (splits > 256) {                     // fold groups of consecutive splits in place first (see wgrad_fold_kernel)
+        const int group = (splits + 127) / 128, groups = (splits + group - 1) / group;
+        const int lanes = lanes_for(group, groups);
+        const int64_t E = 256 / lanes, bx = (total + E - 1) / E;
+        if (bx > 0x7fffffff || groups > 65535) return XB_ERANGE;
+        wgrad_fold_kernel<<<dim3((unsigned)bx, (unsigned)groups), 256, 0, (cudaStream_t)stream>>>(partials, splits, group, lanes, total);
+        step = group;
+    }
+    const int lanes = lanes_for((splits + step - 1) / step, 1);
+    const int64_t E = 256 / lanes;
+    if ((total + E - 1) / E > 0x7fffffff) return XB_ERANGE;
+    wgrad_reduce_kernel<<<(int)((total + E - 1) / E), 256, 0, (cudaStream_t)stream>>>(partials, splits, step, lanes, N, C, KH, KW, scale, dw,
+                                                                                  accumulate);
     return xb_launch_status();
 }

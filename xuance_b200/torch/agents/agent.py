@@ -13,6 +13,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from ... import _lib
 from ...common import BaseCallback, space2shape
 from ...common.statistic_tools import RunningMeanStd
 from ..rl_models import REGISTRY_Representation, ActivationFunctions
@@ -59,6 +60,7 @@ class Agent(ABC):
         self.training_frequency = getattr(config, "training_frequency", 1)
         self.n_epochs = getattr(config, "n_epochs", 1)
         self.device = self.config.device = set_device(self.config.device)
+        _lib.use_device(self.device)
         self.train_envs = envs
         self.render = getattr(config, "render", False)
         self.fps = getattr(config, "fps", 50)

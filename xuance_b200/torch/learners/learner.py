@@ -11,6 +11,8 @@ from pathlib import Path
 import torch
 import torch.distributed as dist
 
+from ... import _lib
+
 
 class Learner(ABC):
     def __init__(self, config, model, callback):
@@ -43,6 +45,7 @@ class Learner(ABC):
         if self.device.type != "cuda":
             raise RuntimeError("xuance_b200 learners run on CUDA devices only (config.device=%r); there is no "
                                "CPU fallback" % (config.device,))
+        _lib.use_device(self.device)
         self.model_dir = getattr(config, "model_dir", "./models")
         self.total_iters = self.estimate_total_iterations()
         self.iterations = 0

@@ -36,7 +36,16 @@ def init_distributed_mode(master_port=None, backend=None):
 
 def allreduce_sum_(t):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        from xuance_b200 import _lib
+        prof = _lib.profile
+        if prof is not None and "nccl_all_reduce" in prof:      # bench.py's per-phase breakdown: CUDA events around the collective
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            e1.record()
+            prof["nccl_all_reduce"].append((e0, e1))
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t
 
 

@@ -194,9 +194,10 @@ def _taps(geom):
 
 
 def gemm_gather(x_pl, w_pl, geom, bias=None, relu=False, out_f32=None, out_pl=None, out_ld=None, out_c0=0, relu_mask=None,
-                n_tile=None):
+                n_tile=None, mask_ld=0, mask_c0=0, colsum=None):
     """One K12 launch.  ``x_pl`` [PA, B, IH, IW, C] (any shape with that element order), ``w_pl`` [PB, N, K]; outputs are
-    caller-allocated: ``out_f32`` [rows, out_ld] and / or ``out_pl`` [P_out, rows, out_ld]."""
+    caller-allocated: ``out_f32`` [rows, out_ld] and / or ``out_pl`` [P_out, rows, out_ld]; ``colsum`` float32
+    [ceil(M / 128), N] receives the per-tile column sums of the result (bias-gradient partials, see ``bias_grad``)."""
     PB, N, K = w_pl.shape
     PA = x_pl.shape[0]
     assert K == geom.K and PA <= PB, (K, geom.K, PA, PB)
@@ -208,11 +209,18 @@ def gemm_gather(x_pl, w_pl, geom, bias=None, relu=False, out_f32=None, out_pl=No
     op, os_ = _plane_arg(out_pl) if out_pl is not None else (None, 0)
     _log_flops("xb_gemm_gather_tc", geom.M, N, K, PA, PB)
     _lib.call("xb_gemm_gather_tc", PA, PB, xp, xs, wp, ws, _lib.ptr(bias) if bias is not None else None,
-              _lib.ptr(relu_mask) if relu_mask is not None else None, geom.B, geom.IH, geom.IW, geom.C, geom.OY, geom.OX,
+              _lib.ptr(relu_mask) if relu_mask is not None else None, mask_ld, mask_c0, geom.B, geom.IH, geom.IW, geom.C,
+              geom.OY, geom.OX,
               geom.sy, geom.sx, geom.T, dy.data_ptr(), dx.data_ptr(), N, n_tile, 1 if relu else 0, op, os_,
               out_pl.shape[0] if out_pl is not None else 0, _lib.ptr(out_f32) if out_f32 is not None else None, geom.out_H,
-              geom.out_W, geom.oys, geom.oxs, geom.oy0, geom.ox0, out_ld, out_c0)
+              geom.out_W, geom.oys, geom.oxs, geom.oy0, geom.ox0, out_ld, out_c0, _lib.ptr(colsum) if colsum is not None else None)
     return out_f32, out_pl
+
+
+def bias_grad(colsum, N):
+    """Column-sum partials (any shape [..., N], contiguous) -> [N]: the bias gradient of the layer whose output gradient the
+    producing K12 launch wrote; the partials are added in a fixed order by xb_wgrad_reduce."""
+    return wgrad_reduce(colsum.view(-1, 1, N), N, 1, 1, 1).view(N)
 
 
 def wgrad_gather(x_pl, g_pl, geom, splits, n_tile=None):
@@ -427,14 +435,21 @@ class BoxGeometry:
     def M(self):                  # rows the kernel computes (padded grid)
         return self.B * self.hp_out * self.sites_per_row
 
+    @property
+    def m_tiles(self):            # work items along M (rows of a ``colsum`` buffer)
+        return -(-self.B * self.hp_out // self.box_h)
+
 
 _BOXTAB = {}
 import os as _os
-BOX_WGRAD = _os.environ.get("XB_K12_BOX_WGRAD", "1") != "0"     # conv2 / conv3 weight gradients through TMA boxes too
+# weight gradients with both operands as TMA boxes, per layer (measured at B = 8192, 3 planes: conv3 785 us box vs 837 us
+# gathered; conv2 947 us box vs 851 us gathered - its 16 pixel-pair chunks re-read G once per pair of chunks)
+BOX_WGRAD = _os.environ.get("XB_K12_BOX_WGRAD", "3")
+BOX_WGRAD2, BOX_WGRAD3 = "2" in BOX_WGRAD, "3" in BOX_WGRAD
 
 
 def gemm_box(x_pl, w_pl, bg, bias=None, relu=False, out_f32=None, out_pl=None, out_ld=None, out_c0=0, relu_mask=None,
-             n_tile=None):
+             n_tile=None, colsum=None):
     """One K12 launch with the A operand fetched by TMA boxes (``x_pl`` [PA, B*hp_in, W, C], padded rows)."""
     PB, N, K = w_pl.shape
     PA = x_pl.shape[0]
@@ -454,7 +469,7 @@ def gemm_box(x_pl, w_pl, bg, bias=None, relu=False, out_f32=None, out_pl=None, o
               _lib.ptr(bias) if bias is not None else None, _lib.ptr(relu_mask) if relu_mask is not None else None,
               bg.mask_W, bg.mask_x0, bg.B, bg.hp_out, bg.y0, bg.y1, N, n_tile, 1 if relu else 0, op, os_,
               out_pl.shape[0] if out_pl is not None else 0, _lib.ptr(out_f32) if out_f32 is not None else None,
-              bg.out_H, bg.out_W, bg.oys, bg.oxs, bg.oy0, bg.ox0, out_ld, out_c0)
+              bg.out_H, bg.out_W, bg.oys, bg.oxs, bg.oy0, bg.ox0, out_ld, out_c0, _lib.ptr(colsum) if colsum is not None else None)
 
 
 def wgrad_box(x_pl, g_pl, bg, box_h, splits):
@@ -649,40 +664,47 @@ class BoxNatureCNN(TensorCoreNatureCNN):
             dwfc = be.wgrad(x3, g4, F_["fwd"], F_["N"], F_["C"], F_["KH"], F_["KW"])
             gfc = [dwfc.reshape(F_["N"], F_["K"]), be.colsum(g4)]
             wt = be.split(sv["w4"].permute(0, 2, 3, 1).reshape(F_["N"], F_["K"]).t().contiguous())      # [P, K (h,w,c), N]
-            g3p = be.empty_planes((B, F_["K"]), dz)
-            gemm_gather(g4, wt, F_["dgrad"], out_pl=g3p, relu_mask=x3[0])
-            g3p = g3p.view(be.planes, B, P["H2"], P["W2"] * P["N3"])
+            # the Linear layer's data gradient lands straight in conv3's PADDED output-gradient tensor: image b's 6400 values
+            # are rows 1 .. H2 of its hp2 rows (a matrix with hp2*W2*N3 elements per row, from column W2*N3); the mask is
+            # the plain [B, 6400] activation; the column sums per (h, w, c) are conv3's bias-gradient partials
+            ld3 = P["hp2"] * P["W2"] * P["N3"]
+            cs3 = torch.empty((-(-B // 128), F_["K"]), dtype=torch.float32, device=dz.device)
+            gemm_gather(g4, wt, F_["dgrad"], out_pl=buf["g3"].view(be.planes, B, ld3), out_ld=ld3, out_c0=P["W2"] * P["N3"],
+                        relu_mask=x3[0], mask_ld=F_["K"], mask_c0=0, colsum=cs3)
+            db3 = bias_grad(cs3, P["N3"])
         else:
             gfc = []
             g3p = be.split(dz * (act3[0] > 0).to(dz.dtype)).view(be.planes, B, P["H2"], P["W2"] * P["N3"])
-        # conv3's output gradient in the padded site space (rows 1 .. H2 of hp2)
-        buf["g3"].view(be.planes, B, P["hp2"], P["W2"] * P["N3"])[:, :, 1:1 + P["H2"]].copy_(g3p)
-        g3 = buf["g3"]
-        G3 = g3.view(be.planes, -1, P["N3"])
+            buf["g3"].view(be.planes, B, P["hp2"], P["W2"] * P["N3"])[:, :, 1:1 + P["H2"]].copy_(g3p)
+            db3 = be.colsum(g3p.view(be.planes, -1, P["N3"]))
+        g3 = buf["g3"]                                                     # conv3's output gradient, rows 1 .. H2 of hp2
         k3 = c3.kernel_size[0]
-        if BOX_WGRAD:
+        if BOX_WGRAD3:
             sp3 = wgrad_box_splits(B * P["hp2"], 6, P["fwd3"].K, P["N3"])
             dw3 = wgrad_reduce(wgrad_box(buf["act2"], g3, P["fwd3"], 6, sp3), P["N3"], P["N2"], k3, k3)
         else:
-            dw3 = be.wgrad(buf["act2"], G3, P["wg3"], P["N3"], P["N2"], k3, k3)
-        db3 = be.colsum(G3)
+            dw3 = be.wgrad(buf["act2"], g3.view(be.planes, -1, P["N3"]), P["wg3"], P["N3"], P["N2"], k3, k3)
         wd3 = be.split(dgrad_weight_matrix(c3.weight.detach(), P["taps3"]))
-        gemm_box(g3, wd3, P["dg3"], out_pl=buf["g2"], out_ld=P["N2"], relu_mask=buf["act2"][0])
+        cs2 = torch.empty((P["dg3"].m_tiles, P["N2"]), dtype=torch.float32, device=dz.device)
+        gemm_box(g3, wd3, P["dg3"], out_pl=buf["g2"], out_ld=P["N2"], relu_mask=buf["act2"][0], colsum=cs2)
+        db2 = bias_grad(cs2, P["N2"])
         G2 = buf["g2"].view(be.planes, -1, P["N2"])
         k2 = c2.kernel_size[0]
-        if BOX_WGRAD:
+        if BOX_WGRAD2:
             sp2 = wgrad_box_splits(B * P["hp2"], 6, P["fwd2"].K, P["N2"])
             dw2 = wgrad_reduce(wgrad_box(buf["act1_pairs"], buf["g2"], P["fwd2"], 6, sp2), P["N2"], P["N1"], k2, k2)
         else:
             dw2 = be.wgrad(buf["act1"], G2, P["wg2"], P["N2"], P["N1"], k2, k2)
-        db2 = be.colsum(G2)
+        cs1 = torch.empty((sum(bg.m_tiles for bg, _ in P["dg2"]), P["N1"]), dtype=torch.float32, device=dz.device)
+        row = 0
         for bg, taps in P["dg2"]:
             wd = be.split(dgrad_weight_matrix(c2.weight.detach(), taps))
-            gemm_box(buf["g2"], wd, bg, out_pl=buf["g1"], out_ld=P["N1"], relu_mask=buf["act1"][0])
+            gemm_box(buf["g2"], wd, bg, out_pl=buf["g1"], out_ld=P["N1"], relu_mask=buf["act1"][0], colsum=cs1[row:row + bg.m_tiles])
+            row += bg.m_tiles
+        db1 = bias_grad(cs1, P["N1"])
         G1 = buf["g1"].view(be.planes, -1, P["N1"])
         k1 = c1.kernel_size[0]
         dw1 = be.wgrad(sv["x"], G1, P["wg1"], P["N1"], self.in_hwc[2], k1, k1, sv["scale"])
-        db1 = be.colsum(G1)
         return [dw1, db1, dw2, db2, dw3, db3] + gfc
 
 
