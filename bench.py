@@ -291,8 +291,13 @@ def run_own_arm(args):
     torch.backends.cudnn.benchmark = True
     assert N_ENVS % world == 0
     n_local = N_ENVS // world
+    if args.shard_of > 1:      # diagnostic: ONE rank's share of a --shard-of G job run alone (no collective): its step time
+        assert world == 1      # bounds the G-GPU scaling efficiency from the compute side; the line is marked, not a bench value
+        n_local = N_ENVS // args.shard_of
     cfg = ppo_namespace(device, n_local, world > 1, args.compute)
     cfg.tc_planes = args.tc_planes
+    if args.shard_of > 1:
+        cfg.parallels = n_local
     cfg.use_cuda_graph = bool(args.graph) if args.graph >= 0 else True     # same execution mode at every N
     obs_space, act_space = Box(0, 255, OBS_SHAPE, np.uint8), Discrete(N_ACTIONS)
     agent = PPO_Agent(cfg, envs=None, observation_space=obs_space, action_space=act_space)  # buffer: n_local envs
@@ -356,6 +361,12 @@ def run_own_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
     value = N_ENVS * T * args.steps / (elapsed_ms / 1000.0)
+    if args.shard_of > 1:
+        print(json.dumps({"diagnostic": "one rank's shard of a %d-GPU job, alone, no collective" % args.shard_of,
+                          "rows_per_update": n_local * T // N_MINIBATCH, "ms_per_step": elapsed_ms / args.steps,
+                          "ms_per_update": elapsed_ms / args.steps / (N_EPOCHS * N_MINIBATCH),
+                          "implied_value_at_%d_gpus_without_collective" % args.shard_of: value}))
+        return
 
     # ---- e2e: rollout in pinned HOST memory -> 128 x store (H2D) + finish_path + train_epochs + info D2H
     e2e = None
@@ -403,7 +414,7 @@ def run_own_arm(args):
     hbm_peak, tc_peak, peak_src = measured_peaks()
     roofline, kernel_ms = None, {}
     names = ["xb_gemm_gather_tc", "xb_gemm_box_tc", "xb_wgrad_gather_tc", "xb_wgrad_box_tc", "xb_wgrad_reduce", "xb_split_bf16",
-             "xb_pack_conv_weight", "xb_gather_obs_planes", "xb_gather_obs", "xb_ppo_loss_fwd_bwd",
+             "xb_pack_conv_weight", "xb_pack_weights", "xb_gather_obs_planes", "xb_gather_obs", "xb_ppo_loss_fwd_bwd",
              "xb_adam_step", "xb_grad_sumsq", "xb_gather_scalars", "nccl_all_reduce"]
     from xuance_b200.torch.utils import tc_conv
     saved_graph = agent.config.use_cuda_graph
@@ -502,6 +513,7 @@ def run_own_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--shard-of", type=int, default=1, help="diagnostic (1 GPU): time one rank's shard of a G-GPU job alone")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="xuance_b200", choices=["xuance_b200", "reference"])

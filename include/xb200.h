@@ -269,6 +269,26 @@ int xb_gather_obs_planes(const uint8_t *src, const int64_t *idx, int64_t B, int6
                          void *stream);
 int xb_pack_conv_weight(const float *w, int N, int C, int KH, int KW, int planes, float scale,
                         void *out /* bf16 [planes, N, KH*KW*C] */, void *stream);
+/* One operand form of one weight (xb_pack_weights): torch weight w [N, C, KH, KW] float32 (a Linear layer over a flattened
+ * [C, H, W] feature map is N x C x H x W) -> bf16 planes out [planes][rows][cols] of scale * w, with
+ *   mode 0: rows = N, cols = (kh, kw, c)            the B operand of the forward GEMM (= xb_pack_conv_weight)
+ *   mode 1: rows = (kh, kw, c), cols = N            its transpose: the B operand of a Linear layer's data gradient
+ *   mode 2: rows = C, cols = (tap, n), tap t = (kh[t], kw[t])   the B operand of one stride phase of a convolution's data
+ *                                                    gradient (flipped taps in the order of the launch's chunks) */
+#define XB_PACK_MAX_JOBS 16
+#define XB_PACK_MAX_TAPS 16
+typedef struct XbPackJob {
+    const float *w;
+    void *out;
+    int N, C, KH, KW;
+    int mode, n_taps;
+    signed char kh[XB_PACK_MAX_TAPS], kw[XB_PACK_MAX_TAPS];
+    float scale;
+    int planes;
+} XbPackJob;
+/* Every operand form an encoder needs for one update in ONE launch: jobs is a HOST array (copied into the launch parameters),
+ * n_jobs <= XB_PACK_MAX_JOBS.  Replaces one xb_pack_conv_weight / transpose / xb_split_bf16 launch per form. */
+int xb_pack_weights(const XbPackJob *jobs, int n_jobs, void *stream);
 int xb_gemm_gather_tc(int planes_a, int planes_b, const void *in, int64_t in_plane, const void *w, int64_t w_plane,
                       const float *bias, const void *relu_mask, int64_t mask_ld, int mask_c0, int B, int IH, int IW, int C,
                       int OY, int OX, int sy, int sx, int T, const int8_t *dy, const int8_t *dx, int N, int n_tile, int relu,

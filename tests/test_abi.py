@@ -119,6 +119,21 @@ def test_every_entry_point_validates_before_touching_the_device():
     assert gg(ld=32) == EINVAL                         # output row shorter than out_c0 + N
     assert gg(ld=68, c0=4) == EALIGN                   # 16-byte output segments
     assert gg(w=odd) == EALIGN
+    from xuance_b200._lib import XbPackJob
+    jobs = (XbPackJob * 2)()
+    for J in jobs:
+        J.w, J.out, J.N, J.C, J.KH, J.KW, J.mode, J.n_taps, J.scale, J.planes = junk.value, junk.value, 8, 8, 3, 3, 0, 0, 1.0, 3
+    pk = lambda n=2: lib.xb_pack_weights(ctypes.addressof(jobs), n, None)
+    assert pk(0) == EINVAL and pk(17) == EINVAL
+    jobs[1].planes = 4
+    assert pk() == EINVAL
+    jobs[1].planes, jobs[1].mode, jobs[1].n_taps = 3, 2, 17
+    assert pk() == ERANGE                               # tap list
+    jobs[1].n_taps = 2
+    jobs[1].kh[1] = 3
+    assert pk() == ERANGE                               # tap outside the kernel
+    jobs[1].kh[1], jobs[1].w = 2, None
+    assert pk() == EINVAL
     wg = lambda splits=1, out=junk, g_ld=64: lib.xb_wgrad_gather_tc(2, 2, junk, 1024, junk, 1024, g_ld, 1, 10, 10, 64, 10, 10, 1,
                                                                   1, 9, taps, taps, 64, 64, splits, out, None)
     assert wg(splits=5) == EINVAL                      # 100 sites cannot feed 5 splits

@@ -278,6 +278,29 @@ def test_box_convolutions_forward_and_data_gradient(planes, atol):
                                    err_msg="gathered over padded rows, cin=%d" % cin)
 
 
+def test_pack_weights_one_launch_equals_the_single_form_launches():
+    """xb_pack_weights: forward pack, transposed pack and data-gradient matrices of several weights in one launch are bit-equal
+    to xb_pack_conv_weight / transpose + xb_split_bf16 / dgrad_weight_matrix + xb_split_bf16."""
+    from xuance_b200 import _lib
+    from xuance_b200.torch.utils import tc_conv as tc
+    torch.manual_seed(2)
+    w2 = torch.randn(64, 32, 4, 4, device=DEV)
+    w3 = torch.randn(64, 64, 3, 3, device=DEV)
+    w4 = torch.randn(48, 64, 5, 5, device=DEV)
+    taps3 = [(kh, kw) for kh in range(3) for kw in range(3)]
+    taps2 = [(1, 0), (1, 2), (3, 0), (3, 2)]
+    for planes in (2, 3):
+        outs = tc.pack_weights([(w2, _lib.PACK_FORWARD, None, 1.0 / 255.0), (w3, _lib.PACK_DGRAD, taps3, 1.0),
+                                (w2, _lib.PACK_DGRAD, taps2, 1.0), (w4, _lib.PACK_FORWARD, None, 1.0),
+                                (w4, _lib.PACK_TRANSPOSED, None, 1.0)], planes, DEV)
+        want = [tc.pack_conv_weight(w2, planes, 1.0 / 255.0), tc.split_bf16(tc.dgrad_weight_matrix(w3, taps3), planes),
+                tc.split_bf16(tc.dgrad_weight_matrix(w2, taps2), planes), tc.pack_conv_weight(w4, planes),
+                tc.split_bf16(w4.permute(0, 2, 3, 1).reshape(48, 1600).t().contiguous(), planes)]
+        for i, (a, b) in enumerate(zip(outs, want)):
+            assert a.shape == b.shape, (i, a.shape, b.shape)
+            assert torch.equal(a.view(torch.int16), b.view(torch.int16)), "form %d planes %d" % (i, planes)
+
+
 @pytest.mark.parametrize("planes,atol", [(2, 5e-5), (3, 3e-6)])
 def test_linear_data_gradient_into_padded_rows_with_mask_and_colsum(planes, atol):
     """The Linear layer's data gradient written at a column offset of wider rows (conv3's padded output-gradient tensor), with

@@ -16,9 +16,10 @@ def main():
     n_envs, T = int(os.environ.get("XB_PROF_ENVS", "256")), int(os.environ.get("XB_PROF_T", "32"))
     cfg = bench.ppo_namespace(dev, n_envs, False, "tc")
     cfg.tc_planes = 3
+    cfg.parallels = n_envs
     cfg.horizon_size = T
     cfg.buffer_size = n_envs * T
-    cfg.n_minibatch = n_envs * T // 8192
+    cfg.n_minibatch = max(1, n_envs * T // 8192)
     cfg.use_cuda_graph = False
     agent = PPO_Agent(cfg, envs=None, observation_space=Box(0, 255, bench.OBS_SHAPE, np.uint8), action_space=Discrete(bench.N_ACTIONS))
     rng = np.random.default_rng(0)

@@ -41,6 +41,7 @@ _SIGNATURES = {
     "xb_split_bf16": (c_int, [_P, c_int64, c_int, _P, _P]),
     "xb_gather_obs_planes": (c_int, [_P, _P, c_int64, c_int64, c_int, _P, _P]),
     "xb_pack_conv_weight": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P]),
+    "xb_pack_weights": (c_int, [_P, c_int, _P]),
     "xb_gemm_gather_tc": (c_int, [c_int, c_int, _P, c_int64, _P, c_int64, _P, _P, c_int64, c_int] + [c_int] * 9
                           + [_P, _P, c_int, c_int, c_int, _P, c_int64, c_int, _P] + [c_int] * 6 + [c_int64, c_int, _P, _P]),
     "xb_gemm_box_tc": (c_int, [c_int, c_int, _P, c_int64, c_int, c_int, c_int64, c_int, c_int, c_int, c_int, c_int, _P, _P, _P,
@@ -130,6 +131,15 @@ def stream():
 
 
 _KERNELS_PER_CALL = {"xb_gather_scalars": 2}   # calls that launch more than one kernel (second one: normalise)
+class XbPackJob(ctypes.Structure):
+    """include/xb200.h ``XbPackJob`` (one operand form of one weight for ``xb_pack_weights``)."""
+    _fields_ = [("w", ctypes.c_void_p), ("out", ctypes.c_void_p), ("N", c_int), ("C", c_int), ("KH", c_int), ("KW", c_int),
+                ("mode", c_int), ("n_taps", c_int), ("kh", ctypes.c_int8 * 16), ("kw", ctypes.c_int8 * 16),
+                ("scale", c_float), ("planes", c_int)]
+
+
+PACK_FORWARD, PACK_TRANSPOSED, PACK_DGRAD = 0, 1, 2
+
 profile = None   # optional {abi_name: [(start_event, end_event), ...]} filled when set (bench.py roofline timing)
 nvtx = os.environ.get("XB_NVTX", "0") == "1"   # NVTX range per ABI call (nsys / ncu --nvtx timelines); off by default
 

@@ -576,6 +576,41 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float *__restric
     }
 }
 
+// every operand form of several weights in ONE launch (the per-update operand preparation of an encoder: forward packs,
+// transposed packs and data-gradient matrices); a block works on one job, jobs own consecutive block ranges
+struct PackJobs {
+    XbPackJob job[XB_PACK_MAX_JOBS];
+    unsigned first_block[XB_PACK_MAX_JOBS + 1];
+    int n;
+};
+
+__global__ void __launch_bounds__(256) pack_jobs_kernel(const __grid_constant__ PackJobs pj) {
+    int ji = 0;
+    while (ji + 1 < pj.n && blockIdx.x >= pj.first_block[ji + 1]) ++ji;
+    const XbPackJob &J = pj.job[ji];
+    const int64_t K = (int64_t)J.C * J.KH * J.KW, total = J.mode == 2 ? (int64_t)J.C * J.n_taps * J.N : (int64_t)J.N * K;
+    const int64_t i = (int64_t)(blockIdx.x - pj.first_block[ji]) * 256 + threadIdx.x;
+    if (i >= total) return;
+    int64_t src;
+    if (J.mode == 0) {
+        src = xb_pack_weight_src(i, J.C, J.KH, J.KW);                       // [N][(kh, kw, c)]
+    } else if (J.mode == 1) {
+        const int64_t k = i / J.N, n = i - k * J.N;                        // [(kh, kw, c)][N]
+        src = xb_pack_weight_src(n * K + k, J.C, J.KH, J.KW);
+    } else {
+        const int64_t tn = (int64_t)J.n_taps * J.N, c = i / tn, r = i - c * tn;   // [C][(tap, n)]
+        const int t = (int)(r / J.N), n = (int)(r - (int64_t)t * J.N);
+        src = (((int64_t)n * J.C + c) * J.KH + J.kh[t]) * J.KW + J.kw[t];
+    }
+    float v = __fmul_rn(J.w[src], J.scale);
+    __nv_bfloat16 *out = (__nv_bfloat16 *)J.out;
+    for (int q = 0; q < J.planes; ++q) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        out[(int64_t)q * total + i] = h;
+        v -= __bfloat162float(h);
+    }
+}
+
 // ---------------------------------------------------------------- TMA descriptors (host)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -715,6 +750,33 @@ extern "C" int xb_pack_conv_weight(const float *w, int N, int C, int KH, int KW,
     if (planes == 1) pack_weight_kernel<1><<<grid, 256, 0, s>>>(w, N, C, KH, KW, scale, (__nv_bfloat16 *)out);
     else if (planes == 2) pack_weight_kernel<2><<<grid, 256, 0, s>>>(w, N, C, KH, KW, scale, (__nv_bfloat16 *)out);
     else pack_weight_kernel<3><<<grid, 256, 0, s>>>(w, N, C, KH, KW, scale, (__nv_bfloat16 *)out);
+    return xb_launch_status();
+}
+
+extern "C" int xb_pack_weights(const XbPackJob *jobs, int n_jobs, void *stream) {
+    if (!jobs || n_jobs <= 0 || n_jobs > XB_PACK_MAX_JOBS) return XB_EINVAL;
+    PackJobs pj;
+    pj.n = n_jobs;
+    uint64_t blocks = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        const XbPackJob &J = jobs[j];
+        if (!J.w || !J.out || J.N <= 0 || J.C <= 0 || J.KH <= 0 || J.KW <= 0 || J.planes < 1 || J.planes > 3 || J.mode < 0 ||
+            J.mode > 2)
+            return XB_EINVAL;
+        if (J.mode == 2) {
+            if (J.n_taps <= 0 || J.n_taps > XB_PACK_MAX_TAPS) return XB_ERANGE;
+            for (int t = 0; t < J.n_taps; ++t)
+                if (J.kh[t] < 0 || J.kh[t] >= J.KH || J.kw[t] < 0 || J.kw[t] >= J.KW) return XB_ERANGE;
+        }
+        if (!xb_aligned(J.out, 2) || !xb_aligned(J.w, 4)) return XB_EALIGN;
+        const int64_t total = J.mode == 2 ? (int64_t)J.C * J.n_taps * J.N : (int64_t)J.N * J.C * J.KH * J.KW;
+        pj.job[j] = J;
+        pj.first_block[j] = (unsigned)blocks;
+        blocks += (uint64_t)((total + 255) / 256);
+        if (blocks > 0x7fffffffull) return XB_ERANGE;
+    }
+    pj.first_block[n_jobs] = (unsigned)blocks;
+    pack_jobs_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(pj);
     return xb_launch_status();
 }
 

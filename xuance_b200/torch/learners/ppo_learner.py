@@ -27,6 +27,33 @@ class PPO_Learner(Learner):
         self.clip_range = getattr(config, "clip_range", 0.0)
         self._stats = self.optimizer.bucket.tail[:8]      # the logged sums travel in the gradient bucket's tail
         self._scratch = _lib.scratch(self.device)
+        self._early = None
+        self._hook_early_allreduce()
+
+    def _hook_early_allreduce(self):
+        """Sharded training: the bulk of the gradient (the 6400->512 layer and the heads, 98 % of the parameters) is final
+        before the convolution backward starts, so its all-reduce is issued there (async, on NCCL's stream) and overlaps the
+        convolution backward; what remains - [statistics | convolution gradients], the front of the bucket - is one small
+        latency-bound all-reduce at the end.  Needs an encoder that reports when those gradients are in place
+        (BoxNatureCNN.grads_ready) and the bucket laid out in parameter order; XB_EARLY_ALLREDUCE=0 keeps one collective."""
+        import os
+        enc = getattr(getattr(self.model, "representation", None), "_tc", None)       # set by _PixelEncoder.set_compute("tc")
+        if self.world_size <= 1 or enc is None or not hasattr(enc, "grads_ready") or os.environ.get("XB_EARLY_ALLREDUCE", "1") == "0":
+            return
+        bucket = self.optimizer.bucket
+
+        def ready(first_param):
+            if self.world_size <= 1 or self._early is not None:
+                return
+            off = bucket.offset_of(first_param)
+            enc_ids = {id(p) for p in enc.parameters()}
+            late = {id(p) for p in (enc.fc.weight, enc.fc.bias)}
+            for p, o in zip(bucket.params, bucket.offsets):      # everything from `off` on must already be final
+                if (o >= off) != (id(p) in late or id(p) not in enc_ids):
+                    return
+            import torch.distributed as dist
+            self._early = (off, dist.all_reduce(bucket.grad[off:], op=dist.ReduceOp.SUM, async_op=True))
+        enc.grads_ready = ready
 
     def _lr_total_iters(self):
         return self.total_iters
@@ -60,7 +87,13 @@ class PPO_Learner(Learner):
         self.optimizer.zero_grad()
         torch.autograd.backward([logits_c, v_c], [dlogits, dvalue])
         if self.world_size > 1:
-            allreduce_sum_(self.optimizer.bucket.grad_all)   # the ONE collective of an update: gradient + logged statistics
+            if self._early is not None:                      # the tail end of the bucket is already being reduced
+                off, work = self._early
+                self._early = None
+                allreduce_sum_(self.optimizer.bucket.grad_all[:self.optimizer.bucket.TAIL + off])
+                work.wait()
+            else:
+                allreduce_sum_(self.optimizer.bucket.grad_all)   # ONE collective: gradient + logged statistics
         self.optimizer.launch(max_norm=self.grad_clip_norm if self.use_grad_clip else None)
 
     def host_pre_step(self):

@@ -22,7 +22,9 @@ def cudnn_rnn_front(module):
 
 
 class FlatBucket:
-    TAIL = 32   # float32 slots after the last gradient: per-update statistics ride in the SAME all-reduce as the gradient
+    TAIL = 32   # float32 slots BEFORE the first gradient: per-update statistics ride in the same all-reduce as the gradient
+                # (in front, so that [statistics | first parameters] stays one contiguous piece when the gradients of the
+                # LAST parameters - final first in a backward pass - are reduced early, see PPO_Learner._early_allreduce)
 
     def __init__(self, params, front=()):
         """``front``: parameters to lay out first (see ``cudnn_rnn_front``); ``self.params`` keeps the caller's order."""
@@ -50,8 +52,8 @@ class FlatBucket:
         self.numel = off
         self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
         self.grad_all = torch.zeros(off + self.TAIL, dtype=torch.float32, device=dev)   # what a sharded learner all-reduces
-        self.grad = self.grad_all[:off]
-        self.tail = self.grad_all[off:]
+        self.tail = self.grad_all[:self.TAIL]
+        self.grad = self.grad_all[self.TAIL:]
         for p, o in zip(plist, self.offsets):
             v = self._view(self.flat, p, o)
             v.copy_(p.data)
@@ -65,6 +67,13 @@ class FlatBucket:
             o, i, h, w = p.shape
             return chunk.view(o, h, w, i).permute(0, 3, 1, 2)
         return chunk.view(p.shape)
+
+    def offset_of(self, p):
+        """Element offset of parameter ``p`` inside ``flat`` / ``grad``."""
+        for q, o in zip(self.params, self.offsets):
+            if q is p:
+                return o
+        raise KeyError("parameter is not in this bucket")
 
     def views(self, buf):
         return [self._view(buf, p, o) for p, o in zip(self.params, self.offsets)]

@@ -144,6 +144,29 @@ def split_bf16(x, planes=2):
     return out
 
 
+def pack_weights(jobs, planes, device):
+    """Several operand forms in ONE launch (``xb_pack_weights``).  ``jobs``: list of (w [N, C, KH, KW] float32, mode, taps, scale)
+    with mode _lib.PACK_FORWARD -> [planes, N, KH*KW*C], PACK_TRANSPOSED -> [planes, KH*KW*C, N], PACK_DGRAD -> [planes, C,
+    len(taps)*N] (taps = [(kh, kw), ...]); returns the bfloat16 plane tensors in job order."""
+    import ctypes
+    arr = (_lib.XbPackJob * len(jobs))()
+    outs = []
+    for j, (w, mode, taps, scale) in enumerate(jobs):
+        assert w.is_contiguous() and w.dtype == torch.float32 and w.dim() == 4
+        N, C, KH, KW = w.shape
+        shape = {_lib.PACK_FORWARD: (N, KH * KW * C), _lib.PACK_TRANSPOSED: (KH * KW * C, N),
+                 _lib.PACK_DGRAD: (C, len(taps or ()) * N)}[mode]
+        out = torch.empty((planes,) + shape, dtype=torch.bfloat16, device=device)
+        J = arr[j]
+        J.w, J.out, J.N, J.C, J.KH, J.KW, J.mode, J.scale, J.planes = w.data_ptr(), out.data_ptr(), N, C, KH, KW, mode, scale, planes
+        J.n_taps = len(taps) if mode == _lib.PACK_DGRAD else 0
+        for t, (kh, kw) in enumerate(taps or ()):
+            J.kh[t], J.kw[t] = kh, kw
+        outs.append(out)
+    _lib.call("xb_pack_weights", ctypes.addressof(arr), len(jobs))
+    return outs
+
+
 def pack_conv_weight(w, planes=2, scale=1.0):
     """[N, C, KH, KW] float32 CUDA -> bfloat16 [planes, N, KH*KW*C] in (kh, kw, c) column order, times ``scale``."""
     w = w.contiguous()
@@ -217,10 +240,10 @@ def gemm_gather(x_pl, w_pl, geom, bias=None, relu=False, out_f32=None, out_pl=No
     return out_f32, out_pl
 
 
-def bias_grad(colsum, N):
+def bias_grad(colsum, N, out=None, accumulate=False):
     """Column-sum partials (any shape [..., N], contiguous) -> [N]: the bias gradient of the layer whose output gradient the
-    producing K12 launch wrote; the partials are added in a fixed order by xb_wgrad_reduce."""
-    return wgrad_reduce(colsum.view(-1, 1, N), N, 1, 1, 1).view(N)
+    producing K12 launch wrote; the partials are added in a fixed order by xb_wgrad_reduce (which uses them as scratch)."""
+    return wgrad_reduce(colsum.view(-1, 1, N), N, 1, 1, 1, out=out, accumulate=accumulate).view(N)
 
 
 def wgrad_gather(x_pl, g_pl, geom, splits, n_tile=None):
@@ -287,10 +310,10 @@ class CudaBackend:
         gemm_gather(x_pl, w_pl, geom, bias=bias, relu=relu, out_f32=out_f32, out_pl=out_pl, out_ld=out_ld, out_c0=out_c0,
                     relu_mask=mask)
 
-    def wgrad(self, x_pl, g_pl, geom, N, C, KH, KW, scale=1.0):
+    def wgrad(self, x_pl, g_pl, geom, N, C, KH, KW, scale=1.0, out=None, accumulate=False):
         nt = N // n_tile_for(N, g_pl.shape[0])
         splits = wgrad_splits(geom.M, geom.K, nt)
-        return wgrad_reduce(wgrad_gather(x_pl, g_pl, geom, splits), N, C, KH, KW, scale=scale)
+        return wgrad_reduce(wgrad_gather(x_pl, g_pl, geom, splits), N, C, KH, KW, scale=scale, out=out, accumulate=accumulate)
 
     def colsum(self, g_pl):
         # bias gradient: reduce the bf16 planes straight into float32 (no float32 copy of the [P, sites, N] tensor)
@@ -522,7 +545,7 @@ class BoxNatureCNN(TensorCoreNatureCNN):
     plane, 4 channels) and its weight gradient keep the gathered path, with the padded tensors described to it as ordinary
     geometries."""
 
-    HP = {0: None}
+    grads_ready = None      # optional callable(first_final_parameter), see backward()
 
     def _box_ok(self):
         cs = self.convs
@@ -619,59 +642,89 @@ class BoxNatureCNN(TensorCoreNatureCNN):
             self._plans[key]["act1_pairs"] = pairs(self._plans[key]["act1"])
         return self._plans[key]
 
+    def _operands(self, P, scale):
+        """Every weight operand form of one update in ONE launch (xb_pack_weights): forward packs, the Linear layer's
+        transposed pack, the data-gradient matrices of conv3 and of conv2's four stride phases."""
+        c1, c2, c3 = self.convs
+        F, T, D = _lib.PACK_FORWARD, _lib.PACK_TRANSPOSED, _lib.PACK_DGRAD
+        jobs = [(c1.weight.detach(), F, None, scale), (c2.weight.detach(), F, None, 1.0), (c3.weight.detach(), F, None, 1.0),
+                (c3.weight.detach(), D, P["taps3"], 1.0)] + [(c2.weight.detach(), D, taps, 1.0) for _, taps in P["dg2"]]
+        if self.fc is not None:
+            F_ = P["fc"]
+            w4 = self.fc.weight.detach().view(F_["N"], F_["C"], F_["KH"], F_["KW"])
+            jobs += [(w4, F, None, 1.0), (w4, T, None, 1.0)]
+        outs = pack_weights(jobs, self.be.planes, c1.weight.device)
+        n2 = len(P["dg2"])
+        ops = dict(w1=outs[0], w2=outs[1], w3=outs[2], wd3=outs[3], wd2=outs[4:4 + n2])
+        if self.fc is not None:
+            ops.update(wfc=outs[4 + n2], wfc_t=outs[5 + n2])
+        return ops
+
     def forward(self, x_pl, B):
         be, P = self.be, self._plan(B)
         buf = self._buffers(B, x_pl)
         c1, c2, c3 = self.convs
         raw = x_pl.shape[0] == 1 and be.planes > 1
         scale = 1.0 / 255.0 if raw else 1.0
-        w1 = be.pack_weight(c1.weight.detach(), scale)
-        gemm_gather(x_pl, w1, P["fwd1"], bias=c1.bias.detach(), relu=True, out_pl=buf["act1"], out_ld=P["N1"])
-        w2 = be.pack_weight(c2.weight.detach())
-        gemm_box(buf["act1_pairs"], w2, P["fwd2"], bias=c2.bias.detach(), relu=True, out_pl=buf["act2"], out_ld=P["N2"])
-        w3 = be.pack_weight(c3.weight.detach())
+        ops = self._operands(P, scale)
+        gemm_gather(x_pl, ops["w1"], P["fwd1"], bias=c1.bias.detach(), relu=True, out_pl=buf["act1"], out_ld=P["N1"])
+        gemm_box(buf["act1_pairs"], ops["w2"], P["fwd2"], bias=c2.bias.detach(), relu=True, out_pl=buf["act2"], out_ld=P["N2"])
         n3 = P["H2"] * P["W2"]
         act3 = be.empty_planes((B * n3, P["N3"]), x_pl)
         last_conv = self.fc is None
         out3 = be.empty_f32((B * n3, P["N3"]), x_pl) if last_conv else None
-        gemm_box(buf["act2"], w3, P["fwd3"], bias=c3.bias.detach(), relu=True, out_pl=act3, out_f32=out3, out_ld=P["N3"])
-        saved = dict(x=x_pl, act3=act3, scale=scale)
+        gemm_box(buf["act2"], ops["w3"], P["fwd3"], bias=c3.bias.detach(), relu=True, out_pl=act3, out_f32=out3, out_ld=P["N3"])
+        saved = dict(x=x_pl, act3=act3, scale=scale, ops=ops)
         if last_conv:
             self._saved = (B, saved)
             return out3
         F_ = P["fc"]
-        w4 = self.fc.weight.detach().reshape(F_["N"], F_["C"], F_["KH"], F_["KW"])
-        wfc = be.pack_weight(w4)
         y = be.empty_planes((B, F_["N"]), x_pl)
         out = be.empty_f32((B, F_["N"]), x_pl)
-        gemm_gather(act3.view(be.planes, B, F_["K"]), wfc, F_["fwd"], bias=self.fc.bias.detach(), relu=True, out_f32=out, out_pl=y)
-        saved.update(y=y, w4=w4)
+        gemm_gather(act3.view(be.planes, B, F_["K"]), ops["wfc"], F_["fwd"], bias=self.fc.bias.detach(), relu=True, out_f32=out, out_pl=y)
+        saved.update(y=y)
         self._saved = (B, saved)
         return out
+
+    @staticmethod
+    def _into(p):
+        """Where a parameter's gradient goes: straight into an existing contiguous float32 ``.grad`` (added, as autograd's
+        accumulation would - the flat gradient bucket of the fused optimizer), else a fresh tensor returned to autograd."""
+        g = p.grad
+        if g is not None and g.is_contiguous() and g.dtype == torch.float32 and g.device == p.device:
+            return dict(out=g, accumulate=True)
+        return dict(out=None, accumulate=False)
 
     def backward(self, dz):
         be = self.be
         B, sv = self._saved
         P, buf = self._plan(B), self._buffers(B, dz)
         c1, c2, c3 = self.convs
-        n3 = P["H2"] * P["W2"]
-        grads = []
+        ops = sv["ops"]
         act3 = sv["act3"]
+        ret = lambda p, t: None if p.grad is not None and t.data_ptr() == p.grad.data_ptr() else t.view_as(p)
         if self.fc is not None:
             F_ = P["fc"]
             g4 = be.split(dz * (sv["y"][0] > 0).to(dz.dtype))
             x3 = act3.view(be.planes, B, F_["K"])
-            dwfc = be.wgrad(x3, g4, F_["fwd"], F_["N"], F_["C"], F_["KH"], F_["KW"])
-            gfc = [dwfc.reshape(F_["N"], F_["K"]), be.colsum(g4)]
-            wt = be.split(sv["w4"].permute(0, 2, 3, 1).reshape(F_["N"], F_["K"]).t().contiguous())      # [P, K (h,w,c), N]
+            dwfc = be.wgrad(x3, g4, F_["fwd"], F_["N"], F_["C"], F_["KH"], F_["KW"], **self._into(self.fc.weight))
+            dbfc = be.colsum(g4)
+            if self._into(self.fc.bias)["accumulate"]:
+                self.fc.bias.grad.add_(dbfc)
+                dbfc = self.fc.bias.grad
+            gfc = [ret(self.fc.weight, dwfc), ret(self.fc.bias, dbfc)]
+            if self.grads_ready is not None and gfc[0] is None and gfc[1] is None:
+                # the Linear layer's gradients (and those of everything after the encoder) are final and in place while the
+                # whole convolution backward is still ahead: a sharded learner starts reducing them now
+                self.grads_ready(self.fc.weight)
             # the Linear layer's data gradient lands straight in conv3's PADDED output-gradient tensor: image b's 6400 values
             # are rows 1 .. H2 of its hp2 rows (a matrix with hp2*W2*N3 elements per row, from column W2*N3); the mask is
             # the plain [B, 6400] activation; the column sums per (h, w, c) are conv3's bias-gradient partials
             ld3 = P["hp2"] * P["W2"] * P["N3"]
             cs3 = torch.empty((-(-B // 128), F_["K"]), dtype=torch.float32, device=dz.device)
-            gemm_gather(g4, wt, F_["dgrad"], out_pl=buf["g3"].view(be.planes, B, ld3), out_ld=ld3, out_c0=P["W2"] * P["N3"],
+            gemm_gather(g4, ops["wfc_t"], F_["dgrad"], out_pl=buf["g3"].view(be.planes, B, ld3), out_ld=ld3, out_c0=P["W2"] * P["N3"],
                         relu_mask=x3[0], mask_ld=F_["K"], mask_c0=0, colsum=cs3)
-            db3 = bias_grad(cs3, P["N3"])
+            db3 = bias_grad(cs3, P["N3"], **self._into(c3.bias))
         else:
             gfc = []
             g3p = be.split(dz * (act3[0] > 0).to(dz.dtype)).view(be.planes, B, P["H2"], P["W2"] * P["N3"])
@@ -681,31 +734,32 @@ class BoxNatureCNN(TensorCoreNatureCNN):
         k3 = c3.kernel_size[0]
         if BOX_WGRAD3:
             sp3 = wgrad_box_splits(B * P["hp2"], 6, P["fwd3"].K, P["N3"])
-            dw3 = wgrad_reduce(wgrad_box(buf["act2"], g3, P["fwd3"], 6, sp3), P["N3"], P["N2"], k3, k3)
+            dw3 = wgrad_reduce(wgrad_box(buf["act2"], g3, P["fwd3"], 6, sp3), P["N3"], P["N2"], k3, k3, **self._into(c3.weight))
         else:
-            dw3 = be.wgrad(buf["act2"], g3.view(be.planes, -1, P["N3"]), P["wg3"], P["N3"], P["N2"], k3, k3)
-        wd3 = be.split(dgrad_weight_matrix(c3.weight.detach(), P["taps3"]))
+            dw3 = be.wgrad(buf["act2"], g3.view(be.planes, -1, P["N3"]), P["wg3"], P["N3"], P["N2"], k3, k3, **self._into(c3.weight))
         cs2 = torch.empty((P["dg3"].m_tiles, P["N2"]), dtype=torch.float32, device=dz.device)
-        gemm_box(g3, wd3, P["dg3"], out_pl=buf["g2"], out_ld=P["N2"], relu_mask=buf["act2"][0], colsum=cs2)
-        db2 = bias_grad(cs2, P["N2"])
+        gemm_box(g3, ops["wd3"], P["dg3"], out_pl=buf["g2"], out_ld=P["N2"], relu_mask=buf["act2"][0], colsum=cs2)
+        db2 = bias_grad(cs2, P["N2"], **self._into(c2.bias))
         G2 = buf["g2"].view(be.planes, -1, P["N2"])
         k2 = c2.kernel_size[0]
         if BOX_WGRAD2:
             sp2 = wgrad_box_splits(B * P["hp2"], 6, P["fwd2"].K, P["N2"])
-            dw2 = wgrad_reduce(wgrad_box(buf["act1_pairs"], buf["g2"], P["fwd2"], 6, sp2), P["N2"], P["N1"], k2, k2)
+            dw2 = wgrad_reduce(wgrad_box(buf["act1_pairs"], buf["g2"], P["fwd2"], 6, sp2), P["N2"], P["N1"], k2, k2,
+                               **self._into(c2.weight))
         else:
-            dw2 = be.wgrad(buf["act1"], G2, P["wg2"], P["N2"], P["N1"], k2, k2)
+            dw2 = be.wgrad(buf["act1"], G2, P["wg2"], P["N2"], P["N1"], k2, k2, **self._into(c2.weight))
         cs1 = torch.empty((sum(bg.m_tiles for bg, _ in P["dg2"]), P["N1"]), dtype=torch.float32, device=dz.device)
         row = 0
-        for bg, taps in P["dg2"]:
-            wd = be.split(dgrad_weight_matrix(c2.weight.detach(), taps))
+        for (bg, _), wd in zip(P["dg2"], ops["wd2"]):
             gemm_box(buf["g2"], wd, bg, out_pl=buf["g1"], out_ld=P["N1"], relu_mask=buf["act1"][0], colsum=cs1[row:row + bg.m_tiles])
             row += bg.m_tiles
-        db1 = bias_grad(cs1, P["N1"])
+        db1 = bias_grad(cs1, P["N1"], **self._into(c1.bias))
         G1 = buf["g1"].view(be.planes, -1, P["N1"])
         k1 = c1.kernel_size[0]
-        dw1 = be.wgrad(sv["x"], G1, P["wg1"], P["N1"], self.in_hwc[2], k1, k1, sv["scale"])
-        return [dw1, db1, dw2, db2, dw3, db3] + gfc
+        dw1 = be.wgrad(sv["x"], G1, P["wg1"], P["N1"], self.in_hwc[2], k1, k1, sv["scale"], **self._into(c1.weight))
+        convs = [ret(p, t) for p, t in ((c1.weight, dw1), (c1.bias, db1), (c2.weight, dw2), (c2.bias, db2), (c3.weight, dw3),
+                                        (c3.bias, db3))]
+        return convs + gfc
 
 
 class _TCEncoderFn(torch.autograd.Function):
