@@ -44,6 +44,11 @@ def main(argv):
     reps = [a for a in argv if a.endswith(".ncu-rep")]
     jpath = argv[argv.index("--json") + 1] if "--json" in argv else None
     keys = argv[argv.index("--key") + 1:] if "--key" in argv else []
+    sum_key = None
+    if "--sum-key" in argv:          # one entry = the sum over every launch of the capture (e.g. the K12 launches of one update)
+        sum_key = argv[argv.index("--sum-key") + 1]
+        keys = []
+    tot_bytes, tot_us, n_l = 0.0, 0.0, 0
     print("%-52s %9s %10s %10s %8s %7s %6s %6s %6s %10s" % ("kernel (grid)", "dur_us", "dram_rd_MB", "dram_wr_MB", "tensor%",
                                                           "issue%", "l2%", "l1%", "dram%", "xbar_rd_MB"))
     merged = {}
@@ -58,10 +63,17 @@ def main(argv):
                 name, val(d, WANT[0][0]), val(d, WANT[1][0]) / 1e6, val(d, WANT[2][0]) / 1e6, val(d, WANT[3][0]),
                 val(d, WANT[4][0]), val(d, WANT[5][0]), val(d, WANT[6][0]), val(d, WANT[7][0]), val(d, WANT[8][0]) / 1e6,
                 ", ".join("%s %.1f" % (n, p) for p, n in stalls)))
+            tot_bytes += val(d, WANT[1][0]) + val(d, WANT[2][0])
+            tot_us += val(d, WANT[0][0])
+            n_l += 1
             if i < len(keys):
                 merged[keys[i]] = {"dram_bytes_per_launch": val(d, WANT[1][0]) + val(d, WANT[2][0]), "duration_us": val(d, WANT[0][0]),
                                    "source": rep.split("/")[-1]}
             i += 1
+    if sum_key:
+        merged[sum_key] = {"dram_bytes_per_launch": tot_bytes, "duration_us": tot_us, "launches": n_l,
+                           "source": ",".join(r.split("/")[-1] for r in reps)}
+        print("sum over %d launches: %.1f MB DRAM, %.1f us" % (n_l, tot_bytes / 1e6, tot_us))
     if jpath and merged:
         try:
             cur = json.load(open(jpath))

@@ -34,6 +34,11 @@ def main():
     for _ in range(2):
         agent.train_epochs(1)
     torch.cuda.synchronize()
+    if os.environ.get("XB_PROF_PLAIN", "0") == "1":      # under ncu (CUPTI is taken): just run the one update
+        agent.train_epochs(1)
+        torch.cuda.synchronize()
+        print("plain update done")
+        return
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         agent.train_epochs(1)
