@@ -413,7 +413,7 @@ def run_own_arm(args):
     # eagerly right after the timed region (graph replays hide per-kernel events); same buffers, same shapes, same stream
     hbm_peak, tc_peak, peak_src = measured_peaks()
     roofline, kernel_ms = None, {}
-    names = ["xb_gemm_gather_tc", "xb_gemm_box_tc", "xb_wgrad_gather_tc", "xb_wgrad_box_tc", "xb_wgrad_reduce", "xb_split_bf16",
+    names = ["xb_gemm_gather_tc", "xb_gemm_box_tc", "xb_gemm_halo_tc", "xb_wgrad_gather_tc", "xb_wgrad_box_tc", "xb_wgrad_reduce", "xb_split_bf16",
              "xb_pack_conv_weight", "xb_pack_weights", "xb_gather_obs_planes", "xb_gather_obs", "xb_ppo_loss_fwd_bwd",
              "xb_adam_step", "xb_grad_sumsq", "xb_gather_scalars", "nccl_all_reduce"]
     from xuance_b200.torch.utils import tc_conv
@@ -442,7 +442,7 @@ def run_own_arm(args):
             kernel_ms[n] = float(sum(a.elapsed_time(b) for a, b in prof[n]))
     if flog:
         # pair the FLOP log with the events in launch order (each ABI name keeps its own ordered list)
-        it_f = {n: iter(prof[n]) for n in ("xb_gemm_gather_tc", "xb_gemm_box_tc", "xb_wgrad_gather_tc", "xb_wgrad_box_tc")}
+        it_f = {n: iter(prof[n]) for n in ("xb_gemm_gather_tc", "xb_gemm_box_tc", "xb_gemm_halo_tc", "xb_wgrad_gather_tc", "xb_wgrad_box_tc")}
         per_layer, tot_fl, tot_eq, tot_ms = {}, 0.0, 0.0, 0.0
         for nm, tag, fl, eq in flog:
             a, b = next(it_f[nm])
@@ -456,11 +456,13 @@ def run_own_arm(args):
         roofline = {"kernel": "conv_tc_kernel (K12: tcgen05 gathered-operand GEMM; %d launches per update: forward, data and "
                               "weight gradients of conv1-3 + the 6400->512 layer)" % (len(flog) // n_upd),
                     "bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak,
-                    "traffic": ncu_traffic("conv_tc_kernel:" + top[0]),
+                    "traffic": ncu_traffic("conv_tc_kernel:update_B%d_P%d" % (N_ENVS * T // N_MINIBATCH // world, args.tc_planes)),
                     "peak_source": peak_src + ", bf16_tflops_sustained",
                     "algorithmic_flops_per_update": tot_fl / n_upd,
-                    "what": "executed bf16 tensor FLOPs = 2*M*N*K x kept plane products (6 for 3x3 planes, 3 for the raw-pixel "
-                            "first layer) / summed CUDA-event time of the K12 launches",
+                    "what": "algorithmic bf16 tensor FLOPs = 2 x real output sites x N x K (padding / halo / garbage sites of the padded "
+                            "layouts NOT counted) x the plane products float32-grade arithmetic keeps (6 for 3x3 planes, 3 for "
+                            "the raw-pixel first layer) / summed CUDA-event time of the K12 launches; traffic = DRAM bytes of "
+                            "those launches per update (ncu --set full of one update at this shape, profiles/r02_traffic.json)",
                     "fp32_equivalent_tflops": tot_eq / (tot_ms * 1e-3) / 1e12,
                     "avg_update_ms": tot_ms / n_upd, "launches_timed": len(flog),
                     "timed": "CUDA events around every K12 launch of one eager epoch run right after the timed region",

@@ -310,12 +310,33 @@ int xb_gemm_box_tc(int planes_a, int planes_b, const void *in, int64_t in_plane,
                    int hp, int y0, int y1, int N, int n_tile, int relu, void *out_planes, int64_t out_plane, int planes_out,
                    float *out_f32, int out_H, int out_W, int oys, int oxs, int oy0, int ox0, int64_t out_ld, int out_c0,
                    float *colsum, void *stream);
+/* The gathered GEMM with the activation tile RESIDENT in shared memory ("halo" mode): stride-1 gathers over a 64-channel
+ * padded-row tensor in [planes][B*hp rows][W pixels][64] (in_rows = B*hp) - a 3x3 convolution, its data gradient, the stride
+ * phases of a strided convolution's data gradient.  The sites are the positions of the haloed raster: row R (image R / hp,
+ * padded row y = R % hp), column hc = pixel hc + halo_w0 (halo_w0 <= 0, halo_w columns per row; pixels outside [0, W) read
+ * as zero); an M tile is 128 consecutive positions and ONE TMA box per plane holds every input its taps read.  Sub-item j
+ * (n_sub <= 4: the n tiles of a forward layer or the stride phases of a data gradient) multiplies with rows j*N .. of
+ * w [planes_b][n_sub*N][n_chunks*64]; its chunk i reads the site (R + dr[j*n_chunks+i], pixel + dc[..]) - a descriptor
+ * offset into the resident tile.  Valid sites of sub-item j: y0 <= y <= sub_y1[j], 0 <= x <= sub_x1[j]; they land at row
+ * ((b*out_H + (y-y0)*oys + sub_oy0[j])*out_W + x*oxs + sub_ox0[j]) of the output, columns out_c0 + j*N (same_cols: out_c0 for
+ * every sub-item).  n_sub * n_chunks <= 16.  bias / relu / relu_mask (mask_W, mask_x0) / planes / colsum
+ * ([ceil(B*hp*halo_w / 128) * n_sub][N]) as xb_gemm_box_tc. */
+int xb_gemm_halo_tc(int planes_a, int planes_b, const void *in, int64_t in_plane, int W, int64_t in_rows, int halo_w, int halo_w0,
+                    int n_sub, int n_chunks, const int16_t *dr, const int16_t *dc, const void *w, int64_t w_plane,
+                    const float *bias, const void *relu_mask, int mask_W, int mask_x0, int B, int hp, int y0,
+                    const int16_t *sub_y1, const int16_t *sub_x1, int N, int relu, void *out_planes, int64_t out_plane,
+                    int planes_out, float *out_f32, int out_H, int out_W, int oys, int oxs, const int16_t *sub_oy0,
+                    const int16_t *sub_ox0, int64_t out_ld, int out_c0, int same_cols, float *colsum, void *stream);
 /* Weight gradient of the same convolution with both operands fetched by TMA boxes: `in` as for xb_gemm_box_tc, `g` the
  * output gradient in the padded site layout [planes_b][g_rows][box_px*box_c/64 sites][N]; a chunk of the reduction is box_h
  * grid rows (box_w * box_h <= 64 sites), N % 64 == 0; partials: float32 [splits, n_chunks*64, N] (reduce with xb_wgrad_reduce). */
 int xb_wgrad_box_tc(int planes_a, int planes_b, const void *in, int64_t in_plane, int C, int W, int64_t in_rows, int box_c,
                     int box_px, int box_h, int row_step, int n_chunks, const int16_t *c0, const int16_t *w0, const int16_t *r0,
                     const void *g, int64_t g_plane, int64_t g_rows, int N, int splits, float *partials, void *stream);
+/* Diagnostics (XB_K12_TIMING=1 in the environment): per CTA of the LAST K12 launch, clock64 cycles of each warp role and of its
+ * barrier waits: out_host[cta][12] = {MMA total, MMA wait operands, MMA wait epilogue, MMA wait resident tile, producer total,
+ * producer wait ring, producer wait tile buffer, epilogue total, epilogue wait accumulator, ...}.  Synchronises the device. */
+int xb_debug_k12_timing(unsigned long long *out_host, int n_ctas);
 /* Test hook: the raw shared-memory image (first out_bytes, 0xEE = untouched) after ONE TMA box load of the 4-D tensor map the
  * box mode builds - lets the tests pin the layout (pixel packing, row step, 128-byte swizzle, zero fill) byte for byte. */
 int xb_debug_tma_box(const void *in, int64_t in_plane, int planes, int C, int W, int64_t rows, int box_c, int box_px, int box_h,

@@ -324,6 +324,66 @@ def test_linear_data_gradient_into_padded_rows_with_mask_and_colsum(planes, atol
     np.testing.assert_allclose(tc.bias_grad(cs, 64).cpu().numpy(), want.view(B, 10, 64).sum((0, 1)).cpu().numpy(), rtol=0, atol=atol * 8000)
 
 
+@pytest.mark.parametrize("planes,atol", [(2, 5e-5), (3, 3e-6)])
+def test_halo_convolutions_forward_and_data_gradients(planes, atol):
+    """xb_gemm_halo_tc (activation tile resident in shared memory, taps = descriptor offsets into it): conv3 forward, its data
+    gradient, and the four stride phases of conv2's data gradient in ONE launch - against float64 convolutions / autograd, with
+    masks, fused column sums and the padded / strided output placements BoxNatureCNN uses.  B = 37 images: 37 * 144 raster
+    positions are not a multiple of the 128-position M tile, and tiles straddle image boundaries."""
+    import torch.nn as nn
+    from xuance_b200.torch.utils import tc_conv as tc
+    torch.manual_seed(13)
+    B = 37
+    convs = [nn.Conv2d(4, 32, 8, 4, padding=2), nn.Conv2d(32, 64, 4, 2, padding=1), nn.Conv2d(64, 64, 3, 1, padding=1)]
+    enc = tc.BoxNatureCNN([c.to(DEV) for c in convs], None, (84, 84, 4), backend=tc.CudaBackend(planes))
+    P = enc._plan(B)
+    hp1, hp2, off1, W1p, xo1 = P["hp1"], P["hp2"], P["off1"], P["W1p"], P["xo1"]
+    w2, w3, b3 = convs[1].weight.detach(), convs[2].weight.detach(), convs[2].bias.detach()
+    pad2 = lambda t: torch.cat([torch.zeros_like(t[:, :, :1]), t, torch.zeros_like(t[:, :, :1])], 2).reshape(planes, B * hp2, 10, 64)
+    # conv3 forward from the padded act2
+    a2 = torch.rand(B, 10, 10, 64, device=DEV)
+    act2 = pad2(tc.split_bf16(a2, planes))
+    out3 = torch.full((B * 100, 64), float("nan"), device=DEV)
+    act3 = torch.zeros(planes, B * 100, 64, dtype=torch.bfloat16, device=DEV)
+    tc.gemm_halo(act2, tc.pack_conv_weight(w3, planes), P["h_fwd3"], bias=b3, relu=True, out_f32=out3, out_pl=act3, out_ld=64)
+    want3 = F.relu(F.conv2d(a2.permute(0, 3, 1, 2).double(), w3.double(), b3.double(), stride=1, padding=1)).permute(0, 2, 3, 1)
+    np.testing.assert_allclose(out3.view(B, 10, 10, 64).cpu().numpy(), want3.cpu().numpy(), rtol=0, atol=atol)
+    np.testing.assert_allclose(act3.float().sum(0).view(B, 10, 10, 64).cpu().numpy(), want3.cpu().numpy(), rtol=0, atol=atol)
+    # conv3 data gradient into act2's padded layout, mask = act2 plane 0, column sums
+    g3 = torch.randn(B, 10, 10, 64, device=DEV)
+    g3p = pad2(tc.split_bf16(g3, planes))
+    x2 = a2.double().permute(0, 3, 1, 2).requires_grad_(True)
+    (dx2,) = torch.autograd.grad(F.conv2d(x2, w3.double(), stride=1, padding=1), x2, g3.double().permute(0, 3, 1, 2))
+    want = dx2.permute(0, 2, 3, 1) * (act2[0].float().view(B, hp2, 10, 64)[:, 1:11] > 0)
+    d2 = torch.zeros(planes, B * hp2, 10, 64, dtype=torch.bfloat16, device=DEV)
+    cs2 = torch.full((P["h_dg3"].m_tiles, 64), float("nan"), device=DEV)
+    tc.gemm_halo(g3p, tc.split_bf16(tc.dgrad_weight_matrix(w3, P["taps3"]), planes), P["h_dg3"], out_pl=d2, out_ld=64,
+                 relu_mask=act2[0], colsum=cs2)
+    got2 = d2.float().sum(0).view(B, hp2, 10, 64)
+    np.testing.assert_allclose(got2[:, 1:11].cpu().numpy(), want.cpu().numpy(), rtol=0, atol=atol * 4)
+    assert float(got2[:, 0].abs().max()) == 0.0 and float(got2[:, 11].abs().max()) == 0.0
+    np.testing.assert_allclose(tc.bias_grad(cs2, 64).cpu().numpy(), want.sum((0, 1, 2)).cpu().numpy(), rtol=0, atol=atol * 3000)
+    # conv2 data gradient: the four stride phases as the sub-items of one launch, into act1's padded layout (mask: act1 plane 0)
+    a1 = torch.rand(B, 21, 21, 32, device=DEV) - 0.3
+    act1 = torch.zeros(planes, B, hp1, W1p, 32, dtype=torch.bfloat16, device=DEV)
+    act1[:, :, off1:off1 + 21, xo1:xo1 + 21] = tc.split_bf16(a1, planes)
+    act1 = act1.view(planes, B * hp1, W1p, 32)
+    g2 = torch.randn(B, 10, 10, 64, device=DEV)
+    g2p = pad2(tc.split_bf16(g2, planes))
+    x1 = a1.double().permute(0, 3, 1, 2).requires_grad_(True)
+    (dx1,) = torch.autograd.grad(F.conv2d(x1, w2.double(), stride=2, padding=1), x1, g2.double().permute(0, 3, 1, 2))
+    mask1 = act1[0].float().view(B, hp1, W1p, 32)[:, off1:off1 + 21, xo1:xo1 + 21] > 0
+    want1 = dx1.permute(0, 2, 3, 1) * mask1
+    d1 = torch.zeros(planes, B * hp1, 21, 32, dtype=torch.bfloat16, device=DEV)
+    wd2 = torch.cat([tc.split_bf16(tc.dgrad_weight_matrix(w2, taps), planes) for _, taps in P["dg2"]], 1).contiguous()
+    cs1 = torch.full((P["h_dg2"].m_tiles, 32), float("nan"), device=DEV)
+    tc.gemm_halo(g2p, wd2, P["h_dg2"], out_pl=d1, out_ld=32, relu_mask=act1[0], colsum=cs1)
+    got1 = d1.float().sum(0).view(B, hp1, 21, 32)
+    np.testing.assert_allclose(got1[:, off1:off1 + 21].cpu().numpy(), want1.cpu().numpy(), rtol=0, atol=atol * 4)
+    assert float(got1[:, :off1].abs().max()) == 0.0 and off1 + 21 == hp1
+    np.testing.assert_allclose(tc.bias_grad(cs1, 32).cpu().numpy(), want1.sum((0, 1, 2)).cpu().numpy(), rtol=0, atol=atol * 8000)
+
+
 @pytest.mark.parametrize("planes,fwd_tol,grad_tol", [(2, 1e-4, 2e-2), (3, 2e-5, 2e-3)])
 def test_encoder_matches_cudnn_fp32(planes, fwd_tol, grad_tol):
     """Whole encoder forward + backward vs the cuDNN fp32 path.  Per-layer gradients with a given mask are pinned above; here

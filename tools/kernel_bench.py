@@ -332,6 +332,13 @@ def main():
                 tc.gemm_box(g3, wd, bg, out_pl=d1, out_ld=32, relu_mask=act1[0])
         us = timeit(run_dg2, R)
         add(entry("K12-box data gradient conv2 (P=3, 4 phases)", f"M={B * 441} N=32 K=256", us, 4 * g3.numel() * 2 + d1.numel() * 2, hbm, 2.0 * B * 100 * 64 * 512, tpk))
+        us = timeit(lambda: tc.gemm_halo(act2, w3, P["h_fwd3"], relu=True, out_pl=out3, out_ld=64), R)
+        add(entry("K12-halo forward conv3 (P=3)", f"M={B * 100} N=64 K=576", us, act2.numel() * 2 + out3.numel() * 2, hbm, 2.0 * B * 100 * 64 * 576, tpk))
+        us = timeit(lambda: tc.gemm_halo(g3, wd3, P["h_dg3"], out_pl=d2, out_ld=64, relu_mask=act2[0]), R)
+        add(entry("K12-halo data gradient conv3 (P=3)", f"M={B * 100} N=64 K=576", us, g3.numel() * 2 + d2.numel() * 2, hbm, 2.0 * B * 100 * 64 * 576, tpk))
+        wd2_all = torch.cat(wds, 1).contiguous()
+        us = timeit(lambda: tc.gemm_halo(g3, wd2_all, P["h_dg2"], out_pl=d1, out_ld=32, relu_mask=act1[0]), R)
+        add(entry("K12-halo data gradient conv2 (P=3, 4 phases in one launch)", f"M={B * 441} N=32 K=256", us, g3.numel() * 2 + d1.numel() * 2, hbm, 2.0 * B * 100 * 64 * 512, tpk))
         for nm, xp_, bgk, K in (("conv2", act1_pairs, "fwd2", 512), ("conv3", act2, "fwd3", 576)):
             sp = tc.wgrad_box_splits(B * P["hp2"], 6, K, 64)
             us = timeit(lambda: tc.wgrad_box(xp_, g3, P[bgk], 6, sp), R)

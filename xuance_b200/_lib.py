@@ -47,6 +47,10 @@ _SIGNATURES = {
     "xb_gemm_box_tc": (c_int, [c_int, c_int, _P, c_int64, c_int, c_int, c_int64, c_int, c_int, c_int, c_int, c_int, _P, _P, _P,
                                _P, c_int64, _P, _P] + [c_int] * 9 + [_P, c_int64, c_int, _P]
                        + [c_int] * 6 + [c_int64, c_int, _P, _P]),
+    "xb_gemm_halo_tc": (c_int, [c_int, c_int, _P, c_int64, c_int, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, c_int64, _P, _P,
+                                c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, c_int64, c_int, _P, c_int, c_int,
+                                c_int, c_int, _P, _P, c_int64, c_int, c_int, _P, _P]),
+    "xb_debug_k12_timing": (c_int, [_P, c_int]),
     "xb_debug_tma_box": (c_int, [_P, c_int64] + [c_int] * 12 + [ctypes.c_uint32, _P, ctypes.c_uint32, _P]),
     "xb_wgrad_box_tc": (c_int, [c_int, c_int, _P, c_int64, c_int, c_int, c_int64, c_int, c_int, c_int, c_int, c_int, _P, _P, _P,
                                 _P, c_int64, c_int64, c_int, c_int, _P, _P]),

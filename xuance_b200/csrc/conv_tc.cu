@@ -34,6 +34,13 @@ constexpr int EPI_WARPS = 4, PROD_WARPS = XB_CONV_PRODUCERS / 32;
 constexpr int MMA_WARP = EPI_WARPS;
 constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;
 constexpr int MAX_STAGES = 6;
+constexpr int XB_HALO_MAX_CHUNKS = 16;
+constexpr int XB_K12_MAX_DYN_SMEM = 212 * 1024;      // + ~14 KB static (barriers, bias, column sums, tap table) <= 227 KB
+
+// Optional role timing (XB_K12_TIMING=1): clock64 cycles each role of CTA b spent inside its barrier waits, written at kernel
+// exit to xb_k12_timing[b][..]: 0 MMA total, 1 MMA wait full (operands), 2 MMA wait acc_empty (epilogue), 3 MMA wait a_full (halo
+// tile), 4 producer total, 5 producer wait empty (ring), 6 producer wait a_empty, 7 epilogue total, 8 epilogue wait acc_full
+__device__ unsigned long long xb_k12_timing[160][12];
 
 struct ConvParams {
     // TMA descriptors of the operands that are plain matrices (bf16 planes as the outermost dimension): the B operand
@@ -50,6 +57,19 @@ struct ConvParams {
     int a_box, box_w, box_h, box_hp, box_y0, box_y1, box_rs, box_chunks;
     XbDiv box_div_w, box_div_hp;
     int16_t box_c0[16], box_w0[16], box_r[16];
+    // a_halo: stride-1 gathers over a 64-channel padded-row tensor [planes][B*hp rows][W pixels][64] with the activation tile
+    // RESIDENT in shared memory: the sites are the positions P of the haloed raster (row R, column hc: pixel hc + halo_w0,
+    // halo_w columns per row), an M tile is 128 consecutive positions, and ONE box per plane of halo_rows rows x halo_w pixels
+    // (OOB pixels / rows zero-filled) holds every input any tap of the tile reads; chunk kc of sub-item nt reads the 128
+    // consecutive tile rows that start halo_shift[nt*halo_chunks + kc] = dr*halo_w + dc positions after the site's own - a
+    // descriptor offset, not a new load.  Only the weights stream through the ring.  The n tiles of an M tile (stride phases
+    // of a data gradient: own weights rows nt*N.., own output placement sub_oy0 / sub_ox0 and valid extent sub_y1 / sub_x1)
+    // run back to back on the same tile.
+    int a_halo, halo_w, halo_w0, halo_rows, halo_lo, halo_chunks, halo_same_cols, halo_bo;
+    int64_t halo_positions;                // B * hp * halo_w
+    XbDiv halo_div_w;
+    int16_t halo_shift[XB_HALO_MAX_CHUNKS];
+    int16_t sub_oy0[4], sub_ox0[4], sub_y1[4], sub_x1[4];
     XbConvGeom g;                          // g.N = columns per work item (the tile width N)
     const __nv_bfloat16 *in[3];            // A planes: [B, IH, IW, C]
     const __nv_bfloat16 *w[3];             // B planes.  forward: weight [N_total, K].  weight gradient: output gradient [P, w_ld]
@@ -65,6 +85,8 @@ struct ConvParams {
     float *out_f32;                        // forward: nullable.  weight gradient: partials [splits, K, N_total]
     int64_t M;                             // sites B * OY * OX (GEMM rows forward, reduction length for the weight gradient)
     int relu, stages, p_out;
+    uint32_t dyn_smem;                     // dynamic shared memory of the launch (0: stages * stage bytes)
+    int timing;                            // XB_K12_TIMING: fill xb_k12_timing
     // forward: placement of site (b, y, x): row ((b*out_H + y*oys + oy0)*out_W + x*oxs + ox0) of an output matrix whose
     // rows are out_ld elements apart; work item (m tile, n tile nt) fills columns [out_c0 + nt*N, out_c0 + (nt+1)*N)
     int out_H, out_W, oys, oxs, oy0, ox0;
@@ -117,6 +139,33 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr, uint32_t
     d |= (uint64_t)2 << 61;                                   // layout type SWIZZLE_128B
     return d;
 }
+// the same for a start address that is NOT a multiple of the 1024-byte swizzle pattern (a window of a larger tile that starts
+// at an arbitrary 128-byte row); with_offset sets the matrix base offset, bits 49-51 = (start address >> 7) & 7 - NOT needed
+// on B200: the swizzle follows the absolute address bits (see xb_gemm_halo_tc)
+__device__ __forceinline__ uint64_t make_desc_sw128_at(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, int with_offset) {
+    uint64_t d = make_desc_sw128(smem_addr, lbo_bytes, sbo_bytes);
+    if (with_offset) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
+    return d;
+}
+// tcgen05.mma / tcgen05.commit predicated on `leader` (1 in exactly one lane): the warp stays converged around them
+__device__ __forceinline__ void mma_bf16_if(uint32_t leader, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%6, %6, %6, %6}, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_if(uint32_t leader, uint64_t *bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(leader)
+        : "memory");
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
@@ -147,7 +196,7 @@ template <bool WGRAD, int PA, int PB>
 __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
     static_assert(PA >= 1 && PA <= PB && PB <= 3, "plane counts");
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_full[2], acc_empty[2];
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_full[2], acc_empty[2], a_full[2], a_empty[2];
     __shared__ uint32_t tmem_slot;
     __shared__ float s_bias[256];
     __shared__ float s_colsum[4][256];                // per epilogue warp: column sums of its 32 rows (ConvParams.colsum)
@@ -157,15 +206,27 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
     const XbConvGeom &g = p.g;
     const int N = g.N, K = g.T * g.C, S = p.stages;
     const uint32_t a_plane = xb_conv_a_plane_bytes(), w_plane = xb_conv_w_plane_bytes(N);
-    const uint32_t stage_bytes = PA * a_plane + PB * w_plane;
+    const bool halo = !WGRAD && p.a_halo;
+    const uint32_t halo_plane = halo ? (((uint32_t)(p.halo_rows * p.halo_w) * 128u + 1023u) & ~1023u) : 0u;   // one plane of a tile
+    const uint32_t a_buf_bytes = PA * halo_plane, ring_off = 2u * a_buf_bytes;       // two resident A tiles, then the ring
+    const uint32_t stage_bytes = (halo ? 0u : PA * a_plane) + PB * w_plane;
     const int box_rows = p.box_w * p.box_h;                  // a_box: rows of a tile that hold sites (<= 128)
     const int64_t m_tiles = WGRAD ? (K + TILE_M - 1) / TILE_M
+                                  : halo ? (p.halo_positions + TILE_M - 1) / TILE_M
                                   : (p.a_box ? ((int64_t)g.B * p.box_hp + p.box_h - 1) / p.box_h : (p.M + TILE_M - 1) / TILE_M);
     const int64_t mn_tiles = m_tiles * p.n_tiles;
-    const int64_t n_work = WGRAD ? mn_tiles * p.splits : mn_tiles;
+    // the persistent loop walks n_work outer items with n_inner sub-items each: (m tile, n tile[, split]) one by one, or in
+    // halo mode M tiles with their n tiles back to back (they share the resident activation tile)
+    const int64_t n_work = WGRAD ? mn_tiles * p.splits : (halo ? m_tiles : mn_tiles);
+    const int n_inner = halo ? p.n_tiles : 1;
+    // halo: first tensor row of the tile of M tile `t` (floor((128 t + halo_lo) / halo_w), the numerator kept positive)
+    auto halo_row_lo = [&](int64_t t) -> int {
+        const uint32_t num = (uint32_t)(t * TILE_M + p.halo_lo + 4 * p.halo_w);
+        return (int)xb_div(num, p.halo_div_w) - 4;
+    };
     // chunks of one work item
     auto chunks_of = [&](int64_t w) -> int {
-        if (!WGRAD) return p.a_box ? p.box_chunks : K / KC;
+        if (!WGRAD) return halo ? p.halo_chunks : (p.a_box ? p.box_chunks : K / KC);
         const int64_t sp = w / mn_tiles, s0 = sp * p.sites_per_split;
         const int64_t cnt = (p.M - s0) < p.sites_per_split ? (p.M - s0) : p.sites_per_split;
         // a_box: the reduction runs over merged grid rows (p.M of them), box_h rows = box_h * box_w <= 64 sites per chunk
@@ -178,12 +239,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
             // one asynchronous arrival per producer thread (+ the expect_tx arrival of the thread that issues the TMA copies)
-            mbar_init(&full_bar[s], PROD_WARPS * 32 + ((p.a_tma || p.b_tma) ? 1 : 0));
+            mbar_init(&full_bar[s], halo ? 1 : PROD_WARPS * 32 + ((p.a_tma || p.b_tma) ? 1 : 0));
             mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&acc_full[a], 1);
             mbar_init(&acc_empty[a], EPI_WARPS);
+            mbar_init(&a_full[a], 1);
+            mbar_init(&a_empty[a], 1);
         }
         mbar_fence_init();
     }
@@ -192,7 +255,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                      "r"(tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    if (!p.a_box)
+    if (!p.a_box && !halo)
         for (int i = tid; i < K / 8; i += THREADS) s_units[i] = xb_unit(g, i);
     if (WGRAD && p.a_box) {
         // a chunk holds box_h * box_w <= 64 sites: the rows of each 64-site block that no box ever writes must read as zero
@@ -205,20 +268,44 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     const uint32_t smem_base = smem_u32(smem);
+    unsigned long long t_wait[3] = {0, 0, 0};
+    const unsigned long long t_begin = p.timing ? clock64() : 0ull;
+    auto timed_wait = [&](uint64_t *bar, uint32_t parity, int slot) {
+        if (p.timing) {
+            const unsigned long long t0 = clock64();
+            mbar_wait(bar, parity);
+            t_wait[slot] += clock64() - t0;
+        } else {
+            mbar_wait(bar, parity);
+        }
+    };
     if ((p.a_tma || p.b_tma) && (smem_base & 1023u)) __trap();     // the 128-byte swizzle pattern repeats every 1024 B
 
     if (warp > MMA_WARP) {
         // ------------------------------------------------------------------ producers (256 threads)
         const int pt = tid - (MMA_WARP + 1) * 32;
-        uint32_t it = 0;
+        uint32_t it = 0, tile_it = 0;
+        if (!(halo && pt != 0))                                // halo: both operands by TMA, one thread drives them
         for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+          if (halo) {
+              // the activation tile of this M tile: one box per plane into the buffer the tile before the last one used
+              const uint32_t buf = tile_it & 1u;
+              timed_wait(&a_empty[buf], ((tile_it >> 1) & 1u) ^ 1u, 1);
+              mbar_expect_tx(&a_full[buf], (uint32_t)PA * (uint32_t)(p.halo_rows * p.halo_w) * 128u);
+              const int r_lo = halo_row_lo(w);
+#pragma unroll
+              for (int q = 0; q < PA; ++q)
+                  tma_load_box(smem_base + buf * a_buf_bytes + q * halo_plane, &p.tm_a, 0, p.halo_w0, r_lo, 1, q, &a_full[buf]);
+              ++tile_it;
+          }
+          for (int sub = 0; sub < n_inner; ++sub) {
             const int n_chunks = chunks_of(w);
             const int64_t sp = WGRAD ? w / mn_tiles : 0;
             const int64_t rem = WGRAD ? w - sp * mn_tiles : w;
-            const int64_t mt = rem / p.n_tiles;
-            const int nt = (int)(rem - mt * p.n_tiles);
+            const int64_t mt = halo ? w : rem / p.n_tiles;
+            const int nt = halo ? sub : (int)(rem - mt * p.n_tiles);
             XbSite sites[4];                                   // forward: the four rows this thread feeds, fixed for the tile
-            if (!WGRAD && !p.a_tma) {
+            if (!WGRAD && !p.a_tma && !halo) {
 #pragma unroll
                 for (int gi = 0; gi < 4; ++gi) sites[gi] = xb_site(g, mt * TILE_M + xb_fwd_row(pt, gi), p.M);
             }
@@ -226,9 +313,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
             const int64_t site_end = WGRAD ? ((sp + 1) * p.sites_per_split < p.M ? (sp + 1) * p.sites_per_split : p.M) : 0;
             for (int kc = 0; kc < n_chunks; ++kc) {
                 const int stage = (int)(it % (uint32_t)S);
-                mbar_wait(&empty_bar[stage], ((it / (uint32_t)S) & 1u) ^ 1u);
-                const uint32_t base = smem_base + (uint32_t)stage * stage_bytes;
-                const uint32_t wbase = base + PA * a_plane;
+                timed_wait(&empty_bar[stage], ((it / (uint32_t)S) & 1u) ^ 1u, 0);
+                const uint32_t base = smem_base + ring_off + (uint32_t)stage * stage_bytes;
+                const uint32_t wbase = base + (halo ? 0u : PA * a_plane);
                 auto emit_a = [&](uint32_t dst_off, int64_t src) {       // src < 0: the 16 bytes are zero-filled
                     if (p.a_tma) return;
                     const uint32_t nbytes = src >= 0 ? 16u : 0u;
@@ -286,63 +373,92 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                         }
                     }
                 }
-                if (!WGRAD) xb_stage_fwd(g, s_units, pt, sites, kc, emit_a, emit_w);
-                else xb_stage_wgrad(g, s_units, pt, mt, site0, site_end, p.M, p.w_ld, nt * N, emit_a, emit_w);
-                // asynchronous publication: the barrier receives this thread's arrival when the copies issued above have
-                // landed - the producer never waits for its own loads, so up to `stages` chunks of loads are in flight
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full_bar[stage])) : "memory");
+                if (!halo) {
+                    if (!WGRAD) xb_stage_fwd(g, s_units, pt, sites, kc, emit_a, emit_w);
+                    else xb_stage_wgrad(g, s_units, pt, mt, site0, site_end, p.M, p.w_ld, nt * N, emit_a, emit_w);
+                    // asynchronous publication: the barrier receives this thread's arrival when the copies issued above have
+                    // landed - the producer never waits for its own loads, so up to `stages` chunks of loads are in flight
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full_bar[stage])) : "memory");
+                }
                 ++it;
             }
+          }
         }
     } else if (warp == MMA_WARP) {
-        // ------------------------------------------------------------------ MMA issue (one thread)
-        if (lane == 0) {
-            uint32_t it = 0, tcount = 0;
-            for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
-                const int n_chunks = chunks_of(w);
-                const uint32_t a = tcount & 1u;
-                mbar_wait(&acc_empty[a], ((tcount >> 1) & 1u) ^ 1u);     // epilogue drained this accumulator
+        // ------------------------------------------------------------------ MMA issue
+        // The whole warp runs the loop on warp-uniform values and only the tcgen05 instructions are predicated on lane 0:
+        // under a divergent `if (lane == 0)` the compiler wraps every tcgen05.mma in a register -> uniform-register broadcast
+        // loop and rebuilds both 64-bit descriptors per instruction (~35 dependent instructions, ~180 clk per MMA measured -
+        // the issuing thread, not the tensor pipe or the loads, bounded every forward launch: tools/k12_timing.py).  Here a
+        // descriptor is a per-launch TEMPLATE (layout, LBO, SBO) plus a start address in 16-byte units: one add per MMA.
+        const uint32_t leader = lane == 0 ? 1u : 0u;
+        //  A: halo     128-byte swizzle K-major window of the resident tile, K step 32 B, planes halo_plane apart
+        //     cp.async no-swizzle canonical layout (conv_index.h), K step = two core matrices = 256 B
+        //     TMA      128-byte swizzle.  K-major: rows of 128 B, K step 32 B.  MN-major (weight gradient): two blocks of 64
+        //              columns, each [planes][64 sites][128 B]: plane stride a_plane/2, block stride PA*a_plane/2, K step 2048 B
+        //  B: the first (PB - pa) planes, adjacent in the stage, are ONE operand of (PB - pa) * N rows (same three layouts;
+        //     MN-major: one 64-column block per plane, blocks w_plane apart)
+        uint64_t a_tmpl, b_tmpl;
+        uint32_t a_ks, a_pl, b_ks;                           // steps in 16-byte units: per K step of 16, per A plane
+        if (halo) a_tmpl = make_desc_sw128_at(0, 16, 1024, 0), a_ks = 32 >> 4, a_pl = halo_plane >> 4;
+        else if (!p.a_tma) a_tmpl = make_desc(0, KC), a_ks = 256 >> 4, a_pl = a_plane >> 4;
+        else if (!WGRAD) a_tmpl = make_desc_sw128(0, 16, 1024), a_ks = 32 >> 4, a_pl = a_plane >> 4;
+        else a_tmpl = make_desc_sw128(0, PA * (a_plane / 2), 1024), a_ks = 2048 >> 4, a_pl = (a_plane / 2) >> 4;
+        if (!p.b_tma) b_tmpl = make_desc(0, KC), b_ks = 256 >> 4;
+        else if (!WGRAD) b_tmpl = make_desc_sw128(0, 16, 1024), b_ks = 32 >> 4;
+        else b_tmpl = make_desc_sw128(0, w_plane, 1024), b_ks = 2048 >> 4;
+        uint32_t idesc[PA];
+#pragma unroll
+        for (int pa = 0; pa < PA; ++pa) idesc[pa] = WGRAD ? make_idesc_mn(TILE_M, (PB - pa) * N) : make_idesc(TILE_M, (PB - pa) * N);
+        uint32_t it = 0, tcount = 0, tile_it = 0;
+        for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+          uint32_t halo_base = 0;
+          int halo_s0 = 0;
+          if (halo) {
+              const uint32_t buf = tile_it & 1u;
+              timed_wait(&a_full[buf], (tile_it >> 1) & 1u, 2);
+              tc_fence_after();
+              halo_base = smem_base + buf * a_buf_bytes;
+              halo_s0 = (int)(w * TILE_M) - halo_row_lo(w) * p.halo_w;        // tile row of the site of MMA row 0
+          }
+          for (int sub = 0; sub < n_inner; ++sub) {
+            const int n_chunks = chunks_of(w);
+            const uint32_t a = tcount & 1u;
+            timed_wait(&acc_empty[a], ((tcount >> 1) & 1u) ^ 1u, 1);     // epilogue drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem + a * acc_cols;
+            uint32_t acc = 0;
+            for (int kc = 0; kc < n_chunks; ++kc) {
+                const int stage = (int)(it % (uint32_t)S);
+                timed_wait(&full_bar[stage], (it / (uint32_t)S) & 1u, 0);
+                fence_proxy_async();       // the stage was written by cp.async (generic proxy); the MMA reads it through the async proxy
                 tc_fence_after();
-                const uint32_t d_tmem = tmem + a * acc_cols;
-                uint32_t acc = 0;
-                for (int kc = 0; kc < n_chunks; ++kc) {
-                    const int stage = (int)(it % (uint32_t)S);
-                    mbar_wait(&full_bar[stage], (it / (uint32_t)S) & 1u);
-                    fence_proxy_async();       // the stage was written by cp.async (generic proxy); the MMA reads it through the async proxy
-                    tc_fence_after();
-                    const uint32_t base = smem_base + (uint32_t)stage * stage_bytes;
-                    const uint32_t w_addr = base + PA * a_plane;
+                const uint32_t base = smem_base + ring_off + (uint32_t)stage * stage_bytes;
+                const uint32_t w_addr = base + (halo ? 0u : PA * a_plane);
+                const uint32_t a_addr = halo ? halo_base + (uint32_t)(halo_s0 + p.halo_shift[sub * p.halo_chunks + kc]) * 128u : base;
+                // start addresses stay below 2^18 bytes: adding 16-byte units to the template never carries out of the field
+                const uint64_t a0 = a_tmpl + (uint64_t)(a_addr >> 4), b0 = b_tmpl + (uint64_t)(w_addr >> 4);
 #pragma unroll
-                    for (int ks = 0; ks < KC / 16; ++ks) {
-                        // B operand: the first (PB - pa) planes, adjacent in the stage, are ONE operand of (PB - pa) * N rows.
-                        //  cp.async : no-swizzle canonical layout (conv_index.h), K step = two core matrices = 256 B
-                        //  TMA      : 128-byte swizzle.  K-major: rows of 128 B, K step = 32 B inside the row.
-                        //             MN-major (weight gradient, N = 64): one 64-column block per plane, blocks w_plane apart,
-                        //             K step = 16 sites = 2048 B
-                        const uint64_t b_desc = !p.b_tma ? make_desc(w_addr + ks * 256, KC)
-                                                : (!WGRAD ? make_desc_sw128(w_addr + ks * 32, 16, 1024)
-                                                          : make_desc_sw128(w_addr + ks * 2048, w_plane, 1024));
+                for (int ks = 0; ks < KC / 16; ++ks) {
 #pragma unroll
-                        for (int pa = 0; pa < PA; ++pa) {
-                            // A plane pa x B planes 0 .. PB-1-pa -> accumulator groups pa .. PB-1.
-                            // pa = 0 covers every group, so its first instruction of a work item (acc = 0) initialises them all.
-                            const int nb = PB - pa;
-                            const uint32_t idesc = WGRAD ? make_idesc_mn(TILE_M, nb * N) : make_idesc(TILE_M, nb * N);
-                            // A operand by TMA (Linear layers).  K-major: [128 rows][128 B] per plane.  MN-major: two blocks of
-                            // 64 columns, each [planes][64 sites][128 B]: plane stride a_plane/2, block stride PA*a_plane/2
-                            const uint64_t a_desc = !p.a_tma ? make_desc(base + pa * a_plane + ks * 256, KC)
-                                                    : (!WGRAD ? make_desc_sw128(base + pa * a_plane + ks * 32, 16, 1024)
-                                                              : make_desc_sw128(base + pa * (a_plane / 2) + ks * 2048, PA * (a_plane / 2), 1024));
-                            mma_bf16(d_tmem + (uint32_t)(pa * N), a_desc, b_desc, idesc, pa == 0 ? acc : 1u);
-                        }
-                        acc = 1;
+                    for (int pa = 0; pa < PA; ++pa) {
+                        // A plane pa x B planes 0 .. PB-1-pa -> accumulator groups pa .. PB-1.
+                        // pa = 0 covers every group, so its first instruction of a work item (acc = 0) initialises them all.
+                        mma_bf16_if(leader, d_tmem + (uint32_t)(pa * N), a0 + (uint64_t)(ks * a_ks + pa * a_pl), b0 + (uint64_t)(ks * b_ks),
+                                    idesc[pa], pa == 0 ? acc : 1u);
                     }
-                    mma_commit(&empty_bar[stage]);     // the stage is free once these MMAs have read it
-                    ++it;
+                    acc = 1;
                 }
-                mma_commit(&acc_full[a]);
-                ++tcount;
+                mma_commit_if(leader, &empty_bar[stage]);     // the stage is free once these MMAs have read it
+                ++it;
             }
+            mma_commit_if(leader, &acc_full[a]);
+            ++tcount;
+          }
+          if (halo) {
+              mma_commit_if(leader, &a_empty[tile_it & 1u]);         // the tile is free once every MMA issued so far has read it
+              ++tile_it;
+          }
         }
         __syncwarp();
     } else {
@@ -350,14 +466,28 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
         const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
         uint32_t tcount = 0;
         for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+          for (int sub = 0; sub < n_inner; ++sub) {
             const uint32_t a = tcount & 1u;
             const int64_t sp = WGRAD ? w / mn_tiles : 0;
             const int64_t rem = WGRAD ? w - sp * mn_tiles : w;
-            const int64_t mt = rem / p.n_tiles;
-            const int nt = (int)(rem - mt * p.n_tiles);
+            const int64_t mt = halo ? w : rem / p.n_tiles;
+            const int nt = halo ? sub : (int)(rem - mt * p.n_tiles);
+            const int ncol = (halo && p.halo_same_cols) ? 0 : nt;             // column block of the output this item writes
             bool live;
             int64_t orow = 0, mrow = 0;                                   // element offsets of the output row / of its mask row
-            if (!WGRAD && p.a_box) {
+            if (halo) {
+                const int64_t P = mt * TILE_M + tid;                       // position in the haloed raster
+                const uint32_t R = xb_div((uint32_t)P, p.halo_div_w);      // merged (image, padded row) index
+                const int x = (int)((uint32_t)P - R * (uint32_t)p.halo_w) + p.halo_w0;
+                const int b = (int)xb_div(R, p.box_div_hp), y = (int)(R - (uint32_t)b * (uint32_t)p.box_hp);
+                live = P < p.halo_positions && x >= 0 && x <= p.sub_x1[nt] && y >= p.box_y0 && y <= p.sub_y1[nt];
+                if (live) {
+                    const int64_t orw = (int64_t)b * p.out_H + ((y - p.box_y0) * p.oys + p.sub_oy0[nt]);
+                    const int ox = x * p.oxs + p.sub_ox0[nt];
+                    orow = (orw * p.out_W + ox) * p.out_ld + p.out_c0 + (int64_t)ncol * N;
+                    mrow = (orw * p.mask_W + ox + p.mask_x0) * p.mask_ld + p.mask_c0 + (int64_t)ncol * N;
+                }
+            } else if (!WGRAD && p.a_box) {
                 const int gr = (int)xb_div((uint32_t)tid, p.box_div_w), x = tid - gr * p.box_w;
                 const int64_t R = mt * p.box_h + gr;                       // merged (image, padded row) index
                 const int b = (int)xb_div((uint32_t)R, p.box_div_hp), y = (int)(R - (int64_t)b * p.box_hp);
@@ -386,10 +516,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
             if (!WGRAD) {
                 // the bias slice of this n tile (only the epilogue warps read / write s_bias; named barrier 1, 128 threads)
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int i = tid; i < N; i += EPI_WARPS * 32) s_bias[i] = p.bias ? p.bias[nt * N + i] : 0.f;
+                for (int i = tid; i < N; i += EPI_WARPS * 32) s_bias[i] = p.bias ? p.bias[ncol * N + i] : 0.f;
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
-            mbar_wait(&acc_full[a], (tcount >> 1) & 1u);
+            timed_wait(&acc_full[a], (tcount >> 1) & 1u, 0);
             tc_fence_after();
             for (int c0 = 0; c0 < N; c0 += 32) {
                 float v[32];
@@ -474,7 +604,15 @@ __global__ void __launch_bounds__(THREADS, 1) conv_tc_kernel(const __grid_consta
                         ((s_colsum[0][i] + s_colsum[1][i]) + s_colsum[2][i]) + s_colsum[3][i];
             }
             ++tcount;
+          }
         }
+    }
+    if (p.timing && blockIdx.x < 160) {
+        const unsigned long long tot = clock64() - t_begin;
+        unsigned long long *o = xb_k12_timing[blockIdx.x];
+        if (warp == MMA_WARP && lane == 0) o[0] = tot, o[1] = t_wait[0], o[2] = t_wait[1], o[3] = t_wait[2];
+        if (warp == MMA_WARP + 1 && lane == 0) o[4] = tot, o[5] = t_wait[0], o[6] = t_wait[1];
+        if (tid == 0) o[7] = tot, o[8] = t_wait[0];
     }
     // ---- teardown
     tc_fence_before();
@@ -697,7 +835,16 @@ int fill_params(ConvParams &p, int pa, int pb, const void *in, int64_t in_plane,
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) return XB_ERANGE;
     p.stages = stages;
-    p.a_tma = p.b_tma = p.a_box = 0;
+    p.a_tma = p.b_tma = p.a_box = p.a_halo = 0;
+    p.dyn_smem = 0;
+    {
+        static int timing = -1;
+        if (timing < 0) {
+            const char *e = getenv("XB_K12_TIMING");
+            timing = (e && atoi(e) != 0) ? 1 : 0;
+        }
+        p.timing = timing;
+    }
     p.box_w = p.box_h = p.box_hp = 1, p.box_y0 = p.box_y1 = 0, p.box_rs = 1, p.box_chunks = 0;
     return XB_OK;
 }
@@ -706,11 +853,11 @@ template <bool WGRAD, int PA, int PB>
 int launch_pp(const ConvParams &p, int64_t work, void *stream) {
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(conv_tc_kernel<WGRAD, PA, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(conv_tc_kernel<WGRAD, PA, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, XB_K12_MAX_DYN_SMEM);
         attr = true;
     }
     const int grid = (int)(work < xb_sm_count() ? work : xb_sm_count());
-    const size_t smem = (size_t)p.stages * (PA * xb_conv_a_plane_bytes() + PB * xb_conv_w_plane_bytes(p.g.N));
+    const size_t smem = p.dyn_smem ? p.dyn_smem : (size_t)p.stages * (PA * xb_conv_a_plane_bytes() + PB * xb_conv_w_plane_bytes(p.g.N));
     conv_tc_kernel<WGRAD, PA, PB><<<grid, THREADS, smem, (cudaStream_t)stream>>>(p);
     return xb_launch_status();
 }
@@ -876,6 +1023,92 @@ extern "C" int xb_gemm_box_tc(int planes_a, int planes_b, const void *in, int64_
     return launch<false>(planes_a, planes_b, p, tiles, stream);
 }
 
+// The same GEMM with the activation tile resident in shared memory (ConvParams a_halo): stride-1 gathers over a 64-channel
+// padded-row tensor - a 3x3 convolution, its data gradient, the stride phases of a strided convolution's data gradient.
+extern "C" int xb_gemm_halo_tc(int planes_a, int planes_b, const void *in, int64_t in_plane, int W, int64_t in_rows, int halo_w,
+                               int halo_w0, int n_sub, int n_chunks, const int16_t *dr, const int16_t *dc, const void *w,
+                               int64_t w_plane, const float *bias, const void *relu_mask, int mask_W, int mask_x0, int B, int hp,
+                               int y0, const int16_t *sub_y1, const int16_t *sub_x1, int N, int relu, void *out_planes,
+                               int64_t out_plane, int planes_out, float *out_f32, int out_H, int out_W, int oys, int oxs,
+                               const int16_t *sub_oy0, const int16_t *sub_ox0, int64_t out_ld, int out_c0, int same_cols,
+                               float *colsum, void *stream) {
+    if (!dr || !dc || !sub_y1 || !sub_x1 || !sub_oy0 || !sub_ox0) return XB_EINVAL;
+    if (n_sub <= 0 || n_sub > 4 || n_chunks <= 0 || n_sub * n_chunks > XB_HALO_MAX_CHUNKS) return XB_ERANGE;
+    if (W <= 0 || halo_w < W || halo_w > 64 || halo_w0 > 0 || halo_w0 + halo_w < W || hp <= 0 || B <= 0 || y0 < 0) return XB_EINVAL;
+    if (in_rows != (int64_t)B * hp) return XB_EINVAL;
+    ConvParams p;
+    int8_t zero[XB_CONV_MAX_TAPS] = {0};
+    // generic checks: one "tap" of 64 channels per chunk, N columns per sub-item
+    const int rc = fill_params(p, planes_a, planes_b, in, in_plane, w, w_plane, B, 1, 1, 64, 1, 1, 1, 1, n_chunks, zero, zero,
+                               n_sub * N, N);
+    if (rc != XB_OK) return rc;
+    if (!out_planes && !out_f32) return XB_EINVAL;
+    if (out_planes && (planes_out < 1 || planes_out > 3)) return XB_EINVAL;
+    if (out_ld % 8 != 0 || out_c0 % 8 != 0 || out_plane % 8 != 0) return XB_EALIGN;
+    if ((out_planes && !xb_aligned(out_planes, 16)) || (out_f32 && !xb_aligned(out_f32, 16)) ||
+        (relu_mask && !xb_aligned(relu_mask, 16)))
+        return XB_EALIGN;
+    if (out_ld < (int64_t)out_c0 + (same_cols ? N : n_sub * N)) return XB_EINVAL;
+    if (!tma_enabled()) return XB_EINVAL;
+    // shifts: positions of the haloed raster; the tile must hold [128 t + lo, 128 t + 127 + hi] for every t
+    int lo = 0, hi = 0;
+    for (int i = 0; i < n_sub * n_chunks; ++i) {
+        // a shift is a linear offset in the raster: the pixel a VALID site (x in [0, sub_x1]) reads must stay in its own row
+        const int sx1 = sub_x1[i / n_chunks];
+        if (dc[i] < halo_w0 || sx1 + dc[i] > halo_w0 + halo_w - 1) return XB_ERANGE;
+        const int sh = dr[i] * halo_w + dc[i];
+        p.halo_shift[i] = (int16_t)sh;
+        lo = sh < lo ? sh : lo, hi = sh > hi ? sh : hi;
+    }
+    for (int i = n_sub * n_chunks; i < XB_HALO_MAX_CHUNKS; ++i) p.halo_shift[i] = 0;
+    const int halo_rows = (halo_w - 1 + TILE_M + hi - lo + halo_w - 1) / halo_w;
+    if (halo_rows > 256) return XB_ERANGE;
+    const uint32_t halo_plane = (((uint32_t)(halo_rows * halo_w) * 128u) + 1023u) & ~1023u;
+    const uint32_t a_bytes = 2u * (uint32_t)planes_a * halo_plane, stage_bytes = (uint32_t)planes_b * xb_conv_w_plane_bytes(N);
+    if (a_bytes + 2u * stage_bytes > (uint32_t)XB_K12_MAX_DYN_SMEM) return XB_ERANGE;
+    int stages = (int)(((uint32_t)XB_K12_MAX_DYN_SMEM - a_bytes) / stage_bytes);
+    p.stages = stages > MAX_STAGES ? MAX_STAGES : stages;
+    p.dyn_smem = a_bytes + (uint32_t)p.stages * stage_bytes;
+    const int64_t K = (int64_t)n_chunks * KC;
+    if (!make_tmap_box(&p.tm_a, in, 64, W, in_rows, planes_a, in_plane, 64, halo_w, halo_rows, 1)) return XB_EINVAL;
+    if (!make_tmap(&p.tm_b, w, K, (int64_t)n_sub * N, planes_b, K, w_plane, N)) return XB_EINVAL;
+    p.a_halo = 1, p.b_tma = 1;
+    p.halo_w = halo_w, p.halo_w0 = halo_w0, p.halo_rows = halo_rows, p.halo_lo = lo, p.halo_chunks = n_chunks;
+    p.halo_same_cols = same_cols ? 1 : 0;
+    // measured on B200 (tests/test_gpu_tc_conv.py, halo test): the 128-byte swizzle of a descriptor whose start is an
+    // arbitrary 128-byte row of a 1024-byte-aligned tile is a function of the ABSOLUTE shared-memory address, exactly as TMA
+    // wrote it - the matrix-base-offset field must stay 0 (XB_K12_HALO_BO=1 sets it to (addr >> 7) & 7: wrong results)
+    const char *bo = getenv("XB_K12_HALO_BO");
+    p.halo_bo = bo ? atoi(bo) : 0;
+    p.halo_positions = (int64_t)B * hp * halo_w;
+    if (p.halo_positions + 4 * halo_w + TILE_M >= ((int64_t)1 << 31)) return XB_ERANGE;
+    p.halo_div_w = xb_div_make((uint32_t)halo_w);
+    p.box_hp = hp, p.box_y0 = y0, p.box_div_hp = xb_div_make((uint32_t)hp);
+    for (int i = 0; i < 4; ++i) {
+        const int j = i < n_sub ? i : 0;
+        if (sub_y1[j] < y0 || sub_y1[j] >= hp || sub_x1[j] < 0 || sub_x1[j] >= W + 64) return XB_ERANGE;
+        if ((int64_t)(sub_y1[j] - y0) * oys + sub_oy0[j] >= out_H || (int64_t)sub_x1[j] * oxs + sub_ox0[j] >= out_W || sub_oy0[j] < 0 ||
+            sub_ox0[j] < 0)
+            return XB_EINVAL;
+        p.sub_y1[i] = sub_y1[j], p.sub_x1[i] = sub_x1[j], p.sub_oy0[i] = sub_oy0[j], p.sub_ox0[i] = sub_ox0[j];
+    }
+    p.bias = bias;
+    p.mask = (const __nv_bfloat16 *)relu_mask;
+    p.mask_W = mask_W > 0 ? mask_W : out_W, p.mask_x0 = mask_W > 0 ? mask_x0 : 0;
+    p.mask_ld = out_ld, p.mask_c0 = out_c0;
+    p.colsum = colsum;
+    __nv_bfloat16 *ob = (__nv_bfloat16 *)out_planes;
+    p.p_out = ob ? planes_out : 0;
+    for (int q = 0; q < 3; ++q) p.out[q] = (ob && q < planes_out) ? ob + q * out_plane : nullptr;
+    p.out_f32 = out_f32;
+    p.relu = relu;
+    p.out_H = out_H, p.out_W = out_W, p.oys = oys, p.oxs = oxs, p.oy0 = 0, p.ox0 = 0;
+    p.out_ld = out_ld, p.out_c0 = out_c0;
+    p.splits = 1, p.sites_per_split = 0, p.w_ld = 0;
+    const int64_t tiles = (p.halo_positions + TILE_M - 1) / TILE_M;
+    return launch<false>(planes_a, planes_b, p, tiles, stream);
+}
+
 extern "C" int xb_wgrad_gather_tc(int planes_a, int planes_b, const void *in, int64_t in_plane, const void *g, int64_t g_plane,
                                   int64_t g_ld, int B, int IH, int IW, int C, int OY, int OX, int sy, int sx, int T,
                                   const int8_t *dy, const int8_t *dx, int N, int n_tile, int splits, float *partials,
@@ -966,6 +1199,14 @@ __global__ void tma_probe_kernel(const __grid_constant__ CUtensorMap tm, int c0,
 
 // test hook: loads ONE box of the 4-D map make_tmap_box would build and returns the first out_bytes of shared memory (0xEE =
 // never written), so that the layout assumptions of the box mode can be checked byte for byte (tests/test_gpu_tc_conv.py)
+// XB_K12_TIMING=1 diagnostics: the role timing table of the last K12 launch (see xb_k12_timing), copied to a HOST array
+extern "C" int xb_debug_k12_timing(unsigned long long *out_host, int n_ctas) {
+    if (!out_host || n_ctas <= 0 || n_ctas > 160) return XB_EINVAL;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out_host, xb_k12_timing, sizeof(unsigned long long) * 12 * n_ctas);
+    return e == cudaSuccess ? XB_OK : (int)e;
+}
+
 extern "C" int xb_debug_tma_box(const void *in, int64_t in_plane, int planes, int C, int W, int64_t rows, int box_c, int box_px,
                                 int box_h, int row_step, int c0, int c1, int c2, int c3, uint32_t expect_bytes, void *out,
                                 uint32_t out_bytes, void *stream) {

@@ -202,9 +202,12 @@ def _products(pa, pb):
     return sum(pb - i for i in range(pa))
 
 
-def _log_flops(name, rows, cols, depth, pa, pb):
+def _log_flops(name, rows, cols, depth, pa, pb, useful=None):
+    """bench.py's roofline log: the ALGORITHMIC flops of a launch - 2 * useful * depth with ``useful`` = (rows x cols) pairs
+    that are real outputs (padding / halo / garbage sites of the padded layouts excluded; default rows * cols) - times the
+    plane products float32-grade arithmetic needs, and the same without the plane factor (float32-equivalent)."""
     if flop_log is not None:
-        eq = 2.0 * rows * cols * depth
+        eq = 2.0 * (rows * cols if useful is None else useful) * depth
         flop_log.append((name, "M=%d N=%d K=%d PA=%d PB=%d" % (rows, cols, depth, pa, pb), eq * _products(pa, pb), eq))
 
 
@@ -256,7 +259,8 @@ def wgrad_gather(x_pl, g_pl, geom, splits, n_tile=None):
     partials = torch.empty((splits, geom.K, N), dtype=torch.float32, device=g_pl.device)
     dy, dx = _taps(geom)
     xp, xs = _plane_arg(x_pl)
-    _log_flops("xb_wgrad_gather_tc", geom.K, N, geom.M, PA, PB)
+    um = getattr(geom, "useful_M", None)
+    _log_flops("xb_wgrad_gather_tc", geom.K, N, geom.M, PA, PB, useful=None if um is None else geom.K * N * um / geom.M)
     _lib.call("xb_wgrad_gather_tc", PA, PB, xp, xs, _lib.ptr(g_pl), g_pl.stride(0), g_pl.stride(1), geom.B, geom.IH, geom.IW,
               geom.C, geom.OY, geom.OX, geom.sy, geom.sx, geom.T, dy.data_ptr(), dx.data_ptr(), N, n_tile, splits,
               _lib.ptr(partials))
@@ -469,6 +473,12 @@ import os as _os
 # gathered; conv2 947 us box vs 851 us gathered - its 16 pixel-pair chunks re-read G once per pair of chunks)
 BOX_WGRAD = _os.environ.get("XB_K12_BOX_WGRAD", "3")
 BOX_WGRAD2, BOX_WGRAD3 = "2" in BOX_WGRAD, "3" in BOX_WGRAD
+# xb_gemm_halo_tc (activation tile resident in shared memory, taps = descriptor offsets): "2" = conv2's data gradient (its
+# four stride phases become ONE launch: 868 us vs 892 us as four box launches at B = 8192), "3" = also conv3 forward / data
+# gradient (473 / 479 us vs 461 / 469 us as box launches: no gain - with 64-column tiles the tensor pipe waits for its own
+# shared-memory operand reads, not for the fill of the ring), "0" = box launches only
+HALO_MODE = _os.environ.get("XB_K12_HALO", "2")
+HALO, HALO3 = HALO_MODE != "0", HALO_MODE in ("1", "3")
 
 
 def gemm_box(x_pl, w_pl, bg, bias=None, relu=False, out_f32=None, out_pl=None, out_ld=None, out_c0=0, relu_mask=None,
@@ -486,13 +496,80 @@ def gemm_box(x_pl, w_pl, bg, bias=None, relu=False, out_f32=None, out_pl=None, o
     xp, xs = _plane_arg(x_pl)
     wp, ws = _plane_arg(w_pl)
     op, os_ = _plane_arg(out_pl) if out_pl is not None else (None, 0)
-    _log_flops("xb_gemm_box_tc", bg.M, N, K, PA, PB)
+    _log_flops("xb_gemm_box_tc", bg.M, N, K, PA, PB, useful=bg.B * (bg.y1 - bg.y0 + 1) * bg.box_px * N)
     _lib.call("xb_gemm_box_tc", PA, PB, xp, xs, bg.C, bg.W, bg.B * bg.hp_in, bg.box_c, bg.box_px, bg.box_h, bg.row_step,
               len(bg.chunks), c0.data_ptr(), w0.data_ptr(), r0.data_ptr(), wp, ws,
               _lib.ptr(bias) if bias is not None else None, _lib.ptr(relu_mask) if relu_mask is not None else None,
               bg.mask_W, bg.mask_x0, bg.B, bg.hp_out, bg.y0, bg.y1, N, n_tile, 1 if relu else 0, op, os_,
               out_pl.shape[0] if out_pl is not None else 0, _lib.ptr(out_f32) if out_f32 is not None else None,
               bg.out_H, bg.out_W, bg.oys, bg.oxs, bg.oy0, bg.ox0, out_ld, out_c0, _lib.ptr(colsum) if colsum is not None else None)
+
+
+@dataclass
+class HaloGeometry:
+    """One ``xb_gemm_halo_tc`` call (include/xb200.h): stride-1 gathers over a 64-channel padded-row tensor
+    [planes][B*hp][W][64] with the activation tile resident in shared memory; ``subs`` = one entry per sub-item
+    (n tile / stride phase): dict(shifts=[(dr, dc), ...], y1, x1, oy0, ox0)."""
+    B: int
+    W: int
+    hp: int
+    halo_w: int
+    halo_w0: int
+    subs: List[dict]
+    y0: int
+    N: int
+    out_H: int
+    out_W: int
+    oys: int = 1
+    oxs: int = 1
+    same_cols: bool = False
+    mask_W: int = 0
+    mask_x0: int = 0
+
+    @property
+    def n_chunks(self):
+        return len(self.subs[0]["shifts"])
+
+    @property
+    def K(self):
+        return 64 * self.n_chunks
+
+    @property
+    def M(self):                  # positions of the haloed raster (rows the kernel computes)
+        return self.B * self.hp * self.halo_w
+
+    @property
+    def m_tiles(self):            # work items along M times sub-items (rows of a ``colsum`` buffer)
+        return -(-self.M // 128) * len(self.subs)
+
+
+_HALOTAB = {}
+
+
+def gemm_halo(x_pl, w_pl, hg, bias=None, relu=False, out_f32=None, out_pl=None, out_ld=None, out_c0=0, relu_mask=None, colsum=None):
+    """One K12 launch in halo mode (``x_pl`` [PA, B*hp, W, 64] padded rows, ``w_pl`` [PB, n_sub*N, n_chunks*64])."""
+    PB, Nw, K = w_pl.shape
+    PA = x_pl.shape[0]
+    n_sub = len(hg.subs)
+    assert K == hg.K and Nw == n_sub * hg.N and PA <= PB and tuple(x_pl.shape[1:]) == (hg.B * hg.hp, hg.W, 64), (x_pl.shape, w_pl.shape)
+    out_ld = (hg.N if hg.same_cols else Nw) if out_ld is None else out_ld
+    key = id(hg)
+    if key not in _HALOTAB:
+        i16 = lambda v: torch.tensor(v, dtype=torch.int16)
+        _HALOTAB[key] = (hg, i16([d[0] for sb in hg.subs for d in sb["shifts"]]), i16([d[1] for sb in hg.subs for d in sb["shifts"]]),
+                         i16([sb["y1"] for sb in hg.subs]), i16([sb["x1"] for sb in hg.subs]),
+                         i16([sb["oy0"] for sb in hg.subs]), i16([sb["ox0"] for sb in hg.subs]))
+    _, dr, dc, y1, x1, oy0, ox0 = _HALOTAB[key]
+    xp, xs = _plane_arg(x_pl)
+    wp, ws = _plane_arg(w_pl)
+    op, os_ = _plane_arg(out_pl) if out_pl is not None else (None, 0)
+    _log_flops("xb_gemm_halo_tc", hg.M, Nw, K, PA, PB, useful=sum(hg.B * (sb["y1"] - hg.y0 + 1) * (sb["x1"] + 1) * hg.N for sb in hg.subs))
+    _lib.call("xb_gemm_halo_tc", PA, PB, xp, xs, hg.W, hg.B * hg.hp, hg.halo_w, hg.halo_w0, n_sub, hg.n_chunks, dr.data_ptr(),
+              dc.data_ptr(), wp, ws, _lib.ptr(bias) if bias is not None else None,
+              _lib.ptr(relu_mask) if relu_mask is not None else None, hg.mask_W, hg.mask_x0, hg.B, hg.hp, hg.y0, y1.data_ptr(),
+              x1.data_ptr(), hg.N, 1 if relu else 0, op, os_, out_pl.shape[0] if out_pl is not None else 0,
+              _lib.ptr(out_f32) if out_f32 is not None else None, hg.out_H, hg.out_W, hg.oys, hg.oxs, oy0.data_ptr(), ox0.data_ptr(),
+              out_ld, out_c0, 1 if hg.same_cols else 0, _lib.ptr(colsum) if colsum is not None else None)
 
 
 def wgrad_box(x_pl, g_pl, bg, box_h, splits):
@@ -508,7 +585,7 @@ def wgrad_box(x_pl, g_pl, bg, box_h, splits):
     c0, w0, r0 = _BOXTAB[key]
     partials = torch.empty((splits, bg.K, N), dtype=torch.float32, device=g_pl.device)
     xp, xs = _plane_arg(x_pl)
-    _log_flops("xb_wgrad_box_tc", bg.K, N, g_rows * spr, PA, PB)
+    _log_flops("xb_wgrad_box_tc", bg.K, N, g_rows * spr, PA, PB, useful=bg.K * N * (bg.B * (bg.y1 - bg.y0 + 1) * spr) / (g_rows * spr))
     _lib.call("xb_wgrad_box_tc", PA, PB, xp, xs, bg.C, bg.W, bg.B * bg.hp_in, bg.box_c, bg.box_px, box_h, bg.row_step,
               len(bg.chunks), c0.data_ptr(), w0.data_ptr(), r0.data_ptr(), _lib.ptr(g_pl), g_pl.stride(0), g_rows, N, splits,
               _lib.ptr(partials))
@@ -591,6 +668,7 @@ class BoxNatureCNN(TensorCoreNatureCNN):
         w1.dy = [d - s1 * off1 for d in w1.dy]
         w1.out_H = hp1
         P["wg1"] = w1.check()
+        P["wg1"].useful_M = B * H1 * W1
         # ---- conv2 forward (box over act1's pixel-pair view [B*hp1, W1p/2, 64]): chunk = (kh, kw0 and kw0 + 1) x 32 channels
         ch2 = [(0, (kw - p2 + xo1) // 2, kh) for kh in range(k2) for kw in range(0, k2, 2)]
         P["fwd2"] = BoxGeometry(B=B, C=64, W=W1p // 2, hp_in=hp1, box_c=64, box_px=W2, box_h=hp2, row_step=2, chunks=ch2,
@@ -598,6 +676,7 @@ class BoxNatureCNN(TensorCoreNatureCNN):
         P["wg2"] = GatherGeometry(B=B, IH=hp1, IW=W1p, C=32, OY=hp2, OX=W2, sy=2, sx=2,
                                   dy=[kh for kh in range(k2) for _ in range(k2)],
                                   dx=[kw - p2 + xo1 for _ in range(k2) for kw in range(k2)], out_H=hp2, out_W=W2).check()
+        P["wg2"].useful_M = B * H2 * W2
         # ---- conv3 forward (box): chunk = one tap x 64 channels; result goes to the PLAIN [B, H3*W3*64] matrix the Linear reads
         taps3 = [(kh, kw) for kh in range(k3) for kw in range(k3)]
         P["taps3"] = taps3
@@ -606,6 +685,7 @@ class BoxNatureCNN(TensorCoreNatureCNN):
                                 out_H=H3, out_W=W3, oy0=0)
         P["wg3"] = GatherGeometry(B=B, IH=hp2, IW=W2, C=64, OY=hp2, OX=W2, sy=1, sx=1, dy=[kh - p3 for kh, _ in taps3],
                                   dx=[kw - p3 for _, kw in taps3], out_H=hp2, out_W=W2).check()
+        P["wg3"].useful_M = B * H2 * W2
         # ---- conv3 data gradient (box over the padded output gradient): flipped taps, written into act2's layout
         P["dg3"] = BoxGeometry(B=B, C=64, W=W2, hp_in=hp2, box_c=64, box_px=W2, box_h=hp2, row_step=1,
                                chunks=[(0, p3 - kw, p3 - kh) for kh, kw in taps3], hp_out=hp2, y0=1, y1=H2,
@@ -623,6 +703,17 @@ class BoxNatureCNN(TensorCoreNatureCNN):
                                         mask_W=W1p, mask_x0=xo1),
                             taps))
         P["dg2"] = dg2
+        # ---- the same three stride-1 gathers in halo mode (activation tile resident, only the weights stream)
+        full = dict(y1=H2, x1=W2 - 1, oy0=0, ox0=0)
+        P["h_fwd3"] = HaloGeometry(B=B, W=W2, hp=hp2, halo_w=W2 + 2, halo_w0=-1, y0=1, N=c3.out_channels, out_H=H3, out_W=W3,
+                                   subs=[dict(full, shifts=[(kh - p3, kw - p3) for kh, kw in taps3])])
+        P["h_dg3"] = HaloGeometry(B=B, W=W2, hp=hp2, halo_w=W2 + 2, halo_w0=-1, y0=1, N=c2.out_channels, out_H=hp2, out_W=W2,
+                                  subs=[dict(full, oy0=1, shifts=[(p3 - kh, p3 - kw) for kh, kw in taps3])])
+        subs2 = [dict(shifts=[(ch[2], ch[1]) for ch in bg.chunks], y1=bg.y1, x1=bg.box_px - 1, oy0=bg.oy0, ox0=bg.ox0) for bg, _ in dg2]
+        P["h_dg2"] = None
+        if len(subs2) <= 4 and len({len(sb["shifts"]) for sb in subs2}) == 1 and len(subs2) * len(subs2[0]["shifts"]) <= 16:
+            P["h_dg2"] = HaloGeometry(B=B, W=W2, hp=hp2, halo_w=W2 + 2, halo_w0=-1, y0=0, N=c1.out_channels, out_H=hp1, out_W=W1,
+                                      oys=2, oxs=2, same_cols=True, mask_W=W1p, mask_x0=xo1, subs=subs2)
         if self.fc is not None:
             N, K = self.fc.weight.shape
             assert K == H3 * W3 * c3.out_channels
@@ -656,6 +747,8 @@ class BoxNatureCNN(TensorCoreNatureCNN):
         outs = pack_weights(jobs, self.be.planes, c1.weight.device)
         n2 = len(P["dg2"])
         ops = dict(w1=outs[0], w2=outs[1], w3=outs[2], wd3=outs[3], wd2=outs[4:4 + n2])
+        if HALO and P["h_dg2"] is not None:
+            ops["wd2_all"] = torch.cat(ops["wd2"], 1)             # the phases' matrices stacked as the sub-items' weight rows
         if self.fc is not None:
             ops.update(wfc=outs[4 + n2], wfc_t=outs[5 + n2])
         return ops
@@ -673,7 +766,8 @@ class BoxNatureCNN(TensorCoreNatureCNN):
         act3 = be.empty_planes((B * n3, P["N3"]), x_pl)
         last_conv = self.fc is None
         out3 = be.empty_f32((B * n3, P["N3"]), x_pl) if last_conv else None
-        gemm_box(buf["act2"], ops["w3"], P["fwd3"], bias=c3.bias.detach(), relu=True, out_pl=act3, out_f32=out3, out_ld=P["N3"])
+        (gemm_halo if HALO3 else gemm_box)(buf["act2"], ops["w3"], P["h_fwd3"] if HALO3 else P["fwd3"], bias=c3.bias.detach(), relu=True,
+                                          out_pl=act3, out_f32=out3, out_ld=P["N3"])
         saved = dict(x=x_pl, act3=act3, scale=scale, ops=ops)
         if last_conv:
             self._saved = (B, saved)
@@ -737,8 +831,9 @@ class BoxNatureCNN(TensorCoreNatureCNN):
             dw3 = wgrad_reduce(wgrad_box(buf["act2"], g3, P["fwd3"], 6, sp3), P["N3"], P["N2"], k3, k3, **self._into(c3.weight))
         else:
             dw3 = be.wgrad(buf["act2"], g3.view(be.planes, -1, P["N3"]), P["wg3"], P["N3"], P["N2"], k3, k3, **self._into(c3.weight))
-        cs2 = torch.empty((P["dg3"].m_tiles, P["N2"]), dtype=torch.float32, device=dz.device)
-        gemm_box(g3, ops["wd3"], P["dg3"], out_pl=buf["g2"], out_ld=P["N2"], relu_mask=buf["act2"][0], colsum=cs2)
+        dg3 = P["h_dg3"] if HALO3 else P["dg3"]
+        cs2 = torch.empty((dg3.m_tiles, P["N2"]), dtype=torch.float32, device=dz.device)
+        (gemm_halo if HALO3 else gemm_box)(g3, ops["wd3"], dg3, out_pl=buf["g2"], out_ld=P["N2"], relu_mask=buf["act2"][0], colsum=cs2)
         db2 = bias_grad(cs2, P["N2"], **self._into(c2.bias))
         G2 = buf["g2"].view(be.planes, -1, P["N2"])
         k2 = c2.kernel_size[0]
@@ -748,11 +843,15 @@ class BoxNatureCNN(TensorCoreNatureCNN):
                                **self._into(c2.weight))
         else:
             dw2 = be.wgrad(buf["act1"], G2, P["wg2"], P["N2"], P["N1"], k2, k2, **self._into(c2.weight))
-        cs1 = torch.empty((sum(bg.m_tiles for bg, _ in P["dg2"]), P["N1"]), dtype=torch.float32, device=dz.device)
-        row = 0
-        for (bg, _), wd in zip(P["dg2"], ops["wd2"]):
-            gemm_box(buf["g2"], wd, bg, out_pl=buf["g1"], out_ld=P["N1"], relu_mask=buf["act1"][0], colsum=cs1[row:row + bg.m_tiles])
-            row += bg.m_tiles
+        if "wd2_all" in ops:
+            cs1 = torch.empty((P["h_dg2"].m_tiles, P["N1"]), dtype=torch.float32, device=dz.device)
+            gemm_halo(buf["g2"], ops["wd2_all"], P["h_dg2"], out_pl=buf["g1"], out_ld=P["N1"], relu_mask=buf["act1"][0], colsum=cs1)
+        else:
+            cs1 = torch.empty((sum(bg.m_tiles for bg, _ in P["dg2"]), P["N1"]), dtype=torch.float32, device=dz.device)
+            row = 0
+            for (bg, _), wd in zip(P["dg2"], ops["wd2"]):
+                gemm_box(buf["g2"], wd, bg, out_pl=buf["g1"], out_ld=P["N1"], relu_mask=buf["act1"][0], colsum=cs1[row:row + bg.m_tiles])
+                row += bg.m_tiles
         db1 = bias_grad(cs1, P["N1"], **self._into(c1.bias))
         G1 = buf["g1"].view(be.planes, -1, P["N1"])
         k1 = c1.kernel_size[0]
