@@ -299,6 +299,19 @@ def test_pack_weights_one_launch_equals_the_single_form_launches():
         for i, (a, b) in enumerate(zip(outs, want)):
             assert a.shape == b.shape, (i, a.shape, b.shape)
             assert torch.equal(a.view(torch.int16), b.view(torch.int16)), "form %d planes %d" % (i, planes)
+    # many taps (a Linear layer over a [C, H, W] feature map): the shared-memory tiled transposes of pack and reduce
+    w5 = torch.randn(64, 32, 10, 10, device=DEV)
+    f, t = tc.pack_weights([(w5, _lib.PACK_FORWARD, None, 1.0), (w5, _lib.PACK_TRANSPOSED, None, 0.5)], 3, DEV)
+    kmaj = w5.permute(0, 2, 3, 1).reshape(64, 3200)
+    assert torch.equal(f.view(torch.int16), tc.split_bf16(kmaj.contiguous(), 3).view(torch.int16))
+    assert torch.equal(t.view(torch.int16), tc.split_bf16((kmaj * 0.5).t().contiguous(), 3).view(torch.int16))
+    part = torch.randn(3, 3200, 64, device=DEV)
+    want_dw = (part.double().sum(0) * 0.25).t().reshape(64, 10, 10, 32).permute(0, 3, 1, 2)
+    dw = tc.wgrad_reduce(part.clone(), 64, 32, 10, 10, scale=0.25)
+    np.testing.assert_allclose(dw.cpu().numpy(), want_dw.cpu().numpy(), rtol=0, atol=2e-6)
+    acc = torch.ones(64, 32, 10, 10, device=DEV)
+    tc.wgrad_reduce(part.clone(), 64, 32, 10, 10, out=acc, accumulate=True, scale=0.25)
+    np.testing.assert_allclose(acc.cpu().numpy(), want_dw.cpu().numpy() + 1.0, rtol=0, atol=2e-6)
 
 
 @pytest.mark.parametrize("planes,atol", [(2, 5e-5), (3, 3e-6)])
