@@ -6,7 +6,7 @@ N=${1:-2}
 mkdir -p gpurun_out
 export NCCL_DEBUG=WARN
 run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node "$1" --master-addr 127.0.0.1 --master-port "$2" "${@:3}"; }
-timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench N=1 rc=$?"
+timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline ${XB_N1_FLAGS:-} > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench N=1 rc=$?"
 cut -c1-330 gpurun_out/bench_n1.json
 timeout 900 bash -c "$(declare -f run); run $N 29511 bench.py --gpus $N --steps 10 --warmup 3" > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench N=$N rc=$?"
 cut -c1-330 gpurun_out/bench_n$N.json; tail -4 gpurun_out/bench_n$N.err
