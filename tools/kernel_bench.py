@@ -4,7 +4,7 @@ shapes (SURVEY.md section 7 "hard parts": at the named PPO shape K2/K4/K5 move <
 bandwidth fraction is also reported at a scaled shape).  CUDA events on the launching stream, >= 3 warm-ups, L2
 flushed between timed launches (256 MB memset).  Prints one JSON object; profiles/rNN_kernels.json keeps a copy.
 
-    python tools/kernel_bench.py [--only k2,k4] [--reps 20]      (k12 / k3p: experimental tensor-core layers)
+    python tools/kernel_bench.py [--only k2,k4] [--reps 20]      (k12 / k12box / k3p: the tensor-core encoder layers, gathered and TMA-box / halo variants)
 """
 import argparse
 import json

@@ -1,24 +1,33 @@
 // K12: gathered-operand GEMM on the 5th-generation tensor cores (tcgen05.mma, TMEM accumulators) for the NatureCNN layers
-// (cnn.py:45-50, 84-101) - forward, data gradient and weight gradient of the three convolutions and the hidden layer, the
-// 85 % of the fp32 PPO step that cuDNN's CUDA-core fp32 convolutions take.
+// (cnn.py:45-50, 84-101) - forward, data gradient, weight gradient and bias gradient of the three convolutions and the hidden
+// layer, the 85 % of the fp32 PPO step that cuDNN's CUDA-core fp32 convolutions took (DESIGN.md sections 3, 3a, 7).
 //
 //   D[m, n] = sum_{t, c} in[b, y*sy + dy[t], x*sx + dx[t], c] * W[n, t*C + c]  (+ bias[n], ReLU)      conv_index.h
 //
 // Numerics: every fp32 operand travels as 1-3 bf16 planes (x = sum of its planes); the kept plane products are accumulated
 // in fp32 in TMEM, one accumulator per order of magnitude, and added smallest first in the epilogue (see the kernel).
 //
-// Structure (one CTA per SM, persistent over work items = (128-row tile, column tile), 13 warps):
-//   warps 5-12 producers : 256 threads, row-coalesced mapping (conv_index.h): per K chunk of 64 each thread issues its
-//                          16-byte cp.async units straight into the K-major (MN-major for the weight gradient) no-swizzle
-//                          canonical layout (zero-fill for padding taps / tail rows) and hands the stage's full barrier an
-//                          ASYNCHRONOUS arrival (cp.async.mbarrier.arrive.noinc) - no producer ever waits for a load, so
-//                          all `stages` chunks are in flight.
-//   warp 4     MMA       : lane 0 waits full[stage], issues PA tcgen05.mma per K step of 16 (A plane pa x the first PB - pa
-//                          weight planes, which sit adjacent in the stage and are ONE operand of (PB - pa) * N rows) and
-//                          commits onto empty[stage]; after the last chunk commits onto acc_full[a].  Two accumulator sets.
+// Structure (one CTA per SM, persistent over work items = (128-row tile, column tile[, split]), 13 warps):
+//   warps 5-12 producers : four ways to fill a stage, chosen per operand by the host entry point:
+//                          * TMA tiles with the 128-byte swizzle for plain matrices (packed weights, output gradients, the
+//                            Linear layer's inputs), all planes of an operand in one cp.async.bulk.tensor;
+//                          * TMA boxes over padded-row activations (a_box: xb_gemm_box_tc / xb_wgrad_box_tc), rank-5 view
+//                            {channel, pixel, row phase, row / stride, plane};
+//                          * a RESIDENT activation tile (a_halo: xb_gemm_halo_tc) - one box per plane and M tile, taps are
+//                            descriptor offsets, only the weights stream through the ring;
+//                          * 16-byte cp.async gathers into the no-swizzle canonical layout (conv1's raw pixels), 256
+//                            threads, row-coalesced mapping (conv_index.h), zero-fill for padding taps, ASYNCHRONOUS
+//                            arrival on the stage's full barrier (cp.async.mbarrier.arrive.noinc).
+//                          One elected thread arms the barrier with the TMA byte count; no producer waits for a load.
+//   warp 4     MMA       : the warp runs the loop on uniform values, the tcgen05 instructions are predicated on lane 0:
+//                          wait full[stage], PA tcgen05.mma per K step of 16 (A plane pa x the first PB - pa B planes,
+//                          adjacent in the stage = ONE operand of (PB - pa) * N rows; descriptor = per-launch template +
+//                          start address), commit onto empty[stage]; after the last chunk commit onto acc_full[a].  Two
+//                          accumulator sets in TMEM.
 //   warps 0-3  epilogue  : thread = row = TMEM lane.  tcgen05.ld 32 columns at a time from each accumulator group, added
-//                          smallest first, bias + ReLU / ReLU-derivative mask, then the row is written as fp32 and / or as
-//                          the bf16 planes the next layer consumes.
+//                          smallest first, bias + ReLU / ReLU-derivative mask, the row written as fp32 and / or as the bf16
+//                          planes the next layer consumes (into its padded layout), and the column sums of the tile
+//                          (the bias-gradient partials of the layer below).
 #include <cstdlib>
 
 #include <cuda.h>      // CUtensorMap + the cuTensorMapEncodeTiled prototype (resolved at run time through the runtime API)
