@@ -119,6 +119,15 @@ def test_every_entry_point_validates_before_touching_the_device():
     assert gg(ld=32) == EINVAL                         # output row shorter than out_c0 + N
     assert gg(ld=68, c0=4) == EALIGN                   # 16-byte output segments
     assert gg(w=odd) == EALIGN
+    # halo mode: argument validation that precedes any CUDA / driver call
+    i16 = (ctypes.c_int16 * 16)()
+    halo = lambda n_sub=1, n_chunks=9, W=10, hw=12, w0=-1, rows=24, B=2, hp=12, tabs=i16: lib.xb_gemm_halo_tc(
+        3, 3, junk, 1024, W, rows, hw, w0, n_sub, n_chunks, tabs, tabs, junk, 1024, None, None, 0, 0, B, hp, 1, i16, i16, 64, 1,
+        junk, 1024, 3, None, 10, 10, 1, 1, i16, i16, 64, 0, 0, None, None)
+    assert halo(tabs=None) == EINVAL
+    assert halo(n_sub=5) == ERANGE and halo(n_sub=2, n_chunks=9) == ERANGE      # at most 4 sub-items, 16 chunks in all
+    assert halo(hw=8) == EINVAL                                                # the raster row must hold the tensor row
+    assert halo(w0=1) == EINVAL and halo(rows=25) == EINVAL                     # pixel origin <= 0; in_rows = B * hp
     from xuance_b200._lib import XbPackJob
     jobs = (XbPackJob * 2)()
     for J in jobs:
