@@ -237,3 +237,51 @@ def test_sibling_learners_live(ref, kind):
     sd1, sd2 = model.state_dict(), om.state_dict()
     for k in sd1:
         np.testing.assert_allclose(sd2[k].numpy(), sd1[k].numpy(), rtol=1e-5, atol=1e-6, err_msg=k)
+
+
+def _same(a, b, path=""):
+    """Structural equality of nested dict / list / ndarray / scalar results."""
+    if isinstance(a, dict):
+        assert isinstance(b, dict) and set(a) == set(b), (path, sorted(a), sorted(b) if isinstance(b, dict) else b)
+        for k in a:
+            _same(a[k], b[k], path + "/" + str(k))
+    elif isinstance(a, (list, tuple)):
+        assert len(a) == len(b), path
+        for i, (x, y) in enumerate(zip(a, b)):
+            _same(x, y, path + "[%d]" % i)
+    elif isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
+        assert np.array_equal(np.asarray(a), np.asarray(b)), path
+    else:
+        assert a == b, (path, a, b)
+
+
+def test_multi_agent_vector_env_live(ref):
+    """DummyVecMultiAgentEnv + XuanCeMultiAgentEnvWrapper (the QMIX caller side, vector_envs/dummy/dummy_vec_maenv.py:17-84,
+    environment/utils/wrapper.py:141-226) next to the live reference classes over the SAME raw synthetic environments:
+    identical observations, reward / terminated dicts, truncation flags and infos (episode_step, episode_score, agent_mask,
+    avail_actions, state, reset_obs / reset_avail_actions / reset_state at episode ends) step for step."""
+    from xuance.environment.utils.wrapper import XuanCeMultiAgentEnvWrapper as RefWrapper
+    from xuance.environment.vector_envs.dummy.dummy_vec_maenv import DummyVecMultiAgentEnv as RefVec
+    from xuance_b200.environment.ma_envs import SyntheticSMACEnv, XuanCeMultiAgentEnvWrapper
+    from xuance_b200.environment.vector_envs.dummy_vec_maenv import DummyVecMultiAgentEnv
+    kw = dict(n_agents=3, obs_dim=16, state_dim=20, n_actions=5, episode_limit=7, p_death=0.1)
+    n_envs = 3
+    mk_ref = [lambda env_seed=0: RefWrapper(SyntheticSMACEnv(seed=env_seed, **kw)) for _ in range(n_envs)]
+    mk_own = [lambda env_seed=0: XuanCeMultiAgentEnvWrapper(SyntheticSMACEnv(seed=env_seed, **kw)) for _ in range(n_envs)]
+    rv, ov = RefVec(mk_ref, 11), DummyVecMultiAgentEnv(mk_own, 11)
+    assert rv.num_envs == ov.num_envs and rv.agents == ov.agents and rv.num_agents == ov.num_agents
+    assert rv.max_episode_steps == ov.max_episode_steps and rv.state_space.shape == ov.state_space.shape
+    (ro, ri), (oo, oi) = rv.reset(), ov.reset()
+    _same(ro, oo, "reset obs"), _same(ri, oi, "reset info")
+    rng = np.random.default_rng(2)
+    ends = 0
+    for t in range(40):
+        # a random AVAILABLE action per agent (the same for both stacks)
+        acts = [{a: int(rng.choice(np.flatnonzero(rv.buf_avail_actions[e][a]))) for a in rv.agents} for e in range(n_envs)]
+        r, o = rv.step(acts), ov.step(acts)
+        for name, x, y in zip(("obs", "rewards", "terminated", "truncated", "infos"), r, o):
+            _same(x, y, "t=%d %s" % (t, name))
+        _same(rv.buf_state, ov.buf_state, "state"), _same(rv.buf_avail_actions, ov.buf_avail_actions, "avail")
+        ends += sum("reset_obs" in i for i in r[4])
+    assert ends >= 5                                    # episode ends (death of all agents / truncation) were exercised
+    rv.close(), ov.close()
