@@ -110,7 +110,7 @@ class _PixelEncoder(nn.Module):
             x = self._as_input_f32_nhwc(observations)
             planes = tc_conv.split_bf16(x, P)
         B = planes.shape[1]
-        z = tc_conv.tc_encode(self._tc, planes, B) if torch.is_grad_enabled() else self._tc.forward(planes, B)
+        z = tc_conv.tc_encode(self._tc, planes, B) if torch.is_grad_enabled() else self._tc.forward(planes, B, keep=False)
         if self._tc_pooled:         # [B*OY*OX, C] NHWC rows of the last convolution -> global max over the sites (cnn.py:47-48)
             z = z.view(B, -1, z.shape[-1]).amax(dim=1)
         return z

@@ -374,7 +374,8 @@ class TensorCoreNatureCNN:
         return layers
 
     # ---- forward: returns float32 [sites of the last layer, features]; keeps what backward needs
-    def forward(self, x_pl, B):
+    def forward(self, x_pl, B, keep=True):
+        """``keep=False`` (inference under no_grad): nothing a pending backward needs is overwritten."""
         be, plan = self.be, self._plan(B)
         raw = x_pl.shape[0] == 1 and be.planes > 1          # one exact plane of uint8 values: 1/255 goes into the weights
         saved, cur, out_f32 = [], x_pl, None
@@ -389,7 +390,8 @@ class TensorCoreNatureCNN:
             be.gemm(cur, w_pl, g, bias=mod.bias.detach(), relu=True, out_f32=out_f32, out_pl=out_pl, out_ld=N)
             saved.append(dict(x=cur, y=out_pl, w4=w4, scale=scale))
             cur = out_pl
-        self._saved = (B, saved)
+        if keep:
+            self._saved = (B, saved)
         return out_f32
 
     # ---- backward: dz float32 = gradient w.r.t. the array forward() returned; returns gradients in parameters() order
@@ -721,8 +723,11 @@ class BoxNatureCNN(TensorCoreNatureCNN):
         self._plans[B] = P
         return P
 
-    def _buffers(self, B, like):
-        key = ("buf", B)
+    def _buffers(self, B, like, keep=True):
+        """Persistent zero-initialised padded tensors of batch size B.  ``keep=False``: a second set for inference calls
+        (rollout / target / double-Q forwards under no_grad), so that they never overwrite the activations a pending
+        backward of the SAME encoder still needs (act1 / act2 are both layer outputs and saved activations)."""
+        key = ("buf", B) if keep else ("buf_inference", B)
         if key not in self._plans:
             P, be = self._plan(B), self.be
             z = lambda *shape: torch.zeros((be.planes,) + shape, dtype=torch.bfloat16, device=like.device)
@@ -753,9 +758,10 @@ class BoxNatureCNN(TensorCoreNatureCNN):
             ops.update(wfc=outs[4 + n2], wfc_t=outs[5 + n2])
         return ops
 
-    def forward(self, x_pl, B):
+    def forward(self, x_pl, B, keep=True):
+        """``keep=False`` (inference under no_grad): own activation buffers, ``_saved`` untouched."""
         be, P = self.be, self._plan(B)
-        buf = self._buffers(B, x_pl)
+        buf = self._buffers(B, x_pl, keep)
         c1, c2, c3 = self.convs
         raw = x_pl.shape[0] == 1 and be.planes > 1
         scale = 1.0 / 255.0 if raw else 1.0
@@ -770,14 +776,16 @@ class BoxNatureCNN(TensorCoreNatureCNN):
                                           out_pl=act3, out_f32=out3, out_ld=P["N3"])
         saved = dict(x=x_pl, act3=act3, scale=scale, ops=ops)
         if last_conv:
-            self._saved = (B, saved)
+            if keep:
+                self._saved = (B, saved)
             return out3
         F_ = P["fc"]
         y = be.empty_planes((B, F_["N"]), x_pl)
         out = be.empty_f32((B, F_["N"]), x_pl)
         gemm_gather(act3.view(be.planes, B, F_["K"]), ops["wfc"], F_["fwd"], bias=self.fc.bias.detach(), relu=True, out_f32=out, out_pl=y)
         saved.update(y=y)
-        self._saved = (B, saved)
+        if keep:
+            self._saved = (B, saved)
         return out
 
     @staticmethod
