@@ -8,8 +8,10 @@ mixer, QMIX_Learner.update.  TEST INFRASTRUCTURE (see oracle/__init__).
   * MixingQNetwork forward / Qtarget / Q_tot / copy_target ............... architectures/multi_agent/value_factorization.py:17-174
   * build_training_data + _forward_transitions + QMIX_Learner.update ..... learners/base/marl_learner.py:319-408,
                                                  learners/multi_agent_rl/iql_learner.py:37-83, qmix_learner.py:24-112
-Scope: one parameter-sharing group ("shared"), use_rnn=True, use_actions_mask=False (the reference's RNN+mask path
-crashes, SURVEY.md headline 6).  Module / parameter names mirror the reference so its state_dict loads 1:1."""
+Scope: one parameter-sharing group ("shared"), use_rnn=True; use_actions_mask=False as the reference runs it, and the masked
+variant the reference evidently intends (its RNN+mask path crashes on one slice, SURVEY.md headline 6), pinned against the
+live reference with that slice corrected at test time.  Module / parameter names mirror the reference so its state_dict
+loads 1:1."""
 import copy
 import numpy as np
 import torch
@@ -161,8 +163,9 @@ class QMIXLearnerOracle:
         """``use_actions_mask=True`` is the INTENDED masking of iql_learner.py:60-81 / value_factorization.py:86-89 for
         use_rnn (the double-Q arg-max sees unavailable actions at -1e10; target values of unavailable actions at step t+1
         become -1e10) with the time axis sliced as ``[:, :, 1:]``.  The reference at 4f0b05b slices the AGENT axis there
-        (``[:, 1:]``) and raises a shape error, so this variant cannot be pinned to a live run: "parity unpinned" for the
-        masked branch only - it is anchored on the unmasked branch (which is pinned) plus the two masking statements.
+        (``[:, 1:]``) and raises a shape error, so this variant cannot be pinned to the reference as it is; it is pinned to
+        the live reference learner with that ONE expression corrected in memory at test time
+        (tests/test_oracle_vs_reference.py::test_qmix_action_mask_variant_against_the_reference_with_its_slice_corrected).
         ``detach_q_eval=True`` reproduces the reference AS IS: iql_learner.py:57-59 slices ``q_eval`` to
         ``[:, :, :-1]`` INSIDE ``torch.no_grad()``, so with use_rnn=True the sliced tensor carries no graph and the
         agent networks receive no gradient - only the mixer trains (verified against the live reference:

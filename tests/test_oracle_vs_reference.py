@@ -285,3 +285,73 @@ def test_multi_agent_vector_env_live(ref):
         ends += sum("reset_obs" in i for i in r[4])
     assert ends >= 5                                    # episode ends (death of all agents / truncation) were exercised
     rv.close(), ov.close()
+
+
+def test_qmix_action_mask_variant_against_the_reference_with_its_slice_corrected(ref, monkeypatch):
+    """use_rnn=True with use_actions_mask=True: the reference slices the AGENT axis of the availability mask
+    (iql_learner.py:78, ``[:, 1:]``) and raises; the evidently intended statement slices the time axis (``[:, :, 1:]``).
+    The oracle's masked variant (and through it xb_qmix_select_fwd's masked arg-max / target, tests/test_gpu_qmix.py) is pinned
+    here against the LIVE reference learner with that ONE expression corrected at run time - the reference source is read
+    from /root/reference, patched in memory and executed; nothing of it is stored in this repository."""
+    import inspect
+    import textwrap
+    from gymnasium.spaces import Box, Discrete
+    from xuance.common.memory_tools_marl import MARL_OffPolicyBuffer_RNN
+    from xuance.torch.learners.multi_agent_rl import iql_learner as iql
+    torch.manual_seed(1)
+    n, obs_dim, A, S, T = 4, 24, 7, 30, 9
+    keys, model, lrn, om, orc = _qmix_pair(n, obs_dim, A, S, T)
+    lrn.use_actions_mask = lrn.config.use_actions_mask = True
+    orc.use_actions_mask = True
+    n_envs, C, Be = 3, 12, 6
+    rb = MARL_OffPolicyBuffer_RNN(agent_keys=keys, state_space=Box(-1, 1, (S,)),
+                                  obs_space={k: Box(-1, 1, (obs_dim,)) for k in keys},
+                                  act_space={k: Discrete(A) for k in keys}, n_envs=n_envs, buffer_size=C,
+                                  batch_size=Be, max_episode_steps=T, use_actions_mask=True,
+                                  avail_actions_shape={k: (A,) for k in keys})
+    rng = np.random.default_rng(4)
+
+    def avail(shape_prefix):
+        a = rng.random(shape_prefix + (A,)) < 0.6
+        a[..., 0] = True                                    # never an all-unavailable row
+        return a
+    for ev in qmix_episode_stream(np.random.default_rng(3), keys, n_envs, T, obs_dim, A, S, 5):
+        if ev[0] == 'store':
+            rb.store(avail_actions={k: avail((n_envs,)) for k in keys}, **ev[1])
+        else:
+            rb.finish_path(ev[1], avail_actions={k: avail(()) for k in keys}, **ev[2])
+    np.random.seed(0)
+    sample = rb.sample()
+    assert sample['avail_actions'][keys[0]].shape == (Be, T + 1, A)
+    # 1. the reference as it is cannot run this configuration
+    snap = {k: v.clone() for k, v in model.state_dict().items()}
+    with pytest.raises((RuntimeError, IndexError)):
+        lrn.update(sample)
+    model.load_state_dict(snap)
+    lrn.iterations = 0
+    # 2. the same learner with the one slice corrected
+    src = textwrap.dedent(inspect.getsource(iql.IQL_Learner._forward_transitions))
+    bad = "batch.avail_actions.group(group)[:, 1:]"
+    assert src.count(bad) == 1, "the reference's masked RNN branch changed - re-read iql_learner.py:60-81"
+    scope = {}
+    exec(compile(src.replace(bad, "batch.avail_actions.group(group)[:, :, 1:]"), "iql_learner.py (slice corrected)", "exec"),
+         vars(iql), scope)
+    monkeypatch.setattr(iql.IQL_Learner, "_forward_transitions", scope["_forward_transitions"])
+    for it in range(3):
+        np.random.seed(10 + it)
+        s = rb.sample()
+        i1, i2 = lrn.update(s), orc.update(s)
+        np.testing.assert_allclose(i1['loss_Q'], i2['loss_Q'], rtol=1e-5)
+        np.testing.assert_allclose(i1['predictQ'], i2['predictQ'], rtol=1e-5, atol=1e-7)
+    sd1, sd2 = model.state_dict(), om.state_dict()
+    for k in sd1:
+        np.testing.assert_allclose(sd2[k].numpy(), sd1[k].numpy(), rtol=1e-5, atol=1e-6, err_msg=k)
+    # the masks mattered: the same first update without them has a different loss
+    _, _, _, om_m, orc_m = _qmix_pair(n, obs_dim, A, S, T)
+    _, _, _, om_u, orc_u = _qmix_pair(n, obs_dim, A, S, T)
+    om_m.load_state_dict(snap, strict=True), om_u.load_state_dict(snap, strict=True)
+    om_m.copy_target(), om_u.copy_target()
+    orc_m.use_actions_mask = True
+    np.random.seed(10)
+    s = rb.sample()
+    assert abs(orc_m.update(s)['loss_Q'] - orc_u.update(s)['loss_Q']) > 1e-6
