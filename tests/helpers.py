@@ -80,3 +80,17 @@ def qmix_episode_stream(rng, keys, n_envs, T, obs_dim, A, S, episodes):
                                              state=rng.normal(size=S).astype(np.float32)))
 
 
+def same_structure(a, b, path=""):
+    """Structural equality of nested dict / list / ndarray / scalar results."""
+    if isinstance(a, dict):
+        assert isinstance(b, dict) and set(a) == set(b), (path, sorted(a), sorted(b) if isinstance(b, dict) else b)
+        for k in a:
+            same_structure(a[k], b[k], path + "/" + str(k))
+    elif isinstance(a, (list, tuple)):
+        assert len(a) == len(b), path
+        for i, (x, y) in enumerate(zip(a, b)):
+            same_structure(x, y, path + "[%d]" % i)
+    elif isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
+        assert np.array_equal(np.asarray(a), np.asarray(b)), path
+    else:
+        assert a == b, (path, a, b)

@@ -205,3 +205,53 @@ def test_shm_vec_env_exposes_shared_block_without_copy():
     obs, *_ = envs.step_wait(copy=False)
     assert obs is envs.buf_obs and obs.dtype == np.uint8 and obs.shape == (4, 84, 84, 4) and obs.any()
     envs.close()
+
+
+def _ma_fns(n, kw):
+    from xuance_b200.environment.ma_envs import SyntheticSMACEnv, XuanCeMultiAgentEnvWrapper
+    return [lambda env_seed=0: XuanCeMultiAgentEnvWrapper(SyntheticSMACEnv(seed=env_seed, **kw)) for _ in range(n)]
+
+
+@pytest.mark.parametrize("context,in_series", [("fork", 1), ("spawn", 2)])
+def test_subproc_multi_agent_vector_env_equals_the_dummy_one(context, in_series):
+    """SubprocVecMultiAgentEnv (subproc_vec_maenv.py:8-145): the same environments in worker processes give the same
+    observations, rewards, terminations, infos (incl. reset_* at episode ends) and state / availability latches as
+    DummyVecMultiAgentEnv, step for step; seeds env_seed + i; AlreadyStepping / NotStepping errors; idempotent close."""
+    from xuance_b200.environment import REGISTRY_VEC_ENV, make_envs
+    from xuance_b200.environment.vector_envs import (DummyVecMultiAgentEnv, SubprocVecMultiAgentEnv, AlreadySteppingError,
+                                                     NotSteppingError)
+    from helpers import same_structure as _same
+    kw = dict(n_agents=3, obs_dim=16, state_dim=20, n_actions=5, episode_limit=6, p_death=0.1)
+    n = 4
+    dv, sv = DummyVecMultiAgentEnv(_ma_fns(n, kw), 7), SubprocVecMultiAgentEnv(_ma_fns(n, kw), 7, context=context, in_series=in_series)
+    try:
+        assert REGISTRY_VEC_ENV["Subproc_StarCraft2"] is SubprocVecMultiAgentEnv
+        assert sv.num_envs == n and sv.agents == dv.agents and sv.max_episode_steps == dv.max_episode_steps
+        assert sv.state_space.shape == dv.state_space.shape and sv.env_info["num_agents"] == 3
+        _same(dv.reset(), sv.reset(), "reset")
+        with pytest.raises(NotSteppingError):
+            sv.step_wait()
+        rng = np.random.default_rng(0)
+        ends = 0
+        for t in range(25):
+            acts = [{a: int(rng.choice(np.flatnonzero(dv.buf_avail_actions[e][a]))) for a in dv.agents} for e in range(n)]
+            sv.step_async(acts)
+            with pytest.raises(AlreadySteppingError):
+                sv.step_async(acts)
+            r_s = sv.step_wait()
+            r_d = dv.step(acts)
+            _same(r_d, r_s, "t=%d" % t)
+            _same(dv.buf_state, sv.buf_state, "state"), _same(dv.buf_avail_actions, sv.buf_avail_actions, "avail")
+            ends += sum("reset_obs" in i for i in r_s[4])
+        assert ends >= 4
+    finally:
+        sv.close(), sv.close(), dv.close()
+    cfg = Namespace(env_name="StarCraft2", env_id="5m_vs_6m", vectorize="Subproc_StarCraft2", parallels=2, env_seed=3,
+                    episode_limit=5)
+    envs = make_envs(cfg)
+    try:
+        assert isinstance(envs, SubprocVecMultiAgentEnv) and envs.num_agents == 5 and envs.max_episode_steps == 5
+        obs, infos = envs.reset()
+        assert len(obs) == 2 and obs[0]["agent_0"].shape == (72,) and infos[1]["state"].shape == (98,)
+    finally:
+        envs.close()

@@ -8,7 +8,7 @@ import pytest
 import torch
 import torch.nn as nn
 
-from helpers import synth_rollout, fill_buffers, qmix_episode_stream
+from helpers import synth_rollout, fill_buffers, qmix_episode_stream, same_structure as _same
 
 pytestmark = pytest.mark.reference
 
@@ -237,22 +237,6 @@ def test_sibling_learners_live(ref, kind):
     sd1, sd2 = model.state_dict(), om.state_dict()
     for k in sd1:
         np.testing.assert_allclose(sd2[k].numpy(), sd1[k].numpy(), rtol=1e-5, atol=1e-6, err_msg=k)
-
-
-def _same(a, b, path=""):
-    """Structural equality of nested dict / list / ndarray / scalar results."""
-    if isinstance(a, dict):
-        assert isinstance(b, dict) and set(a) == set(b), (path, sorted(a), sorted(b) if isinstance(b, dict) else b)
-        for k in a:
-            _same(a[k], b[k], path + "/" + str(k))
-    elif isinstance(a, (list, tuple)):
-        assert len(a) == len(b), path
-        for i, (x, y) in enumerate(zip(a, b)):
-            _same(x, y, path + "[%d]" % i)
-    elif isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
-        assert np.array_equal(np.asarray(a), np.asarray(b)), path
-    else:
-        assert a == b, (path, a, b)
 
 
 def test_multi_agent_vector_env_live(ref):

@@ -2,7 +2,7 @@
 from .envs import REGISTRY_ENV, XuanCeEnvWrapper, CartPoleEnv, SyntheticAtariEnv
 from .ma_envs import SyntheticSMACEnv, XuanCeMultiAgentEnvWrapper
 from .vector_envs import (REGISTRY_VEC_ENV, VecEnv, DummyVecEnv, DummyVecEnv_Atari, SubprocVecEnv, SubprocVecEnv_Atari,
-                          ShmSubprocVecEnv, ShmSubprocVecEnv_Atari, DummyVecMultiAgentEnv)
+                          ShmSubprocVecEnv, ShmSubprocVecEnv_Atari, DummyVecMultiAgentEnv, SubprocVecMultiAgentEnv)
 from .tensor_env import TensorEnvWrapper
 
 
@@ -17,9 +17,12 @@ def make_envs(config):
     base_seed = getattr(config, "env_seed", 1) + rank * n
     if getattr(config, "env_name", None) == "StarCraft2":       # SMAC-shaped synthetic multi-agent env (QMIX path)
         kw = {k: getattr(config, k) for k in ("episode_limit", "p_death", "p_mask") if hasattr(config, k)}
-        fns = [lambda env_seed=None, **_: XuanCeMultiAgentEnvWrapper(SyntheticSMACEnv(seed=env_seed, map_name=config.env_id, **kw))
+        map_name = config.env_id
+        fns = [lambda env_seed=None, **_: XuanCeMultiAgentEnvWrapper(SyntheticSMACEnv(seed=env_seed, map_name=map_name, **kw))
                for _ in range(n)]
-        return DummyVecMultiAgentEnv(fns, base_seed)
+        vec = getattr(config, "vectorize", "Dummy_StarCraft2")
+        vec_cls = REGISTRY_VEC_ENV[vec] if vec in ("SubprocVecMultiAgentEnv", "Subproc_StarCraft2") else DummyVecMultiAgentEnv
+        return vec_cls(fns, base_seed)
     env_cls = REGISTRY_ENV[config.env_id]
 
     def thunk(i):
