@@ -255,3 +255,29 @@ def test_subproc_multi_agent_vector_env_equals_the_dummy_one(context, in_series)
         assert len(obs) == 2 and obs[0]["agent_0"].shape == (72,) and infos[1]["state"].shape == (98,)
     finally:
         envs.close()
+
+
+def test_shipped_configs_define_every_key_their_classes_read():
+    """Static check (the classes themselves need a GPU): every ``config.X`` an agent / learner of a shipped yaml reads without a
+    getattr / hasattr default is a key of basic.yaml + that yaml - ``get_runner(algo, env)`` cannot die on an AttributeError."""
+    import glob
+    import re
+    import yaml
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "xuance_b200")
+    rd = lambda *p: open(os.path.join(root, *p)).read()
+    base = set(yaml.safe_load(rd("configs", "basic.yaml")))
+    per_agent = {"QMIX": ["torch/agents/marl.py", "torch/learners/qmix_learner.py"],
+                 "PPO": ["torch/agents/on_policy.py", "torch/agents/ppo_agent.py", "torch/learners/ppo_learner.py"],
+                 "PerDQN": ["torch/agents/off_policy.py", "torch/agents/dqn_agent.py", "torch/learners/dqn_learner.py"],
+                 "SAC": ["torch/agents/off_policy.py", "torch/agents/sac_agent.py", "torch/learners/sac_learner.py"]}
+    common = ["torch/agents/agent.py", "torch/learners/learner.py"]
+    seen = set()
+    for y in sorted(glob.glob(os.path.join(root, "configs", "*", "*.yaml"))):
+        cfg = yaml.safe_load(open(y))
+        seen.add(cfg["agent"])
+        src = "".join(rd(*f.split("/")) for f in per_agent[cfg["agent"]] + common)
+        hard = set(re.findall(r"(?<![a-zA-Z_])(?:self\.)?config\.([a-zA-Z_][a-zA-Z0-9_]*)\b(?!\s*=[^=])", src))
+        soft = set(re.findall(r"(?:getattr|hasattr)\((?:self\.)?config,\s*.([a-zA-Z_0-9]+).", src))
+        missing = sorted(hard - soft - base - set(cfg))
+        assert not missing, (os.path.relpath(y, root), missing)
+    assert seen == set(per_agent)
