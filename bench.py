@@ -498,9 +498,10 @@ def run_own_arm(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32" if args.compute != "bf16" else "bf16",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_minibatch": N_ENVS * T // N_MINIBATCH,
-                       "parallelism": ("dp%d (envs sharded; per update the flat gradient bucket is all-reduced in two pieces: Linear + head "
-                                       "gradients early, overlapping the convolution backward, then [statistics | convolution "
-                                       "gradients]; XB_EARLY_ALLREDUCE=0: one piece)" % world) if world > 1 else "dp1 (single GPU, no collective)",
+                       "parallelism": ("dp%d (envs sharded; ONE all-reduce of the flat gradient bucket + statistics per update%s)"
+                                       % (world, "; XB_EARLY_ALLREDUCE=1: Linear + head gradients reduced early, two pieces"
+                                          if os.environ.get("XB_EARLY_ALLREDUCE", "0") == "1" else ""))
+                                      if world > 1 else "dp1 (single GPU, no collective)",
                        "compute": {"fp32": "fp32, TF32 disabled (reference arithmetic)", "fp32_cl": "fp32, TF32 disabled, channels-last convolutions", "tf32": "fp32 storage, TF32 convs/matmuls",
                                    "bf16": "bf16 autocast convs, fp32 master weights",
                                    "tc": "tcgen05 layers (K12): every fp32 operand as %d bf16 planes (exact to 2^-%d), raw uint8 pixels as "
